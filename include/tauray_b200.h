@@ -1,0 +1,343 @@
+/* tauray_b200.h -- C ABI of the B200-native path-tracing hot path.
+ *
+ * This library replaces three pieces of vga-group/tauray behind its renderer/stage surface:
+ *   rt_pipeline            (src/rt_pipeline.cc:13-192)           -> CUDA kernel launch table
+ *   path_tracer_stage      (src/path_tracer_stage.cc:30-147)     -> tr_pt_create / tr_pt_render
+ *   acceleration_structure (src/acceleration_structure.cc:8-443) -> on-device LBVH built by tr_pt_set_scene
+ * plus the multi-GPU gather of stitch_stage/device_transfer (src/stitch_stage.cc:128-196,
+ * src/device_transfer.cc:140-347) -> strip buffers exchanged over NVLink + tr_pt_unshuffle.
+ *
+ * Conventions: every entry point returns 0 or a negative tr_status, never
+ * throws; the caller owns all input memory (it is copied during the call); the library owns
+ * device memory; one host thread per context; all GPU work is ordered on the context's stream
+ * (the stream plays the role of the reference's `dependencies`). There is NO CPU fallback:
+ * tr_pt_create fails with TR_ERR_NO_DEVICE when no sm_100 device is usable.
+ *
+ * All table structs below are the reference's own GPU wire formats (GLSL `scalar` layout),
+ * so Tauray's scene_stage can hand over its staging data unchanged. Matrices are
+ * column-major (glm), as in the reference.
+ */
+#ifndef TAURAY_B200_H
+#define TAURAY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TR_B200_ABI_VERSION 1
+
+typedef enum tr_status {
+    TR_OK = 0,
+    TR_ERR_INVALID_ARGUMENT = -1,
+    TR_ERR_NO_DEVICE = -2,       /* no CUDA device / not sm_100: there is no fallback */
+    TR_ERR_CUDA = -3,            /* a CUDA runtime call failed, see tr_pt_last_error */
+    TR_ERR_UNSUPPORTED = -4,     /* option combination outside the hot-path scope */
+    TR_ERR_NO_SCENE = -5,
+    TR_ERR_OUT_OF_MEMORY = -6
+} tr_status;
+
+/* ---- enums: values equal the reference's ------------------------------------------- */
+/* rt_stage::sampler_type, src/rt_stage.hh:21-27 */
+enum { TR_SAMPLER_UNIFORM_RANDOM = 0, TR_SAMPLER_SOBOL_OWEN = 1,
+       TR_SAMPLER_SOBOL_Z_ORDER_2D = 2, TR_SAMPLER_SOBOL_Z_ORDER_3D = 3 };
+/* film_filter, src/rt_common.hh:8-13 */
+enum { TR_FILM_POINT = 0, TR_FILM_BOX = 1, TR_FILM_BLACKMAN_HARRIS = 2 };
+/* multiple_importance_sampling_mode, src/rt_common.hh:16-21 */
+enum { TR_MIS_DISABLED = 0, TR_MIS_BALANCE_HEURISTIC = 1, TR_MIS_POWER_HEURISTIC = 2 };
+/* bounce_sampling_mode, src/rt_common.hh:24-29 */
+enum { TR_BOUNCE_HEMISPHERE = 0, TR_BOUNCE_COSINE_HEMISPHERE = 1, TR_BOUNCE_MATERIAL = 2 };
+/* tri_light_sampling_mode, src/rt_common.hh:32-37 */
+enum { TR_TRI_LIGHT_AREA = 0, TR_TRI_LIGHT_SOLID_ANGLE = 1, TR_TRI_LIGHT_HYBRID = 2 };
+/* distribution_strategy, src/distribution_strategy.hh:8-18 */
+enum { TR_DISTRIBUTION_DUPLICATE = 0, TR_DISTRIBUTION_SCANLINE = 1,
+       TR_DISTRIBUTION_SHUFFLED_STRIPS = 2 };
+/* camera::projection_type (perspective / orthographic share one layout, src/camera.cc:397-407) */
+enum { TR_PROJECTION_PERSPECTIVE = 0, TR_PROJECTION_ORTHOGRAPHIC = 1 };
+/* feature_stage::feature, src/feature_stage.cc:35-66 (the AOV tracer) */
+enum { TR_FEATURE_ALBEDO = 0, TR_FEATURE_WORLD_NORMAL = 1, TR_FEATURE_VIEW_NORMAL = 2,
+       TR_FEATURE_WORLD_POS = 3, TR_FEATURE_VIEW_POS = 4, TR_FEATURE_DISTANCE = 5,
+       TR_FEATURE_INSTANCE_ID = 9 };
+/* kernel organisation of the hot loop (ours) */
+enum { TR_KERNEL_WAVEFRONT = 0, TR_KERNEL_MEGAKERNEL = 1 };
+/* texture formats accepted in tr_texture */
+enum { TR_TEXTURE_RGBA8_UNORM = 0, TR_TEXTURE_RGBA32F = 1 };
+
+/* ---- scene tables ------------------------------------------------------------------ */
+/* mesh::vertex, src/mesh.hh:19-25 == shader/scene.glsl:14-20 */
+typedef struct tr_vertex {
+    float pos[3];
+    float normal[3];
+    float uv[2];
+    float tangent[4];
+} tr_vertex; /* 48 B */
+
+/* material_buffer, src/scene_stage.cc:17-30 == shader/material.glsl:9-22 */
+typedef struct tr_material {
+    float albedo_factor[4];
+    float metallic_roughness_factor[4]; /* x = metallic, y = roughness */
+    float emission_factor[4];
+    float transmittance;
+    float ior;
+    float normal_factor;
+    uint32_t flags;                     /* bit0 double sided, bit1 transient */
+    int32_t albedo_tex_id;              /* -1 = none */
+    int32_t metallic_roughness_tex_id;
+    int32_t normal_tex_id;
+    int32_t emission_tex_id;
+} tr_material; /* 80 B */
+
+/* instance_buffer, src/scene_stage.cc:32-44 == shader/scene.glsl:43-53 */
+typedef struct tr_instance {
+    int32_t light_base_id;              /* -1: not emissive; else first tri-light index */
+    int32_t sh_grid_index;
+    uint32_t pad;
+    float shadow_terminator_mul;
+    float model[16];
+    float model_normal[16];             /* inverse transpose of model */
+    float model_prev[16];
+    tr_material mat;
+} tr_instance; /* 288 B */
+
+/* directional_light_entry, src/scene_stage.cc:46-62 == shader/light.glsl:7-13 */
+typedef struct tr_directional_light {
+    float color[3];
+    int32_t shadow_map_index;
+    float dir[3];
+    float dir_cutoff;                   /* cos(radians(angle)) */
+} tr_directional_light; /* 32 B */
+
+/* point_light_entry (also spotlights), src/scene_stage.cc:64-98 == shader/light.glsl:15-27 */
+typedef struct tr_point_light {
+    float color[3];
+    float dir[3];
+    float pos[3];
+    float radius;
+    float dir_cutoff;
+    float dir_falloff;                  /* 0: not a spotlight */
+    float cutoff_radius;
+    float spot_radius;
+    int32_t shadow_map_index;
+    int32_t padding;
+} tr_point_light; /* 64 B */
+
+/* tri_light_entry, src/scene_stage.cc:103-111 == shader/light.glsl:29-37; built on the device
+ * (extract_tri_lights.comp:17-54), exposed only through tr_pt_read_tri_lights for tests. */
+typedef struct tr_tri_light {
+    float pos[3][3];
+    uint32_t emission_factor;           /* R9G9B9E5 */
+    uint32_t instance_id;
+    uint32_t primitive_id;
+    uint32_t uv[3];                     /* half2 */
+    int32_t emission_tex_id;
+} tr_tri_light; /* 64 B */
+
+/* matrix_camera_data_buffer, src/camera.cc:397-407 == shader/camera.glsl:13-23 */
+typedef struct tr_camera_data {
+    float view[16];
+    float view_inverse[16];
+    float view_proj[16];
+    float proj_inverse[16];
+    float origin[4];
+    float dof_params[4];                /* focus distance, aperture radius, angle, sides */
+    float projection_info[4];
+    float pan[4];
+} tr_camera_data; /* 320 B */
+
+/* camera_pair, shader/scene.glsl:176-180 */
+typedef struct tr_camera_pair {
+    tr_camera_data current;
+    tr_camera_data previous;
+} tr_camera_pair; /* 640 B */
+
+/* alias_table_entry, src/environment_map.hh:37-43 == shader/alias_table.glsl:7-13 */
+typedef struct tr_alias_table_entry {
+    uint32_t alias_id;
+    uint32_t probability;
+    float pdf;
+    float alias_pdf;
+} tr_alias_table_entry; /* 16 B */
+
+/* One entry per instance: the mesh it references (mesh::get_vertices/get_indices,
+ * src/mesh.hh:60-63) and the opaque flag the reference gives the BLAS geometry
+ * (= !material::potentially_transparent(), src/material.cc:7-11; src/scene_stage.cc:1410). */
+typedef struct tr_mesh_ref {
+    const tr_vertex* vertices;
+    const uint32_t* indices;
+    uint32_t vertex_count;
+    uint32_t index_count;
+    uint32_t opaque;
+    uint32_t reserved;
+} tr_mesh_ref;
+
+/* A texture of the sampler table (src/sampler_table.cc); bilinear, repeat, LOD 0. */
+typedef struct tr_texture {
+    const void* data;
+    uint32_t width;
+    uint32_t height;
+    uint32_t format;                    /* TR_TEXTURE_* */
+    uint32_t reserved;
+} tr_texture;
+
+/* What scene_stage flattens for the tracer (src/scene_stage.cc:1066-1116,1277-1354). */
+typedef struct tr_pt_scene_desc {
+    uint32_t instance_count;
+    uint32_t point_light_count;
+    uint32_t directional_light_count;
+    uint32_t texture_count;
+    const tr_instance* instances;
+    const tr_mesh_ref* meshes;          /* instance_count entries */
+    const tr_point_light* point_lights;
+    const tr_directional_light* directional_lights;
+    const tr_texture* textures;
+    float environment_factor[4];        /* scene_metadata.environment_factor */
+    int32_t environment_proj;           /* -1: no environment map (the only supported value) */
+    uint32_t reserved;
+} tr_pt_scene_desc;
+
+/* ---- options: field names and meaning follow path_tracer_stage::options
+ * (src/path_tracer_stage.hh:13-30) <- rt_camera_stage::options (src/rt_camera_stage.hh:17-25)
+ * <- rt_stage::options (src/rt_stage.hh:29-40). tr_pt_default_options() fills the CLI
+ * defaults of src/options.hh (which create_renderer always copies over the struct defaults,
+ * src/tauray.cc:392-403,472-488). ----------------------------------------------------- */
+typedef struct tr_pt_options {
+    /* rt_stage::options */
+    int32_t max_ray_depth;              /* 8 */
+    float min_ray_dist;                 /* 1e-4 */
+    int32_t rng_seed;                   /* 0 */
+    int32_t local_sampler;              /* TR_SAMPLER_UNIFORM_RANDOM */
+    /* rt_camera_stage::options */
+    int32_t samples_per_pixel;          /* 1 */
+    int32_t samples_per_pass;           /* 1 */
+    int32_t projection;                 /* TR_PROJECTION_PERSPECTIVE */
+    int32_t transparent_background;     /* 0 */
+    uint32_t active_viewport_count;     /* 1 */
+    /* path_tracer_stage::options */
+    int32_t use_shadow_terminator_fix;  /* 0 */
+    int32_t use_white_albedo_on_first_bounce; /* 0 */
+    int32_t hide_lights;                /* 0 */
+    int32_t film;                       /* TR_FILM_POINT */
+    int32_t mis_mode;                   /* TR_MIS_POWER_HEURISTIC */
+    float film_radius;                  /* 0.5 */
+    float russian_roulette_delta;       /* 0 = off */
+    float indirect_clamping;            /* 0 = off */
+    float regularization_gamma;         /* 0 = off */
+    int32_t depth_of_field;             /* 0 */
+    float sampling_weight_point_lights; /* 1 */
+    float sampling_weight_directional_lights; /* 1 */
+    float sampling_weight_envmap;       /* 1 */
+    float sampling_weight_emissive_triangles; /* 1 */
+    int32_t bounce_mode;                /* TR_BOUNCE_MATERIAL */
+    int32_t tri_light_mode;             /* TR_TRI_LIGHT_SOLID_ANGLE (CLI default) */
+    /* ours */
+    int32_t kernel_mode;                /* TR_KERNEL_WAVEFRONT */
+    int32_t reserved[5];
+} tr_pt_options;
+
+/* distribution_params, src/distribution_strategy.hh:20-27 */
+typedef struct tr_pt_distribution {
+    uint32_t size[2];
+    int32_t strategy;
+    uint32_t index;
+    uint32_t count;
+    int32_t primary;
+} tr_pt_distribution;
+
+/* Counters of the last tr_pt_render (timer "path tracing", src/rt_stage.cc:60) */
+typedef struct tr_pt_stats {
+    uint64_t closest_rays;              /* traversal queries issued (closest hit) */
+    uint64_t shadow_rays;               /* traversal queries issued (shadow / any hit) */
+    uint64_t paths;                     /* camera paths started */
+    uint64_t node_visits;               /* only in instrumented runs (tr_pt_set_instrumentation) */
+    uint64_t triangle_tests;
+    uint64_t kernel_launches;           /* kernels launched by the last tr_pt_render */
+    float render_ms;                    /* CUDA-event time of the last tr_pt_render */
+    float trace_ms;                     /* sum over trace kernels, instrumented runs only */
+    float bvh_build_ms;                 /* last tr_pt_set_scene */
+    uint32_t bvh_node_count;
+    uint32_t triangle_count;
+    uint32_t tri_light_count;
+} tr_pt_stats;
+
+typedef struct tr_pt_ctx tr_pt_ctx;     /* one per GPU == one path_tracer_stage */
+
+/* ---- entry points ---------------------------------------------------------------------- */
+
+/* CLI defaults (src/options.hh:43-49,170-214,292-294,358-366,438-488,513-532). */
+void tr_pt_default_options(tr_pt_options* opt);
+
+/* == path_tracer_stage ctor (src/path_tracer_stage.cc:30-116): selects the kernel permutation
+ * (the reference's shader #defines) from `opt`. */
+int tr_pt_create(tr_pt_ctx** out, int cuda_device, const tr_pt_options* opt);
+void tr_pt_destroy(tr_pt_ctx* ctx);
+
+/* == scene_stage upload + ensure_blas + TLAS build (src/scene_stage.cc:821-872,1419-1468,
+ * 1620-1723): copies the tables, pre-transforms vertices (pre_transform.comp), extracts
+ * tri-lights (extract_tri_lights.comp) and builds the LBVH on the device. */
+int tr_pt_set_scene(tr_pt_ctx* ctx, const tr_pt_scene_desc* scene);
+
+/* == camera UBO upload (src/scene_stage.cc:1145-1174); `pairs` = view_count tr_camera_pair. */
+int tr_pt_set_cameras(tr_pt_ctx* ctx, const tr_camera_pair* pairs, uint32_t view_count);
+
+/* == rt_camera_stage::reset_distribution_params (src/rt_camera_stage.cc:141-145) */
+int tr_pt_set_distribution(tr_pt_ctx* ctx, const tr_pt_distribution* dist);
+
+/* == rt_camera_stage::reset_accumulated_samples + rt_stage::reset_sample_counter
+ * (src/rt_renderer.cc:67-81) */
+int tr_pt_reset_accumulation(tr_pt_ctx* ctx, int reset_sample_counter);
+
+/* == stage::run (src/stage.cc:35-76) for path_tracer_stage: all passes of one frame
+ * (samples_per_pixel / samples_per_pass launches of the hot loop), asynchronous on `cuda_stream`
+ * (NULL = the context's own stream). */
+int tr_pt_render(tr_pt_ctx* ctx, void* cuda_stream);
+
+/* == feature_stage (src/feature_stage.cc:21-110, shader/rt_feature.rgen): one AOV pass. */
+int tr_pt_render_feature(tr_pt_ctx* ctx, int feature, const float default_value[4],
+                         void* cuda_stream);
+
+/* Blocks until the context's stream is idle (the reference waits on timeline semaphores). */
+int tr_pt_sync(tr_pt_ctx* ctx);
+
+/* Device pointer + geometry of the colour target this context renders into:
+ * primary: size.x * size.y * views float4 (the full image, gbuffer `color`, rgba32f);
+ * non-primary: the linear strip image of get_distribution_target_size(): count * views float4
+ * (src/distribution_strategy.cc:5-19). */
+int tr_pt_get_color_buffer(tr_pt_ctx* ctx, void** device_ptr, size_t* bytes);
+
+/* == headless staging copy (src/headless.cc:125-171): D2H of the colour target. */
+int tr_pt_read_color(tr_pt_ctx* ctx, float* rgba32f_host, size_t bytes);
+
+/* == stitch_shuffled_strips.comp:21-63 / stitch_scanline.comp for ONE source strip: scatters
+ * `strip` (count*views float4, device memory, e.g. one slice of an all-gather result) of the
+ * device that rendered [index, index+count) into `full_image` (size.x*size.y*views float4). */
+int tr_pt_unshuffle(tr_pt_ctx* ctx, const void* strip_device, uint32_t index, uint32_t count,
+                    void* full_image_device, void* cuda_stream);
+
+/* Fused render->stitch over NVLink peer memory: the last accumulation pass of tr_pt_render
+ * also stores every finished pixel into each registered peer image (device pointers mapped
+ * into this process, e.g. with cudaIpcOpenMemHandle) at its un-shuffled position, so no
+ * separate gather/stitch pass runs. Pass n = 0 to disable. */
+int tr_pt_set_peer_images(tr_pt_ctx* ctx, void* const* full_image_device_ptrs, int n);
+
+int tr_pt_get_stats(tr_pt_ctx* ctx, tr_pt_stats* stats);
+int tr_pt_set_instrumentation(tr_pt_ctx* ctx, int enabled);
+
+/* Test hooks (device results copied to the host). */
+int tr_pt_read_tri_lights(tr_pt_ctx* ctx, tr_tri_light* out, uint32_t capacity);
+/* Traces `n` rays (origin.xyz,tmin / dir.xyz,tmax as 8 floats each) through the LBVH with the
+ * closest-hit kernel; out = n * {int instance_id, int primitive_id, float u, float v, float t}. */
+int tr_pt_trace_rays(tr_pt_ctx* ctx, const float* rays, uint32_t n, void* hits_out);
+/* Fills `out` (n*4 uint32) with the sampler draw `draw_index` (-1: film sample) for n
+ * pixel coordinates (n*4 uint32: x, y, view, sample). Exercises the device sampler only. */
+int tr_pt_sample_test(tr_pt_ctx* ctx, const uint32_t* coords, uint32_t n, int draw_index,
+                      uint32_t* out);
+
+const char* tr_pt_last_error(tr_pt_ctx* ctx);   /* ctx may be NULL: last create error */
+int tr_pt_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

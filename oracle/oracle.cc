@@ -1,0 +1,1313 @@
+// oracle.cc -- TEST INFRASTRUCTURE ONLY (see oracle/README.md).
+//
+// CPU restatement of Tauray's path-tracing hot path, written from the GLSL:
+//   shader/path_tracer.rgen:77-127      -> render_pass()
+//   shader/path_tracer.glsl:35-576      -> shadow_ray, *_mis_pdf, get_intersection_info,
+//                                          sample_explicit_light, next_event_estimation,
+//                                          evaluate_ray, get_world_camera_ray, write_all_outputs
+//   shader/rt.glsl:28-335               -> get_interpolated_vertex, pixel mapping, NEE probabilities
+//   shader/scene.glsl:88-152            -> sample_material
+//   shader/camera.glsl:25-59            -> get_camera_ray
+//   shader/gbuffer.glsl:18-28           -> accumulate_gbuffer_color
+//   shader/rt_common*.r{chit,ahit,miss,int} -> trace_closest / trace_shadow
+//   shader/pre_transform.comp, shader/extract_tri_lights.comp -> set_scene preprocessing
+//   shader/rt_feature.rgen + src/feature_stage.cc:32-69 -> render_feature
+// and the host side that feeds them: src/rt_stage.cc:76-85, src/rt_camera_stage.cc:74-101,
+// src/path_tracer_stage.cc:118-147, src/distribution_strategy.cc.
+//
+// Parity status: the geometry part (camera rays, closest hit, interpolation, material albedo) is
+// pinned by the reference's six feature goldens (tests/golden/, tests/test_oracle_golden.py); the
+// sampler / BSDF / NEE / accumulation arithmetic is pinned only statistically by
+// validate_path-tracer.exr -- "parity unpinned" by the reference's own tests for those parts.
+#include "oracle.h"
+#include "oracle_bvh.h"
+#include "oracle_shading.h"
+#include <atomic>
+#include <string>
+#include <thread>
+
+using namespace orc;
+
+namespace {
+
+struct texture_data
+{
+    uint32_t w = 0, h = 0, format = 0;
+    std::vector<uint8_t> bytes;
+};
+
+struct pt_vertex_data
+{
+    vec3 pos;
+    vec3 hard_normal;
+    vec3 smooth_normal;
+    vec3 mapped_normal;
+    int instance_id;
+};
+
+struct vertex_data
+{
+    vec3 pos;
+    vec3 hard_normal;
+    vec3 smooth_normal;
+    vec3 mapped_normal;
+    vec2 uv;
+    vec3 tangent;
+    vec3 bitangent;
+    bool back_facing;
+    int instance_id;
+    int primitive_id;
+};
+
+struct intersection_pdf
+{
+    float point_light_pdf;
+    float directional_light_pdf;
+    float tri_light_pdf;
+    float envmap_pdf;
+};
+
+struct hit_payload
+{
+    uint32_t random_seed;
+    int instance_id;
+    int primitive_id;
+    vec2 barycentrics;
+};
+
+struct counters
+{
+    uint64_t closest = 0, shadow = 0, paths = 0, nodes = 0, tris = 0;
+};
+
+} // namespace
+
+struct orc_ctx
+{
+    tr_pt_options opt;
+    int threads = 1;
+    std::string error;
+
+    // scene
+    bool has_scene = false;
+    std::vector<tr_instance> instances;
+    std::vector<std::vector<tr_vertex>> vertices; // pre-transformed (pre_transform.comp)
+    std::vector<std::vector<uint32_t>> indices;
+    std::vector<uint32_t> opaque;
+    std::vector<tr_point_light> point_lights;
+    std::vector<tr_directional_light> directional_lights;
+    std::vector<tr_tri_light> tri_lights;
+    std::vector<texture_data> textures;
+    vec4 environment_factor = V4(0, 0, 0, 0);
+    int environment_proj = -1;
+    bool any_non_opaque = false;
+    bvh accel;
+
+    // cameras / distribution / counters
+    std::vector<tr_camera_pair> cameras;
+    tr_pt_distribution dist{};
+    uint32_t frame_counter = 0;
+    int accumulated_samples = 0;
+    std::vector<float> color; // float4 per slot
+    tr_pt_stats stats{};
+
+    // ------------------------------------------------------------------------------------
+    // layout helpers (src/distribution_strategy.cc:5-60)
+    // ------------------------------------------------------------------------------------
+    uint32_t views() const { return (uint32_t)cameras.size(); }
+    void ray_count(uint32_t& rx, uint32_t& ry) const
+    {
+        switch(dist.strategy)
+        {
+        case TR_DISTRIBUTION_SCANLINE:
+            rx = dist.size[0];
+            ry = (dist.size[1] - dist.index + dist.count - 1) / dist.count;
+            break;
+        case TR_DISTRIBUTION_SHUFFLED_STRIPS:
+            rx = dist.count; ry = 1;
+            break;
+        default:
+            rx = dist.size[0]; ry = dist.size[1];
+            break;
+        }
+    }
+    size_t layer_size() const
+    {
+        if(dist.primary || dist.strategy == TR_DISTRIBUTION_DUPLICATE)
+            return (size_t)dist.size[0] * dist.size[1];
+        uint32_t rx, ry;
+        ray_count(rx, ry);
+        return (size_t)rx * ry;
+    }
+    // src/distribution_strategy.cc:62-69
+    static unsigned calculate_shuffled_strips_b(uint32_t w, uint32_t h)
+    {
+        unsigned n = w * h;
+        unsigned b = 31;
+        while((n >> b) < 128 && b > 0) b--;
+        return b;
+    }
+    // shader/rt.glsl:172-179
+    uint32_t permute_region_id(uint32_t i) const
+    {
+        uint32_t b = calculate_shuffled_strips_b(dist.size[0], dist.size[1]);
+        uint32_t region_size = ((dist.size[0] * dist.size[1]) + (1u << b) - 1) >> b;
+        uint32_t region_id = i / region_size;
+        uint32_t k = bitreverse_(region_id) >> (32 - b);
+        return k * region_size + i % region_size;
+    }
+    // shader/rt.glsl:181-222: returns false when this launch id renders nothing.
+    bool map_launch(uint32_t lx, uint32_t ly, int& px, int& py, size_t& write_index) const
+    {
+        uint32_t W = dist.size[0], H = dist.size[1];
+        switch(dist.strategy)
+        {
+        case TR_DISTRIBUTION_SCANLINE:
+            px = (int)lx;
+            py = (int)(ly * dist.count + dist.index);
+            write_index = dist.primary ? (size_t)py * W + px : (size_t)ly * W + lx;
+            return true;
+        case TR_DISTRIBUTION_SHUFFLED_STRIPS:
+        {
+            uint32_t j = permute_region_id(dist.index + lx);
+            if(j >= W * H) return false;
+            px = (int)(j % W);
+            py = (int)(j / W);
+            write_index = dist.primary ? (size_t)j : (size_t)lx;
+            return true;
+        }
+        default:
+            px = (int)lx; py = (int)ly;
+            write_index = (size_t)ly * W + lx;
+            return true;
+        }
+    }
+
+    // ------------------------------------------------------------------------------------
+    // textures: bilinear, repeat, LOD 0 (what the RT stages see)
+    // ------------------------------------------------------------------------------------
+    vec4 texel(const texture_data& t, int x, int y) const
+    {
+        size_t i = ((size_t)y * t.w + x) * 4;
+        if(t.format == TR_TEXTURE_RGBA32F)
+        {
+            const float* f = reinterpret_cast<const float*>(t.bytes.data());
+            return V4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+        }
+        const uint8_t* b = t.bytes.data();
+        return V4((float)b[i] / 255.0f, (float)b[i + 1] / 255.0f, (float)b[i + 2] / 255.0f, (float)b[i + 3] / 255.0f);
+    }
+    vec4 sample_texture(int id, vec2 uv) const
+    {
+        const texture_data& t = textures[id];
+        float x = uv.x * (float)t.w - 0.5f;
+        float y = uv.y * (float)t.h - 0.5f;
+        if(!(fabsf(x) < 1e9f)) x = 0.0f;
+        if(!(fabsf(y) < 1e9f)) y = 0.0f;
+        float fx0 = floorf(x), fy0 = floorf(y);
+        float fx = x - fx0, fy = y - fy0;
+        int w = (int)t.w, h = (int)t.h;
+        int x0 = (int)fx0 % w; if(x0 < 0) x0 += w;
+        int y0 = (int)fy0 % h; if(y0 < 0) y0 += h;
+        int x1 = x0 + 1 == w ? 0 : x0 + 1;
+        int y1 = y0 + 1 == h ? 0 : y0 + 1;
+        vec4 top = mix_(texel(t, x0, y0), texel(t, x1, y0), fx);
+        vec4 bot = mix_(texel(t, x0, y1), texel(t, x1, y1), fx);
+        return mix_(top, bot, fy);
+    }
+
+    // ------------------------------------------------------------------------------------
+    // shader/rt.glsl:302-335
+    // ------------------------------------------------------------------------------------
+    void get_nee_sampling_probabilities(float& point, float& triangle, float& directional, float& envmap) const
+    {
+        point = (opt.sampling_weight_point_lights > 0 && !point_lights.empty()) ? opt.sampling_weight_point_lights : 0.0f;
+        triangle = (opt.sampling_weight_emissive_triangles > 0 && !tri_lights.empty()) ? opt.sampling_weight_emissive_triangles : 0.0f;
+        directional = (opt.sampling_weight_directional_lights > 0 && !directional_lights.empty()) ? opt.sampling_weight_directional_lights : 0.0f;
+        envmap = (opt.sampling_weight_envmap > 0 && environment_proj >= 0) ? opt.sampling_weight_envmap : 0.0f;
+        float sum = point + triangle + directional + envmap;
+        float inv_sum = sum <= 0.0f ? 0.0f : (1.0f / sum + 1e-5f);
+        point *= inv_sum;
+        triangle *= inv_sum;
+        directional *= inv_sum;
+        envmap *= inv_sum;
+    }
+
+    // ------------------------------------------------------------------------------------
+    // shader/rt.glsl:28-101 with PRE_TRANSFORMED_VERTICES
+    // ------------------------------------------------------------------------------------
+    vertex_data get_interpolated_vertex(vec3 view, vec2 bary, int instance_id, int primitive_id, vec3 pos, float& pdf) const
+    {
+        const tr_instance& o = instances[instance_id];
+        const uint32_t* idx = &indices[instance_id][3 * (size_t)primitive_id];
+        const tr_vertex& v0 = vertices[instance_id][idx[0]];
+        const tr_vertex& v1 = vertices[instance_id][idx[1]];
+        const tr_vertex& v2 = vertices[instance_id][idx[2]];
+        vec3 b = V3(1.0f - bary.x - bary.y, bary.x, bary.y);
+        vec3 p0 = ld3(v0.pos), p1 = ld3(v1.pos), p2 = ld3(v2.pos);
+
+        vertex_data interp;
+        interp.pos = p0 * b.x + p1 * b.y + p2 * b.z;
+
+        if(opt.sampling_weight_emissive_triangles > 0)
+        {
+            if(o.light_base_id >= 0)
+                pdf = sample_triangle_light_pdf(opt.tri_light_mode, interp.pos - pos, p0 - pos, p1 - pos, p2 - pos);
+            else pdf = 0.0f;
+        }
+        interp.smooth_normal = normalize(ld3(v0.normal) * b.x + ld3(v1.normal) * b.y + ld3(v2.normal) * b.z);
+        if(o.mat.normal_tex_id >= 0)
+        {
+            vec3 t = ld3(v0.tangent) * b.x + ld3(v1.tangent) * b.y + ld3(v2.tangent) * b.z;
+            float tw = v0.tangent[3] * b.x + v1.tangent[3] * b.y + v2.tangent[3] * b.z;
+            interp.tangent = normalize(t);
+            interp.bitangent = normalize(cross(interp.smooth_normal, interp.tangent) * tw);
+        }
+        else interp.tangent = interp.bitangent = V3(0);
+        interp.uv = V2(
+            v0.uv[0] * b.x + v1.uv[0] * b.y + v2.uv[0] * b.z,
+            v0.uv[1] * b.x + v1.uv[1] * b.y + v2.uv[1] * b.z
+        );
+        interp.hard_normal = normalize(cross(p1 - p0, p2 - p0));
+        interp.back_facing = dot(interp.hard_normal, view) > 0;
+        if(interp.back_facing)
+        {
+            interp.smooth_normal = -interp.smooth_normal;
+            interp.hard_normal = -interp.hard_normal;
+        }
+        interp.mapped_normal = interp.smooth_normal;
+        interp.instance_id = instance_id;
+        interp.primitive_id = primitive_id;
+        return interp;
+    }
+    // shader/rt.glsl:103-117
+    vec2 get_interpolated_uv(vec2 bary, int instance_id, int primitive_id) const
+    {
+        const uint32_t* idx = &indices[instance_id][3 * (size_t)primitive_id];
+        const tr_vertex& v0 = vertices[instance_id][idx[0]];
+        const tr_vertex& v1 = vertices[instance_id][idx[1]];
+        const tr_vertex& v2 = vertices[instance_id][idx[2]];
+        vec3 b = V3(1.0f - bary.x - bary.y, bary.x, bary.y);
+        return V2(
+            v0.uv[0] * b.x + v1.uv[0] * b.y + v2.uv[0] * b.z,
+            v0.uv[1] * b.x + v1.uv[1] * b.y + v2.uv[1] * b.z
+        );
+    }
+    // alpha of rt_common.rahit / rt_common_shadow.rahit / shader/rt.glsl:136-144
+    float hit_alpha(int instance_id, int primitive_id, vec2 bary) const
+    {
+        const tr_material& mat = instances[instance_id].mat;
+        float alpha = mat.albedo_factor[3];
+        if(mat.albedo_tex_id >= 0)
+            alpha *= sample_texture(mat.albedo_tex_id, get_interpolated_uv(bary, instance_id, primitive_id)).w;
+        return alpha;
+    }
+
+    // shader/scene.glsl:88-152 + shader/rt.glsl:120-134
+    sampled_material sample_material(int instance_id, vertex_data& v) const
+    {
+        const tr_instance& o = instances[instance_id];
+        const tr_material& mat = o.mat;
+        sampled_material res;
+        res.albedo = V4(mat.albedo_factor[0], mat.albedo_factor[1], mat.albedo_factor[2], mat.albedo_factor[3]);
+        if(mat.albedo_tex_id >= 0)
+        {
+            vec4 tex_col = sample_texture(mat.albedo_tex_id, v.uv);
+            vec3 lin = inverse_srgb_correction(xyz(tex_col));
+            res.albedo = res.albedo * V4(lin, tex_col.w);
+        }
+        vec2 mr = V2(mat.metallic_roughness_factor[0], mat.metallic_roughness_factor[1]);
+        if(mat.metallic_roughness_tex_id >= 0)
+        {
+            vec4 t = sample_texture(mat.metallic_roughness_tex_id, v.uv);
+            mr = mr * V2(t.z, t.y);
+        }
+        res.metallic = mr.x;
+        res.roughness = mr.y * mr.y;
+        if(mat.normal_tex_id >= 0)
+        {
+            mat3 tbn = {v.tangent, v.bitangent, v.smooth_normal};
+            vec4 t = sample_texture(mat.normal_tex_id, v.uv);
+            vec3 ts_normal = normalize(V3(t.x * 2.0f - 1.0f, t.y * 2.0f - 1.0f, t.z * 2.0f - 1.0f));
+            v.mapped_normal = normalize(mul(tbn, ts_normal * V3(mat.normal_factor, mat.normal_factor, 1.0f)));
+            if(any_nan(v.mapped_normal)) v.mapped_normal = v.smooth_normal;
+        }
+        res.emission = V3(mat.emission_factor[0], mat.emission_factor[1], mat.emission_factor[2]);
+        if(mat.emission_tex_id >= 0)
+            res.emission = res.emission * xyz(sample_texture(mat.emission_tex_id, v.uv));
+        res.transmittance = mat.transmittance;
+        if(v.back_facing && res.transmittance > 0.0001f)
+        {
+            res.ior_in = mat.ior;
+            res.ior_out = 1.0f;
+        }
+        else
+        {
+            res.ior_in = 1.0f;
+            res.ior_out = mat.ior;
+        }
+        float f0 = (res.ior_out - res.ior_in) / (res.ior_out + res.ior_in);
+        f0 *= f0;
+        res.f0 = f0;
+        res.flags = mat.flags;
+        res.shadow_terminator_mul = o.shadow_terminator_mul;
+        return res;
+    }
+
+    // ------------------------------------------------------------------------------------
+    // traceRayEXT (closest): rt_common.rchit/.rmiss/.rahit + rt_common_point_light.rint/.rchit.
+    // Any-hit invocations are emulated in increasing-t order (one valid order of the
+    // reference's undefined one): each non-opaque candidate draws pcg(random_seed).
+    // ------------------------------------------------------------------------------------
+    void trace_closest(vec3 pos, float tmin, vec3 dir, bool include_lights, hit_payload& payload, counters& c) const
+    {
+        c.closest++;
+        float cur_tmin = tmin;
+        for(;;)
+        {
+            hit_record h;
+            bool tri_hit = accel.closest(pos, dir, cur_tmin, INFINITY, h, &c.nodes, &c.tris);
+            int light_id = -1;
+            float light_t = 0.0f;
+            if(include_lights)
+            {
+                for(size_t i = 0; i < point_lights.size(); ++i)
+                {
+                    const tr_point_light& pl = point_lights[i];
+                    if(pl.radius == 0.0f) continue; // degenerate AABB at the origin, scene_stage.cc:1367
+                    float t = sphere_intersection(ld3(pl.pos), pl.radius, pos, dir);
+                    if(!(t > 0)) continue;
+                    if(!(t >= cur_tmin)) continue;
+                    if(light_id < 0 || t < light_t) { light_id = (int)i; light_t = t; }
+                }
+            }
+            if(light_id >= 0 && (!tri_hit || light_t < h.t))
+            {
+                payload.instance_id = -1;
+                payload.primitive_id = light_id;
+                payload.barycentrics = V2(light_t, 0.0f);
+                return;
+            }
+            if(!tri_hit)
+            {
+                payload.instance_id = -1;
+                payload.primitive_id = -1;
+                payload.barycentrics = V2(0, 0);
+                return;
+            }
+            if(!opaque[h.instance_id])
+            {
+                float alpha_cutoff = (float)pcg(payload.random_seed) * TR_INV_UINT32_MAX;
+                if(hit_alpha(h.instance_id, h.primitive_id, V2(h.u, h.v)) <= alpha_cutoff)
+                {
+                    cur_tmin = h.t;
+                    continue;
+                }
+            }
+            payload.instance_id = h.instance_id;
+            payload.primitive_id = h.primitive_id;
+            payload.barycentrics = V2(h.u, h.v);
+            return;
+        }
+    }
+
+    // shader/path_tracer.glsl:35-52 + rt_common_shadow.{rchit,rahit,rmiss}; light spheres are
+    // excluded (mask 0xFD). Non-opaque factors are multiplied in (t, instance, primitive) order.
+    float shadow_ray(vec3 pos, float min_dist, vec3 dir, float max_dist, counters& c) const
+    {
+        c.shadow++;
+        struct factor { float t; int inst, prim; float f; };
+        std::vector<factor> factors;
+        bool blocked = false;
+        accel.any(pos, dir, min_dist, max_dist, [&](const tri_record& tr, float t, float u, float v) {
+            if(tr.opaque) { blocked = true; return false; }
+            float alpha = hit_alpha(tr.instance_id, tr.primitive_id, V2(u, v));
+            factors.push_back({t, tr.instance_id, tr.primitive_id, 1.0f - alpha});
+            return true;
+        }, &c.nodes, &c.tris);
+        if(blocked) return 0.0f;
+        std::sort(factors.begin(), factors.end(), [](const factor& a, const factor& b) {
+            if(a.t != b.t) return a.t < b.t;
+            if(a.inst != b.inst) return a.inst < b.inst;
+            return a.prim < b.prim;
+        });
+        float visibility = 1.0f;
+        for(const factor& f: factors)
+        {
+            visibility *= f.f;
+            if(visibility == 0.0f) break;
+        }
+        return visibility;
+    }
+
+    // shader/path_tracer.glsl:54-76
+    float bsdf_mis_pdf(const intersection_pdf& nee_pdf, float bsdf_pdf) const
+    {
+        if(bsdf_pdf == 0.0f) return 1.0f;
+        float point_prob, triangle_prob, dir_prob, envmap_prob;
+        get_nee_sampling_probabilities(point_prob, triangle_prob, dir_prob, envmap_prob);
+        float avg_nee_pdf =
+            nee_pdf.directional_light_pdf * dir_prob / (float)std::max<uint32_t>((uint32_t)directional_lights.size(), 1) +
+            nee_pdf.tri_light_pdf * triangle_prob / (float)std::max<uint32_t>((uint32_t)tri_lights.size(), 1) +
+            nee_pdf.envmap_pdf * envmap_prob +
+            nee_pdf.point_light_pdf * point_prob / (float)std::max<uint32_t>((uint32_t)point_lights.size(), 1);
+        if(opt.mis_mode == TR_MIS_POWER_HEURISTIC)
+            return (avg_nee_pdf * avg_nee_pdf + bsdf_pdf * bsdf_pdf) / bsdf_pdf;
+        else if(opt.mis_mode == TR_MIS_BALANCE_HEURISTIC)
+            return avg_nee_pdf + bsdf_pdf;
+        else return avg_nee_pdf > 0 ? INFINITY : bsdf_pdf;
+    }
+    // shader/path_tracer.glsl:78-89
+    float nee_mis_pdf(float nee_pdf, float bsdf_pdf) const
+    {
+        if(nee_pdf <= 0.0f) return -nee_pdf;
+        if(opt.mis_mode == TR_MIS_POWER_HEURISTIC)
+            return (nee_pdf * nee_pdf + bsdf_pdf * bsdf_pdf) / nee_pdf;
+        else if(opt.mis_mode == TR_MIS_BALANCE_HEURISTIC)
+            return nee_pdf + bsdf_pdf;
+        else return nee_pdf;
+    }
+
+    // shader/path_tracer.glsl:91-201
+    bool get_intersection_info(vec3 origin, vec3 view, const hit_payload& payload, pt_vertex_data& v,
+                               intersection_pdf& nee_pdf, sampled_material& mat, vec3& light) const
+    {
+        nee_pdf.point_light_pdf = 0;
+        nee_pdf.directional_light_pdf = 0;
+        nee_pdf.tri_light_pdf = 0;
+        nee_pdf.envmap_pdf = 0;
+        mat = sampled_material{};
+        mat.metallic = 1;
+        mat.albedo = V4(0, 0, 0, 0);
+
+        if(payload.instance_id >= 0)
+        {
+            float pdf = 0.0f;
+            vertex_data vd = get_interpolated_vertex(view, payload.barycentrics, payload.instance_id, payload.primitive_id, origin, pdf);
+            mat = sample_material(payload.instance_id, vd);
+            mat.albedo.w = 1.0f;
+            if(opt.sampling_weight_emissive_triangles > 0)
+            {
+                nee_pdf.tri_light_pdf = pdf == 0.0f ? 0.0f : pdf;
+                light = mat.emission;
+                mat.emission = V3(0);
+            }
+            else light = V3(0);
+            v.pos = vd.pos;
+            v.hard_normal = vd.hard_normal;
+            v.smooth_normal = vd.smooth_normal;
+            v.mapped_normal = vd.mapped_normal;
+            v.instance_id = vd.instance_id;
+            return true;
+        }
+        else if(payload.primitive_id >= 0)
+        {
+            const tr_point_light& pl = point_lights[payload.primitive_id];
+            vec3 color = get_spotlight_intensity(pl, view) * ld3(pl.color) / (pl.radius * pl.radius * TR_PI);
+            if(opt.sampling_weight_point_lights > 0)
+            {
+                mat.emission = V3(0);
+                light = color;
+                nee_pdf.point_light_pdf = sample_point_light_pdf(pl, origin);
+            }
+            else
+            {
+                light = V3(0);
+                mat.emission = color;
+            }
+            v.pos = origin + payload.barycentrics.x * view;
+            v.hard_normal = V3(0);
+            v.smooth_normal = V3(0);
+            v.mapped_normal = normalize(v.pos - ld3(pl.pos));
+            v.instance_id = -1;
+            mat.albedo = V4(0, 0, 0, 1);
+            return false;
+        }
+        else
+        {
+            vec4 color = environment_factor;
+            mat.emission = V3(0);
+            light = V3(0);
+            for(size_t i = 0; i < directional_lights.size(); ++i)
+            {
+                const tr_directional_light& dl = directional_lights[i];
+                if(dl.dir_cutoff >= 1.0f) continue;
+                float visible = step_(dl.dir_cutoff, dot(view, -ld3(dl.dir)));
+                vec3 col = visible * ld3(dl.color) / (2.0f * TR_PI * (1.0f - dl.dir_cutoff));
+                if(opt.sampling_weight_directional_lights > 0)
+                {
+                    light += col;
+                    nee_pdf.directional_light_pdf += visible * sample_directional_light_pdf(dl);
+                }
+                else mat.emission += col;
+            }
+            v.instance_id = -1;
+            v.pos = origin;
+            v.hard_normal = V3(0);
+            v.smooth_normal = V3(0);
+            v.mapped_normal = -view;
+            mat.albedo = V4(0, 0, 0, 0);
+            if(opt.sampling_weight_envmap > 0)
+            {
+                light += xyz(color);
+                nee_pdf.envmap_pdf = environment_proj >= 0 ? 0.0f /* envmap unsupported */ : 0.0f;
+            }
+            else mat.emission += xyz(color);
+            return false;
+        }
+    }
+
+    // shader/path_tracer.glsl:203-289
+    vec3 sample_explicit_light(uvec4 rand_uint, vec3 pos, vec3& out_dir, float& out_length, float& pdf) const
+    {
+        float point_prob, triangle_prob, dir_prob, envmap_prob;
+        get_nee_sampling_probabilities(point_prob, triangle_prob, dir_prob, envmap_prob);
+        vec4 u = to_unit(rand_uint);
+        if(opt.sampling_weight_point_lights > 0 && (u.w -= point_prob) < 0)
+        {
+            const int light_count = (int)point_lights.size();
+            // light.glsl:39-43
+            int light_index = clampi_((int)(u.z * (float)light_count), 0, light_count - 1);
+            float weight = (float)std::max(light_count, 1);
+            const tr_point_light& pl = point_lights[light_index];
+            vec3 color;
+            sample_point_light(pl, V2(u.x, u.y), pos, out_dir, out_length, color, pdf);
+            pdf *= point_prob / weight;
+            return color;
+        }
+        else if(opt.sampling_weight_emissive_triangles > 0 && (u.w -= triangle_prob) < 0)
+        {
+            const int light_count = (int)tri_lights.size();
+            int light_index = clampi_((int)(u.z * (float)light_count), 0, light_count - 1);
+            const tr_tri_light& tl = tri_lights[light_index];
+            vec3 A = ld3(tl.pos[0]) - pos;
+            vec3 B = ld3(tl.pos[1]) - pos;
+            vec3 C = ld3(tl.pos[2]) - pos;
+            vec3 color = r9g9b9e5_to_rgb(tl.emission_factor);
+            float tri_pdf = 0.0f;
+            out_dir = sample_triangle_light(opt.tri_light_mode, V2(u.x, u.y), A, B, C, tri_pdf);
+            out_length = ray_plane_intersection_dist(out_dir, A, B, C);
+            if(isinf_(tri_pdf) || tri_pdf <= 0 || out_length <= opt.min_ray_dist || any_nan(out_dir))
+            {
+                pdf = 1.0f;
+                out_dir = V3(0);
+                return V3(0);
+            }
+            if(tl.emission_tex_id >= 0)
+            {
+                vec3 bary = get_barycentric_coords(out_dir * out_length, A, B, C);
+                vec2 uv0 = V2(half_to_float_(tl.uv[0] & 0xFFFFu), half_to_float_(tl.uv[0] >> 16));
+                vec2 uv1 = V2(half_to_float_(tl.uv[1] & 0xFFFFu), half_to_float_(tl.uv[1] >> 16));
+                vec2 uv2 = V2(half_to_float_(tl.uv[2] & 0xFFFFu), half_to_float_(tl.uv[2] >> 16));
+                vec2 uv = bary.x * uv0 + bary.y * uv1 + bary.z * uv2;
+                color = color * xyz(sample_texture(tl.emission_tex_id, uv));
+            }
+            out_length -= opt.min_ray_dist;
+            pdf = triangle_prob * tri_pdf / (float)light_count;
+            return color;
+        }
+        else if(opt.sampling_weight_envmap > 0 && (u.w -= envmap_prob) < 0)
+        {
+            // Environment maps are outside this round's scope; envmap_prob is
+            // 0 because set_scene rejects environment_proj >= 0, so this is only reachable
+            // through rounding of u.w and contributes nothing, like the fall-through below.
+            pdf = 1.0f;
+            out_dir = V3(0);
+            out_length = 0.0f;
+            return V3(0);
+        }
+        else if(opt.sampling_weight_directional_lights > 0 && (u.w -= dir_prob) < 0)
+        {
+            const int light_count = (int)directional_lights.size();
+            int light_index = clampi_((int)(u.z * (float)light_count), 0, light_count - 1);
+            const tr_directional_light& dl = directional_lights[light_index];
+            out_length = INFINITY;
+            vec3 color;
+            sample_directional_light(dl, V2(u.x, u.y), out_dir, color, pdf);
+            pdf *= dir_prob / (float)light_count;
+            return color;
+        }
+        // "Should never be reached, hopefully." -- out_dir / pdf are undefined in the GLSL; the
+        // restatement pins them to a zero contribution with pdf 1.
+        pdf = 1.0f;
+        out_dir = V3(0);
+        out_length = 0.0f;
+        return V3(0);
+    }
+
+    bool nee_enabled() const
+    {
+        return (opt.sampling_weight_point_lights > 0 && !point_lights.empty()) ||
+            (opt.sampling_weight_directional_lights > 0 && !directional_lights.empty()) ||
+            (opt.sampling_weight_emissive_triangles > 0 && !tri_lights.empty()) ||
+            (opt.sampling_weight_envmap > 0 && environment_proj >= 0);
+    }
+
+    // shader/path_tracer.glsl:291-300
+    static void correct_lobes_for_normal_map(vec3 sample_dir, vec3 geometric_normal, bsdf_lobes& lobes)
+    {
+        if(dot(geometric_normal, sample_dir) < 0)
+        {
+            lobes.diffuse = 0;
+            lobes.dielectric_reflection = 0;
+            lobes.metallic_reflection = 0;
+        }
+        else lobes.transmission = 0;
+    }
+
+    // shader/path_tracer.glsl:302-344
+    vec3 next_event_estimation(uvec4 rand_uint, const mat3& tbn, vec3 shading_view, const sampled_material& mat,
+                               const pt_vertex_data& v, bsdf_lobes& lobes, counters& c) const
+    {
+        if(nee_enabled())
+        {
+            vec3 out_dir;
+            float out_length = 0.0f;
+            float light_pdf;
+            vec3 contrib = sample_explicit_light(rand_uint, v.pos, out_dir, out_length, light_pdf);
+            vec3 shading_light = mul(out_dir, tbn);
+            lobes = bsdf_lobes{0, 0, 0, 0};
+            float bsdf_pdf = material_bsdf_pdf(opt.bounce_mode, shading_light, shading_view, mat, lobes);
+            correct_lobes_for_normal_map(out_dir, v.hard_normal, lobes);
+            if(contrib.x > 0.0001f || contrib.y > 0.0001f || contrib.z > 0.0001f)
+                contrib *= shadow_ray(v.pos, opt.min_ray_dist, out_dir, out_length, c);
+            contrib /= nee_mis_pdf(light_pdf, bsdf_pdf);
+            return contrib;
+        }
+        return V3(0);
+    }
+
+    // shader/path_tracer.glsl:356-365
+    float clamp_contribution_mul(vec3 contrib) const
+    {
+        if(opt.indirect_clamping > 0.0f)
+        {
+            float m = rgb_to_luminance(contrib);
+            if(m > opt.indirect_clamping) return opt.indirect_clamping / m;
+        }
+        return 1;
+    }
+
+    uvec4 generate_ray_sample_uint(local_sampler& ls, uint32_t bounce_index) const
+    {
+        if(opt.local_sampler == TR_SAMPLER_SOBOL_OWEN)
+        {
+            uint32_t msb = (uint32_t)(opt.max_ray_depth > 8 ? 8 : opt.max_ray_depth);
+            return get_shuffled_scrambled_sobol_pt_uint(ls.ss_seed, bounce_index, msb);
+        }
+        return pcg4d(ls.rs_seed);
+    }
+
+    // shader/path_tracer.glsl:367-498
+    void evaluate_ray(local_sampler& lsampler, vec3 pos, vec3 view, vec4& diffuse, vec4& reflection,
+                      pt_vertex_data& first_hit_vertex, sampled_material& first_hit_material, counters& c) const
+    {
+        vec3 attenuation = V3(1);
+        vec3 diffuse_rgb = V3(0), reflection_rgb = V3(0);
+        float diffuse_a = 0, reflection_a = 0;
+        float regularization = 1.0f;
+        float bsdf_pdf = 0.0f;
+        bsdf_lobes primary_lobes = {0, 0, 0, 1};
+        hit_payload payload;
+        payload.random_seed = pcg4d(lsampler.rs_seed).x;
+        const uint32_t max_bounces = (uint32_t)opt.max_ray_depth;
+        for(uint32_t bounce = 0; bounce < max_bounces; ++bounce)
+        {
+            bool include_lights = !(opt.hide_lights && bounce == 0);
+            trace_closest(pos, bounce == 0 ? 0.0f : opt.min_ray_dist, view, include_lights, payload, c);
+
+            pt_vertex_data v;
+            sampled_material mat;
+            intersection_pdf nee_pdf;
+            vec3 light;
+            bool terminal = !get_intersection_info(pos, view, payload, v, nee_pdf, mat, light) || bounce == max_bounces - 1;
+
+            float mis_pdf = bsdf_mis_pdf(nee_pdf, bsdf_pdf);
+            float mis_weight = 1.0f;
+            if(bsdf_pdf != 0)
+            {
+                attenuation /= bsdf_pdf;
+                mis_weight = bsdf_pdf / mis_pdf;
+            }
+            light = attenuation * mis_weight * (mat.emission + light);
+            if(bounce != 0) light *= clamp_contribution_mul(light);
+            add_demodulated_color(primary_lobes, light, diffuse_rgb, reflection_rgb);
+
+            if(bounce == 0)
+            {
+                first_hit_vertex = v;
+                first_hit_material = mat;
+                first_hit_material.emission = light;
+            }
+
+            if(opt.regularization_gamma != 0.0f)
+            {
+                if(bsdf_pdf != 0.0f)
+                    regularization *= max_(1 - opt.regularization_gamma / pow_(bsdf_pdf, 0.25f), 0.0f);
+                mat.roughness = 1.0f - ((1.0f - mat.roughness) * regularization);
+            }
+
+            mat3 tbn = create_tangent_space(v.mapped_normal);
+            vec3 shading_view = view_to_tangent_space(view, tbn);
+
+            if(!terminal)
+            {
+                bsdf_lobes lobes = {0, 0, 0, 0};
+                vec3 radiance = attenuation * next_event_estimation(
+                    generate_ray_sample_uint(lsampler, bounce * 2), tbn, shading_view, mat, v, lobes, c);
+                if(bounce != 0)
+                {
+                    radiance *= modulate_bsdf(mat, lobes);
+                    radiance *= clamp_contribution_mul(radiance);
+                }
+                else primary_lobes = lobes;
+                add_demodulated_color(primary_lobes, radiance, diffuse_rgb, reflection_rgb);
+                if(bounce == 1) diffuse_a = reflection_a = 1.0f / length(v.pos - pos);
+            }
+
+            if(terminal) break;
+
+            bsdf_lobes lobes = {0, 0, 0, 0};
+            vec4 ray_sample = to_unit(generate_ray_sample_uint(lsampler, bounce * 2 + 1));
+            material_bsdf_sample(opt.bounce_mode, ray_sample, shading_view, mat, view, lobes, bsdf_pdf);
+            view = mul(tbn, view);
+
+            correct_lobes_for_normal_map(v.hard_normal, view, lobes);
+
+            if(bounce != 0) attenuation *= modulate_bsdf(mat, lobes);
+            else primary_lobes = lobes;
+
+            pos = v.pos;
+            if(opt.russian_roulette_delta > 0)
+            {
+                float qi = min_(1.0f, 1.0f / opt.russian_roulette_delta);
+                if(ray_sample.w > qi) break;
+            }
+            if(max_(attenuation.x, max_(attenuation.y, attenuation.z)) <= 0.0f) break;
+        }
+        diffuse = V4(diffuse_rgb, diffuse_a);
+        reflection = V4(reflection_rgb, reflection_a);
+    }
+
+    // shader/camera.glsl:25-59 (projection types 0 and 1)
+    void get_camera_ray(const tr_camera_data& cam, vec2 pixel_coord, vec2 screen_size, vec2 dof_u, vec3& origin, vec3& dir) const
+    {
+        vec2 uv = pixel_coord / screen_size;
+        uv = V2(uv.x * 2.0f - 1.0f, uv.y * 2.0f - 1.0f);
+        mat4 proj_inverse, view_inverse;
+        memcpy(proj_inverse.m, cam.proj_inverse, 64);
+        memcpy(view_inverse.m, cam.view_inverse, 64);
+        if(opt.projection == TR_PROJECTION_PERSPECTIVE)
+        {
+            if(opt.depth_of_field)
+            {
+                vec2 aperture_offset = cam.dof_params[3] == 0 ?
+                    sample_concentric_disk(dof_u) :
+                    sample_regular_polygon(dof_u, cam.dof_params[2], (uint32_t)cam.dof_params[3]);
+                vec3 view_origin = V3(aperture_offset.x * cam.dof_params[1], aperture_offset.y * cam.dof_params[1], 0);
+                vec3 view_dir = xyz(mul(proj_inverse, V4(uv.x, uv.y, 1, 1))) * cam.dof_params[0];
+                view_dir = normalize(view_dir - view_origin);
+                origin = xyz(mul(view_inverse, V4(view_origin, 1.0f)));
+                dir = normalize(xyz(mul(view_inverse, V4(view_dir, 0))));
+            }
+            else
+            {
+                origin = V3(cam.origin[0], cam.origin[1], cam.origin[2]);
+                vec4 t = mul(proj_inverse, V4(uv.x, uv.y, 1, 1));
+                dir = normalize(xyz(mul(view_inverse, V4(t.x, t.y, t.z, 0))));
+            }
+        }
+        else
+        {
+            origin = xyz(mul(view_inverse, mul(proj_inverse, V4(uv.x, uv.y, 0, 1))));
+            dir = normalize(xyz(mul(view_inverse, V4(0, 0, -1, 0))));
+        }
+    }
+
+    // shader/rt.glsl:234-241
+    void get_screen_camera_ray(const tr_camera_data& cam, int px, int py, vec2 pixel_offset, vec2 dof_u, vec3& origin, vec3& dir) const
+    {
+        vec2 p = V2((float)px + (pixel_offset.x * 0.5f + 0.5f), (float)py + (pixel_offset.y * 0.5f + 0.5f));
+        p.y = (float)dist.size[1] - p.y;
+        get_camera_ray(cam, p, V2((float)dist.size[0], (float)dist.size[1]), dof_u, origin, dir);
+    }
+
+    // shader/path_tracer.glsl:504-533
+    void get_world_camera_ray(local_sampler& ls, int px, int py, uint32_t view, vec3& origin, vec3& dir) const
+    {
+        vec2 cam_offset = V2(0, 0);
+        if(opt.film != TR_FILM_POINT) // control.antialiasing == 1
+        {
+            if(opt.film == TR_FILM_BOX)
+            {
+                vec4 r = to_unit(pcg4d(ls.rs_seed));
+                cam_offset = V2(r.x * 2.0f - 1.0f, r.y * 2.0f - 1.0f);
+            }
+            else
+            {
+                vec4 r = to_unit(pcg4d(ls.rs_seed));
+                cam_offset = sample_blackman_harris_concentric_disk(V2(r.x, r.y)) * 2.0f;
+            }
+            cam_offset = cam_offset * (2.0f * opt.film_radius);
+        }
+        vec2 dof_u = V2(0.5f, 0.5f);
+        if(opt.depth_of_field)
+        {
+            vec4 r = to_unit(pcg4d(ls.rs_seed));
+            dof_u = V2(r.x, r.y);
+        }
+        get_screen_camera_ray(cameras[view].current, px, py, cam_offset, dof_u, origin, dir);
+    }
+
+    // ------------------------------------------------------------------------------------
+    // one pass of path_tracer.rgen over this device's launch ids
+    // ------------------------------------------------------------------------------------
+    void render_pass(uint32_t pass_index, uint32_t sample_counter, uint32_t rng_seed, uint32_t samples_accumulated,
+                     uint64_t max_slots, counters& total)
+    {
+        uint32_t rx, ry;
+        ray_count(rx, ry);
+        const uint32_t V = views();
+        const size_t layer = layer_size();
+        const uint32_t spp_pass = (uint32_t)opt.samples_per_pass;
+        const uint32_t previous_samples = pass_index * spp_pass;
+        uint64_t slots_per_view = (uint64_t)rx * ry;
+        if(max_slots > 0 && max_slots < slots_per_view) slots_per_view = max_slots;
+        const uint64_t total_slots = slots_per_view * V;
+
+        std::atomic<uint64_t> next{0};
+        std::vector<counters> per_thread(threads);
+        auto worker = [&](int tid) {
+            counters& c = per_thread[tid];
+            const uint64_t chunk = 256;
+            for(;;)
+            {
+                uint64_t begin = next.fetch_add(chunk);
+                if(begin >= total_slots) break;
+                uint64_t end = std::min(begin + chunk, total_slots);
+                for(uint64_t s = begin; s < end; ++s)
+                {
+                    uint32_t view = (uint32_t)(s / slots_per_view);
+                    uint64_t r = s % slots_per_view;
+                    uint32_t lx = (uint32_t)(r % rx), ly = (uint32_t)(r / rx);
+                    int px, py;
+                    size_t write_index;
+                    if(!map_launch(lx, ly, px, py, write_index)) continue;
+
+                    pt_vertex_data first_hit_vertex{};
+                    sampled_material first_hit_material{};
+                    vec3 sum_color = V3(0);
+                    for(uint32_t i = 0; i < spp_pass; ++i)
+                    {
+                        local_sampler ls = init_local_sampler(
+                            uvec4{(uint32_t)px, (uint32_t)py, view, previous_samples + i}, sample_counter, rng_seed);
+                        vec3 origin, dir;
+                        get_world_camera_ray(ls, px, py, view, origin, dir);
+                        vec4 diffuse, reflection;
+                        c.paths++;
+                        evaluate_ray(ls, origin, dir, diffuse, reflection, first_hit_vertex, first_hit_material, c);
+                        sampled_material m = first_hit_material;
+                        if(opt.use_white_albedo_on_first_bounce)
+                        {
+                            m.albedo.x = 1; m.albedo.y = 1; m.albedo.z = 1;
+                        }
+                        sum_color += first_hit_material.emission + modulate_color(m, xyz(diffuse), xyz(reflection));
+                    }
+                    vec3 col = sum_color / (float)spp_pass;
+                    // write_all_outputs (path_tracer.glsl:535-576) + accumulate_gbuffer_color (gbuffer.glsl:18-28)
+                    uint32_t prev_samples = samples_accumulated + previous_samples;
+                    float alpha = opt.transparent_background ? first_hit_material.albedo.w : 1.0f;
+                    vec4 out = V4(col, alpha);
+                    float* dst = &color[((size_t)view * layer + write_index) * 4];
+                    if(prev_samples != 0)
+                    {
+                        vec4 prev = V4(dst[0], dst[1], dst[2], dst[3]);
+                        uint32_t tot = spp_pass + prev_samples;
+                        out = mix_(out, prev, (float)prev_samples / (float)tot);
+                    }
+                    dst[0] = out.x; dst[1] = out.y; dst[2] = out.z; dst[3] = out.w;
+                }
+            }
+        };
+        std::vector<std::thread> pool;
+        for(int t = 1; t < threads; ++t) pool.emplace_back(worker, t);
+        worker(0);
+        for(auto& t: pool) t.join();
+        for(const counters& c: per_thread)
+        {
+            total.closest += c.closest; total.shadow += c.shadow; total.paths += c.paths;
+            total.nodes += c.nodes; total.tris += c.tris;
+        }
+    }
+};
+
+// -------------------------------------------------------------------------------------------------
+// C interface
+// -------------------------------------------------------------------------------------------------
+static std::string g_last_error;
+
+static int fail(orc_ctx* ctx, int code, const std::string& msg)
+{
+    if(ctx) ctx->error = msg; else g_last_error = msg;
+    return code;
+}
+
+static int check_options(const tr_pt_options* o, std::string& why)
+{
+    if(o->max_ray_depth < 1) { why = "max_ray_depth must be >= 1"; return TR_ERR_INVALID_ARGUMENT; }
+    if(o->samples_per_pass < 1 || o->samples_per_pixel < o->samples_per_pass) { why = "bad samples_per_pixel/samples_per_pass"; return TR_ERR_INVALID_ARGUMENT; }
+    if(o->local_sampler != TR_SAMPLER_UNIFORM_RANDOM && o->local_sampler != TR_SAMPLER_SOBOL_OWEN)
+    { why = "sobol-z samplers are outside the hot-path scope"; return TR_ERR_UNSUPPORTED; }
+    if(o->projection != TR_PROJECTION_PERSPECTIVE && o->projection != TR_PROJECTION_ORTHOGRAPHIC)
+    { why = "only matrix cameras are supported"; return TR_ERR_UNSUPPORTED; }
+    return TR_OK;
+}
+
+extern "C" {
+
+int orc_create(orc_ctx** out, const tr_pt_options* opt, int threads)
+{
+    if(!out || !opt) return fail(nullptr, TR_ERR_INVALID_ARGUMENT, "null argument");
+    std::string why;
+    int rc = check_options(opt, why);
+    if(rc) return fail(nullptr, rc, why);
+    orc_ctx* c = new orc_ctx();
+    c->opt = *opt;
+    c->threads = threads > 0 ? threads : (int)std::max(1u, std::thread::hardware_concurrency());
+    *out = c;
+    return TR_OK;
+}
+
+void orc_destroy(orc_ctx* ctx) { delete ctx; }
+
+int orc_set_scene(orc_ctx* ctx, const tr_pt_scene_desc* s)
+{
+    if(!ctx || !s) return fail(ctx, TR_ERR_INVALID_ARGUMENT, "null argument");
+    if(s->environment_proj >= 0) return fail(ctx, TR_ERR_UNSUPPORTED, "environment maps are outside the hot-path scope");
+    ctx->instances.assign(s->instances, s->instances + s->instance_count);
+    ctx->vertices.assign(s->instance_count, {});
+    ctx->indices.assign(s->instance_count, {});
+    ctx->opaque.assign(s->instance_count, 1);
+    ctx->point_lights.assign(s->point_lights, s->point_lights + s->point_light_count);
+    ctx->directional_lights.assign(s->directional_lights, s->directional_lights + s->directional_light_count);
+    ctx->textures.clear();
+    for(uint32_t i = 0; i < s->texture_count; ++i)
+    {
+        texture_data t;
+        t.w = s->textures[i].width; t.h = s->textures[i].height; t.format = s->textures[i].format;
+        size_t bytes = (size_t)t.w * t.h * (t.format == TR_TEXTURE_RGBA32F ? 16 : 4);
+        t.bytes.assign((const uint8_t*)s->textures[i].data, (const uint8_t*)s->textures[i].data + bytes);
+        ctx->textures.push_back(std::move(t));
+    }
+    ctx->environment_factor = V4(s->environment_factor[0], s->environment_factor[1], s->environment_factor[2], s->environment_factor[3]);
+    ctx->environment_proj = s->environment_proj;
+    ctx->any_non_opaque = false;
+
+    std::vector<tri_record> tris;
+    size_t tri_light_count = 0;
+    for(uint32_t i = 0; i < s->instance_count; ++i)
+    {
+        const tr_mesh_ref& m = s->meshes[i];
+        const tr_instance& o = ctx->instances[i];
+        ctx->opaque[i] = m.opaque;
+        if(!m.opaque) ctx->any_non_opaque = true;
+        // shader/pre_transform.comp:26-42
+        mat4 model; memcpy(model.m, o.model, 64);
+        mat4 model_normal; memcpy(model_normal.m, o.model_normal, 64);
+        mat3 mn = upper3(model_normal);
+        bool flip = determinant(mn) < 0;
+        std::vector<tr_vertex>& vv = ctx->vertices[i];
+        vv.assign(m.vertices, m.vertices + m.vertex_count);
+        for(tr_vertex& v: vv)
+        {
+            vec3 p = xyz(mul(model, V4(v.pos[0], v.pos[1], v.pos[2], 1)));
+            vec3 n = normalize(mul(mn, ld3(v.normal)));
+            vec3 t = normalize(mul(mn, V3(v.tangent[0], v.tangent[1], v.tangent[2])));
+            float tw = v.tangent[3];
+            if(flip) { n = -n; t = -t; tw = -tw; }
+            v.pos[0] = p.x; v.pos[1] = p.y; v.pos[2] = p.z;
+            v.normal[0] = n.x; v.normal[1] = n.y; v.normal[2] = n.z;
+            v.tangent[0] = t.x; v.tangent[1] = t.y; v.tangent[2] = t.z; v.tangent[3] = tw;
+        }
+        ctx->indices[i].assign(m.indices, m.indices + m.index_count);
+        uint32_t ntri = m.index_count / 3;
+        for(uint32_t p = 0; p < ntri; ++p)
+        {
+            tri_record tr;
+            tr.v0 = ld3(vv[m.indices[3 * p + 0]].pos);
+            tr.v1 = ld3(vv[m.indices[3 * p + 1]].pos);
+            tr.v2 = ld3(vv[m.indices[3 * p + 2]].pos);
+            tr.instance_id = (int32_t)i;
+            tr.primitive_id = (int32_t)p;
+            tr.opaque = m.opaque;
+            tris.push_back(tr);
+        }
+        if(o.light_base_id >= 0) tri_light_count = std::max(tri_light_count, (size_t)o.light_base_id + ntri);
+    }
+    // shader/extract_tri_lights.comp:17-54 (PRE_TRANSFORMED_VERTICES variant)
+    ctx->tri_lights.assign(tri_light_count, tr_tri_light{});
+    for(uint32_t i = 0; i < s->instance_count; ++i)
+    {
+        const tr_instance& o = ctx->instances[i];
+        if(o.light_base_id < 0) continue;
+        const std::vector<tr_vertex>& vv = ctx->vertices[i];
+        const std::vector<uint32_t>& ii = ctx->indices[i];
+        for(uint32_t p = 0; p < ii.size() / 3; ++p)
+        {
+            tr_tri_light& l = ctx->tri_lights[o.light_base_id + p];
+            l.emission_tex_id = o.mat.emission_tex_id;
+            l.emission_factor = rgb_to_r9g9b9e5(V3(o.mat.emission_factor[0], o.mat.emission_factor[1], o.mat.emission_factor[2]));
+            l.instance_id = i;
+            l.primitive_id = p;
+            for(int k = 0; k < 3; ++k)
+            {
+                const tr_vertex& v = vv[ii[3 * p + k]];
+                l.pos[k][0] = v.pos[0]; l.pos[k][1] = v.pos[1]; l.pos[k][2] = v.pos[2];
+                l.uv[k] = float_to_half_(v.uv[0]) | (float_to_half_(v.uv[1]) << 16);
+            }
+        }
+    }
+    ctx->stats.triangle_count = (uint32_t)tris.size();
+    ctx->stats.tri_light_count = (uint32_t)tri_light_count;
+    ctx->accel.build(std::move(tris));
+    ctx->stats.bvh_node_count = (uint32_t)ctx->accel.nodes.size();
+    ctx->has_scene = true;
+    return TR_OK;
+}
+
+int orc_set_cameras(orc_ctx* ctx, const tr_camera_pair* pairs, uint32_t view_count)
+{
+    if(!ctx || !pairs || view_count == 0) return fail(ctx, TR_ERR_INVALID_ARGUMENT, "null argument");
+    ctx->cameras.assign(pairs, pairs + view_count);
+    return TR_OK;
+}
+
+int orc_set_distribution(orc_ctx* ctx, const tr_pt_distribution* d)
+{
+    if(!ctx || !d) return fail(ctx, TR_ERR_INVALID_ARGUMENT, "null argument");
+    if(d->size[0] == 0 || d->size[1] == 0) return fail(ctx, TR_ERR_INVALID_ARGUMENT, "empty image");
+    if(d->strategy < 0 || d->strategy > 2) return fail(ctx, TR_ERR_INVALID_ARGUMENT, "bad strategy");
+    if(d->strategy == TR_DISTRIBUTION_SCANLINE && (d->count == 0 || d->index >= d->count))
+        return fail(ctx, TR_ERR_INVALID_ARGUMENT, "bad scanline index/count");
+    ctx->dist = *d;
+    if(d->strategy == TR_DISTRIBUTION_DUPLICATE) ctx->dist.primary = 1;
+    return TR_OK;
+}
+
+int orc_reset_accumulation(orc_ctx* ctx, int reset_sample_counter)
+{
+    if(!ctx) return TR_ERR_INVALID_ARGUMENT;
+    ctx->accumulated_samples = 0;
+    if(reset_sample_counter) ctx->frame_counter = 0;
+    return TR_OK;
+}
+
+static int prepare_target(orc_ctx* ctx)
+{
+    if(!ctx->has_scene) return fail(ctx, TR_ERR_NO_SCENE, "no scene");
+    if(ctx->cameras.empty() || ctx->dist.size[0] == 0) return fail(ctx, TR_ERR_INVALID_ARGUMENT, "cameras/distribution not set");
+    size_t need = ctx->layer_size() * ctx->views() * 4;
+    if(ctx->color.size() != need) ctx->color.assign(need, 0.0f);
+    return TR_OK;
+}
+
+int orc_render(orc_ctx* ctx, uint64_t max_slots)
+{
+    if(!ctx) return TR_ERR_INVALID_ARGUMENT;
+    int rc = prepare_target(ctx);
+    if(rc) return rc;
+    // src/rt_stage.cc:76-85, src/rt_camera_stage.cc:74-101
+    uint32_t sample_counter = ctx->frame_counter * (uint32_t)ctx->opt.samples_per_pixel;
+    uint32_t seed = (uint32_t)ctx->opt.rng_seed;
+    uint32_t rng_seed = ctx->opt.rng_seed != 0 ? pcg(seed) : 0;
+    ctx->frame_counter++;
+    uint32_t samples_accumulated = (uint32_t)ctx->accumulated_samples;
+    ctx->accumulated_samples += ctx->opt.samples_per_pixel;
+    counters total;
+    uint32_t pass_count = (uint32_t)(ctx->opt.samples_per_pixel / ctx->opt.samples_per_pass);
+    for(uint32_t pass = 0; pass < pass_count; ++pass)
+        ctx->render_pass(pass, sample_counter, rng_seed, samples_accumulated, max_slots, total);
+    ctx->stats.closest_rays = total.closest;
+    ctx->stats.shadow_rays = total.shadow;
+    ctx->stats.paths = total.paths;
+    ctx->stats.node_visits = total.nodes;
+    ctx->stats.triangle_tests = total.tris;
+    return TR_OK;
+}
+
+// shader/rt_feature.rgen:18-47 + rt_feature.rahit (alpha cutoff 1e-4) + rt_feature.rchit
+int orc_render_feature(orc_ctx* ctx, int feature, const float default_value[4])
+{
+    if(!ctx) return TR_ERR_INVALID_ARGUMENT;
+    int rc = prepare_target(ctx);
+    if(rc) return rc;
+    uint32_t rx, ry;
+    ctx->ray_count(rx, ry);
+    const size_t layer = ctx->layer_size();
+    for(uint32_t view = 0; view < ctx->views(); ++view)
+    {
+        const tr_camera_data& cam = ctx->cameras[view].current;
+        mat4 cam_view; memcpy(cam_view.m, cam.view, 64);
+        std::atomic<uint32_t> next_row{0};
+        auto worker = [&]() {
+            for(;;)
+            {
+                uint32_t ly = next_row.fetch_add(1);
+                if(ly >= ry) break;
+                for(uint32_t lx = 0; lx < rx; ++lx)
+                {
+                    int px, py; size_t write_index;
+                    if(!ctx->map_launch(lx, ly, px, py, write_index)) continue;
+                    vec3 origin, dir;
+                    ctx->get_screen_camera_ray(cam, px, py, V2(0, 0), V2(0.5f, 0.5f), origin, dir);
+                    vec4 data = V4(default_value[0], default_value[1], default_value[2], default_value[3]);
+                    float cur_tmin = ctx->opt.min_ray_dist;
+                    vec3 o = V3(cam.origin[0], cam.origin[1], cam.origin[2]);
+                    for(;;)
+                    {
+                        hit_record h;
+                        if(!ctx->accel.closest(o, dir, cur_tmin, INFINITY, h)) break;
+                        if(!ctx->opaque[h.instance_id] &&
+                           ctx->hit_alpha(h.instance_id, h.primitive_id, V2(h.u, h.v)) <= 0.0001f)
+                        {
+                            cur_tmin = h.t;
+                            continue;
+                        }
+                        float pdf;
+                        vertex_data v = ctx->get_interpolated_vertex(dir, V2(h.u, h.v), h.instance_id, h.primitive_id, o, pdf);
+                        sampled_material mat = ctx->sample_material(h.instance_id, v);
+                        switch(feature)
+                        {
+                        default:
+                        case TR_FEATURE_ALBEDO: data = mat.albedo; break;
+                        case TR_FEATURE_WORLD_NORMAL: data = V4(v.mapped_normal, 1); break;
+                        case TR_FEATURE_VIEW_NORMAL: data = V4(xyz(mul(cam_view, V4(v.mapped_normal, 0))), 1); break;
+                        case TR_FEATURE_WORLD_POS: data = V4(v.pos, 1); break;
+                        case TR_FEATURE_VIEW_POS: data = mul(cam_view, V4(v.pos, 1)); break;
+                        case TR_FEATURE_DISTANCE: data = V4(h.t, h.t, h.t, 1); break;
+                        case TR_FEATURE_INSTANCE_ID: data = V4((float)h.instance_id, (float)h.primitive_id, 0, 1); break;
+                        }
+                        break;
+                    }
+                    float* dst = &ctx->color[((size_t)view * layer + write_index) * 4];
+                    dst[0] = data.x; dst[1] = data.y; dst[2] = data.z; dst[3] = data.w;
+                }
+            }
+        };
+        std::vector<std::thread> pool;
+        for(int t = 1; t < ctx->threads; ++t) pool.emplace_back(worker);
+        worker();
+        for(auto& t: pool) t.join();
+    }
+    return TR_OK;
+}
+
+int orc_read_color(orc_ctx* ctx, float* out, size_t bytes)
+{
+    if(!ctx || !out) return TR_ERR_INVALID_ARGUMENT;
+    if(bytes != ctx->color.size() * 4) return fail(ctx, TR_ERR_INVALID_ARGUMENT, "size mismatch: target has " + std::to_string(ctx->color.size() * 4) + " bytes");
+    memcpy(out, ctx->color.data(), bytes);
+    return TR_OK;
+}
+
+int orc_get_stats(orc_ctx* ctx, tr_pt_stats* stats)
+{
+    if(!ctx || !stats) return TR_ERR_INVALID_ARGUMENT;
+    *stats = ctx->stats;
+    return TR_OK;
+}
+
+int orc_read_tri_lights(orc_ctx* ctx, tr_tri_light* out, uint32_t capacity)
+{
+    if(!ctx) return TR_ERR_INVALID_ARGUMENT;
+    uint32_t n = (uint32_t)std::min<size_t>(capacity, ctx->tri_lights.size());
+    if(out && n) memcpy(out, ctx->tri_lights.data(), n * sizeof(tr_tri_light));
+    return (int)ctx->tri_lights.size();
+}
+
+int orc_trace_rays(orc_ctx* ctx, const float* rays, uint32_t n, void* hits_out)
+{
+    if(!ctx || !ctx->has_scene) return TR_ERR_NO_SCENE;
+    struct out_hit { int32_t inst, prim; float u, v, t; };
+    out_hit* out = (out_hit*)hits_out;
+    std::atomic<uint32_t> next{0};
+    auto worker = [&]() {
+        for(;;)
+        {
+            uint32_t b = next.fetch_add(1024);
+            if(b >= n) break;
+            for(uint32_t i = b; i < std::min(n, b + 1024); ++i)
+            {
+                const float* r = rays + 8 * (size_t)i;
+                hit_record h;
+                bool ok = ctx->accel.closest(V3(r[0], r[1], r[2]), V3(r[4], r[5], r[6]), r[3], r[7], h);
+                if(ok) out[i] = {h.instance_id, h.primitive_id, h.u, h.v, h.t};
+                else out[i] = {-1, -1, 0, 0, 0};
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for(int t = 1; t < ctx->threads; ++t) pool.emplace_back(worker);
+    worker();
+    for(auto& t: pool) t.join();
+    return TR_OK;
+}
+
+int orc_sample_test(orc_ctx* ctx, const uint32_t* coords, uint32_t n, int draw_index, uint32_t* out)
+{
+    if(!ctx) return TR_ERR_INVALID_ARGUMENT;
+    uint32_t sample_counter = ctx->frame_counter * (uint32_t)ctx->opt.samples_per_pixel;
+    uint32_t seed = (uint32_t)ctx->opt.rng_seed;
+    uint32_t rng_seed = ctx->opt.rng_seed != 0 ? pcg(seed) : 0;
+    for(uint32_t i = 0; i < n; ++i)
+    {
+        uvec4 c = {coords[4 * i], coords[4 * i + 1], coords[4 * i + 2], coords[4 * i + 3]};
+        local_sampler ls = init_local_sampler(c, sample_counter, rng_seed);
+        uvec4 r;
+        if(draw_index < 0) r = pcg4d(ls.rs_seed);
+        else r = ctx->generate_ray_sample_uint(ls, (uint32_t)draw_index);
+        out[4 * i] = r.x; out[4 * i + 1] = r.y; out[4 * i + 2] = r.z; out[4 * i + 3] = r.w;
+    }
+    return TR_OK;
+}
+
+int orc_unshuffle(orc_ctx* ctx, const float* strip, uint32_t index, uint32_t count, float* full_image)
+{
+    if(!ctx || !strip || !full_image) return TR_ERR_INVALID_ARGUMENT;
+    const uint32_t W = ctx->dist.size[0], H = ctx->dist.size[1];
+    const uint32_t V = ctx->views();
+    for(uint32_t view = 0; view < V; ++view)
+        for(uint32_t i = 0; i < count; ++i)
+        {
+            uint32_t j;
+            if(ctx->dist.strategy == TR_DISTRIBUTION_SHUFFLED_STRIPS) j = ctx->permute_region_id(index + i);
+            else return fail(ctx, TR_ERR_UNSUPPORTED, "unshuffle: shuffled strips only");
+            if(j >= W * H) continue;
+            memcpy(full_image + ((size_t)view * W * H + j) * 4, strip + ((size_t)view * count + i) * 4, 16);
+        }
+    return TR_OK;
+}
+
+int orc_math(int op, const float* a, const float* b, float* out, uint32_t n)
+{
+    for(uint32_t i = 0; i < n; ++i)
+    {
+        switch(op)
+        {
+        case 0: out[i] = sin_(a[i]); break;
+        case 1: out[i] = cos_(a[i]); break;
+        case 2: out[i] = atan2_(a[i], b[i]); break;
+        case 3: out[i] = pow_(a[i], b[i]); break;
+        case 4: out[i] = log2_(a[i]); break;
+        case 5: out[i] = exp2_(a[i]); break;
+        case 6: out[i] = asin_(a[i]); break;
+        case 7: out[i] = acos_(a[i]); break;
+        default: return TR_ERR_INVALID_ARGUMENT;
+        }
+    }
+    return TR_OK;
+}
+
+const char* orc_last_error(orc_ctx* ctx) { return ctx ? ctx->error.c_str() : g_last_error.c_str(); }
+
+} // extern "C"

@@ -1,0 +1,668 @@
+// tr_abi.cu -- the C ABI of include/tauray_b200.h: context, scene upload, frame loop.
+//
+// Host-side mirror of what the reference does around the hot loop:
+//   tr_pt_create            path_tracer_stage ctor                 src/path_tracer_stage.cc:30-116
+//   tr_pt_set_scene         scene_stage upload + ensure_blas       src/scene_stage.cc:821-872,1066-1116,1498-1541
+//   tr_pt_render            rt_stage::update + record_command_buffers + rt_camera_stage::update
+//                           src/rt_stage.cc:76-133, src/rt_camera_stage.cc:74-101, path_tracer_stage.cc:118-147
+// There is no CPU fallback anywhere in this file: without a usable sm_100 device every entry point
+// fails with TR_ERR_NO_DEVICE / TR_ERR_CUDA.
+#include "tr_path.cuh"
+#include "tr_render.h"
+#include "tr_build.h"
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace trd;
+
+struct tr_pt_ctx
+{
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    tr_pt_options opt{};
+    std::string error;
+
+    // scene
+    bool has_scene = false;
+    DeviceScene scene{};
+    std::vector<void*> scene_allocs;
+    // cameras / distribution / targets
+    tr_camera_pair* cameras = nullptr;
+    uint32_t views = 0;
+    tr_pt_distribution dist{};
+    bool has_dist = false;
+    float4* color = nullptr;
+    size_t color_pixels = 0;
+    tr_wavefront wf{};
+    std::vector<void*> wf_allocs;
+    Counters* counters = nullptr;
+    // frame state (rt_stage::frame_counter, rt_camera_stage::accumulated_samples)
+    uint32_t frame_counter = 0;
+    int accumulated_samples = 0;
+    int instrumentation = 0;
+    tr_pt_stats stats{};
+    bool rendered = false;
+    float4* peers[8] = {};
+    int peer_count = 0;
+};
+
+static std::string g_create_error;
+
+static int fail(tr_pt_ctx* ctx, int code, const std::string& msg)
+{
+    if(ctx) ctx->error = msg; else g_create_error = msg;
+    return code;
+}
+static int fail_cuda(tr_pt_ctx* ctx, cudaError_t e, const char* what)
+{
+    std::string msg = std::string(what) + ": " + cudaGetErrorString(e);
+    cudaGetLastError();
+    return fail(ctx, e == cudaErrorMemoryAllocation ? TR_ERR_OUT_OF_MEMORY : TR_ERR_CUDA, msg);
+}
+#define TRY_CUDA(ctx, x) do { cudaError_t e_ = (x); if(e_ != cudaSuccess) return fail_cuda(ctx, e_, #x); } while(0)
+
+namespace {
+struct DeviceGuard
+{
+    int prev = 0;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); cudaSetDevice(dev); }
+    ~DeviceGuard() { cudaSetDevice(prev); }
+};
+
+template<typename T> cudaError_t dev_alloc(std::vector<void*>& list, T** p, size_t count)
+{
+    cudaError_t e = cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T));
+    if(e == cudaSuccess) list.push_back(*p);
+    return e;
+}
+
+void free_list(std::vector<void*>& list)
+{
+    for(void* p: list) cudaFree(p);
+    list.clear();
+}
+
+uint32_t host_pcg(uint32_t seed) // src/math.cc:280-285
+{
+    seed = seed * 747796405u + 2891336453u;
+    seed = ((seed >> ((seed >> 28) + 4)) ^ seed) * 277803737u;
+    return (seed >> 22) ^ seed;
+}
+
+unsigned calculate_shuffled_strips_b(uint32_t w, uint32_t h) // src/distribution_strategy.cc:62-69
+{
+    unsigned n = w * h;
+    unsigned b = 31;
+    while((n >> b) < 128 && b > 0) b--;
+    return b;
+}
+
+int check_options(const tr_pt_options* o, std::string& why)
+{
+    if(o->max_ray_depth < 1 || o->max_ray_depth > 64) { why = "max_ray_depth must be in [1, 64]"; return TR_ERR_INVALID_ARGUMENT; }
+    if(o->samples_per_pass < 1 || o->samples_per_pixel < o->samples_per_pass) { why = "bad samples_per_pixel/samples_per_pass"; return TR_ERR_INVALID_ARGUMENT; }
+    if(o->local_sampler != TR_SAMPLER_UNIFORM_RANDOM && o->local_sampler != TR_SAMPLER_SOBOL_OWEN)
+    { why = "sobol-z samplers are outside the hot-path scope"; return TR_ERR_UNSUPPORTED; }
+    if(o->projection != TR_PROJECTION_PERSPECTIVE && o->projection != TR_PROJECTION_ORTHOGRAPHIC)
+    { why = "only matrix cameras are supported"; return TR_ERR_UNSUPPORTED; }
+    if(o->film < 0 || o->film > 2 || o->mis_mode < 0 || o->mis_mode > 2 || o->bounce_mode < 0 || o->bounce_mode > 2 ||
+       o->tri_light_mode < 0 || o->tri_light_mode > 2 || o->kernel_mode < 0 || o->kernel_mode > 1)
+    { why = "enum option out of range"; return TR_ERR_INVALID_ARGUMENT; }
+    return TR_OK;
+}
+
+void fill_frame(const tr_pt_ctx* c, FrameParams& f)
+{
+    const tr_pt_distribution& d = c->dist;
+    f.size_x = d.size[0]; f.size_y = d.size[1];
+    f.index = d.index; f.count = d.count;
+    f.strategy = d.strategy; f.primary = d.primary;
+    f.strips_b = calculate_shuffled_strips_b(d.size[0], d.size[1]);
+    f.region_size = ((d.size[0] * d.size[1]) + (1u << f.strips_b) - 1) >> f.strips_b;
+    switch(d.strategy)
+    {
+    case TR_DISTRIBUTION_SCANLINE:
+        f.ray_count_x = d.size[0];
+        f.ray_count_y = (d.size[1] - d.index + d.count - 1) / d.count;
+        break;
+    case TR_DISTRIBUTION_SHUFFLED_STRIPS:
+        f.ray_count_x = d.count; f.ray_count_y = 1;
+        break;
+    default:
+        f.ray_count_x = d.size[0]; f.ray_count_y = d.size[1];
+        break;
+    }
+    f.views = c->views;
+    f.layer_size = (d.primary || d.strategy == TR_DISTRIBUTION_DUPLICATE) ? d.size[0] * d.size[1] : f.ray_count_x * f.ray_count_y;
+    f.samples_accumulated = 0; f.sample_counter = 0; f.rng_seed = 0; f.previous_samples = 0;
+    f.max_sobol_bounces = (uint32_t)(c->opt.max_ray_depth > 8 ? 8 : c->opt.max_ray_depth);
+}
+
+void fill_params(const tr_pt_ctx* c, RenderParams& P)
+{
+    memset(&P, 0, sizeof(P));
+    P.scene = c->scene;
+    P.opt = c->opt;
+    fill_frame(c, P.frame);
+    P.cameras = c->cameras;
+    P.color = c->color;
+    P.counters = c->counters;
+    P.stats = c->instrumentation;
+    for(int i = 0; i < c->peer_count; ++i) P.peers[i] = c->peers[i];
+    P.peer_count = c->peer_count;
+    P.last_pass = 0;
+}
+
+// (re)allocates the colour target and the wavefront buffers for the current cameras/distribution
+int prepare_targets(tr_pt_ctx* c)
+{
+    if(!c->has_scene) return fail(c, TR_ERR_NO_SCENE, "tr_pt_set_scene has not been called");
+    if(!c->has_dist || c->views == 0) return fail(c, TR_ERR_INVALID_ARGUMENT, "cameras / distribution not set");
+    FrameParams f;
+    fill_frame(c, f);
+    const size_t pixels = (size_t)f.layer_size * f.views;
+    if(pixels != c->color_pixels || !c->color)
+    {
+        if(c->color) cudaFree(c->color);
+        c->color = nullptr;
+        TRY_CUDA(c, cudaMalloc((void**)&c->color, std::max<size_t>(pixels, 1) * sizeof(float4)));
+        TRY_CUDA(c, cudaMemsetAsync(c->color, 0, std::max<size_t>(pixels, 1) * sizeof(float4), c->stream));
+        c->color_pixels = pixels;
+    }
+    const uint64_t slots64 = (uint64_t)f.ray_count_x * f.ray_count_y * f.views;
+    if(slots64 >= (1ull << 31)) return fail(c, TR_ERR_UNSUPPORTED, "more than 2^31 launch slots per pass");
+    const uint32_t slots = (uint32_t)slots64;
+    if(c->opt.kernel_mode == TR_KERNEL_WAVEFRONT && (c->wf.capacity < slots || !c->wf.counts))
+    {
+        free_list(c->wf_allocs);
+        tr_wavefront& w = c->wf;
+        memset(&w, 0, sizeof(w));
+        const size_t n = std::max<uint32_t>(slots, 1);
+        TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.pos_pdf, n));
+        TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.dir_seed, n));
+        TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.atten_reg, n));
+        TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.lobes, n));
+        TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.diffuse, n));
+        TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.reflection, n));
+        TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.fh_emission, n));
+        TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.fh_albedo, n));
+        TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.rs_seed, n));
+        TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.hits, n));
+        TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.nee, 4 * n));
+        TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.sum_color, c->opt.samples_per_pass > 1 ? n : 1));
+        TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.queue[0], n));
+        TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.queue[1], n));
+        TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.shadow_queue, n));
+        TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.counts, 2 * 64 + 2));
+        w.capacity = slots;
+    }
+    return TR_OK;
+}
+
+void free_scene(tr_pt_ctx* c)
+{
+    free_list(c->scene_allocs);
+    memset(&c->scene, 0, sizeof(c->scene));
+    c->has_scene = false;
+}
+} // namespace
+
+extern "C" {
+
+int tr_pt_abi_version(void) { return TR_B200_ABI_VERSION; }
+
+void tr_pt_default_options(tr_pt_options* o)
+{
+    if(!o) return;
+    memset(o, 0, sizeof(*o));
+    o->max_ray_depth = 8;
+    o->min_ray_dist = 1e-4f;
+    o->rng_seed = 0;
+    o->local_sampler = TR_SAMPLER_UNIFORM_RANDOM;
+    o->samples_per_pixel = 1;
+    o->samples_per_pass = 1;
+    o->projection = TR_PROJECTION_PERSPECTIVE;
+    o->active_viewport_count = 1;
+    o->film = TR_FILM_POINT;
+    o->mis_mode = TR_MIS_POWER_HEURISTIC;
+    o->film_radius = 0.5f;
+    o->sampling_weight_point_lights = 1.0f;
+    o->sampling_weight_directional_lights = 1.0f;
+    o->sampling_weight_envmap = 1.0f;
+    o->sampling_weight_emissive_triangles = 1.0f;
+    o->bounce_mode = TR_BOUNCE_MATERIAL;
+    o->tri_light_mode = TR_TRI_LIGHT_SOLID_ANGLE;
+    o->kernel_mode = TR_KERNEL_WAVEFRONT;
+}
+
+int tr_pt_create(tr_pt_ctx** out, int cuda_device, const tr_pt_options* opt)
+{
+    if(!out || !opt) return fail(nullptr, TR_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    std::string why;
+    int rc = check_options(opt, why);
+    if(rc) return fail(nullptr, rc, why);
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if(e != cudaSuccess || count == 0)
+    {
+        cudaGetLastError();
+        return fail(nullptr, TR_ERR_NO_DEVICE, std::string("no CUDA device (") + cudaGetErrorString(e) + "); tauray_b200 has no CPU fallback");
+    }
+    if(cuda_device < 0 || cuda_device >= count) return fail(nullptr, TR_ERR_INVALID_ARGUMENT, "cuda_device out of range");
+    cudaDeviceProp prop;
+    if(cudaGetDeviceProperties(&prop, cuda_device) != cudaSuccess) return fail(nullptr, TR_ERR_NO_DEVICE, "cannot query device");
+    if(prop.major != 10)
+        return fail(nullptr, TR_ERR_NO_DEVICE, "device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                    ", this library carries sm_100a code only");
+    DeviceGuard guard(cuda_device);
+    tr_pt_ctx* c = new tr_pt_ctx();
+    c->device = cuda_device;
+    c->sm_count = prop.multiProcessorCount;
+    c->opt = *opt;
+    auto bail = [&](cudaError_t err, const char* what) { int r = fail_cuda(nullptr, err, what); tr_pt_destroy(c); return r; };
+    if((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    if((e = cudaEventCreate(&c->ev_begin)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if((e = cudaEventCreate(&c->ev_end)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if((e = cudaMalloc((void**)&c->counters, sizeof(Counters))) != cudaSuccess) return bail(e, "cudaMalloc(counters)");
+    if((e = cudaMemset(c->counters, 0, sizeof(Counters))) != cudaSuccess) return bail(e, "cudaMemset(counters)");
+    if((e = tr_render_init_constants()) != cudaSuccess) return bail(e, "upload of the Sobol table");
+    *out = c;
+    return TR_OK;
+}
+
+void tr_pt_destroy(tr_pt_ctx* c)
+{
+    if(!c) return;
+    DeviceGuard guard(c->device);
+    if(c->stream) cudaStreamSynchronize(c->stream);
+    free_scene(c);
+    free_list(c->wf_allocs);
+    if(c->cameras) cudaFree(c->cameras);
+    if(c->color) cudaFree(c->color);
+    if(c->counters) cudaFree(c->counters);
+    if(c->ev_begin) cudaEventDestroy(c->ev_begin);
+    if(c->ev_end) cudaEventDestroy(c->ev_end);
+    if(c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int tr_pt_set_scene(tr_pt_ctx* c, const tr_pt_scene_desc* s)
+{
+    if(!c || !s) return fail(c, TR_ERR_INVALID_ARGUMENT, "null argument");
+    if(s->environment_proj >= 0) return fail(c, TR_ERR_UNSUPPORTED, "environment maps are outside the hot-path scope");
+    if(s->instance_count && (!s->instances || !s->meshes)) return fail(c, TR_ERR_INVALID_ARGUMENT, "null instance tables");
+    DeviceGuard guard(c->device);
+    TRY_CUDA(c, cudaStreamSynchronize(c->stream));
+    free_scene(c);
+    std::vector<void*>& A = c->scene_allocs;
+    cudaStream_t st = c->stream;
+
+    // ---- layout of the concatenated buffers
+    std::vector<tr_build_instance> binst(s->instance_count);
+    std::vector<DeviceInstance> dinst(s->instance_count);
+    uint64_t vtotal = 0, itotal = 0, ttotal = 0;
+    uint64_t tri_light_count = 0;
+    bool any_non_opaque = false;
+    for(uint32_t i = 0; i < s->instance_count; ++i)
+    {
+        const tr_mesh_ref& m = s->meshes[i];
+        if(m.index_count % 3) return fail(c, TR_ERR_INVALID_ARGUMENT, "index_count is not a multiple of 3");
+        if((m.vertex_count && !m.vertices) || (m.index_count && !m.indices)) return fail(c, TR_ERR_INVALID_ARGUMENT, "null mesh data");
+        binst[i].vertex_base = (uint32_t)vtotal;
+        binst[i].index_base = (uint32_t)itotal;
+        binst[i].triangle_base = (uint32_t)ttotal;
+        binst[i].triangle_count = m.index_count / 3;
+        binst[i].opaque = m.opaque ? 1u : 0u;
+        if(!m.opaque) any_non_opaque = true;
+        DeviceInstance& d = dinst[i];
+        memset(&d, 0, sizeof(d));
+        d.mat = s->instances[i].mat;
+        d.light_base_id = s->instances[i].light_base_id;
+        d.vertex_base = (uint32_t)vtotal;
+        d.index_base = (uint32_t)itotal;
+        d.opaque = binst[i].opaque;
+        d.shadow_terminator_mul = s->instances[i].shadow_terminator_mul;
+        const tr_material& mat = d.mat;
+        const int32_t tex_ids[4] = {mat.albedo_tex_id, mat.metallic_roughness_tex_id, mat.normal_tex_id, mat.emission_tex_id};
+        for(int32_t t: tex_ids)
+            if(t >= (int32_t)s->texture_count) return fail(c, TR_ERR_INVALID_ARGUMENT, "texture id out of range");
+        if(d.light_base_id >= 0) tri_light_count = std::max<uint64_t>(tri_light_count, (uint64_t)d.light_base_id + binst[i].triangle_count);
+        vtotal += m.vertex_count; itotal += m.index_count; ttotal += binst[i].triangle_count;
+    }
+    if(vtotal >= (1ull << 32) || itotal >= (1ull << 32) || ttotal >= (1ull << 28))
+        return fail(c, TR_ERR_UNSUPPORTED, "scene too large (>= 2^28 triangles)");
+
+    // ---- upload + pre_transform.comp
+    tr_vertex *v_raw = nullptr, *v_world = nullptr;
+    uint32_t* indices = nullptr;
+    float* matrices = nullptr;
+    std::vector<void*> tmp;
+    struct TmpFree { std::vector<void*>& l; ~TmpFree() { free_list(l); } } tmp_free{tmp};
+    TRY_CUDA(c, dev_alloc(tmp, &v_raw, vtotal));
+    TRY_CUDA(c, dev_alloc(tmp, &matrices, 32 * (size_t)s->instance_count));
+    TRY_CUDA(c, dev_alloc(A, &v_world, vtotal));
+    TRY_CUDA(c, dev_alloc(A, &indices, itotal));
+    std::vector<float> hm(32 * (size_t)s->instance_count);
+    for(uint32_t i = 0; i < s->instance_count; ++i)
+    {
+        const tr_mesh_ref& m = s->meshes[i];
+        memcpy(&hm[32 * (size_t)i], s->instances[i].model, 64);
+        memcpy(&hm[32 * (size_t)i + 16], s->instances[i].model_normal, 64);
+        if(m.vertex_count) TRY_CUDA(c, cudaMemcpyAsync(v_raw + binst[i].vertex_base, m.vertices, sizeof(tr_vertex) * (size_t)m.vertex_count, cudaMemcpyHostToDevice, st));
+        if(m.index_count) TRY_CUDA(c, cudaMemcpyAsync(indices + binst[i].index_base, m.indices, sizeof(uint32_t) * (size_t)m.index_count, cudaMemcpyHostToDevice, st));
+    }
+    if(!hm.empty()) TRY_CUDA(c, cudaMemcpyAsync(matrices, hm.data(), hm.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    for(uint32_t i = 0; i < s->instance_count; ++i)
+        TRY_CUDA(c, tr_build_pre_transform(st, v_raw + binst[i].vertex_base, v_world + binst[i].vertex_base, s->meshes[i].vertex_count,
+                                           matrices + 32 * (size_t)i, matrices + 32 * (size_t)i + 16));
+
+    // ---- tables
+    DeviceInstance* d_instances = nullptr;
+    TRY_CUDA(c, dev_alloc(A, &d_instances, s->instance_count));
+    if(s->instance_count) TRY_CUDA(c, cudaMemcpyAsync(d_instances, dinst.data(), sizeof(DeviceInstance) * dinst.size(), cudaMemcpyHostToDevice, st));
+    tr_point_light* d_pl = nullptr;
+    tr_directional_light* d_dl = nullptr;
+    TRY_CUDA(c, dev_alloc(A, &d_pl, s->point_light_count));
+    TRY_CUDA(c, dev_alloc(A, &d_dl, s->directional_light_count));
+    if(s->point_light_count) TRY_CUDA(c, cudaMemcpyAsync(d_pl, s->point_lights, sizeof(tr_point_light) * s->point_light_count, cudaMemcpyHostToDevice, st));
+    if(s->directional_light_count) TRY_CUDA(c, cudaMemcpyAsync(d_dl, s->directional_lights, sizeof(tr_directional_light) * s->directional_light_count, cudaMemcpyHostToDevice, st));
+
+    std::vector<DeviceTexture> htex(s->texture_count);
+    for(uint32_t i = 0; i < s->texture_count; ++i)
+    {
+        const tr_texture& t = s->textures[i];
+        if(!t.data || t.width == 0 || t.height == 0 || t.format > TR_TEXTURE_RGBA32F) return fail(c, TR_ERR_INVALID_ARGUMENT, "bad texture");
+        const size_t bytes = (size_t)t.width * t.height * (t.format == TR_TEXTURE_RGBA32F ? 16 : 4);
+        uint8_t* d = nullptr;
+        TRY_CUDA(c, dev_alloc(A, &d, bytes));
+        TRY_CUDA(c, cudaMemcpyAsync(d, t.data, bytes, cudaMemcpyHostToDevice, st));
+        htex[i].data = d; htex[i].width = t.width; htex[i].height = t.height; htex[i].format = t.format; htex[i].pad = 0;
+    }
+    DeviceTexture* d_tex = nullptr;
+    TRY_CUDA(c, dev_alloc(A, &d_tex, s->texture_count));
+    if(s->texture_count) TRY_CUDA(c, cudaMemcpyAsync(d_tex, htex.data(), sizeof(DeviceTexture) * htex.size(), cudaMemcpyHostToDevice, st));
+
+    // ---- extract_tri_lights.comp
+    tr_tri_light* d_tl = nullptr;
+    TRY_CUDA(c, dev_alloc(A, &d_tl, tri_light_count));
+    if(tri_light_count) TRY_CUDA(c, cudaMemsetAsync(d_tl, 0, sizeof(tr_tri_light) * tri_light_count, st));
+    for(uint32_t i = 0; i < s->instance_count; ++i)
+    {
+        if(dinst[i].light_base_id < 0) continue;
+        TRY_CUDA(c, tr_build_extract_tri_lights(st, v_world + binst[i].vertex_base, indices + binst[i].index_base, binst[i].triangle_count,
+                                                i, dinst[i].light_base_id, dinst[i].mat.emission_factor, dinst[i].mat.emission_tex_id, d_tl));
+    }
+
+    // ---- LBVH
+    TRY_CUDA(c, cudaEventRecord(c->ev_begin, st));
+    tr_build_input bin;
+    bin.vertices = v_world; bin.indices = indices; bin.instances = binst.data();
+    bin.instance_count = s->instance_count; bin.triangle_count = (uint32_t)ttotal;
+    tr_build_output bout;
+    TRY_CUDA(c, tr_build_bvh(st, bin, &bout));
+    A.push_back(bout.nodes);
+    A.push_back(bout.tris);
+    TRY_CUDA(c, cudaEventRecord(c->ev_end, st));
+    TRY_CUDA(c, cudaStreamSynchronize(st));
+    float build_ms = 0.0f;
+    cudaEventElapsedTime(&build_ms, c->ev_begin, c->ev_end);
+    if(bout.depth >= TR_BVH_STACK)
+    {
+        free_scene(c);
+        return fail(c, TR_ERR_UNSUPPORTED, "BVH depth " + std::to_string(bout.depth) + " exceeds the traversal stack");
+    }
+
+    DeviceScene& ds = c->scene;
+    ds.bvh.nodes = bout.nodes; ds.bvh.tris = bout.tris; ds.bvh.node_count = bout.node_count; ds.bvh.tri_count = (uint32_t)ttotal;
+    ds.bvh.top_nodes = 0;
+    ds.instances = d_instances; ds.vertices = v_world; ds.indices = indices;
+    ds.point_lights = d_pl; ds.directional_lights = d_dl; ds.tri_lights = d_tl; ds.textures = d_tex;
+    ds.instance_count = s->instance_count; ds.point_light_count = s->point_light_count;
+    ds.directional_light_count = s->directional_light_count; ds.tri_light_count = (uint32_t)tri_light_count;
+    memcpy(ds.environment_factor, s->environment_factor, 16);
+    ds.environment_proj = s->environment_proj;
+    ds.any_non_opaque = any_non_opaque ? 1u : 0u;
+    c->has_scene = true;
+    c->stats.bvh_build_ms = build_ms;
+    c->stats.bvh_node_count = bout.node_count;
+    c->stats.triangle_count = (uint32_t)ttotal;
+    c->stats.tri_light_count = (uint32_t)tri_light_count;
+    return TR_OK;
+}
+
+int tr_pt_set_cameras(tr_pt_ctx* c, const tr_camera_pair* pairs, uint32_t view_count)
+{
+    if(!c || !pairs || view_count == 0) return fail(c, TR_ERR_INVALID_ARGUMENT, "null argument");
+    DeviceGuard guard(c->device);
+    TRY_CUDA(c, cudaStreamSynchronize(c->stream));
+    if(view_count != c->views || !c->cameras)
+    {
+        if(c->cameras) cudaFree(c->cameras);
+        c->cameras = nullptr;
+        TRY_CUDA(c, cudaMalloc((void**)&c->cameras, sizeof(tr_camera_pair) * view_count));
+        c->views = view_count;
+    }
+    TRY_CUDA(c, cudaMemcpyAsync(c->cameras, pairs, sizeof(tr_camera_pair) * view_count, cudaMemcpyHostToDevice, c->stream));
+    TRY_CUDA(c, cudaStreamSynchronize(c->stream));
+    return TR_OK;
+}
+
+int tr_pt_set_distribution(tr_pt_ctx* c, const tr_pt_distribution* d)
+{
+    if(!c || !d) return fail(c, TR_ERR_INVALID_ARGUMENT, "null argument");
+    if(d->size[0] == 0 || d->size[1] == 0) return fail(c, TR_ERR_INVALID_ARGUMENT, "empty image");
+    if(d->strategy < 0 || d->strategy > 2) return fail(c, TR_ERR_INVALID_ARGUMENT, "bad distribution strategy");
+    if(d->strategy == TR_DISTRIBUTION_SCANLINE && (d->count == 0 || d->index >= d->count))
+        return fail(c, TR_ERR_INVALID_ARGUMENT, "bad scanline index/count");
+    if((uint64_t)d->size[0] * d->size[1] >= (1ull << 31)) return fail(c, TR_ERR_UNSUPPORTED, "image too large");
+    c->dist = *d;
+    if(d->strategy == TR_DISTRIBUTION_DUPLICATE) c->dist.primary = 1;
+    c->has_dist = true;
+    return TR_OK;
+}
+
+int tr_pt_reset_accumulation(tr_pt_ctx* c, int reset_sample_counter)
+{
+    if(!c) return TR_ERR_INVALID_ARGUMENT;
+    c->accumulated_samples = 0;
+    if(reset_sample_counter) c->frame_counter = 0;
+    return TR_OK;
+}
+
+int tr_pt_render(tr_pt_ctx* c, void* cuda_stream)
+{
+    if(!c) return TR_ERR_INVALID_ARGUMENT;
+    DeviceGuard guard(c->device);
+    int rc = prepare_targets(c);
+    if(rc) return rc;
+    // A caller-provided stream is ordered after our own setup work.
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+    if(st != c->stream) TRY_CUDA(c, cudaStreamSynchronize(c->stream));
+    RenderParams P;
+    fill_params(c, P);
+    // src/rt_stage.cc:76-85 (sampling UBO), src/rt_camera_stage.cc:74-101 (distribution UBO)
+    P.frame.sample_counter = c->frame_counter * (uint32_t)c->opt.samples_per_pixel;
+    P.frame.rng_seed = c->opt.rng_seed != 0 ? host_pcg((uint32_t)c->opt.rng_seed) : 0;
+    P.frame.samples_accumulated = (uint32_t)c->accumulated_samples;
+    c->frame_counter++;
+    c->accumulated_samples += c->opt.samples_per_pixel;
+
+    TRY_CUDA(c, cudaMemsetAsync(c->counters, 0, sizeof(Counters), st));
+    TRY_CUDA(c, cudaEventRecord(c->ev_begin, st));
+    uint64_t launches = 0;
+    const uint32_t pass_count = (uint32_t)(c->opt.samples_per_pixel / c->opt.samples_per_pass); // path_tracer_stage.cc:37
+    for(uint32_t pass = 0; pass < pass_count; ++pass)
+    {
+        P.frame.previous_samples = pass * (uint32_t)c->opt.samples_per_pass; // path_tracer_stage.cc:141
+        P.last_pass = pass + 1 == pass_count;
+        cudaError_t e = c->opt.kernel_mode == TR_KERNEL_WAVEFRONT ?
+            tr_render_pass_wavefront(st, P, c->wf, c->sm_count, &launches) :
+            tr_render_pass_megakernel(st, P, c->sm_count, &launches);
+        if(e != cudaSuccess) return fail_cuda(c, e, "render pass launch");
+    }
+    TRY_CUDA(c, cudaEventRecord(c->ev_end, st));
+    c->stats.kernel_launches = launches;
+    c->rendered = true;
+    return TR_OK;
+}
+
+int tr_pt_render_feature(tr_pt_ctx* c, int feature, const float default_value[4], void* cuda_stream)
+{
+    if(!c || !default_value) return TR_ERR_INVALID_ARGUMENT;
+    DeviceGuard guard(c->device);
+    int rc = prepare_targets(c);
+    if(rc) return rc;
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+    if(st != c->stream) TRY_CUDA(c, cudaStreamSynchronize(c->stream));
+    RenderParams P;
+    fill_params(c, P);
+    TRY_CUDA(c, tr_render_feature(st, P, feature, default_value));
+    return TR_OK;
+}
+
+int tr_pt_sync(tr_pt_ctx* c)
+{
+    if(!c) return TR_ERR_INVALID_ARGUMENT;
+    DeviceGuard guard(c->device);
+    TRY_CUDA(c, cudaStreamSynchronize(c->stream));
+    return TR_OK;
+}
+
+int tr_pt_get_color_buffer(tr_pt_ctx* c, void** device_ptr, size_t* bytes)
+{
+    if(!c || !device_ptr || !bytes) return TR_ERR_INVALID_ARGUMENT;
+    DeviceGuard guard(c->device);
+    int rc = prepare_targets(c);
+    if(rc) return rc;
+    *device_ptr = c->color;
+    *bytes = c->color_pixels * sizeof(float4);
+    return TR_OK;
+}
+
+int tr_pt_read_color(tr_pt_ctx* c, float* out, size_t bytes)
+{
+    if(!c || !out) return TR_ERR_INVALID_ARGUMENT;
+    DeviceGuard guard(c->device);
+    if(!c->color) return fail(c, TR_ERR_INVALID_ARGUMENT, "nothing rendered yet");
+    if(bytes != c->color_pixels * sizeof(float4))
+        return fail(c, TR_ERR_INVALID_ARGUMENT, "size mismatch: target has " + std::to_string(c->color_pixels * sizeof(float4)) + " bytes");
+    TRY_CUDA(c, cudaMemcpyAsync(out, c->color, bytes, cudaMemcpyDeviceToHost, c->stream));
+    TRY_CUDA(c, cudaStreamSynchronize(c->stream));
+    return TR_OK;
+}
+
+int tr_pt_unshuffle(tr_pt_ctx* c, const void* strip_device, uint32_t index, uint32_t count, void* full_image_device, void* cuda_stream)
+{
+    if(!c || !strip_device || !full_image_device) return TR_ERR_INVALID_ARGUMENT;
+    if(!c->has_dist || c->views == 0) return fail(c, TR_ERR_INVALID_ARGUMENT, "cameras / distribution not set");
+    if(c->dist.strategy != TR_DISTRIBUTION_SHUFFLED_STRIPS) return fail(c, TR_ERR_UNSUPPORTED, "unshuffle: shuffled strips only");
+    DeviceGuard guard(c->device);
+    FrameParams f;
+    fill_frame(c, f);
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+    TRY_CUDA(c, tr_render_unshuffle(st, f, (const float4*)strip_device, index, count, (float4*)full_image_device));
+    return TR_OK;
+}
+
+int tr_pt_set_peer_images(tr_pt_ctx* c, void* const* ptrs, int n)
+{
+    if(!c || n < 0 || n > 8 || (n > 0 && !ptrs)) return fail(c, TR_ERR_INVALID_ARGUMENT, "0..8 peer images");
+    for(int i = 0; i < n; ++i) c->peers[i] = (float4*)ptrs[i];
+    c->peer_count = n;
+    return TR_OK;
+}
+
+int tr_pt_get_stats(tr_pt_ctx* c, tr_pt_stats* stats)
+{
+    if(!c || !stats) return TR_ERR_INVALID_ARGUMENT;
+    DeviceGuard guard(c->device);
+    if(c->rendered)
+    {
+        TRY_CUDA(c, cudaEventSynchronize(c->ev_end));
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, c->ev_begin, c->ev_end);
+        c->stats.render_ms = ms;
+        Counters h;
+        TRY_CUDA(c, cudaMemcpy(&h, c->counters, sizeof(h), cudaMemcpyDeviceToHost));
+        c->stats.closest_rays = h.closest_rays;
+        c->stats.shadow_rays = h.shadow_rays;
+        c->stats.paths = h.paths;
+        c->stats.node_visits = h.node_visits;
+        c->stats.triangle_tests = h.triangle_tests;
+    }
+    *stats = c->stats;
+    return TR_OK;
+}
+
+int tr_pt_set_instrumentation(tr_pt_ctx* c, int enabled)
+{
+    if(!c) return TR_ERR_INVALID_ARGUMENT;
+    c->instrumentation = enabled ? 1 : 0;
+    return TR_OK;
+}
+
+int tr_pt_read_tri_lights(tr_pt_ctx* c, tr_tri_light* out, uint32_t capacity)
+{
+    if(!c) return TR_ERR_INVALID_ARGUMENT;
+    if(!c->has_scene) return fail(c, TR_ERR_NO_SCENE, "no scene");
+    DeviceGuard guard(c->device);
+    const uint32_t n = std::min(capacity, c->scene.tri_light_count);
+    if(out && n) TRY_CUDA(c, cudaMemcpy(out, c->scene.tri_lights, sizeof(tr_tri_light) * n, cudaMemcpyDeviceToHost));
+    return (int)c->scene.tri_light_count;
+}
+
+int tr_pt_trace_rays(tr_pt_ctx* c, const float* rays, uint32_t n, void* hits_out)
+{
+    if(!c || (n && (!rays || !hits_out))) return TR_ERR_INVALID_ARGUMENT;
+    if(!c->has_scene) return fail(c, TR_ERR_NO_SCENE, "no scene");
+    DeviceGuard guard(c->device);
+    if(n == 0) return TR_OK;
+    float* d_rays = nullptr;
+    void* d_hits = nullptr;
+    std::vector<void*> tmp;
+    struct TmpFree { std::vector<void*>& l; ~TmpFree() { free_list(l); } } tmp_free{tmp};
+    TRY_CUDA(c, dev_alloc(tmp, &d_rays, 8 * (size_t)n));
+    TRY_CUDA(c, dev_alloc(tmp, (uint8_t**)&d_hits, 20 * (size_t)n));
+    TRY_CUDA(c, cudaMemcpyAsync(d_rays, rays, 32 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    RenderParams P;
+    memset(&P, 0, sizeof(P));
+    P.scene = c->scene;
+    P.opt = c->opt;
+    TRY_CUDA(c, tr_render_trace_rays(c->stream, P, d_rays, n, d_hits));
+    TRY_CUDA(c, cudaMemcpyAsync(hits_out, d_hits, 20 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    TRY_CUDA(c, cudaStreamSynchronize(c->stream));
+    return TR_OK;
+}
+
+int tr_pt_sample_test(tr_pt_ctx* c, const uint32_t* coords, uint32_t n, int draw_index, uint32_t* out)
+{
+    if(!c || (n && (!coords || !out))) return TR_ERR_INVALID_ARGUMENT;
+    DeviceGuard guard(c->device);
+    if(n == 0) return TR_OK;
+    uint32_t *d_in = nullptr, *d_out = nullptr;
+    std::vector<void*> tmp;
+    struct TmpFree { std::vector<void*>& l; ~TmpFree() { free_list(l); } } tmp_free{tmp};
+    TRY_CUDA(c, dev_alloc(tmp, &d_in, 4 * (size_t)n));
+    TRY_CUDA(c, dev_alloc(tmp, &d_out, 4 * (size_t)n));
+    TRY_CUDA(c, cudaMemcpyAsync(d_in, coords, 16 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    RenderParams P;
+    memset(&P, 0, sizeof(P));
+    P.opt = c->opt;
+    P.frame.sample_counter = c->frame_counter * (uint32_t)c->opt.samples_per_pixel;
+    P.frame.rng_seed = c->opt.rng_seed != 0 ? host_pcg((uint32_t)c->opt.rng_seed) : 0;
+    P.frame.max_sobol_bounces = (uint32_t)(c->opt.max_ray_depth > 8 ? 8 : c->opt.max_ray_depth);
+    TRY_CUDA(c, tr_render_sample_test(c->stream, P, d_in, n, draw_index, d_out));
+    TRY_CUDA(c, cudaMemcpyAsync(out, d_out, 16 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    TRY_CUDA(c, cudaStreamSynchronize(c->stream));
+    return TR_OK;
+}
+
+const char* tr_pt_last_error(tr_pt_ctx* c) { return c ? c->error.c_str() : g_create_error.c_str(); }
+
+} // extern "C"

@@ -1,0 +1,39 @@
+// tr_build.h -- host entry points of the on-device scene preprocessing / LBVH build (tr_bvh.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "../../include/tauray_b200.h"
+
+struct tr_build_instance
+{
+    uint32_t vertex_base;     // into the concatenated world-space vertex buffer
+    uint32_t index_base;
+    uint32_t triangle_base;   // running triangle count before this instance
+    uint32_t triangle_count;
+    uint32_t opaque;
+};
+
+struct tr_build_input
+{
+    const tr_vertex* vertices;            // device, world space
+    const uint32_t* indices;              // device
+    const tr_build_instance* instances;   // host
+    uint32_t instance_count;
+    uint32_t triangle_count;
+};
+
+struct tr_build_output
+{
+    float4* nodes;            // device, 4 float4 per node, breadth-first order; caller frees
+    float4* tris;             // device, 3 float4 per triangle in leaf order; caller frees
+    uint32_t node_count;
+    uint32_t depth;           // number of breadth-first levels
+    float eps;                // box inflation
+};
+
+cudaError_t tr_build_pre_transform(cudaStream_t stream, const tr_vertex* in, tr_vertex* out, uint32_t count,
+                                   const float* model_dev, const float* model_normal_dev);
+cudaError_t tr_build_extract_tri_lights(cudaStream_t stream, const tr_vertex* verts, const uint32_t* indices,
+                                        uint32_t triangle_count, uint32_t instance_id, int32_t light_base_id,
+                                        const float emission[3], int32_t emission_tex_id, tr_tri_light* out);
+cudaError_t tr_build_bvh(cudaStream_t stream, const tr_build_input& in, tr_build_output* out);

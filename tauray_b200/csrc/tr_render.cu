@@ -1,0 +1,503 @@
+// tr_render.cu -- the render kernels: the replacement of rt_pipeline::trace_rays
+// (src/rt_pipeline.cc:13-19) + shader/path_tracer.rgen for one pass.
+//
+// Wavefront organisation (kernel_mode = TR_KERNEL_WAVEFRONT), per pass and bounce b:
+//   k_wf_generate       camera rays for every launch slot                    -> queue[0]
+//   k_wf_trace_closest  closest-hit traversal of queue[b&1]                  -> hits
+//   k_wf_shade          hit shading, emission MIS, NEE sample, BSDF sample   -> queue[(b+1)&1], shadow_queue
+//   k_wf_trace_shadow   any-hit traversal of shadow_queue, NEE accumulate
+//   k_wf_finish         path_tracer.rgen:112 + running-mean accumulate (+ NVLink peer stores)
+// Survivors are compacted into the next queue with a warp ballot + prefix popcount and ONE
+// atomicAdd per warp, so later bounces run on dense warps. Queue sizes never visit the host:
+// kernels are launched as persistent grids (SM count x resident blocks) that read the counts
+// from HBM and stride over the queue.
+// kernel_mode = TR_KERNEL_MEGAKERNEL runs the same device functions in one launch (state in
+// registers); it exists as the A/B baseline for the wavefront numbers.
+#include "tr_path.cuh"
+#include "tr_render.h"
+
+namespace trd {
+
+constexpr int WF_BLOCK = 128;
+
+// ---- SoA <-> registers ---------------------------------------------------------------------------
+TRD void store_ray(const tr_wavefront& wf, uint32_t id, const PathState& s)
+{
+    wf.pos_pdf[id] = make_float4(s.pos.x, s.pos.y, s.pos.z, s.bsdf_pdf);
+    wf.dir_seed[id] = make_float4(s.view.x, s.view.y, s.view.z, __uint_as_float(s.random_seed));
+}
+TRD void store_state(const tr_wavefront& wf, uint32_t id, const PathState& s)
+{
+    store_ray(wf, id, s);
+    wf.atten_reg[id] = make_float4(s.attenuation.x, s.attenuation.y, s.attenuation.z, s.regularization);
+    wf.lobes[id] = make_float4(s.primary_lobes.transmission, s.primary_lobes.diffuse,
+                               s.primary_lobes.dielectric_reflection, s.primary_lobes.metallic_reflection);
+    wf.diffuse[id] = make_float4(s.diffuse.x, s.diffuse.y, s.diffuse.z, 0.0f);
+    wf.reflection[id] = make_float4(s.reflection.x, s.reflection.y, s.reflection.z, 0.0f);
+}
+TRD void store_first_hit(const tr_wavefront& wf, uint32_t id, const PathState& s)
+{
+    wf.fh_emission[id] = make_float4(s.fh_emission.x, s.fh_emission.y, s.fh_emission.z, s.fh_albedo.w);
+    wf.fh_albedo[id] = make_float4(s.fh_albedo.x, s.fh_albedo.y, s.fh_albedo.z, s.fh_metallic);
+}
+TRD void load_state(const tr_wavefront& wf, uint32_t id, PathState& s)
+{
+    const float4 a = wf.pos_pdf[id], b = wf.dir_seed[id], c = wf.atten_reg[id], d = wf.lobes[id];
+    const float4 e = wf.diffuse[id], f = wf.reflection[id];
+    s.pos = V3(a.x, a.y, a.z); s.bsdf_pdf = a.w;
+    s.view = V3(b.x, b.y, b.z); s.random_seed = __float_as_uint(b.w);
+    s.attenuation = V3(c.x, c.y, c.z); s.regularization = c.w;
+    s.primary_lobes = LOBES(d.x, d.y, d.z, d.w);
+    s.diffuse = V3(e.x, e.y, e.z);
+    s.reflection = V3(f.x, f.y, f.z);
+}
+TRD void load_first_hit(const tr_wavefront& wf, uint32_t id, PathState& s)
+{
+    const float4 a = wf.fh_emission[id], b = wf.fh_albedo[id];
+    s.fh_emission = V3(a.x, a.y, a.z);
+    s.fh_albedo = V4(b.x, b.y, b.z, a.w);
+    s.fh_metallic = b.w;
+}
+TRD void store_job(const tr_wavefront& wf, uint32_t id, const NeeJob& j)
+{
+    float4* o = wf.nee + 4 * (size_t)id;
+    o[0] = make_float4(j.dir.x, j.dir.y, j.dir.z, j.tmax);
+    o[1] = make_float4(j.contrib.x, j.contrib.y, j.contrib.z, j.mis_pdf);
+    o[2] = make_float4(j.attenuation.x, j.attenuation.y, j.attenuation.z, j.w_diffuse);
+    o[3] = make_float4(j.modulate.x, j.modulate.y, j.modulate.z, j.w_reflection);
+}
+TRD void load_job(const tr_wavefront& wf, uint32_t id, int bounce, NeeJob& j)
+{
+    const float4* o = wf.nee + 4 * (size_t)id;
+    const float4 a = o[0], b = o[1], c = o[2], d = o[3];
+    j.dir = V3(a.x, a.y, a.z); j.tmax = a.w;
+    j.contrib = V3(b.x, b.y, b.z); j.mis_pdf = b.w;
+    j.attenuation = V3(c.x, c.y, c.z); j.w_diffuse = c.w;
+    j.modulate = V3(d.x, d.y, d.z); j.w_reflection = d.w;
+    j.needs_shadow_ray = 1;
+    j.bounce = bounce;
+}
+
+// Warp-aggregated append: one atomicAdd per warp. Must be reached by all 32 lanes.
+TRD void warp_push(uint32_t* __restrict__ queue, uint32_t* __restrict__ count, bool pred, uint32_t value)
+{
+    const uint32_t mask = __ballot_sync(0xFFFFFFFFu, pred);
+    if(mask == 0) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if(lane == leader) base = atomicAdd(count, __popc(mask));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    if(pred) queue[base + __popc(mask & ((1u << lane) - 1u))] = value;
+}
+
+TRD void flush_counters(Counters* c, unsigned long long closest, unsigned long long shadow, unsigned long long paths,
+                        unsigned long long nodes, unsigned long long tris)
+{
+    // warp reduce then one atomic per warp and counter
+    for(int off = 16; off > 0; off >>= 1)
+    {
+        closest += __shfl_xor_sync(0xFFFFFFFFu, closest, off);
+        shadow += __shfl_xor_sync(0xFFFFFFFFu, shadow, off);
+        paths += __shfl_xor_sync(0xFFFFFFFFu, paths, off);
+        nodes += __shfl_xor_sync(0xFFFFFFFFu, nodes, off);
+        tris += __shfl_xor_sync(0xFFFFFFFFu, tris, off);
+    }
+    if((threadIdx.x & 31) == 0)
+    {
+        if(closest) atomicAdd(&c->closest_rays, closest);
+        if(shadow) atomicAdd(&c->shadow_rays, shadow);
+        if(paths) atomicAdd(&c->paths, paths);
+        if(nodes) atomicAdd(&c->node_visits, nodes);
+        if(tris) atomicAdd(&c->triangle_tests, tris);
+    }
+}
+
+// ---- wavefront kernels ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(WF_BLOCK) k_wf_generate(const RenderParams P, const tr_wavefront wf, uint32_t sample_in_pass,
+                                                           uint32_t total_slots, uint32_t* __restrict__ queue, uint32_t* __restrict__ count)
+{
+    unsigned long long paths = 0;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t rounded = (total_slots + 31u) & ~31u;
+    for(uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < rounded; slot += stride)
+    {
+        bool valid = false;
+        if(slot < total_slots)
+        {
+            uint32_t px, py, view, widx;
+            valid = map_slot(P.frame, slot, px, py, view, widx);
+            if(valid)
+            {
+                PathState s;
+                uvec4 ss, rs;
+                path_begin(P, px, py, view, sample_in_pass, s, ss, rs);
+                store_state(wf, slot, s);
+                store_first_hit(wf, slot, s);
+                wf.rs_seed[slot] = make_uint4(rs.x, rs.y, rs.z, rs.w);
+                paths++;
+            }
+        }
+        warp_push(queue, count, valid, slot);
+    }
+    flush_counters(P.counters, 0, 0, paths, 0, 0);
+}
+
+template<bool STATS>
+__global__ void __launch_bounds__(WF_BLOCK) k_wf_trace_closest(const RenderParams P, const tr_wavefront wf, uint32_t bounce,
+                                                                const uint32_t* __restrict__ queue, const uint32_t* __restrict__ count)
+{
+    const uint32_t n = *count;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    TraceStats st; st.nodes = 0; st.tris = 0;
+    unsigned long long rays = 0;
+    const bool include_lights = !(P.opt.hide_lights && bounce == 0);
+    const float tmin = bounce == 0 ? 0.0f : P.opt.min_ray_dist;
+    for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    {
+        const uint32_t id = queue[i];
+        const float4 o = wf.pos_pdf[id];
+        const float4 d = wf.dir_seed[id];
+        uint32_t seed = __float_as_uint(d.w);
+        Hit h;
+        closest_hit<STATS>(P, V3(o.x, o.y, o.z), tmin, V3(d.x, d.y, d.z), include_lights, seed, h, st);
+        wf.hits[id] = make_int4(h.instance_id, h.primitive_id, __float_as_int(h.u), __float_as_int(h.v));
+        if(P.scene.any_non_opaque) wf.dir_seed[id].w = __uint_as_float(seed);
+        rays++;
+    }
+    flush_counters(P.counters, rays, 0, 0, st.nodes, st.tris);
+}
+
+__global__ void __launch_bounds__(WF_BLOCK) k_wf_shade(const RenderParams P, const tr_wavefront wf, uint32_t bounce, uint32_t sample_in_pass,
+                                                        const uint32_t* __restrict__ queue, const uint32_t* __restrict__ count,
+                                                        uint32_t* __restrict__ next_queue, uint32_t* __restrict__ next_count,
+                                                        uint32_t* __restrict__ shadow_queue, uint32_t* __restrict__ shadow_count)
+{
+    const uint32_t n = *count;
+    const uint32_t rounded = (n + 31u) & ~31u;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += stride)
+    {
+        bool alive = false, shadow = false;
+        uint32_t id = 0;
+        if(i < n)
+        {
+            id = queue[i];
+            PathState s;
+            load_state(wf, id, s);
+            const int4 hr = wf.hits[id];
+            Hit h;
+            h.instance_id = hr.x; h.primitive_id = hr.y; h.u = __int_as_float(hr.z); h.v = __int_as_float(hr.w); h.t = h.u; h.flags = 0;
+            uint32_t px, py, view, widx;
+            map_slot(P.frame, id, px, py, view, widx);
+            // the Sobol state is a pure function of the sample coordinate: recompute, do not store
+            local_sampler ls = init_local_sampler(px, py, view, P.frame.previous_samples + sample_in_pass,
+                                                  P.frame.sample_counter, P.frame.rng_seed);
+            uvec4 rs;
+            if(P.opt.local_sampler != TR_SAMPLER_SOBOL_OWEN)
+            {
+                const uint4 r = wf.rs_seed[id];
+                rs.x = r.x; rs.y = r.y; rs.z = r.z; rs.w = r.w;
+            }
+            else rs = ls.rs_seed;
+            NeeJob job;
+            alive = shade_bounce(P, bounce, h, s, ls.ss_seed, rs, job);
+            if(job.bounce >= 0)
+            {
+                if(job.needs_shadow_ray) { store_job(wf, id, job); shadow = true; }
+                else nee_finish(P, job, 1.0f, s);
+            }
+            store_state(wf, id, s);
+            if(bounce == 0) store_first_hit(wf, id, s);
+            if(P.opt.local_sampler != TR_SAMPLER_SOBOL_OWEN) wf.rs_seed[id] = make_uint4(rs.x, rs.y, rs.z, rs.w);
+        }
+        warp_push(next_queue, next_count, alive, id);
+        warp_push(shadow_queue, shadow_count, shadow, id);
+    }
+}
+
+template<bool STATS>
+__global__ void __launch_bounds__(WF_BLOCK) k_wf_trace_shadow(const RenderParams P, const tr_wavefront wf, uint32_t bounce,
+                                                               const uint32_t* __restrict__ queue, const uint32_t* __restrict__ count)
+{
+    const uint32_t n = *count;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    TraceStats st; st.nodes = 0; st.tris = 0;
+    unsigned long long rays = 0;
+    for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    {
+        const uint32_t id = queue[i];
+        NeeJob job;
+        load_job(wf, id, (int)bounce, job);
+        const float4 o = wf.pos_pdf[id];
+        const float vis = shadow_visibility<STATS>(P, V3(o.x, o.y, o.z), P.opt.min_ray_dist, job.dir, job.tmax, st);
+        rays++;
+        PathState s;
+        const float4 e = wf.diffuse[id], f = wf.reflection[id];
+        s.diffuse = V3(e.x, e.y, e.z);
+        s.reflection = V3(f.x, f.y, f.z);
+        nee_finish(P, job, vis, s);
+        wf.diffuse[id] = make_float4(s.diffuse.x, s.diffuse.y, s.diffuse.z, 0.0f);
+        wf.reflection[id] = make_float4(s.reflection.x, s.reflection.y, s.reflection.z, 0.0f);
+    }
+    flush_counters(P.counters, 0, rays, 0, st.nodes, st.tris);
+}
+
+__global__ void __launch_bounds__(WF_BLOCK) k_wf_finish(const RenderParams P, const tr_wavefront wf, uint32_t sample_in_pass, uint32_t total_slots)
+{
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t spp = (uint32_t)P.opt.samples_per_pass;
+    for(uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < total_slots; slot += stride)
+    {
+        uint32_t px, py, view, widx;
+        if(!map_slot(P.frame, slot, px, py, view, widx)) continue;
+        PathState s;
+        const float4 e = wf.diffuse[slot], f = wf.reflection[slot];
+        s.diffuse = V3(e.x, e.y, e.z);
+        s.reflection = V3(f.x, f.y, f.z);
+        load_first_hit(wf, slot, s);
+        vec3 c = path_color(P, s);
+        if(spp > 1)
+        {
+            vec3 sum = V3(0);
+            if(sample_in_pass != 0) { const float4 q = wf.sum_color[slot]; sum = V3(q.x, q.y, q.z); }
+            sum += c;
+            if(sample_in_pass + 1 < spp) { wf.sum_color[slot] = make_float4(sum.x, sum.y, sum.z, 0.0f); continue; }
+            c = sum / (float)spp;
+        }
+        const float alpha = P.opt.transparent_background ? s.fh_albedo.w : 1.0f;
+        const float4 o = accumulate(P, c, alpha, widx);
+        store_to_peers(P, o, px, py, view);
+    }
+}
+
+// ---- megakernel ----------------------------------------------------------------------------------
+template<bool STATS>
+__global__ void __launch_bounds__(WF_BLOCK) k_megakernel(const RenderParams P, uint32_t total_slots)
+{
+    const uint32_t stride = gridDim.x * blockDim.x;
+    TraceStats st; st.nodes = 0; st.tris = 0;
+    unsigned long long closest = 0, shadow = 0, paths = 0;
+    const uint32_t spp = (uint32_t)P.opt.samples_per_pass;
+    for(uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < total_slots; slot += stride)
+    {
+        uint32_t px, py, view, widx;
+        if(!map_slot(P.frame, slot, px, py, view, widx)) continue;
+        vec3 sum = V3(0);
+        float alpha = 1.0f;
+        for(uint32_t i = 0; i < spp; ++i)
+        {
+            PathState s;
+            uvec4 ss, rs;
+            path_begin(P, px, py, view, i, s, ss, rs);
+            paths++;
+            for(uint32_t bounce = 0; bounce < (uint32_t)P.opt.max_ray_depth; ++bounce)
+            {
+                Hit h;
+                closest_hit<STATS>(P, s.pos, bounce == 0 ? 0.0f : P.opt.min_ray_dist, s.view,
+                                   !(P.opt.hide_lights && bounce == 0), s.random_seed, h, st);
+                closest++;
+                NeeJob job;
+                const bool alive = shade_bounce(P, bounce, h, s, ss, rs, job);
+                if(job.bounce >= 0)
+                {
+                    float vis = 1.0f;
+                    if(job.needs_shadow_ray)
+                    {
+                        vis = shadow_visibility<STATS>(P, s.pos, P.opt.min_ray_dist, job.dir, job.tmax, st);
+                        shadow++;
+                    }
+                    nee_finish(P, job, vis, s);
+                }
+                if(!alive) break;
+            }
+            sum += path_color(P, s);
+            alpha = P.opt.transparent_background ? s.fh_albedo.w : 1.0f;
+        }
+        const float4 o = accumulate(P, sum / (float)spp, alpha, widx);
+        store_to_peers(P, o, px, py, view);
+    }
+    flush_counters(P.counters, closest, shadow, paths, st.nodes, st.tris);
+}
+
+// ---- feature (AOV) tracer: shader/rt_feature.rgen:18-47, rt_feature.rahit, rt_feature.rchit ------
+__global__ void __launch_bounds__(WF_BLOCK) k_feature(const RenderParams P, int feature, float4 default_value, uint32_t total_slots)
+{
+    const uint32_t stride = gridDim.x * blockDim.x;
+    TraceStats st; st.nodes = 0; st.tris = 0;
+    for(uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < total_slots; slot += stride)
+    {
+        uint32_t px, py, view, widx;
+        if(!map_slot(P.frame, slot, px, py, view, widx)) continue;
+        const tr_camera_data& cam = P.cameras[view].current;
+        vec3 origin, dir;
+        get_screen_camera_ray(P, cam, px, py, V2(0, 0), V2(0.5f, 0.5f), origin, dir);
+        const vec3 o = V3(cam.origin[0], cam.origin[1], cam.origin[2]);
+        vec4 data = V4(default_value.x, default_value.y, default_value.z, default_value.w);
+        float cur_tmin = P.opt.min_ray_dist;
+        for(;;)
+        {
+            Hit h;
+            if(!traverse<false, false>(P.scene.bvh, o, dir, cur_tmin, inf_(), h, st, [](int, int, float, float, float) {})) break;
+            if(!(h.flags & TR_TRI_FLAG_OPAQUE) && hit_alpha(P.scene, h.instance_id, h.primitive_id, h.u, h.v) <= 0.0001f)
+            {
+                cur_tmin = h.t;
+                continue;
+            }
+            const DeviceInstance& inst = P.scene.instances[h.instance_id];
+            float pdf;
+            SurfaceVertex v = get_interpolated_vertex(P, inst, dir, h.u, h.v, h.primitive_id, o, pdf);
+            sampled_material mat = sample_material(P, inst, v);
+            switch(feature)
+            {
+            default:
+            case TR_FEATURE_ALBEDO: data = mat.albedo; break;
+            case TR_FEATURE_WORLD_NORMAL: data = V4(v.mapped_normal, 1); break;
+            case TR_FEATURE_VIEW_NORMAL: data = V4(xyz(mul4(cam.view, V4(v.mapped_normal, 0))), 1); break;
+            case TR_FEATURE_WORLD_POS: data = V4(v.pos, 1); break;
+            case TR_FEATURE_VIEW_POS: data = mul4(cam.view, V4(v.pos, 1)); break;
+            case TR_FEATURE_DISTANCE: data = V4(h.t, h.t, h.t, 1); break;
+            case TR_FEATURE_INSTANCE_ID: data = V4((float)h.instance_id, (float)h.primitive_id, 0, 1); break;
+            }
+            break;
+        }
+        P.color[widx] = make_float4(data.x, data.y, data.z, data.w);
+    }
+}
+
+// ---- test hooks ----------------------------------------------------------------------------------
+struct OutHit { int inst, prim; float u, v, t; };
+
+__global__ void k_trace_rays(const RenderParams P, const float* __restrict__ rays, uint32_t n, OutHit* __restrict__ out)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    const float* r = rays + 8 * (size_t)i;
+    Hit h;
+    TraceStats st; st.nodes = 0; st.tris = 0;
+    bool ok = traverse<false, false>(P.scene.bvh, V3(r[0], r[1], r[2]), V3(r[4], r[5], r[6]), r[3], r[7], h, st,
+                                     [](int, int, float, float, float) {});
+    OutHit o;
+    if(ok) { o.inst = h.instance_id; o.prim = h.primitive_id; o.u = h.u; o.v = h.v; o.t = h.t; }
+    else { o.inst = -1; o.prim = -1; o.u = 0; o.v = 0; o.t = 0; }
+    out[i] = o;
+}
+
+__global__ void k_sample_test(const RenderParams P, const uint32_t* __restrict__ coords, uint32_t n, int draw_index, uint32_t* __restrict__ out)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    local_sampler ls = init_local_sampler(coords[4 * i], coords[4 * i + 1], coords[4 * i + 2], coords[4 * i + 3],
+                                          P.frame.sample_counter, P.frame.rng_seed);
+    uvec4 r;
+    if(draw_index < 0) r = pcg4d(ls.rs_seed);
+    else r = generate_ray_sample_uint(P, ls.ss_seed, ls.rs_seed, (uint32_t)draw_index);
+    out[4 * i] = r.x; out[4 * i + 1] = r.y; out[4 * i + 2] = r.z; out[4 * i + 3] = r.w;
+}
+
+// stitch_shuffled_strips.comp:21-63 for one source strip (blend_ratio = 1)
+__global__ void k_unshuffle(const FrameParams f, const float4* __restrict__ strip, uint32_t index, uint32_t count, float4* __restrict__ full)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t view = blockIdx.y;
+    if(i >= count) return;
+    const uint32_t j = permute_region_id(f, index + i);
+    if(j >= f.size_x * f.size_y) return;
+    full[(size_t)view * f.size_x * f.size_y + j] = strip[(size_t)view * count + i];
+}
+
+} // namespace trd
+
+using namespace trd;
+
+cudaError_t tr_render_init_constants()
+{
+    return cudaMemcpyToSymbol(c_sobol_table, TR_SOBOL_TABLE, sizeof(TR_SOBOL_TABLE));
+}
+
+static int grid_for(int sm_count, int blocks_per_sm, uint32_t work)
+{
+    long long need = ((long long)work + WF_BLOCK - 1) / WF_BLOCK;
+    long long cap = (long long)sm_count * blocks_per_sm;
+    long long g = need < cap ? need : cap;
+    return (int)(g < 1 ? 1 : g);
+}
+
+cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const RenderParams& P, const tr_wavefront& wf, int sm_count, uint64_t* launches)
+{
+    const uint32_t total = P.frame.ray_count_x * P.frame.ray_count_y * P.frame.views;
+    if(total == 0) return cudaSuccess;
+    const uint32_t D = (uint32_t)P.opt.max_ray_depth;
+    const uint32_t spp = (uint32_t)P.opt.samples_per_pass;
+    const int grid_full = grid_for(sm_count, 16, total);
+    const int grid_persist = sm_count * 8;
+    for(uint32_t i = 0; i < spp; ++i)
+    {
+        cudaError_t e = cudaMemsetAsync(wf.counts, 0, sizeof(uint32_t) * (2 * D + 2), stream);
+        if(e != cudaSuccess) return e;
+        uint32_t* active_counts = wf.counts;          // [D + 1]
+        uint32_t* shadow_counts = wf.counts + D + 1;  // [D]
+        k_wf_generate<<<grid_full, WF_BLOCK, 0, stream>>>(P, wf, i, total, wf.queue[0], active_counts);
+        ++*launches;
+        for(uint32_t b = 0; b < D; ++b)
+        {
+            uint32_t* q_in = wf.queue[b & 1];
+            uint32_t* q_out = wf.queue[(b + 1) & 1];
+            if(P.stats) k_wf_trace_closest<true><<<grid_persist, WF_BLOCK, 0, stream>>>(P, wf, b, q_in, active_counts + b);
+            else k_wf_trace_closest<false><<<grid_persist, WF_BLOCK, 0, stream>>>(P, wf, b, q_in, active_counts + b);
+            k_wf_shade<<<grid_persist, WF_BLOCK, 0, stream>>>(P, wf, b, i, q_in, active_counts + b, q_out, active_counts + b + 1,
+                                                              wf.shadow_queue, shadow_counts + b);
+            *launches += 2;
+            if(b + 1 < D)
+            {
+                if(P.stats) k_wf_trace_shadow<true><<<grid_persist, WF_BLOCK, 0, stream>>>(P, wf, b, wf.shadow_queue, shadow_counts + b);
+                else k_wf_trace_shadow<false><<<grid_persist, WF_BLOCK, 0, stream>>>(P, wf, b, wf.shadow_queue, shadow_counts + b);
+                ++*launches;
+            }
+        }
+        k_wf_finish<<<grid_full, WF_BLOCK, 0, stream>>>(P, wf, i, total);
+        ++*launches;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t tr_render_pass_megakernel(cudaStream_t stream, const RenderParams& P, int sm_count, uint64_t* launches)
+{
+    const uint32_t total = P.frame.ray_count_x * P.frame.ray_count_y * P.frame.views;
+    if(total == 0) return cudaSuccess;
+    const int grid = grid_for(sm_count, 8, total);
+    if(P.stats) k_megakernel<true><<<grid, WF_BLOCK, 0, stream>>>(P, total);
+    else k_megakernel<false><<<grid, WF_BLOCK, 0, stream>>>(P, total);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+cudaError_t tr_render_feature(cudaStream_t stream, const RenderParams& P, int feature, const float dv[4])
+{
+    const uint32_t total = P.frame.ray_count_x * P.frame.ray_count_y * P.frame.views;
+    if(total == 0) return cudaSuccess;
+    k_feature<<<(total + WF_BLOCK - 1) / WF_BLOCK, WF_BLOCK, 0, stream>>>(P, feature, make_float4(dv[0], dv[1], dv[2], dv[3]), total);
+    return cudaGetLastError();
+}
+
+cudaError_t tr_render_trace_rays(cudaStream_t stream, const RenderParams& P, const float* rays_dev, uint32_t n, void* hits_dev)
+{
+    if(n == 0) return cudaSuccess;
+    k_trace_rays<<<(n + 127) / 128, 128, 0, stream>>>(P, rays_dev, n, (OutHit*)hits_dev);
+    return cudaGetLastError();
+}
+
+cudaError_t tr_render_sample_test(cudaStream_t stream, const RenderParams& P, const uint32_t* coords_dev, uint32_t n, int draw_index, uint32_t* out_dev)
+{
+    if(n == 0) return cudaSuccess;
+    k_sample_test<<<(n + 127) / 128, 128, 0, stream>>>(P, coords_dev, n, draw_index, out_dev);
+    return cudaGetLastError();
+}
+
+cudaError_t tr_render_unshuffle(cudaStream_t stream, const FrameParams& f, const float4* strip, uint32_t index, uint32_t count, float4* full_image)
+{
+    if(count == 0 || f.views == 0) return cudaSuccess;
+    dim3 grid((count + 255) / 256, f.views);
+    k_unshuffle<<<grid, 256, 0, stream>>>(f, strip, index, count, full_image);
+    return cudaGetLastError();
+}

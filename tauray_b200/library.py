@@ -1,0 +1,198 @@
+"""ctypes binding of libtauray_b200.so (include/tauray_b200.h).
+
+`PathTracer` is the Python spelling of one `tr_pt_ctx`, i.e. of one `path_tracer_stage` of the
+reference (src/path_tracer_stage.hh:10-52): construct with options, `set_scene`, `set_cameras`,
+`set_distribution`, then `render()` once per frame. The library is loaded from the package
+directory (built in-tree by `__graft_entry__.build()` / `make -C tauray_b200/csrc`); a missing
+library or a missing GPU is an error -- there is no fallback path.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+from .distribution import target_shape
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtauray_b200.so")
+_lib = None
+
+EXPORTS = [
+    "tr_pt_default_options", "tr_pt_create", "tr_pt_destroy", "tr_pt_set_scene", "tr_pt_set_cameras",
+    "tr_pt_set_distribution", "tr_pt_reset_accumulation", "tr_pt_render", "tr_pt_render_feature", "tr_pt_sync",
+    "tr_pt_get_color_buffer", "tr_pt_read_color", "tr_pt_unshuffle", "tr_pt_set_peer_images", "tr_pt_get_stats",
+    "tr_pt_set_instrumentation", "tr_pt_read_tri_lights", "tr_pt_trace_rays", "tr_pt_sample_test",
+    "tr_pt_last_error", "tr_pt_abi_version",
+]
+
+
+class TaurayB200Error(RuntimeError):
+    def __init__(self, what, code, message):
+        super().__init__("%s failed with %d: %s" % (what, code, message))
+        self.code = code
+
+
+def lib():
+    """Load libtauray_b200.so and declare every prototype of include/tauray_b200.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(tauray_b200 has no CPU fallback)" % LIB_PATH)
+    l = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    l.tr_pt_default_options.argtypes = [C.POINTER(abi.Options)]
+    l.tr_pt_default_options.restype = None
+    l.tr_pt_create.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(abi.Options)]
+    l.tr_pt_destroy.argtypes = [vp]
+    l.tr_pt_destroy.restype = None
+    l.tr_pt_set_scene.argtypes = [vp, C.POINTER(abi.SceneDesc)]
+    l.tr_pt_set_cameras.argtypes = [vp, vp, C.c_uint32]
+    l.tr_pt_set_distribution.argtypes = [vp, C.POINTER(abi.Distribution)]
+    l.tr_pt_reset_accumulation.argtypes = [vp, C.c_int]
+    l.tr_pt_render.argtypes = [vp, vp]
+    l.tr_pt_render_feature.argtypes = [vp, C.c_int, C.POINTER(C.c_float), vp]
+    l.tr_pt_sync.argtypes = [vp]
+    l.tr_pt_get_color_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    l.tr_pt_read_color.argtypes = [vp, vp, C.c_size_t]
+    l.tr_pt_unshuffle.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, vp]
+    l.tr_pt_set_peer_images.argtypes = [vp, C.POINTER(vp), C.c_int]
+    l.tr_pt_get_stats.argtypes = [vp, C.POINTER(abi.Stats)]
+    l.tr_pt_set_instrumentation.argtypes = [vp, C.c_int]
+    l.tr_pt_read_tri_lights.argtypes = [vp, vp, C.c_uint32]
+    l.tr_pt_trace_rays.argtypes = [vp, vp, C.c_uint32, vp]
+    l.tr_pt_sample_test.argtypes = [vp, vp, C.c_uint32, C.c_int, vp]
+    l.tr_pt_last_error.argtypes = [vp]
+    l.tr_pt_last_error.restype = C.c_char_p
+    l.tr_pt_abi_version.argtypes = []
+    if l.tr_pt_abi_version() != abi.ABI_VERSION:
+        raise ImportError("libtauray_b200.so has ABI %d, expected %d" % (l.tr_pt_abi_version(), abi.ABI_VERSION))
+    _lib = l
+    return l
+
+
+class PathTracer:
+    """One path_tracer_stage on one GPU."""
+
+    def __init__(self, options, device=0):
+        self._l = lib()
+        self._ctx = C.c_void_p()
+        self.options = abi.copy_options(options)
+        self.device = device
+        rc = self._l.tr_pt_create(C.byref(self._ctx), device, C.byref(self.options))
+        if rc:
+            raise TaurayB200Error("tr_pt_create", rc, self._l.tr_pt_last_error(None).decode())
+        self._dist = None
+        self._views = 0
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._l.tr_pt_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc, what):
+        if rc < 0:
+            raise TaurayB200Error(what, rc, self._l.tr_pt_last_error(self._ctx).decode())
+        return rc
+
+    # -- reference-shaped calls -----------------------------------------------------------
+    def set_scene(self, scene):
+        d = scene.desc() if hasattr(scene, "desc") else scene
+        self._check(self._l.tr_pt_set_scene(self._ctx, C.byref(d)), "tr_pt_set_scene")
+
+    def set_cameras(self, pairs):
+        pairs = np.ascontiguousarray(pairs, dtype=abi.CAMERA_PAIR)
+        self._views = pairs.shape[0]
+        self._check(self._l.tr_pt_set_cameras(self._ctx, pairs.ctypes.data, pairs.shape[0]), "tr_pt_set_cameras")
+
+    def set_distribution(self, dist):
+        """rt_camera_stage::reset_distribution_params."""
+        self._dist = dist
+        self._check(self._l.tr_pt_set_distribution(self._ctx, C.byref(dist)), "tr_pt_set_distribution")
+
+    reset_distribution_params = set_distribution
+
+    def reset_accumulation(self, reset_sample_counter=True):
+        """reset_accumulated_samples (+ reset_sample_counter), src/rt_renderer.cc:67-81."""
+        self._check(self._l.tr_pt_reset_accumulation(self._ctx, 1 if reset_sample_counter else 0),
+                    "tr_pt_reset_accumulation")
+
+    def render(self, stream=None):
+        """stage::run: all passes of one frame, asynchronous."""
+        self._check(self._l.tr_pt_render(self._ctx, stream), "tr_pt_render")
+
+    def render_feature(self, feature, default=(0.0, 0.0, 0.0, 0.0), stream=None):
+        dv = (C.c_float * 4)(*default)
+        self._check(self._l.tr_pt_render_feature(self._ctx, feature, dv, stream), "tr_pt_render_feature")
+
+    def sync(self):
+        self._check(self._l.tr_pt_sync(self._ctx), "tr_pt_sync")
+
+    # -- results --------------------------------------------------------------------------
+    def target_shape(self):
+        return target_shape(self._dist, self._views)
+
+    def read_color(self, out=None):
+        shape = self.target_shape()
+        if out is None:
+            out = np.empty(shape, dtype=np.float32)
+        assert out.nbytes == int(np.prod(shape)) * 4 and out.flags["C_CONTIGUOUS"]
+        self._check(self._l.tr_pt_read_color(self._ctx, out.ctypes.data, out.nbytes), "tr_pt_read_color")
+        return out
+
+    def read_color_into(self, host_ptr, nbytes):
+        self._check(self._l.tr_pt_read_color(self._ctx, host_ptr, nbytes), "tr_pt_read_color")
+
+    def color_buffer(self):
+        """(device pointer, bytes) of the colour target."""
+        p, n = C.c_void_p(), C.c_size_t()
+        self._check(self._l.tr_pt_get_color_buffer(self._ctx, C.byref(p), C.byref(n)), "tr_pt_get_color_buffer")
+        return p.value, n.value
+
+    def unshuffle(self, strip_ptr, index, count, full_image_ptr, stream=None):
+        self._check(self._l.tr_pt_unshuffle(self._ctx, strip_ptr, index, count, full_image_ptr, stream), "tr_pt_unshuffle")
+
+    def set_peer_images(self, ptrs):
+        arr = (C.c_void_p * max(len(ptrs), 1))(*ptrs)
+        self._check(self._l.tr_pt_set_peer_images(self._ctx, arr, len(ptrs)), "tr_pt_set_peer_images")
+
+    def stats(self):
+        s = abi.Stats()
+        self._check(self._l.tr_pt_get_stats(self._ctx, C.byref(s)), "tr_pt_get_stats")
+        return s.as_dict()
+
+    def set_instrumentation(self, enabled):
+        self._check(self._l.tr_pt_set_instrumentation(self._ctx, 1 if enabled else 0), "tr_pt_set_instrumentation")
+
+    # -- test hooks -----------------------------------------------------------------------
+    def tri_lights(self):
+        n = self._check(self._l.tr_pt_read_tri_lights(self._ctx, None, 0), "tr_pt_read_tri_lights")
+        out = np.zeros(max(n, 1), dtype=abi.TRI_LIGHT)
+        self._check(self._l.tr_pt_read_tri_lights(self._ctx, out.ctypes.data, n), "tr_pt_read_tri_lights")
+        return out[:n]
+
+    def trace_rays(self, rays):
+        rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 8)
+        out = np.zeros(rays.shape[0], dtype=abi.HIT)
+        self._check(self._l.tr_pt_trace_rays(self._ctx, rays.ctypes.data, rays.shape[0], out.ctypes.data), "tr_pt_trace_rays")
+        return out
+
+    def sample_test(self, coords, draw_index):
+        coords = np.ascontiguousarray(coords, dtype=np.uint32).reshape(-1, 4)
+        out = np.zeros_like(coords)
+        self._check(self._l.tr_pt_sample_test(self._ctx, coords.ctypes.data, coords.shape[0], draw_index, out.ctypes.data), "tr_pt_sample_test")
+        return out

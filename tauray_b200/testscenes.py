@@ -1,0 +1,149 @@
+"""Small procedural scenes used by the parity tests, smoke() and quick benches.
+
+`cornell` is a closed box with coloured walls, an emissive ceiling quad, a metallic and a rough
+dielectric block, optional sphere light / spotlight / directional light and an optional
+alpha-textured card -- every NEE class and hit type of the hot path in a few hundred triangles.
+"""
+import numpy as np
+
+from . import abi
+from .scene import Scene, make_material, look_at_transform, perspective_camera, camera_pairs
+
+
+def quad(p0, p1, p2, p3, subdiv=1):
+    """Two-triangle (or subdivided) quad p0-p1-p2-p3 (counter-clockwise seen from its front)."""
+    p0, p1, p2, p3 = [np.asarray(p, dtype=np.float64) for p in (p0, p1, p2, p3)]
+    n = np.cross(p1 - p0, p3 - p0)
+    n /= np.linalg.norm(n)
+    t = (p1 - p0) / np.linalg.norm(p1 - p0)
+    s = subdiv
+    verts = np.zeros((s + 1) * (s + 1), dtype=abi.VERTEX)
+    k = 0
+    for j in range(s + 1):
+        for i in range(s + 1):
+            u, v = i / s, j / s
+            pos = (1 - u) * (1 - v) * p0 + u * (1 - v) * p1 + u * v * p2 + (1 - u) * v * p3
+            verts[k]["pos"] = pos
+            verts[k]["normal"] = n
+            verts[k]["uv"] = (u, v)
+            verts[k]["tangent"] = tuple(t) + (1.0,)
+            k += 1
+    idx = []
+    for j in range(s):
+        for i in range(s):
+            a = j * (s + 1) + i
+            idx += [a, a + 1, a + s + 2, a, a + s + 2, a + s + 1]
+    return verts, np.asarray(idx, dtype=np.uint32)
+
+
+def box(lo, hi, subdiv=1):
+    lo = np.asarray(lo, dtype=np.float64)
+    hi = np.asarray(hi, dtype=np.float64)
+    x0, y0, z0 = lo
+    x1, y1, z1 = hi
+    faces = [
+        ((x0, y0, z1), (x1, y0, z1), (x1, y1, z1), (x0, y1, z1)),  # +z
+        ((x1, y0, z0), (x0, y0, z0), (x0, y1, z0), (x1, y1, z0)),  # -z
+        ((x1, y0, z1), (x1, y0, z0), (x1, y1, z0), (x1, y1, z1)),  # +x
+        ((x0, y0, z0), (x0, y0, z1), (x0, y1, z1), (x0, y1, z0)),  # -x
+        ((x0, y1, z1), (x1, y1, z1), (x1, y1, z0), (x0, y1, z0)),  # +y
+        ((x0, y0, z0), (x1, y0, z0), (x1, y0, z1), (x0, y0, z1)),  # -y
+    ]
+    vs, is_ = [], []
+    base = 0
+    for f in faces:
+        v, i = quad(*f, subdiv=subdiv)
+        vs.append(v)
+        is_.append(i + base)
+        base += v.shape[0]
+    return np.concatenate(vs), np.concatenate(is_)
+
+
+def merge(parts):
+    vs, is_ = [], []
+    base = 0
+    for v, i in parts:
+        vs.append(v)
+        is_.append(i + base)
+        base += v.shape[0]
+    return np.concatenate(vs), np.concatenate(is_)
+
+
+def checker_texture(n=64, cells=8, alpha_holes=True, seed=3):
+    rng = np.random.RandomState(seed)
+    tex = np.zeros((n, n, 4), dtype=np.uint8)
+    yy, xx = np.mgrid[0:n, 0:n]
+    c = ((xx * cells // n) + (yy * cells // n)) % 2
+    tex[..., 0] = np.where(c, 230, 40)
+    tex[..., 1] = np.where(c, 200, 90)
+    tex[..., 2] = rng.randint(20, 250, size=(n, n))
+    if alpha_holes:
+        r = np.hypot(xx - n / 2, yy - n / 2)
+        tex[..., 3] = np.clip((r - n * 0.15) * 16, 0, 255).astype(np.uint8)
+    else:
+        tex[..., 3] = 255
+    return tex
+
+
+def cornell(subdiv=4, sphere_light=True, spotlight=True, directional=True, alpha_card=True,
+            transmissive=True, rotate_block=True):
+    s = Scene()
+    w = 2.0
+    white = make_material(albedo=(0.8, 0.8, 0.8, 1))
+    red = make_material(albedo=(0.8, 0.08, 0.02, 1))
+    blue = make_material(albedo=(0.02, 0.05, 0.8, 1), roughness=0.5)
+    mirror = make_material(albedo=(0.9, 0.9, 0.9, 1), roughness=0.0)
+    # floor, ceiling, back wall (one instance), then the side walls and a smooth front-left wall
+    fl = quad((-w, -w, w), (w, -w, w), (w, -w, -w), (-w, -w, -w), subdiv)
+    ce = quad((-w, w, -w), (w, w, -w), (w, w, w), (-w, w, w), subdiv)
+    ba = quad((-w, -w, -w), (w, -w, -w), (w, w, -w), (-w, w, -w), subdiv)
+    s.add_instance(*merge([fl, ce, ba]), white)
+    s.add_instance(*quad((-w, -w, w), (-w, -w, -w), (-w, w, -w), (-w, w, w), subdiv), red)
+    s.add_instance(*quad((w, -w, -w), (w, -w, w), (w, w, w), (w, w, -w), subdiv), blue)
+    # behind the camera: a mirror wall closing the box
+    s.add_instance(*quad((w, -w, 3 * w), (-w, -w, 3 * w), (-w, w, 3 * w), (w, w, 3 * w), 1), mirror)
+    for zs in (w, 2 * w):
+        pass
+    side = merge([
+        quad((-w, -w, 3 * w), (-w, -w, w), (-w, w, w), (-w, w, 3 * w), 1),
+        quad((w, -w, w), (w, -w, 3 * w), (w, w, 3 * w), (w, w, w), 1),
+        quad((-w, -w, 3 * w), (w, -w, 3 * w), (w, -w, w), (-w, -w, w), 1),
+        quad((-w, w, w), (w, w, w), (w, w, 3 * w), (-w, w, 3 * w), 1),
+    ])
+    s.add_instance(*side, white)
+    # emissive ceiling panel
+    em = make_material(albedo=(0, 0, 0, 1), emission=(12.0, 11.0, 8.0))
+    s.add_instance(*quad((-0.5, w - 0.01, -0.5), (0.5, w - 0.01, -0.5), (0.5, w - 0.01, 0.5), (-0.5, w - 0.01, 0.5), 2), em)
+    # blocks
+    metal = make_material(albedo=(0.72, 0.22, 0.05, 1), metallic=1.0, roughness=0.2)
+    bv, bi = box((-0.6, -0.6, -0.6), (0.6, 0.6, 0.6), 2)
+    t = np.eye(4)
+    if rotate_block:
+        a = 0.5
+        t[:3, :3] = [[np.cos(a), 0, np.sin(a)], [0, 1.3, 0], [-np.sin(a), 0, np.cos(a)]]
+    t[:3, 3] = (-0.8, -w + 0.78, -0.7)
+    s.add_instance(bv, bi, metal, transform=t)
+    glass = make_material(albedo=(0.48, 0.6, 0.28, 1), roughness=0.2, transmittance=1.0 if transmissive else 0.0)
+    t2 = np.eye(4)
+    t2[:3, 3] = (0.9, -w + 0.5, 0.4)
+    t2[0, 0] = t2[1, 1] = t2[2, 2] = 0.8
+    s.add_instance(bv, bi, glass, transform=t2)
+    if alpha_card:
+        tid = s.add_texture(checker_texture())
+        card = make_material(albedo=(1, 1, 1, 1), albedo_tex=tid, roughness=0.6)
+        s.add_instance(*quad((-1.2, -1.0, 1.0), (0.2, -1.0, 1.0), (0.2, 0.4, 1.0), (-1.2, 0.4, 1.0), 1), card)
+    if directional:
+        s.add_directional_light((1.0, 0.87, 0.6), (-0.3, -1.0, -0.4), angle_deg=2.0)
+    if sphere_light:
+        s.add_point_light((3.0, 3.0, 4.0), (1.2, 1.2, 0.2), radius=0.15)
+    if spotlight:
+        s.add_spotlight((20.0, 40.0, 16.0), (-1.5, 1.5, 1.5), (0.6, -1.0, -0.8), 25.0, 2.0, radius=0.05)
+    return s
+
+
+def cornell_camera(aspect=1.0, fov_deg=45.0):
+    return perspective_camera(look_at_transform((0, 0, 5.5), (0, -0.2, 0)), fov_deg, aspect, 0.1, 100.0)
+
+
+def cornell_cameras(aspect=1.0):
+    return camera_pairs([cornell_camera(aspect)])
