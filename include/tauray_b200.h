@@ -245,20 +245,35 @@ typedef struct tr_pt_distribution {
     int32_t primary;
 } tr_pt_distribution;
 
-/* Counters of the last tr_pt_render (timer "path tracing", src/rt_stage.cc:60) */
+/* Counters of the last tr_pt_render (the reference's timer "path tracing", src/rt_stage.cc:60).
+ * Instrumentation flags (tr_pt_set_instrumentation): TR_INSTRUMENT_VISITS counts BVH node visits
+ * and triangle tests (slower kernels); TR_INSTRUMENT_TIMING brackets every kernel launch with CUDA
+ * events on the render stream and sums the durations per kernel class. */
+#define TR_INSTRUMENT_VISITS 1
+#define TR_INSTRUMENT_TIMING 2
 typedef struct tr_pt_stats {
     uint64_t closest_rays;              /* traversal queries issued (closest hit) */
     uint64_t shadow_rays;               /* traversal queries issued (shadow / any hit) */
     uint64_t paths;                     /* camera paths started */
-    uint64_t node_visits;               /* only in instrumented runs (tr_pt_set_instrumentation) */
-    uint64_t triangle_tests;
+    uint64_t closest_node_visits;       /* TR_INSTRUMENT_VISITS */
+    uint64_t closest_triangle_tests;
+    uint64_t shadow_node_visits;
+    uint64_t shadow_triangle_tests;
     uint64_t kernel_launches;           /* kernels launched by the last tr_pt_render */
     float render_ms;                    /* CUDA-event time of the last tr_pt_render */
-    float trace_ms;                     /* sum over trace kernels, instrumented runs only */
+    float closest_ms;                   /* TR_INSTRUMENT_TIMING: summed over launches of the class */
+    float shadow_ms;
+    float shade_ms;
+    float other_ms;
+    uint32_t closest_launches;
+    uint32_t shadow_launches;
+    uint32_t shade_launches;
     float bvh_build_ms;                 /* last tr_pt_set_scene */
     uint32_t bvh_node_count;
+    uint32_t bvh_depth;
     uint32_t triangle_count;
     uint32_t tri_light_count;
+    uint32_t reserved;
 } tr_pt_stats;
 
 typedef struct tr_pt_ctx tr_pt_ctx;     /* one per GPU == one path_tracer_stage */
@@ -321,8 +336,22 @@ int tr_pt_unshuffle(tr_pt_ctx* ctx, const void* strip_device, uint32_t index, ui
  * separate gather/stitch pass runs. Pass n = 0 to disable. */
 int tr_pt_set_peer_images(tr_pt_ctx* ctx, void* const* full_image_device_ptrs, int n);
 
+/* Cross-process exchange of full images for tr_pt_set_peer_images (one process per GPU):
+ * tr_pt_alloc_full_image allocates (or returns) a library-owned size.x*size.y*views float4 image,
+ * tr_pt_ipc_get_handle exports it as a 64-byte cudaIpcMemHandle_t, tr_pt_ipc_open_handle maps a
+ * peer's handle into this process (cudaIpcOpenMemHandle), tr_pt_ipc_close_handle unmaps it. */
+int tr_pt_alloc_full_image(tr_pt_ctx* ctx, void** device_ptr, size_t* bytes);
+int tr_pt_read_full_image(tr_pt_ctx* ctx, float* rgba32f_host, size_t bytes);
+int tr_pt_ipc_get_handle(tr_pt_ctx* ctx, unsigned char handle[64]);
+int tr_pt_ipc_open_handle(tr_pt_ctx* ctx, const unsigned char handle[64], void** device_ptr);
+int tr_pt_ipc_close_handle(tr_pt_ctx* ctx, void* device_ptr);
+/* Render into caller-owned device memory (e.g. a torch tensor registered with NCCL) instead of the
+ * library's own colour target; NULL restores the internal target. `bytes` must equal the size
+ * tr_pt_get_color_buffer reports for the current cameras/distribution. */
+int tr_pt_set_color_buffer(tr_pt_ctx* ctx, void* device_ptr, size_t bytes);
+
 int tr_pt_get_stats(tr_pt_ctx* ctx, tr_pt_stats* stats);
-int tr_pt_set_instrumentation(tr_pt_ctx* ctx, int enabled);
+int tr_pt_set_instrumentation(tr_pt_ctx* ctx, int flags);
 
 /* Test hooks (device results copied to the host). */
 int tr_pt_read_tri_lights(tr_pt_ctx* ctx, tr_tri_light* out, uint32_t capacity);

@@ -77,7 +77,7 @@ struct hit_payload
 
 struct counters
 {
-    uint64_t closest = 0, shadow = 0, paths = 0, nodes = 0, tris = 0;
+    uint64_t closest = 0, shadow = 0, paths = 0, nodes = 0, tris = 0, snodes = 0, stris = 0;
 };
 
 } // namespace
@@ -424,7 +424,7 @@ struct orc_ctx
             float alpha = hit_alpha(tr.instance_id, tr.primitive_id, V2(u, v));
             factors.push_back({t, tr.instance_id, tr.primitive_id, 1.0f - alpha});
             return true;
-        }, &c.nodes, &c.tris);
+        }, &c.snodes, &c.stris);
         if(blocked) return 0.0f;
         std::sort(factors.begin(), factors.end(), [](const factor& a, const factor& b) {
             if(a.t != b.t) return a.t < b.t;
@@ -936,7 +936,7 @@ struct orc_ctx
         for(const counters& c: per_thread)
         {
             total.closest += c.closest; total.shadow += c.shadow; total.paths += c.paths;
-            total.nodes += c.nodes; total.tris += c.tris;
+            total.nodes += c.nodes; total.tris += c.tris; total.snodes += c.snodes; total.stris += c.stris;
         }
     }
 };
@@ -1130,8 +1130,10 @@ int orc_render(orc_ctx* ctx, uint64_t max_slots)
     ctx->stats.closest_rays = total.closest;
     ctx->stats.shadow_rays = total.shadow;
     ctx->stats.paths = total.paths;
-    ctx->stats.node_visits = total.nodes;
-    ctx->stats.triangle_tests = total.tris;
+    ctx->stats.closest_node_visits = total.nodes;
+    ctx->stats.closest_triangle_tests = total.tris;
+    ctx->stats.shadow_node_visits = total.snodes;
+    ctx->stats.shadow_triangle_tests = total.stris;
     return TR_OK;
 }
 

@@ -24,6 +24,7 @@ PROJECTION_PERSPECTIVE, PROJECTION_ORTHOGRAPHIC = range(2)
 FEATURE_ALBEDO, FEATURE_WORLD_NORMAL, FEATURE_VIEW_NORMAL, FEATURE_WORLD_POS, FEATURE_VIEW_POS, FEATURE_DISTANCE = range(6)
 FEATURE_INSTANCE_ID = 9
 KERNEL_WAVEFRONT, KERNEL_MEGAKERNEL = range(2)
+INSTRUMENT_VISITS, INSTRUMENT_TIMING = 1, 2
 TEXTURE_RGBA8_UNORM, TEXTURE_RGBA32F = range(2)
 
 OK = 0
@@ -115,9 +116,14 @@ class Distribution(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("closest_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("paths", C.c_uint64),
-                ("node_visits", C.c_uint64), ("triangle_tests", C.c_uint64), ("kernel_launches", C.c_uint64),
-                ("render_ms", C.c_float), ("trace_ms", C.c_float), ("bvh_build_ms", C.c_float),
-                ("bvh_node_count", C.c_uint32), ("triangle_count", C.c_uint32), ("tri_light_count", C.c_uint32)]
+                ("closest_node_visits", C.c_uint64), ("closest_triangle_tests", C.c_uint64),
+                ("shadow_node_visits", C.c_uint64), ("shadow_triangle_tests", C.c_uint64),
+                ("kernel_launches", C.c_uint64),
+                ("render_ms", C.c_float), ("closest_ms", C.c_float), ("shadow_ms", C.c_float),
+                ("shade_ms", C.c_float), ("other_ms", C.c_float),
+                ("closest_launches", C.c_uint32), ("shadow_launches", C.c_uint32), ("shade_launches", C.c_uint32),
+                ("bvh_build_ms", C.c_float), ("bvh_node_count", C.c_uint32), ("bvh_depth", C.c_uint32),
+                ("triangle_count", C.c_uint32), ("tri_light_count", C.c_uint32), ("reserved", C.c_uint32)]
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_}

@@ -23,6 +23,7 @@ struct tr_pt_ctx
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t last_stream = nullptr;   // stream of the last render (may be the caller's)
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     tr_pt_options opt{};
     std::string error;
@@ -36,8 +37,14 @@ struct tr_pt_ctx
     uint32_t views = 0;
     tr_pt_distribution dist{};
     bool has_dist = false;
-    float4* color = nullptr;
+    float4* color = nullptr;        // the target in use (own_color or an external buffer)
+    float4* own_color = nullptr;
+    float4* external_color = nullptr;
+    size_t external_bytes = 0;
     size_t color_pixels = 0;
+    float4* full_image = nullptr;   // library-owned stitched image (tr_pt_alloc_full_image)
+    size_t full_image_pixels = 0;
+    tr_launch_timer* timer = nullptr;
     tr_wavefront wf{};
     std::vector<void*> wf_allocs;
     Counters* counters = nullptr;
@@ -152,7 +159,7 @@ void fill_params(const tr_pt_ctx* c, RenderParams& P)
     P.cameras = c->cameras;
     P.color = c->color;
     P.counters = c->counters;
-    P.stats = c->instrumentation;
+    P.stats = (c->instrumentation & TR_INSTRUMENT_VISITS) ? 1 : 0;
     for(int i = 0; i < c->peer_count; ++i) P.peers[i] = c->peers[i];
     P.peer_count = c->peer_count;
     P.last_pass = 0;
@@ -166,12 +173,21 @@ int prepare_targets(tr_pt_ctx* c)
     FrameParams f;
     fill_frame(c, f);
     const size_t pixels = (size_t)f.layer_size * f.views;
-    if(pixels != c->color_pixels || !c->color)
+    if(c->external_color)
     {
-        if(c->color) cudaFree(c->color);
-        c->color = nullptr;
-        TRY_CUDA(c, cudaMalloc((void**)&c->color, std::max<size_t>(pixels, 1) * sizeof(float4)));
-        TRY_CUDA(c, cudaMemsetAsync(c->color, 0, std::max<size_t>(pixels, 1) * sizeof(float4), c->stream));
+        if(c->external_bytes != pixels * sizeof(float4))
+            return fail(c, TR_ERR_INVALID_ARGUMENT, "external colour buffer has " + std::to_string(c->external_bytes) +
+                        " bytes, the target needs " + std::to_string(pixels * sizeof(float4)));
+        c->color = c->external_color;
+        c->color_pixels = pixels;
+    }
+    else if(pixels != c->color_pixels || !c->own_color || c->color != c->own_color)
+    {
+        if(c->own_color) cudaFree(c->own_color);
+        c->own_color = nullptr;
+        TRY_CUDA(c, cudaMalloc((void**)&c->own_color, std::max<size_t>(pixels, 1) * sizeof(float4)));
+        TRY_CUDA(c, cudaMemsetAsync(c->own_color, 0, std::max<size_t>(pixels, 1) * sizeof(float4), c->stream));
+        c->color = c->own_color;
         c->color_pixels = pixels;
     }
     const uint64_t slots64 = (uint64_t)f.ray_count_x * f.ray_count_y * f.views;
@@ -284,7 +300,9 @@ void tr_pt_destroy(tr_pt_ctx* c)
     free_scene(c);
     free_list(c->wf_allocs);
     if(c->cameras) cudaFree(c->cameras);
-    if(c->color) cudaFree(c->color);
+    if(c->own_color) cudaFree(c->own_color);
+    if(c->full_image) cudaFree(c->full_image);
+    if(c->timer) { c->timer->destroy(); delete c->timer; }
     if(c->counters) cudaFree(c->counters);
     if(c->ev_begin) cudaEventDestroy(c->ev_begin);
     if(c->ev_end) cudaEventDestroy(c->ev_end);
@@ -431,6 +449,7 @@ int tr_pt_set_scene(tr_pt_ctx* c, const tr_pt_scene_desc* s)
     c->has_scene = true;
     c->stats.bvh_build_ms = build_ms;
     c->stats.bvh_node_count = bout.node_count;
+    c->stats.bvh_depth = bout.depth;
     c->stats.triangle_count = (uint32_t)ttotal;
     c->stats.tri_light_count = (uint32_t)tri_light_count;
     return TR_OK;
@@ -496,17 +515,26 @@ int tr_pt_render(tr_pt_ctx* c, void* cuda_stream)
     TRY_CUDA(c, cudaMemsetAsync(c->counters, 0, sizeof(Counters), st));
     TRY_CUDA(c, cudaEventRecord(c->ev_begin, st));
     uint64_t launches = 0;
+    tr_launch_timer* timer = nullptr;
+    if(c->instrumentation & TR_INSTRUMENT_TIMING)
+    {
+        if(!c->timer) c->timer = new tr_launch_timer();
+        c->timer->reset();
+        timer = c->timer;
+    }
+    else if(c->timer) c->timer->reset();
     const uint32_t pass_count = (uint32_t)(c->opt.samples_per_pixel / c->opt.samples_per_pass); // path_tracer_stage.cc:37
     for(uint32_t pass = 0; pass < pass_count; ++pass)
     {
         P.frame.previous_samples = pass * (uint32_t)c->opt.samples_per_pass; // path_tracer_stage.cc:141
         P.last_pass = pass + 1 == pass_count;
         cudaError_t e = c->opt.kernel_mode == TR_KERNEL_WAVEFRONT ?
-            tr_render_pass_wavefront(st, P, c->wf, c->sm_count, &launches) :
-            tr_render_pass_megakernel(st, P, c->sm_count, &launches);
+            tr_render_pass_wavefront(st, P, c->wf, c->sm_count, &launches, timer) :
+            tr_render_pass_megakernel(st, P, c->sm_count, &launches, timer);
         if(e != cudaSuccess) return fail_cuda(c, e, "render pass launch");
     }
     TRY_CUDA(c, cudaEventRecord(c->ev_end, st));
+    c->last_stream = st;
     c->stats.kernel_launches = launches;
     c->rendered = true;
     return TR_OK;
@@ -523,6 +551,7 @@ int tr_pt_render_feature(tr_pt_ctx* c, int feature, const float default_value[4]
     RenderParams P;
     fill_params(c, P);
     TRY_CUDA(c, tr_render_feature(st, P, feature, default_value));
+    c->last_stream = st;
     return TR_OK;
 }
 
@@ -530,6 +559,7 @@ int tr_pt_sync(tr_pt_ctx* c)
 {
     if(!c) return TR_ERR_INVALID_ARGUMENT;
     DeviceGuard guard(c->device);
+    if(c->last_stream && c->last_stream != c->stream) TRY_CUDA(c, cudaStreamSynchronize(c->last_stream));
     TRY_CUDA(c, cudaStreamSynchronize(c->stream));
     return TR_OK;
 }
@@ -552,8 +582,21 @@ int tr_pt_read_color(tr_pt_ctx* c, float* out, size_t bytes)
     if(!c->color) return fail(c, TR_ERR_INVALID_ARGUMENT, "nothing rendered yet");
     if(bytes != c->color_pixels * sizeof(float4))
         return fail(c, TR_ERR_INVALID_ARGUMENT, "size mismatch: target has " + std::to_string(c->color_pixels * sizeof(float4)) + " bytes");
-    TRY_CUDA(c, cudaMemcpyAsync(out, c->color, bytes, cudaMemcpyDeviceToHost, c->stream));
-    TRY_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaStream_t st = c->last_stream ? c->last_stream : c->stream;
+    TRY_CUDA(c, cudaMemcpyAsync(out, c->color, bytes, cudaMemcpyDeviceToHost, st));
+    TRY_CUDA(c, cudaStreamSynchronize(st));
+    return TR_OK;
+}
+
+int tr_pt_read_full_image(tr_pt_ctx* c, float* out, size_t bytes)
+{
+    if(!c || !out) return TR_ERR_INVALID_ARGUMENT;
+    DeviceGuard guard(c->device);
+    if(!c->full_image) return fail(c, TR_ERR_INVALID_ARGUMENT, "tr_pt_alloc_full_image has not been called");
+    if(bytes != c->full_image_pixels * sizeof(float4)) return fail(c, TR_ERR_INVALID_ARGUMENT, "size mismatch");
+    cudaStream_t st = c->last_stream ? c->last_stream : c->stream;
+    TRY_CUDA(c, cudaMemcpyAsync(out, c->full_image, bytes, cudaMemcpyDeviceToHost, st));
+    TRY_CUDA(c, cudaStreamSynchronize(st));
     return TR_OK;
 }
 
@@ -593,17 +636,96 @@ int tr_pt_get_stats(tr_pt_ctx* c, tr_pt_stats* stats)
         c->stats.closest_rays = h.closest_rays;
         c->stats.shadow_rays = h.shadow_rays;
         c->stats.paths = h.paths;
-        c->stats.node_visits = h.node_visits;
-        c->stats.triangle_tests = h.triangle_tests;
+        c->stats.closest_node_visits = h.closest_nodes;
+        c->stats.closest_triangle_tests = h.closest_tris;
+        c->stats.shadow_node_visits = h.shadow_nodes;
+        c->stats.shadow_triangle_tests = h.shadow_tris;
+        c->stats.closest_ms = c->stats.shadow_ms = c->stats.shade_ms = c->stats.other_ms = 0.0f;
+        c->stats.closest_launches = c->stats.shadow_launches = c->stats.shade_launches = 0;
+        if(c->timer && c->timer->used > 1)
+        {
+            tr_launch_timer& t = *c->timer;
+            for(int i = 0; i + 1 < t.used; ++i)
+            {
+                if(t.cls[i] == TR_KCLASS_END) continue;
+                float d = 0.0f;
+                if(cudaEventElapsedTime(&d, t.events[i], t.events[i + 1]) != cudaSuccess) { cudaGetLastError(); continue; }
+                switch(t.cls[i])
+                {
+                case TR_KCLASS_CLOSEST: c->stats.closest_ms += d; c->stats.closest_launches++; break;
+                case TR_KCLASS_SHADOW: c->stats.shadow_ms += d; c->stats.shadow_launches++; break;
+                case TR_KCLASS_SHADE: c->stats.shade_ms += d; c->stats.shade_launches++; break;
+                default: c->stats.other_ms += d; break;
+                }
+            }
+        }
     }
     *stats = c->stats;
     return TR_OK;
 }
 
-int tr_pt_set_instrumentation(tr_pt_ctx* c, int enabled)
+int tr_pt_set_instrumentation(tr_pt_ctx* c, int flags)
 {
     if(!c) return TR_ERR_INVALID_ARGUMENT;
-    c->instrumentation = enabled ? 1 : 0;
+    c->instrumentation = flags & (TR_INSTRUMENT_VISITS | TR_INSTRUMENT_TIMING);
+    return TR_OK;
+}
+
+int tr_pt_set_color_buffer(tr_pt_ctx* c, void* device_ptr, size_t bytes)
+{
+    if(!c) return TR_ERR_INVALID_ARGUMENT;
+    c->external_color = (float4*)device_ptr;
+    c->external_bytes = device_ptr ? bytes : 0;
+    if(!device_ptr) { c->color = nullptr; c->color_pixels = 0; }
+    return TR_OK;
+}
+
+int tr_pt_alloc_full_image(tr_pt_ctx* c, void** device_ptr, size_t* bytes)
+{
+    if(!c || !device_ptr) return TR_ERR_INVALID_ARGUMENT;
+    if(!c->has_dist || c->views == 0) return fail(c, TR_ERR_INVALID_ARGUMENT, "cameras / distribution not set");
+    DeviceGuard guard(c->device);
+    const size_t pixels = (size_t)c->dist.size[0] * c->dist.size[1] * c->views;
+    if(!c->full_image || c->full_image_pixels != pixels)
+    {
+        if(c->full_image) cudaFree(c->full_image);
+        c->full_image = nullptr;
+        TRY_CUDA(c, cudaMalloc((void**)&c->full_image, pixels * sizeof(float4)));
+        TRY_CUDA(c, cudaMemset(c->full_image, 0, pixels * sizeof(float4)));
+        c->full_image_pixels = pixels;
+    }
+    *device_ptr = c->full_image;
+    if(bytes) *bytes = pixels * sizeof(float4);
+    return TR_OK;
+}
+
+int tr_pt_ipc_get_handle(tr_pt_ctx* c, unsigned char handle[64])
+{
+    if(!c || !handle) return TR_ERR_INVALID_ARGUMENT;
+    if(!c->full_image) return fail(c, TR_ERR_INVALID_ARGUMENT, "tr_pt_alloc_full_image has not been called");
+    DeviceGuard guard(c->device);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    TRY_CUDA(c, cudaIpcGetMemHandle(&h, c->full_image));
+    memcpy(handle, &h, 64);
+    return TR_OK;
+}
+
+int tr_pt_ipc_open_handle(tr_pt_ctx* c, const unsigned char handle[64], void** device_ptr)
+{
+    if(!c || !handle || !device_ptr) return TR_ERR_INVALID_ARGUMENT;
+    DeviceGuard guard(c->device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    TRY_CUDA(c, cudaIpcOpenMemHandle(device_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return TR_OK;
+}
+
+int tr_pt_ipc_close_handle(tr_pt_ctx* c, void* device_ptr)
+{
+    if(!c || !device_ptr) return TR_ERR_INVALID_ARGUMENT;
+    DeviceGuard guard(c->device);
+    TRY_CUDA(c, cudaIpcCloseMemHandle(device_ptr));
     return TR_OK;
 }
 

@@ -91,8 +91,9 @@ TRD void warp_push(uint32_t* __restrict__ queue, uint32_t* __restrict__ count, b
     if(pred) queue[base + __popc(mask & ((1u << lane) - 1u))] = value;
 }
 
+// kind: 0 = closest-hit traversal counters, 1 = shadow traversal counters
 TRD void flush_counters(Counters* c, unsigned long long closest, unsigned long long shadow, unsigned long long paths,
-                        unsigned long long nodes, unsigned long long tris)
+                        unsigned long long nodes, unsigned long long tris, int kind)
 {
     // warp reduce then one atomic per warp and counter
     for(int off = 16; off > 0; off >>= 1)
@@ -108,8 +109,8 @@ TRD void flush_counters(Counters* c, unsigned long long closest, unsigned long l
         if(closest) atomicAdd(&c->closest_rays, closest);
         if(shadow) atomicAdd(&c->shadow_rays, shadow);
         if(paths) atomicAdd(&c->paths, paths);
-        if(nodes) atomicAdd(&c->node_visits, nodes);
-        if(tris) atomicAdd(&c->triangle_tests, tris);
+        if(nodes) atomicAdd(kind ? &c->shadow_nodes : &c->closest_nodes, nodes);
+        if(tris) atomicAdd(kind ? &c->shadow_tris : &c->closest_tris, tris);
     }
 }
 
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_generate(const RenderParams P, 
         }
         warp_push(queue, count, valid, slot);
     }
-    flush_counters(P.counters, 0, 0, paths, 0, 0);
+    flush_counters(P.counters, 0, 0, paths, 0, 0, 0);
 }
 
 template<bool STATS>
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_trace_closest(const RenderParam
         if(P.scene.any_non_opaque) wf.dir_seed[id].w = __uint_as_float(seed);
         rays++;
     }
-    flush_counters(P.counters, rays, 0, 0, st.nodes, st.tris);
+    flush_counters(P.counters, rays, 0, 0, st.nodes, st.tris, 0);
 }
 
 __global__ void __launch_bounds__(WF_BLOCK) k_wf_shade(const RenderParams P, const tr_wavefront wf, uint32_t bounce, uint32_t sample_in_pass,
@@ -240,7 +241,7 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_trace_shadow(const RenderParams
         wf.diffuse[id] = make_float4(s.diffuse.x, s.diffuse.y, s.diffuse.z, 0.0f);
         wf.reflection[id] = make_float4(s.reflection.x, s.reflection.y, s.reflection.z, 0.0f);
     }
-    flush_counters(P.counters, 0, rays, 0, st.nodes, st.tris);
+    flush_counters(P.counters, 0, rays, 0, st.nodes, st.tris, 1);
 }
 
 __global__ void __launch_bounds__(WF_BLOCK) k_wf_finish(const RenderParams P, const tr_wavefront wf, uint32_t sample_in_pass, uint32_t total_slots)
@@ -277,6 +278,7 @@ __global__ void __launch_bounds__(WF_BLOCK) k_megakernel(const RenderParams P, u
 {
     const uint32_t stride = gridDim.x * blockDim.x;
     TraceStats st; st.nodes = 0; st.tris = 0;
+    TraceStats sst; sst.nodes = 0; sst.tris = 0;
     unsigned long long closest = 0, shadow = 0, paths = 0;
     const uint32_t spp = (uint32_t)P.opt.samples_per_pass;
     for(uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < total_slots; slot += stride)
@@ -304,7 +306,7 @@ __global__ void __launch_bounds__(WF_BLOCK) k_megakernel(const RenderParams P, u
                     float vis = 1.0f;
                     if(job.needs_shadow_ray)
                     {
-                        vis = shadow_visibility<STATS>(P, s.pos, P.opt.min_ray_dist, job.dir, job.tmax, st);
+                        vis = shadow_visibility<STATS>(P, s.pos, P.opt.min_ray_dist, job.dir, job.tmax, sst);
                         shadow++;
                     }
                     nee_finish(P, job, vis, s);
@@ -317,7 +319,8 @@ __global__ void __launch_bounds__(WF_BLOCK) k_megakernel(const RenderParams P, u
         const float4 o = accumulate(P, sum / (float)spp, alpha, widx);
         store_to_peers(P, o, px, py, view);
     }
-    flush_counters(P.counters, closest, shadow, paths, st.nodes, st.tris);
+    flush_counters(P.counters, closest, shadow, paths, st.nodes, st.tris, 0);
+    flush_counters(P.counters, 0, 0, 0, sst.nodes, sst.tris, 1);
 }
 
 // ---- feature (AOV) tracer: shader/rt_feature.rgen:18-47, rt_feature.rahit, rt_feature.rchit ------
@@ -423,8 +426,10 @@ static int grid_for(int sm_count, int blocks_per_sm, uint32_t work)
     return (int)(g < 1 ? 1 : g);
 }
 
-cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const RenderParams& P, const tr_wavefront& wf, int sm_count, uint64_t* launches)
+cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const RenderParams& P, const tr_wavefront& wf, int sm_count, uint64_t* launches,
+                                     tr_launch_timer* timer)
 {
+#define MARK(cls) do { if(timer) timer->mark(stream, cls); } while(0)
     const uint32_t total = P.frame.ray_count_x * P.frame.ray_count_y * P.frame.views;
     if(total == 0) return cudaSuccess;
     const uint32_t D = (uint32_t)P.opt.max_ray_depth;
@@ -437,37 +442,47 @@ cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const RenderParams& P,
         if(e != cudaSuccess) return e;
         uint32_t* active_counts = wf.counts;          // [D + 1]
         uint32_t* shadow_counts = wf.counts + D + 1;  // [D]
+        MARK(TR_KCLASS_OTHER);
         k_wf_generate<<<grid_full, WF_BLOCK, 0, stream>>>(P, wf, i, total, wf.queue[0], active_counts);
         ++*launches;
         for(uint32_t b = 0; b < D; ++b)
         {
             uint32_t* q_in = wf.queue[b & 1];
             uint32_t* q_out = wf.queue[(b + 1) & 1];
+            MARK(TR_KCLASS_CLOSEST);
             if(P.stats) k_wf_trace_closest<true><<<grid_persist, WF_BLOCK, 0, stream>>>(P, wf, b, q_in, active_counts + b);
             else k_wf_trace_closest<false><<<grid_persist, WF_BLOCK, 0, stream>>>(P, wf, b, q_in, active_counts + b);
+            MARK(TR_KCLASS_SHADE);
             k_wf_shade<<<grid_persist, WF_BLOCK, 0, stream>>>(P, wf, b, i, q_in, active_counts + b, q_out, active_counts + b + 1,
                                                               wf.shadow_queue, shadow_counts + b);
             *launches += 2;
             if(b + 1 < D)
             {
+                MARK(TR_KCLASS_SHADOW);
                 if(P.stats) k_wf_trace_shadow<true><<<grid_persist, WF_BLOCK, 0, stream>>>(P, wf, b, wf.shadow_queue, shadow_counts + b);
                 else k_wf_trace_shadow<false><<<grid_persist, WF_BLOCK, 0, stream>>>(P, wf, b, wf.shadow_queue, shadow_counts + b);
                 ++*launches;
             }
         }
+        MARK(TR_KCLASS_OTHER);
         k_wf_finish<<<grid_full, WF_BLOCK, 0, stream>>>(P, wf, i, total);
         ++*launches;
     }
+    MARK(TR_KCLASS_END);
+#undef MARK
     return cudaGetLastError();
 }
 
-cudaError_t tr_render_pass_megakernel(cudaStream_t stream, const RenderParams& P, int sm_count, uint64_t* launches)
+cudaError_t tr_render_pass_megakernel(cudaStream_t stream, const RenderParams& P, int sm_count, uint64_t* launches,
+                                      tr_launch_timer* timer)
 {
     const uint32_t total = P.frame.ray_count_x * P.frame.ray_count_y * P.frame.views;
     if(total == 0) return cudaSuccess;
     const int grid = grid_for(sm_count, 8, total);
+    if(timer) timer->mark(stream, TR_KCLASS_OTHER);
     if(P.stats) k_megakernel<true><<<grid, WF_BLOCK, 0, stream>>>(P, total);
     else k_megakernel<false><<<grid, WF_BLOCK, 0, stream>>>(P, total);
+    if(timer) timer->mark(stream, TR_KCLASS_END);
     ++*launches;
     return cudaGetLastError();
 }

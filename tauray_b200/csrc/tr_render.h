@@ -28,11 +28,39 @@ struct tr_wavefront
 
 namespace trd { struct RenderParams; }
 
+// Per-launch CUDA-event timing (TR_INSTRUMENT_TIMING): one event before every kernel launch on the
+// render stream; a launch's duration is the gap to the next event.
+enum { TR_KCLASS_CLOSEST = 0, TR_KCLASS_SHADOW = 1, TR_KCLASS_SHADE = 2, TR_KCLASS_OTHER = 3, TR_KCLASS_END = 4 };
+struct tr_launch_timer
+{
+    static constexpr int MAX_MARKS = 8192;
+    cudaEvent_t events[MAX_MARKS];
+    unsigned char cls[MAX_MARKS];
+    int created = 0;
+    int used = 0;
+    bool overflow = false;
+    void reset() { used = 0; overflow = false; }
+    void mark(cudaStream_t stream, int kclass)
+    {
+        if(used >= MAX_MARKS) { overflow = true; return; }
+        if(used >= created)
+        {
+            if(cudaEventCreate(&events[created]) != cudaSuccess) { overflow = true; return; }
+            created++;
+        }
+        cls[used] = (unsigned char)kclass;
+        cudaEventRecord(events[used], stream);
+        used++;
+    }
+    void destroy() { for(int i = 0; i < created; ++i) cudaEventDestroy(events[i]); created = used = 0; }
+};
+
 cudaError_t tr_render_init_constants();
 // One pass (= samples_per_pass samples of every slot) of path_tracer.rgen.
 cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const trd::RenderParams& P, const tr_wavefront& wf,
-                                     int sm_count, uint64_t* launches);
-cudaError_t tr_render_pass_megakernel(cudaStream_t stream, const trd::RenderParams& P, int sm_count, uint64_t* launches);
+                                     int sm_count, uint64_t* launches, tr_launch_timer* timer);
+cudaError_t tr_render_pass_megakernel(cudaStream_t stream, const trd::RenderParams& P, int sm_count, uint64_t* launches,
+                                      tr_launch_timer* timer);
 cudaError_t tr_render_feature(cudaStream_t stream, const trd::RenderParams& P, int feature, const float default_value[4]);
 cudaError_t tr_render_trace_rays(cudaStream_t stream, const trd::RenderParams& P, const float* rays_dev, uint32_t n, void* hits_dev);
 cudaError_t tr_render_sample_test(cudaStream_t stream, const trd::RenderParams& P, const uint32_t* coords_dev, uint32_t n,

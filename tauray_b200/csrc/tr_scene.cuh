@@ -91,7 +91,8 @@ struct FrameParams
 
 struct Counters
 {
-    unsigned long long closest_rays, shadow_rays, paths, node_visits, triangle_tests;
+    unsigned long long closest_rays, shadow_rays, paths;
+    unsigned long long closest_nodes, closest_tris, shadow_nodes, shadow_tris;
 };
 
 } // namespace trd

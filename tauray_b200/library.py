@@ -23,7 +23,8 @@ EXPORTS = [
     "tr_pt_set_distribution", "tr_pt_reset_accumulation", "tr_pt_render", "tr_pt_render_feature", "tr_pt_sync",
     "tr_pt_get_color_buffer", "tr_pt_read_color", "tr_pt_unshuffle", "tr_pt_set_peer_images", "tr_pt_get_stats",
     "tr_pt_set_instrumentation", "tr_pt_read_tri_lights", "tr_pt_trace_rays", "tr_pt_sample_test",
-    "tr_pt_last_error", "tr_pt_abi_version",
+    "tr_pt_last_error", "tr_pt_abi_version", "tr_pt_alloc_full_image", "tr_pt_ipc_get_handle",
+    "tr_pt_ipc_open_handle", "tr_pt_ipc_close_handle", "tr_pt_set_color_buffer", "tr_pt_read_full_image",
 ]
 
 
@@ -64,6 +65,12 @@ def lib():
     l.tr_pt_read_tri_lights.argtypes = [vp, vp, C.c_uint32]
     l.tr_pt_trace_rays.argtypes = [vp, vp, C.c_uint32, vp]
     l.tr_pt_sample_test.argtypes = [vp, vp, C.c_uint32, C.c_int, vp]
+    l.tr_pt_alloc_full_image.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    l.tr_pt_read_full_image.argtypes = [vp, vp, C.c_size_t]
+    l.tr_pt_ipc_get_handle.argtypes = [vp, C.c_char_p]
+    l.tr_pt_ipc_open_handle.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
+    l.tr_pt_ipc_close_handle.argtypes = [vp, vp]
+    l.tr_pt_set_color_buffer.argtypes = [vp, vp, C.c_size_t]
     l.tr_pt_last_error.argtypes = [vp]
     l.tr_pt_last_error.restype = C.c_char_p
     l.tr_pt_abi_version.argtypes = []
@@ -170,13 +177,39 @@ class PathTracer:
         arr = (C.c_void_p * max(len(ptrs), 1))(*ptrs)
         self._check(self._l.tr_pt_set_peer_images(self._ctx, arr, len(ptrs)), "tr_pt_set_peer_images")
 
+    def set_color_buffer(self, device_ptr, nbytes):
+        """Render into caller-owned device memory (None restores the internal target)."""
+        self._check(self._l.tr_pt_set_color_buffer(self._ctx, device_ptr, nbytes), "tr_pt_set_color_buffer")
+
+    def alloc_full_image(self):
+        p, n = C.c_void_p(), C.c_size_t()
+        self._check(self._l.tr_pt_alloc_full_image(self._ctx, C.byref(p), C.byref(n)), "tr_pt_alloc_full_image")
+        return p.value, n.value
+
+    def read_full_image(self, out):
+        self._check(self._l.tr_pt_read_full_image(self._ctx, out.ctypes.data, out.nbytes), "tr_pt_read_full_image")
+        return out
+
+    def ipc_get_handle(self):
+        buf = C.create_string_buffer(64)
+        self._check(self._l.tr_pt_ipc_get_handle(self._ctx, buf), "tr_pt_ipc_get_handle")
+        return buf.raw
+
+    def ipc_open_handle(self, handle):
+        p = C.c_void_p()
+        self._check(self._l.tr_pt_ipc_open_handle(self._ctx, handle, C.byref(p)), "tr_pt_ipc_open_handle")
+        return p.value
+
+    def ipc_close_handle(self, ptr):
+        self._check(self._l.tr_pt_ipc_close_handle(self._ctx, ptr), "tr_pt_ipc_close_handle")
+
     def stats(self):
         s = abi.Stats()
         self._check(self._l.tr_pt_get_stats(self._ctx, C.byref(s)), "tr_pt_get_stats")
         return s.as_dict()
 
-    def set_instrumentation(self, enabled):
-        self._check(self._l.tr_pt_set_instrumentation(self._ctx, 1 if enabled else 0), "tr_pt_set_instrumentation")
+    def set_instrumentation(self, flags):
+        self._check(self._l.tr_pt_set_instrumentation(self._ctx, int(flags)), "tr_pt_set_instrumentation")
 
     # -- test hooks -----------------------------------------------------------------------
     def tri_lights(self):
