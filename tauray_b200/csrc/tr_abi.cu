@@ -214,7 +214,7 @@ int prepare_targets(tr_pt_ctx* c)
         TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.queue[0], n));
         TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.queue[1], n));
         TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.shadow_queue, n));
-        TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.counts, 2 * 64 + 2));
+        TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.counts, 4 * 64 + 2));
         w.capacity = slots;
     }
     return TR_OK;

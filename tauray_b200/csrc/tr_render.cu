@@ -19,6 +19,7 @@
 namespace trd {
 
 constexpr int WF_BLOCK = 128;
+constexpr int TRACE_BLOCKS_PER_SM = 8;
 
 // ---- SoA <-> registers ---------------------------------------------------------------------------
 TRD void store_ray(const tr_wavefront& wf, uint32_t id, const PathState& s)
@@ -144,29 +145,278 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_generate(const RenderParams P, 
     flush_counters(P.counters, 0, 0, paths, 0, 0, 0);
 }
 
-template<bool STATS>
-__global__ void __launch_bounds__(WF_BLOCK) k_wf_trace_closest(const RenderParams P, const tr_wavefront wf, uint32_t bounce,
-                                                                const uint32_t* __restrict__ queue, const uint32_t* __restrict__ count)
+// ---- persistent-threads traversal kernel ---------------------------------------------------------
+// One kernel for both ray kinds (ANY = shadow rays). Structure after Aila & Laine's persistent
+// "speculative while-while" tracer, re-tuned for sm_100a:
+//   * the grid is SM count x resident blocks; every warp fetches rays from the queue with ONE
+//     atomicAdd per refill (ballot of the idle lanes) and refills as soon as fewer than
+//     FETCH_THRESHOLD lanes are still traversing, so warps stay dense while rays of very different
+//     length retire (measured: the naive one-ray-per-thread loop ran at 5-11 of 32 lanes);
+//   * inner-node loop and leaf loop are separate, a found leaf is postponed until no lane of the
+//     warp can make inner-node progress any more;
+//   * the traversal stack lives in shared memory as a short stack ([entry][thread], conflict-free),
+//     entries beyond SHORT_STACK spill to a per-thread local array;
+//   * nodes (4 x float4) and triangles (3 x float4) are fetched with 128-bit read-only loads.
+constexpr int SHORT_STACK = 16;
+constexpr int FETCH_THRESHOLD = 20;
+constexpr int SENTINEL = 0x76543210;
+constexpr int MAX_FACTORS = 6;
+
+template<bool ANY, bool STATS>
+__global__ void __launch_bounds__(WF_BLOCK) k_wf_trace(const RenderParams P, const tr_wavefront wf, uint32_t bounce,
+                                                        const uint32_t* __restrict__ queue, const uint32_t* __restrict__ count,
+                                                        uint32_t* __restrict__ work_counter)
 {
+    __shared__ int s_stack[SHORT_STACK * WF_BLOCK];
+    int lstack[TR_BVH_STACK - SHORT_STACK];
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
     const uint32_t n = *count;
-    const uint32_t stride = gridDim.x * blockDim.x;
+    const float4* __restrict__ nodes = P.scene.bvh.nodes;
+    const float4* __restrict__ tris = P.scene.bvh.tris;
+    const bool include_lights = !ANY && !(P.opt.hide_lights && bounce == 0);
+    const float ray_tmin = ANY ? P.opt.min_ray_dist : (bounce == 0 ? 0.0f : P.opt.min_ray_dist);
+    const bool transparency = P.scene.any_non_opaque != 0;
+
     TraceStats st; st.nodes = 0; st.tris = 0;
     unsigned long long rays = 0;
-    const bool include_lights = !(P.opt.hide_lights && bounce == 0);
-    const float tmin = bounce == 0 ? 0.0f : P.opt.min_ray_dist;
-    for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+
+    // per-lane ray + traversal state
+    int node = SENTINEL, leaf = 0, sp = 0;
+    bool has_ray = false, exhausted = false;
+    uint32_t id = 0, seed = 0;
+    vec3 org = V3(0), dir = V3(0);
+    float tmin = 0.0f, tmax = 0.0f, best_t = 0.0f;
+    float idx = 0, idy = 0, idz = 0, oodx = 0, oody = 0, oodz = 0;
+    RayPre rp;
+    rp.kx = rp.ky = rp.kz = 0; rp.Sx = rp.Sy = rp.Sz = 0; rp.org = V3(0);
+    Hit best;
+    best.instance_id = -1; best.primitive_id = -1; best.u = best.v = best.t = 0; best.flags = 0;
+    bool found = false;
+    // shadow rays through non-opaque geometry: (t, instance, primitive, 1 - alpha)
+    float ft[MAX_FACTORS], ff[MAX_FACTORS];
+    int fi[MAX_FACTORS], fp[MAX_FACTORS];
+    int nf = 0;
+    float overflow = 1.0f;
+
+#define PUSH(v) do { if(sp < SHORT_STACK) s_stack[sp * WF_BLOCK + tid] = (v); else lstack[sp - SHORT_STACK] = (v); sp++; } while(0)
+#define POP(dst) do { if(sp == 0) dst = SENTINEL; else { sp--; dst = sp < SHORT_STACK ? s_stack[sp * WF_BLOCK + tid] : lstack[sp - SHORT_STACK]; } } while(0)
+
+    for(;;)
     {
-        const uint32_t id = queue[i];
-        const float4 o = wf.pos_pdf[id];
-        const float4 d = wf.dir_seed[id];
-        uint32_t seed = __float_as_uint(d.w);
-        Hit h;
-        closest_hit<STATS>(P, V3(o.x, o.y, o.z), tmin, V3(d.x, d.y, d.z), include_lights, seed, h, st);
-        wf.hits[id] = make_int4(h.instance_id, h.primitive_id, __float_as_int(h.u), __float_as_int(h.v));
-        if(P.scene.any_non_opaque) wf.dir_seed[id].w = __uint_as_float(seed);
-        rays++;
+        // ---- retire finished rays --------------------------------------------------------------
+        if(has_ray && node == SENTINEL)
+        {
+            bool retire = true;
+            if(!ANY)
+            {
+                // sphere lights + the in-t-order any-hit emulation (see closest_hit() in tr_path.cuh)
+                int light_id = -1;
+                float light_t = 0.0f;
+                if(include_lights)
+                {
+                    for(uint32_t i = 0; i < P.scene.point_light_count; ++i)
+                    {
+                        const tr_point_light& pl = P.scene.point_lights[i];
+                        if(pl.radius == 0.0f) continue;
+                        float t = sphere_intersection(ld3(pl.pos), pl.radius, org, dir);
+                        if(!(t > 0)) continue;
+                        if(!(t >= tmin)) continue;
+                        if(light_id < 0 || t < light_t) { light_id = (int)i; light_t = t; }
+                    }
+                }
+                if(light_id >= 0 && (!found || light_t < best.t))
+                    wf.hits[id] = make_int4(-1, light_id, __float_as_int(light_t), 0);
+                else if(!found)
+                    wf.hits[id] = make_int4(-1, -1, 0, 0);
+                else
+                {
+                    bool accept = true;
+                    if(transparency && !(best.flags & TR_TRI_FLAG_OPAQUE))
+                    {
+                        float alpha_cutoff = (float)pcg(seed) * TR_INV_UINT32_MAX;
+                        if(hit_alpha(P.scene, best.instance_id, best.primitive_id, best.u, best.v) <= alpha_cutoff) accept = false;
+                    }
+                    if(accept) wf.hits[id] = make_int4(best.instance_id, best.primitive_id, __float_as_int(best.u), __float_as_int(best.v));
+                    else
+                    {
+                        // ignored by the any-hit test: continue behind it
+                        tmin = best.t;
+                        best_t = tmax;
+                        found = false;
+                        node = 0; leaf = 0; sp = 0;
+                        retire = false;
+                    }
+                }
+                if(retire && transparency) wf.dir_seed[id].w = __uint_as_float(seed);
+            }
+            else
+            {
+                float visibility = found ? 0.0f : 1.0f;   // found == an opaque blocker
+                if(!found && nf > 0)
+                {
+                    for(int k = 0; k < nf; ++k)
+                    {
+                        int m = -1;
+                        for(int j = 0; j < nf; ++j)
+                        {
+                            if(fi[j] == -2) continue;
+                            if(m < 0 || ft[j] < ft[m] || (ft[j] == ft[m] && (fi[j] < fi[m] || (fi[j] == fi[m] && fp[j] < fp[m])))) m = j;
+                        }
+                        visibility *= ff[m];
+                        fi[m] = -2;
+                        if(visibility == 0.0f) break;
+                    }
+                    if(visibility != 0.0f) visibility *= overflow;
+                }
+                NeeJob job;
+                load_job(wf, id, (int)bounce, job);
+                PathState s;
+                const float4 e = wf.diffuse[id], f = wf.reflection[id];
+                s.diffuse = V3(e.x, e.y, e.z);
+                s.reflection = V3(f.x, f.y, f.z);
+                nee_finish(P, job, visibility, s);
+                wf.diffuse[id] = make_float4(s.diffuse.x, s.diffuse.y, s.diffuse.z, 0.0f);
+                wf.reflection[id] = make_float4(s.reflection.x, s.reflection.y, s.reflection.z, 0.0f);
+            }
+            if(retire) has_ray = false;
+        }
+
+        // ---- refill idle lanes: one atomicAdd per warp ----------------------------------------
+        {
+            const bool want = !has_ray && !exhausted;
+            const uint32_t mask = __ballot_sync(0xFFFFFFFFu, want);
+            if(mask)
+            {
+                const int leader = __ffs(mask) - 1;
+                uint32_t base = 0;
+                if(lane == leader) base = atomicAdd(work_counter, (uint32_t)__popc(mask));
+                base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                if(want)
+                {
+                    const uint32_t i = base + __popc(mask & ((1u << lane) - 1u));
+                    if(i < n)
+                    {
+                        id = queue[i];
+                        const float4 o = wf.pos_pdf[id];
+                        org = V3(o.x, o.y, o.z);
+                        if(ANY)
+                        {
+                            const float4 j0 = wf.nee[4 * (size_t)id];
+                            dir = V3(j0.x, j0.y, j0.z);
+                            tmax = j0.w;
+                        }
+                        else
+                        {
+                            const float4 d = wf.dir_seed[id];
+                            dir = V3(d.x, d.y, d.z);
+                            seed = __float_as_uint(d.w);
+                            tmax = inf_();
+                        }
+                        tmin = ray_tmin;
+                        best_t = tmax;
+                        rp = precompute_ray(org, dir);
+                        idx = safe_inv(dir.x); idy = safe_inv(dir.y); idz = safe_inv(dir.z);
+                        oodx = org.x * idx; oody = org.y * idy; oodz = org.z * idz;
+                        node = 0; leaf = 0; sp = 0;
+                        found = false;
+                        nf = 0; overflow = 1.0f;
+                        has_ray = true;
+                        rays++;
+                    }
+                    else exhausted = true;
+                }
+            }
+            if(__ballot_sync(0xFFFFFFFFu, has_ray) == 0) break;
+        }
+
+        // ---- traverse ---------------------------------------------------------------------------
+        while(node != SENTINEL)
+        {
+            // inner nodes, until every lane that can has found a leaf
+            while((unsigned)node < (unsigned)SENTINEL)
+            {
+                if(STATS) st.nodes++;
+                const float4 n0 = __ldg(nodes + 4 * node + 0);
+                const float4 n1 = __ldg(nodes + 4 * node + 1);
+                const float4 n2 = __ldg(nodes + 4 * node + 2);
+                const float4 n3 = __ldg(nodes + 4 * node + 3);
+                float c0min, c0max, c1min, c1max;
+                TR_SLAB(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, tmin, best_t, c0min, c0max);
+                TR_SLAB(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, tmin, best_t, c1min, c1max);
+                const bool h0 = c0min <= c0max;
+                const bool h1 = c1min <= c1max;
+                int r0 = __float_as_int(n3.x), r1 = __float_as_int(n3.y);
+                if(!h0 && !h1) POP(node);
+                else
+                {
+                    node = h0 ? r0 : r1;
+                    if(h0 && h1)
+                    {
+                        if(c1min < c0min) { node = r1; r1 = r0; }
+                        PUSH(r1);
+                    }
+                }
+                // first leaf: postpone it and keep traversing
+                if(node < 0 && leaf >= 0)
+                {
+                    leaf = node;
+                    POP(node);
+                }
+                if(!__any_sync(__activemask(), leaf >= 0)) break;
+            }
+
+            // postponed leaves
+            while(leaf < 0)
+            {
+                const uint32_t lf = (uint32_t)~leaf;
+                const uint32_t first = lf >> 3;
+                const uint32_t cnt = (lf & 7u) + 1u;
+                for(uint32_t i = 0; i < cnt; ++i)
+                {
+                    if(STATS) st.tris++;
+                    const float4 t0 = __ldg(tris + 3 * (first + i) + 0);
+                    const float4 t1 = __ldg(tris + 3 * (first + i) + 1);
+                    const float4 t2 = __ldg(tris + 3 * (first + i) + 2);
+                    float t, u, v;
+                    if(!intersect_triangle(rp, f3(t0), f3(t1), f3(t2), tmin, tmax, t, u, v)) continue;
+                    const int inst = __float_as_int(t0.w), prim = __float_as_int(t1.w);
+                    const uint32_t flags = __float_as_uint(t2.w);
+                    if(ANY)
+                    {
+                        if(flags & TR_TRI_FLAG_OPAQUE)
+                        {
+                            found = true;
+                            node = SENTINEL; sp = 0;   // terminate on the first opaque hit
+                            break;
+                        }
+                        const float f = 1.0f - hit_alpha(P.scene, inst, prim, u, v);
+                        if(nf < MAX_FACTORS) { ft[nf] = t; ff[nf] = f; fi[nf] = inst; fp[nf] = prim; nf++; }
+                        else overflow *= f;
+                        continue;
+                    }
+                    const bool better = !found || t < best.t ||
+                        (t == best.t && (inst < best.instance_id || (inst == best.instance_id && prim < best.primitive_id)));
+                    if(better)
+                    {
+                        found = true;
+                        best.instance_id = inst; best.primitive_id = prim; best.u = u; best.v = v; best.t = t; best.flags = flags;
+                        best_t = t;
+                    }
+                }
+                // another leaf may have been found while this one was postponed
+                leaf = node;
+                if(node < 0) POP(node);
+                if(ANY && found) { leaf = 0; node = SENTINEL; }
+            }
+
+            // too few lanes left busy: go refill
+            if(__popc(__activemask()) < FETCH_THRESHOLD) break;
+        }
     }
-    flush_counters(P.counters, rays, 0, 0, st.nodes, st.tris, 0);
+#undef PUSH
+#undef POP
+    flush_counters(P.counters, ANY ? 0 : rays, ANY ? rays : 0, 0, st.nodes, st.tris, ANY ? 1 : 0);
 }
 
 __global__ void __launch_bounds__(WF_BLOCK) k_wf_shade(const RenderParams P, const tr_wavefront wf, uint32_t bounce, uint32_t sample_in_pass,
@@ -215,33 +465,6 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_shade(const RenderParams P, con
         warp_push(next_queue, next_count, alive, id);
         warp_push(shadow_queue, shadow_count, shadow, id);
     }
-}
-
-template<bool STATS>
-__global__ void __launch_bounds__(WF_BLOCK) k_wf_trace_shadow(const RenderParams P, const tr_wavefront wf, uint32_t bounce,
-                                                               const uint32_t* __restrict__ queue, const uint32_t* __restrict__ count)
-{
-    const uint32_t n = *count;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    TraceStats st; st.nodes = 0; st.tris = 0;
-    unsigned long long rays = 0;
-    for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-    {
-        const uint32_t id = queue[i];
-        NeeJob job;
-        load_job(wf, id, (int)bounce, job);
-        const float4 o = wf.pos_pdf[id];
-        const float vis = shadow_visibility<STATS>(P, V3(o.x, o.y, o.z), P.opt.min_ray_dist, job.dir, job.tmax, st);
-        rays++;
-        PathState s;
-        const float4 e = wf.diffuse[id], f = wf.reflection[id];
-        s.diffuse = V3(e.x, e.y, e.z);
-        s.reflection = V3(f.x, f.y, f.z);
-        nee_finish(P, job, vis, s);
-        wf.diffuse[id] = make_float4(s.diffuse.x, s.diffuse.y, s.diffuse.z, 0.0f);
-        wf.reflection[id] = make_float4(s.reflection.x, s.reflection.y, s.reflection.z, 0.0f);
-    }
-    flush_counters(P.counters, 0, rays, 0, st.nodes, st.tris, 1);
 }
 
 __global__ void __launch_bounds__(WF_BLOCK) k_wf_finish(const RenderParams P, const tr_wavefront wf, uint32_t sample_in_pass, uint32_t total_slots)
@@ -435,13 +658,14 @@ cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const RenderParams& P,
     const uint32_t D = (uint32_t)P.opt.max_ray_depth;
     const uint32_t spp = (uint32_t)P.opt.samples_per_pass;
     const int grid_full = grid_for(sm_count, 16, total);
-    const int grid_persist = sm_count * 8;
+    const int grid_persist = sm_count * TRACE_BLOCKS_PER_SM;
     for(uint32_t i = 0; i < spp; ++i)
     {
-        cudaError_t e = cudaMemsetAsync(wf.counts, 0, sizeof(uint32_t) * (2 * D + 2), stream);
+        cudaError_t e = cudaMemsetAsync(wf.counts, 0, sizeof(uint32_t) * (4 * D + 2), stream);
         if(e != cudaSuccess) return e;
-        uint32_t* active_counts = wf.counts;          // [D + 1]
-        uint32_t* shadow_counts = wf.counts + D + 1;  // [D]
+        uint32_t* active_counts = wf.counts;           // [D + 1]
+        uint32_t* shadow_counts = wf.counts + D + 1;   // [D]
+        uint32_t* work_counters = wf.counts + 2 * D + 1; // [2 D] dynamic-fetch cursors
         MARK(TR_KCLASS_OTHER);
         k_wf_generate<<<grid_full, WF_BLOCK, 0, stream>>>(P, wf, i, total, wf.queue[0], active_counts);
         ++*launches;
@@ -450,8 +674,8 @@ cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const RenderParams& P,
             uint32_t* q_in = wf.queue[b & 1];
             uint32_t* q_out = wf.queue[(b + 1) & 1];
             MARK(TR_KCLASS_CLOSEST);
-            if(P.stats) k_wf_trace_closest<true><<<grid_persist, WF_BLOCK, 0, stream>>>(P, wf, b, q_in, active_counts + b);
-            else k_wf_trace_closest<false><<<grid_persist, WF_BLOCK, 0, stream>>>(P, wf, b, q_in, active_counts + b);
+            if(P.stats) k_wf_trace<false, true><<<grid_persist, WF_BLOCK, 0, stream>>>(P, wf, b, q_in, active_counts + b, work_counters + 2 * b);
+            else k_wf_trace<false, false><<<grid_persist, WF_BLOCK, 0, stream>>>(P, wf, b, q_in, active_counts + b, work_counters + 2 * b);
             MARK(TR_KCLASS_SHADE);
             k_wf_shade<<<grid_persist, WF_BLOCK, 0, stream>>>(P, wf, b, i, q_in, active_counts + b, q_out, active_counts + b + 1,
                                                               wf.shadow_queue, shadow_counts + b);
@@ -459,8 +683,8 @@ cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const RenderParams& P,
             if(b + 1 < D)
             {
                 MARK(TR_KCLASS_SHADOW);
-                if(P.stats) k_wf_trace_shadow<true><<<grid_persist, WF_BLOCK, 0, stream>>>(P, wf, b, wf.shadow_queue, shadow_counts + b);
-                else k_wf_trace_shadow<false><<<grid_persist, WF_BLOCK, 0, stream>>>(P, wf, b, wf.shadow_queue, shadow_counts + b);
+                if(P.stats) k_wf_trace<true, true><<<grid_persist, WF_BLOCK, 0, stream>>>(P, wf, b, wf.shadow_queue, shadow_counts + b, work_counters + 2 * b + 1);
+                else k_wf_trace<true, false><<<grid_persist, WF_BLOCK, 0, stream>>>(P, wf, b, wf.shadow_queue, shadow_counts + b, work_counters + 2 * b + 1);
                 ++*launches;
             }
         }
