@@ -162,7 +162,8 @@ class RtRenderer:
         else:
             import torch
             self._send[:, :my.count].copy_(torch.from_numpy(self.tracer.read_color()))
-        td.all_gather_into_tensor(self._gathered, self._send, group=self.pg)
+        # concatenated-along-dim-0 form: accepted by both NCCL and gloo
+        td.all_gather_into_tensor(self._gathered.view(self.world * self.views, self.max_count, 4), self._send, group=self.pg)
         for r, d in enumerate(self.dists):
             src = self._gathered[r, :, :d.count].contiguous() if d.count != self.max_count else self._gathered[r]
             if self.cuda:

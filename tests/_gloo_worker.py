@@ -1,0 +1,55 @@
+"""world_size-N gloo worker for tests/test_renderer_gloo.py: the host-side N>1 path of RtRenderer (strip ranges,
+all-gather, un-shuffle) on CPU tensors, with the ORACLE standing in for the GPU tracer (test-only injection)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch.distributed as td  # noqa: E402
+
+from tauray_b200 import abi, testscenes  # noqa: E402
+from tauray_b200.renderer import RtRenderer  # noqa: E402
+from oracle.oracle_py import Oracle  # noqa: E402
+
+
+class OracleTracer:
+    """PathTracer-shaped adapter over the oracle."""
+
+    def __init__(self, opt):
+        self.o = Oracle(opt, threads=2)
+
+    def __getattr__(self, name):
+        return getattr(self.o, name)
+
+    def render(self, stream=None):
+        self.o.render()
+
+    def close(self):
+        self.o.close()
+
+
+def main():
+    out_dir = sys.argv[1]
+    workloads = [float(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 and sys.argv[2] else None
+    td.init_process_group("gloo")
+    rank, world = td.get_rank(), td.get_world_size()
+    size = (96, 54)
+    opt = abi.default_options(max_ray_depth=3, samples_per_pixel=2, local_sampler=abi.SAMPLER_SOBOL_OWEN)
+    ren = RtRenderer(opt, size, rank=rank, world=world, stitch="nccl", tracer_factory=OracleTracer, backend_is_cuda=False)
+    cams = testscenes.cornell_cameras(size[0] / size[1])
+    cams = np.concatenate([cams, cams])            # two views
+    ren.set_scene(testscenes.cornell(), cams)
+    if workloads:
+        ren.set_device_workloads(workloads)
+    ren.render()
+    img = ren.image()
+    np.save(os.path.join(out_dir, "rank%d.npy" % rank), img)
+    ren.close()
+    td.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,60 @@
+"""Host logic of the pixel distribution (src/distribution_strategy.cc, shader/rt.glsl:170-222)."""
+import numpy as np
+import pytest
+
+from tauray_b200 import abi, distribution as D
+from tauray_b200.renderer import LoadBalancer
+
+
+@pytest.mark.parametrize("size,b,region", [((1920, 1080), 13, 254), ((512, 512), 11, 128), ((960, 540), 11, 254)])
+def test_shuffled_strips_parameters_from_the_survey(size, b, region):
+    assert D.calculate_shuffled_strips_b(size) == b
+    assert D.get_region_size(size[0] * size[1], b) == region
+
+
+def test_1080p_eight_gpu_split():
+    size = (1920, 1080)
+    ds = D.device_distributions(size, abi.DISTRIBUTION_SHUFFLED_STRIPS, D.even_workloads(8))
+    assert [d.count for d in ds] == [260096] * 8
+    assert [d.index for d in ds] == [260096 * i for i in range(8)]
+    assert sum(d.count for d in ds) == 254 * 8192 >= 1920 * 1080
+
+
+@pytest.mark.parametrize("size", [(1920, 1080), (512, 512), (960, 540), (160, 120), (33, 17)])
+@pytest.mark.parametrize("n", [1, 2, 3, 8])
+def test_partition_is_a_bijection_onto_the_image(size, n):
+    ds = D.device_distributions(size, abi.DISTRIBUTION_SHUFFLED_STRIPS, D.even_workloads(n))
+    seen = np.zeros(size[0] * size[1], dtype=np.int32)
+    end = 0
+    for d in ds:
+        assert d.index == end
+        end = d.index + d.count
+        j = D.permute_region_id(np.arange(d.index, d.index + d.count, dtype=np.uint64), size)
+        j = j[j < size[0] * size[1]].astype(np.int64)
+        np.add.at(seen, j, 1)
+    assert (seen == 1).all()
+
+
+def test_unequal_workloads():
+    size = (640, 360)
+    ds = D.device_distributions(size, abi.DISTRIBUTION_SHUFFLED_STRIPS, [0.5, 0.3, 0.2])
+    total = D.calculate_shuffled_strips_pixels_per_device(size, 1.0)
+    assert ds[0].index == 0 and ds[-1].index + ds[-1].count == total
+    assert abs(ds[0].count / total - 0.5) < 1e-3
+
+
+def test_scanline_and_duplicate():
+    d = D.get_device_distribution_params((100, 37), abi.DISTRIBUTION_SCANLINE, 0, 0, 2, 4, False)
+    assert (d.index, d.count) == (2, 4)
+    assert D.get_ray_count(d) == (100, (37 - 2 + 3) // 4)
+    assert D.target_shape(d, 3) == (3, 9, 100, 4)
+    d = D.make_distribution((100, 37), abi.DISTRIBUTION_DUPLICATE)
+    assert D.get_ray_count(d) == (100, 37) and D.target_shape(d, 2) == (2, 37, 100, 4)
+
+
+def test_load_balancer_matches_the_reference_update():
+    lb = LoadBalancer([0, 0])
+    assert lb.workloads == [0.5, 0.5]
+    w = lb.update([2.0, 1.0])     # device 1 is twice as fast
+    assert w[1] > w[0] and abs(sum(w) - 1.0) < 1e-9
+    assert abs(w[0] - (0.5 * 0.9 + (0.25 / 0.75) * 0.1)) < 1e-9

@@ -1,0 +1,176 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the oracle on the same seeded inputs.
+Tolerance = the north star's 1e-5 relative per channel (helpers.assert_parity); the design target is bit-exactness,
+which every case below also asserts (`exact`)."""
+import numpy as np
+import pytest
+
+from tauray_b200 import abi, distribution, testscenes
+from tauray_b200.library import PathTracer, TaurayB200Error
+from oracle.oracle_py import Oracle
+
+from helpers import assert_parity, bits_equal, full_dist, run
+
+pytestmark = pytest.mark.gpu
+
+SIZE = (64, 48)
+
+
+def both(opt, scene=None, cams=None, dist=None, frames=1, modes=(abi.KERNEL_WAVEFRONT, abi.KERNEL_MEGAKERNEL)):
+    scene = scene or testscenes.cornell()
+    cams = cams if cams is not None else testscenes.cornell_cameras(SIZE[0] / SIZE[1])
+    dist = dist or full_dist(SIZE)
+    ref = run(Oracle(opt), scene, cams, dist, frames)
+    outs = []
+    for mode in modes:
+        o = abi.copy_options(opt)
+        o.kernel_mode = mode
+        with PathTracer(o) as pt:
+            img = run(pt, scene, cams, dist, frames)
+            st = pt.stats()
+        assert st["kernel_launches"] > 0
+        exact = assert_parity(img, ref, "kernel_mode %d" % mode)
+        assert exact, "kernel_mode %d is within 1e-5 but not bit-exact" % mode
+        outs.append(img)
+    return ref, outs
+
+
+OPTION_CASES = {
+    "cli_defaults_depth4": dict(max_ray_depth=4),
+    "sobol_owen": dict(max_ray_depth=4, local_sampler=abi.SAMPLER_SOBOL_OWEN, samples_per_pixel=2),
+    "sobol_depth9_pcg_fallback_dims": dict(max_ray_depth=9, local_sampler=abi.SAMPLER_SOBOL_OWEN),
+    "rng_seed": dict(max_ray_depth=3, rng_seed=1234, local_sampler=abi.SAMPLER_SOBOL_OWEN),
+    "box_filter": dict(max_ray_depth=3, film=abi.FILM_BOX, samples_per_pixel=2),
+    "blackman_harris": dict(max_ray_depth=3, film=abi.FILM_BLACKMAN_HARRIS, film_radius=1.0, samples_per_pixel=2),
+    "depth_of_field": dict(max_ray_depth=3, depth_of_field=1),
+    "mis_balance": dict(max_ray_depth=3, mis_mode=abi.MIS_BALANCE_HEURISTIC),
+    "mis_disabled": dict(max_ray_depth=3, mis_mode=abi.MIS_DISABLED),
+    "bounce_hemisphere": dict(max_ray_depth=3, bounce_mode=abi.BOUNCE_HEMISPHERE),
+    "bounce_cosine": dict(max_ray_depth=3, bounce_mode=abi.BOUNCE_COSINE_HEMISPHERE),
+    "tri_area": dict(max_ray_depth=3, tri_light_mode=abi.TRI_LIGHT_AREA),
+    "tri_hybrid": dict(max_ray_depth=3, tri_light_mode=abi.TRI_LIGHT_HYBRID),
+    "russian_roulette": dict(max_ray_depth=8, russian_roulette_delta=4.0),
+    "indirect_clamping": dict(max_ray_depth=4, indirect_clamping=1.5),
+    "regularization": dict(max_ray_depth=4, regularization_gamma=0.3),
+    "hide_lights": dict(max_ray_depth=3, hide_lights=1),
+    "white_albedo": dict(max_ray_depth=3, use_white_albedo_on_first_bounce=1),
+    "transparent_background": dict(max_ray_depth=2, transparent_background=1),
+    "no_nee": dict(max_ray_depth=4, sampling_weight_point_lights=0.0, sampling_weight_directional_lights=0.0,
+                   sampling_weight_emissive_triangles=0.0, sampling_weight_envmap=0.0),
+    "weighted_nee": dict(max_ray_depth=3, sampling_weight_point_lights=2.0, sampling_weight_emissive_triangles=0.5),
+    "samples_per_pass_2": dict(max_ray_depth=3, samples_per_pixel=4, samples_per_pass=2, local_sampler=abi.SAMPLER_SOBOL_OWEN),
+    "depth_1": dict(max_ray_depth=1),
+}
+
+
+@pytest.mark.parametrize("name", sorted(OPTION_CASES))
+def test_option_matrix(name):
+    both(abi.default_options(**OPTION_CASES[name]))
+
+
+def test_accumulation_over_frames_and_sample_counter():
+    """rt_stage frame counter / rt_camera_stage accumulated samples (src/rt_stage.cc:76-85)."""
+    opt = abi.default_options(max_ray_depth=3, samples_per_pixel=2, local_sampler=abi.SAMPLER_SOBOL_OWEN)
+    both(opt, frames=3)
+    # reset_accumulation(False) keeps the sample counter running
+    scene, cams, dist = testscenes.cornell(), testscenes.cornell_cameras(SIZE[0] / SIZE[1]), full_dist(SIZE)
+    o = Oracle(opt)
+    run(o, scene, cams, dist)
+    o.reset_accumulation(False)
+    o.render()
+    with PathTracer(opt) as pt:
+        run(pt, scene, cams, dist)
+        pt.reset_accumulation(False)
+        pt.render()
+        assert bits_equal(pt.read_color(), o.read_color())
+
+
+@pytest.mark.parametrize("strategy,primary,index,count", [
+    (abi.DISTRIBUTION_DUPLICATE, True, 0, 1),
+    (abi.DISTRIBUTION_SCANLINE, True, 1, 3),
+    (abi.DISTRIBUTION_SCANLINE, False, 2, 3),
+    (abi.DISTRIBUTION_SHUFFLED_STRIPS, True, 0, None),
+    (abi.DISTRIBUTION_SHUFFLED_STRIPS, False, 777, 1500),
+    (abi.DISTRIBUTION_SHUFFLED_STRIPS, False, 0, 1),
+])
+def test_distribution_strategies(strategy, primary, index, count):
+    if count is None:
+        count = distribution.calculate_shuffled_strips_pixels_per_device(SIZE, 1.0)
+    dist = distribution.make_distribution(SIZE, strategy, index, count, primary)
+    both(abi.default_options(max_ray_depth=3, local_sampler=abi.SAMPLER_SOBOL_OWEN), dist=dist)
+
+
+def test_multiple_views():
+    cams = testscenes.cornell_cameras(SIZE[0] / SIZE[1])
+    cams3 = np.concatenate([cams, cams, cams])
+    cams3[1]["current"]["origin"][0] += 0.3
+    ref, outs = both(abi.default_options(max_ray_depth=3, local_sampler=abi.SAMPLER_SOBOL_OWEN), cams=cams3)
+    assert ref.shape[0] == 3 and not bits_equal(ref[0], ref[1]) and not bits_equal(ref[0], ref[2])  # view enters the sampler key
+
+
+def test_scene_variants():
+    for kw in (dict(alpha_card=False, transmissive=False), dict(sphere_light=False, spotlight=False),
+               dict(directional=False), dict(subdiv=1, rotate_block=False)):
+        both(abi.default_options(max_ray_depth=4, local_sampler=abi.SAMPLER_SOBOL_OWEN), scene=testscenes.cornell(**kw),
+             modes=(abi.KERNEL_WAVEFRONT,))
+
+
+def test_device_sampler_is_bit_exact():
+    coords = np.random.RandomState(5).randint(0, 5000, size=(4096, 4)).astype(np.uint32)
+    for sampler in (abi.SAMPLER_SOBOL_OWEN, abi.SAMPLER_UNIFORM_RANDOM):
+        for depth in (2, 4, 12):
+            opt = abi.default_options(max_ray_depth=depth, local_sampler=sampler, rng_seed=99)
+            o = Oracle(opt)
+            with PathTracer(opt) as pt:
+                for draw in (-1, 0, 1, 3, 8, 15):
+                    assert (pt.sample_test(coords, draw) == o.sample_test(coords, draw)).all(), (sampler, depth, draw)
+
+
+def test_traversal_closest_hit_is_bit_exact():
+    """Different trees (device LBVH vs the oracle's SAH BVH), same answer: instance, primitive, u, v, t."""
+    scene = testscenes.cornell(subdiv=6)
+    opt = abi.default_options()
+    o = Oracle(opt)
+    o.set_scene(scene)
+    rng = np.random.RandomState(11)
+    rays = np.zeros((50000, 8), dtype=np.float32)
+    rays[:, :3] = rng.uniform(-1.9, 1.9, size=(50000, 3))
+    d = rng.normal(size=(50000, 3))
+    rays[:, 4:7] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    rays[:25000, 7] = np.inf
+    rays[25000:, 7] = rng.uniform(0.1, 3.0, 25000)
+    rays[25000:, 3] = rng.uniform(0.0, 0.5, 25000)
+    # axis-aligned and degenerate directions
+    rays[:300, 4:7] = np.eye(3, dtype=np.float32)[rng.randint(0, 3, 300)] * rng.choice([-1, 1], 300)[:, None]
+    with PathTracer(opt) as pt:
+        pt.set_scene(scene)
+        got = pt.trace_rays(rays)
+    want = o.trace_rays(rays)
+    assert got.tobytes() == want.tobytes()
+    assert (want["instance_id"] >= 0).mean() > 0.9
+
+
+def test_tri_lights_are_bit_exact():
+    scene = testscenes.cornell()
+    opt = abi.default_options()
+    o = Oracle(opt)
+    o.set_scene(scene)
+    with PathTracer(opt) as pt:
+        pt.set_scene(scene)
+        assert pt.tri_lights().tobytes() == o.tri_lights().tobytes()
+        assert pt.stats()["tri_light_count"] == 8
+
+
+def test_errors_are_reported_not_swallowed():
+    opt = abi.default_options()
+    with PathTracer(opt) as pt:
+        with pytest.raises(TaurayB200Error) as e:
+            pt.render()
+        assert e.value.code == abi.ERR_NO_SCENE
+        sc = testscenes.cornell()
+        sc.environment_proj = 0
+        with pytest.raises(TaurayB200Error) as e:
+            pt.set_scene(sc)
+        assert e.value.code == abi.ERR_UNSUPPORTED
+        pt.set_scene(testscenes.cornell())
+        with pytest.raises(TaurayB200Error):
+            pt.render()      # cameras / distribution missing
