@@ -720,12 +720,15 @@ TRD bool shade_bounce(const RenderParams& P, uint32_t bounce, const Hit& h, Path
     const vec3 shading_view = view_to_tangent_space(view, tbn);
 
     // ---- next event estimation up to the shadow ray, :302-339 and :449-456
+    // The NEE draw is an argument of next_event_estimation(): it is evaluated (and advances the PCG
+    // stream) even when no light class is enabled.
+    const uvec4 nee_rand = generate_ray_sample_uint(P, ss_seed, rs_seed, bounce * 2);
     if(nee_enabled(P))
     {
         vec3 out_dir;
         float out_length = 0.0f;
         float light_pdf;
-        vec3 contrib = sample_explicit_light(P, generate_ray_sample_uint(P, ss_seed, rs_seed, bounce * 2), v_pos, out_dir, out_length, light_pdf);
+        vec3 contrib = sample_explicit_light(P, nee_rand, v_pos, out_dir, out_length, light_pdf);
         vec3 shading_light = mul(out_dir, tbn);
         bsdf_lobes lobes = LOBES(0, 0, 0, 0);
         float bsdf_pdf = material_bsdf_pdf(P.opt.bounce_mode, shading_light, shading_view, mat, lobes);

@@ -146,7 +146,7 @@ def test_traversal_closest_hit_is_bit_exact():
         got = pt.trace_rays(rays)
     want = o.trace_rays(rays)
     assert got.tobytes() == want.tobytes()
-    assert (want["instance_id"] >= 0).mean() > 0.9
+    assert (want["instance_id"] >= 0).mean() > 0.5
 
 
 def test_tri_lights_are_bit_exact():
