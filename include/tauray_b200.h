@@ -342,6 +342,10 @@ int tr_pt_set_peer_images(tr_pt_ctx* ctx, void* const* full_image_device_ptrs, i
  * peer's handle into this process (cudaIpcOpenMemHandle), tr_pt_ipc_close_handle unmaps it. */
 int tr_pt_alloc_full_image(tr_pt_ctx* ctx, void** device_ptr, size_t* bytes);
 int tr_pt_read_full_image(tr_pt_ctx* ctx, float* rgba32f_host, size_t bytes);
+/* Single-process multi-GPU (the reference's own topology, src/context.cc:415): let this context's device
+ * store into memory of `peer_cuda_device` (cudaDeviceEnablePeerAccess); then pass the peer context's
+ * tr_pt_alloc_full_image pointer to tr_pt_set_peer_images directly, no IPC handle needed. */
+int tr_pt_enable_peer_access(tr_pt_ctx* ctx, int peer_cuda_device);
 int tr_pt_ipc_get_handle(tr_pt_ctx* ctx, unsigned char handle[64]);
 int tr_pt_ipc_open_handle(tr_pt_ctx* ctx, const unsigned char handle[64], void** device_ptr);
 int tr_pt_ipc_close_handle(tr_pt_ctx* ctx, void* device_ptr);

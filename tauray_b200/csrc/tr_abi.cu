@@ -699,6 +699,20 @@ int tr_pt_alloc_full_image(tr_pt_ctx* c, void** device_ptr, size_t* bytes)
     return TR_OK;
 }
 
+int tr_pt_enable_peer_access(tr_pt_ctx* c, int peer)
+{
+    if(!c) return TR_ERR_INVALID_ARGUMENT;
+    if(peer == c->device) return TR_OK;
+    DeviceGuard guard(c->device);
+    int can = 0;
+    TRY_CUDA(c, cudaDeviceCanAccessPeer(&can, c->device, peer));
+    if(!can) return fail(c, TR_ERR_UNSUPPORTED, "no peer access between the devices");
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+    if(e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return TR_OK; }
+    if(e != cudaSuccess) return fail_cuda(c, e, "cudaDeviceEnablePeerAccess");
+    return TR_OK;
+}
+
 int tr_pt_ipc_get_handle(tr_pt_ctx* c, unsigned char handle[64])
 {
     if(!c || !handle) return TR_ERR_INVALID_ARGUMENT;

@@ -24,7 +24,7 @@ EXPORTS = [
     "tr_pt_get_color_buffer", "tr_pt_read_color", "tr_pt_unshuffle", "tr_pt_set_peer_images", "tr_pt_get_stats",
     "tr_pt_set_instrumentation", "tr_pt_read_tri_lights", "tr_pt_trace_rays", "tr_pt_sample_test",
     "tr_pt_last_error", "tr_pt_abi_version", "tr_pt_alloc_full_image", "tr_pt_ipc_get_handle",
-    "tr_pt_ipc_open_handle", "tr_pt_ipc_close_handle", "tr_pt_set_color_buffer", "tr_pt_read_full_image",
+    "tr_pt_ipc_open_handle", "tr_pt_ipc_close_handle", "tr_pt_set_color_buffer", "tr_pt_read_full_image", "tr_pt_enable_peer_access",
 ]
 
 
@@ -67,6 +67,7 @@ def lib():
     l.tr_pt_sample_test.argtypes = [vp, vp, C.c_uint32, C.c_int, vp]
     l.tr_pt_alloc_full_image.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     l.tr_pt_read_full_image.argtypes = [vp, vp, C.c_size_t]
+    l.tr_pt_enable_peer_access.argtypes = [vp, C.c_int]
     l.tr_pt_ipc_get_handle.argtypes = [vp, C.c_char_p]
     l.tr_pt_ipc_open_handle.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
     l.tr_pt_ipc_close_handle.argtypes = [vp, vp]

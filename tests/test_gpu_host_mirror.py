@@ -1,0 +1,65 @@
+"""The C++ host mirror (tauray_b200/host/tauray_b200.hh: path_tracer_stage, rt_renderer, load_balancer with the
+reference's names) drives the same C ABI: its image must equal the Python-driven one bit for bit, for one device
+and for two stages stitched through peer images (TR_FAKE_DEVICES=2 == the reference's --fake-devices)."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from tauray_b200 import abi, testscenes
+from tauray_b200.library import PathTracer
+
+from helpers import bits_equal, full_dist, run
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DEMO = os.path.join(ROOT, "tauray_b200", "host", "host_demo")
+
+
+def dump_scene(path, scene, cams):
+    inst = scene.instance_table()
+    with open(path, "wb") as f:
+        f.write(struct.pack("<I", len(scene.meshes)))
+        for i, (v, idx) in enumerate(scene.meshes):
+            f.write(inst[i].tobytes())
+            f.write(struct.pack("<III", v.shape[0], idx.size, scene.opaque[i]))
+            f.write(v.tobytes())
+            f.write(idx.tobytes())
+        f.write(struct.pack("<I", scene.directional_lights.shape[0]))
+        f.write(scene.directional_lights.tobytes())
+        f.write(struct.pack("<I", scene.point_lights.shape[0]))
+        f.write(scene.point_lights.tobytes())
+        f.write(struct.pack("<I", cams.shape[0]))
+        f.write(cams.tobytes())
+
+
+def test_host_mirror_builds_without_a_gpu():
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tauray_b200", "host")], check=True)
+    assert os.path.exists(DEMO)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fake_devices", [1, 2])
+def test_cpp_host_mirror_matches_python(tmp_path, fake_devices):
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tauray_b200", "host")], check=True)
+    size = (160, 90)
+    scene = testscenes.cornell(alpha_card=False)
+    cams = testscenes.cornell_cameras(size[0] / size[1])
+    dump_scene(tmp_path / "scene.bin", scene, cams)
+    env = dict(os.environ, TR_FAKE_DEVICES=str(fake_devices))
+    r = subprocess.run([DEMO, str(tmp_path / "scene.bin"), str(tmp_path / "out.raw"), str(size[0]), str(size[1]), "2", "4", "1"],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr
+    got = np.fromfile(tmp_path / "out.raw", dtype=np.float32).reshape(1, size[1], size[0], 4)
+    opt = abi.default_options(max_ray_depth=4, samples_per_pixel=2, local_sampler=abi.SAMPLER_SOBOL_OWEN)
+    with PathTracer(opt) as pt:
+        want = run(pt, scene, cams, full_dist(size))
+    assert bits_equal(got, want)
+
+
+@pytest.mark.gpu
+def test_cpp_errors_surface_as_runtime_error(tmp_path):
+    r = subprocess.run([DEMO, str(tmp_path / "missing.bin"), str(tmp_path / "o.raw"), "8", "8", "1", "1", "1"],
+                       capture_output=True, text=True)
+    assert r.returncode == 1 and "cannot open" in r.stderr
