@@ -290,9 +290,9 @@ def main():
     tris_c = sv["closest_triangle_tests"] / max(sv["closest_rays"], 1)
     nodes_s = sv["shadow_node_visits"] / max(sv["shadow_rays"], 1)
     tris_s = sv["shadow_triangle_tests"] / max(sv["shadow_rays"], 1)
-    # algorithmic bytes per ray: queue id 4 + ray 32 + result 16 + nodes*64 + tris*48
-    b_closest = 4 + 32 + 16 + nodes_c * 64 + tris_c * 48
-    b_shadow = 4 + 16 + 64 + 32 + nodes_s * 64 + tris_s * 48     # id + origin + job + accumulators RMW
+    # algorithmic bytes per ray: queue id 4 + ray 32 + result 16 + nodes*80 + tris*48
+    b_closest = 4 + 32 + 16 + nodes_c * 80 + tris_c * 48
+    b_shadow = 4 + 16 + 64 + 32 + nodes_s * 80 + tris_s * 48     # id + origin + job + accumulators RMW
     b_shade = 4 + 16 + 6 * 16 * 2 + 12 + 96 + 112 + 64             # id, hit, state r/w, indices, vertices, instance, job
     per_frame_bytes = {"closest": b_closest * st["closest_rays"], "shadow": b_shadow * st["shadow_rays"],
                        "shade": b_shade * st["closest_rays"]}

@@ -11,8 +11,8 @@
 //                        (the reference's radix_sort.cc wraps a Vulkan sort it never calls)
 //   6. hierarchy         Karras 2012 binary radix tree over (code, index) keys
 //   7. refit             bottom-up AABBs with one atomic flag per inner node
-//   8. emit              breadth-first re-layout, subtrees of <= TR_BVH_MAX_LEAF triangles collapsed
-//                        into leaves, boxes inflated by eps = 2^-16 * max|coordinate|
+//   8. emit              breadth-first collapse into an 8-wide compressed BVH (80-byte nodes, <= 3
+//                        triangles per leaf slot), boxes inflated by eps = 2^-16 * max|coordinate|
 #include "tr_scene.cuh"
 #include "tr_math.cuh"
 #include "tr_build.h"
@@ -352,66 +352,187 @@ __global__ void k_refit(const float4* __restrict__ tris, const uint32_t* __restr
 }
 
 // ---------------------------------------------------------------------------------------------
-// 8. breadth-first emission with leaf collapse
+// 8. breadth-first emission of the 8-wide compressed BVH
 // ---------------------------------------------------------------------------------------------
-// frontier entry: Karras inner node id; its output slot is (level_base + position in frontier).
-__device__ __forceinline__ bool is_leaf_range(int2 range) { return range.y - range.x + 1 <= TR_BVH_MAX_LEAF; }
+// One thread per wide node. The node's subtree root is a Karras inner node; its child set starts
+// as the two binary children and the child with the largest surface area is opened (replaced by
+// its two children) until there are 8 or nothing can be opened. A binary subtree with
+// <= TR_BVH_LEAF_TRIS triangles becomes a leaf child. Children are assigned to slots per octant
+// (greedy on dot(centroid offset, slot sign)), boxes are quantised to 8 bits outwards.
+__device__ __forceinline__ int range_size(const int2* __restrict__ ranges, int c) { return c < 0 ? 1 : ranges[c].y - ranges[c].x + 1; }
 
-__global__ void k_emit_level(const int* __restrict__ frontier, int frontier_size, int out_base,
-                             const int2* __restrict__ children, const int2* __restrict__ ranges,
-                             const float* __restrict__ leaf_boxes, const float* __restrict__ inner_boxes,
-                             float eps, float4* __restrict__ nodes, int* __restrict__ next_frontier,
-                             int* __restrict__ next_count, int next_out_base)
+__device__ __forceinline__ void write_wide_node(float4* __restrict__ out, const float* nlo, const float* nhi, int n,
+                                                const float (*clo)[3], const float (*chi)[3], const int* slot_child,
+                                                const uint32_t* meta_of_child, uint32_t imask, uint32_t child_base, uint32_t tri_base)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if(i >= frontier_size) return;
-    const int node = frontier[i];
-    const int2 ch = children[node];
-    int ref[2];
-    float lo[2][3], hi[2][3];
-#pragma unroll
-    for(int c = 0; c < 2; ++c)
+    // per-axis scale 2^e with 255 * 2^e >= extent (one step of margin for the outward rounding)
+    uint32_t ebyte[3];
+    float scale[3];
+    for(int a = 0; a < 3; ++a)
     {
-        const int child = c == 0 ? ch.x : ch.y;
-        const float* box;
-        if(child < 0)
+        float ext = fmaxf(nhi[a] - nlo[a], 1e-30f);
+        int e;
+        frexpf(ext / 254.0f, &e);          // ext/254 = m * 2^e, m in [0.5, 1)  =>  2^e >= ext/254
+        e = max(-126, min(127, e));
+        ebyte[a] = (uint32_t)(e + 127);
+        scale[a] = __uint_as_float(ebyte[a] << 23);
+    }
+    uint32_t q[6][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}};   // qlo xyz, qhi xyz; two words of 4 slots
+    uint32_t meta[2] = {0, 0};
+    for(int s = 0; s < 8; ++s)
+    {
+        const int c = slot_child[s];
+        if(c < 0) continue;
+        meta[s >> 2] |= meta_of_child[c] << (8 * (s & 3));
+        for(int a = 0; a < 3; ++a)
         {
-            const int leaf = ~child;
-            ref[c] = ~((leaf << 3) | 0);
-            box = leaf_boxes + 6 * (size_t)leaf;
+            float fl = floorf((clo[c][a] - nlo[a]) / scale[a]);
+            float fh = ceilf((chi[c][a] - nlo[a]) / scale[a]);
+            int ql = max(0, min(255, (int)fl));
+            int qh = max(0, min(255, (int)fh));
+            while(ql > 0 && nlo[a] + (float)ql * scale[a] > clo[c][a]) ql--;
+            while(qh < 255 && nlo[a] + (float)qh * scale[a] < chi[c][a]) qh++;
+            q[a][s >> 2] |= (uint32_t)ql << (8 * (s & 3));
+            q[3 + a][s >> 2] |= (uint32_t)qh << (8 * (s & 3));
+        }
+    }
+    const uint32_t e4 = ebyte[0] | (ebyte[1] << 8) | (ebyte[2] << 16) | (imask << 24);
+    out[0] = make_float4(nlo[0], nlo[1], nlo[2], __uint_as_float(e4));
+    out[1] = make_float4(__uint_as_float(child_base), __uint_as_float(tri_base), __uint_as_float(meta[0]), __uint_as_float(meta[1]));
+    out[2] = make_float4(__uint_as_float(q[0][0]), __uint_as_float(q[0][1]), __uint_as_float(q[1][0]), __uint_as_float(q[1][1]));
+    out[3] = make_float4(__uint_as_float(q[2][0]), __uint_as_float(q[2][1]), __uint_as_float(q[3][0]), __uint_as_float(q[3][1]));
+    out[4] = make_float4(__uint_as_float(q[4][0]), __uint_as_float(q[4][1]), __uint_as_float(q[5][0]), __uint_as_float(q[5][1]));
+    (void)n;
+}
+
+__global__ void k_wide_level(const int* __restrict__ frontier, int frontier_size, int out_base,
+                             const int2* __restrict__ children, const int2* __restrict__ ranges,
+                             const float* __restrict__ leaf_boxes, const float* __restrict__ inner_boxes, float eps,
+                             const float4* __restrict__ tris_sorted, float4* __restrict__ nodes, float4* __restrict__ tris_out,
+                             int* __restrict__ next_frontier, int* __restrict__ next_count, int next_out_base,
+                             uint32_t* __restrict__ tri_counter)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= frontier_size) return;
+    const int root = frontier[i];
+    int cand[8];
+    int n = 2;
+    cand[0] = children[root].x;
+    cand[1] = children[root].y;
+    while(n < 8)
+    {
+        int best = -1;
+        float best_area = -1.0f;
+        for(int k = 0; k < n; ++k)
+        {
+            const int c = cand[k];
+            if(c < 0 || range_size(ranges, c) <= TR_BVH_LEAF_TRIS) continue;
+            const float* b = inner_boxes + 6 * (size_t)c;
+            const float dx = b[3] - b[0], dy = b[4] - b[1], dz = b[5] - b[2];
+            const float area = dx * dy + dy * dz + dz * dx;
+            if(area > best_area) { best_area = area; best = k; }
+        }
+        if(best < 0) break;
+        const int c = cand[best];
+        cand[best] = children[c].x;
+        cand[n++] = children[c].y;
+    }
+    float clo[8][3], chi[8][3];
+    float nlo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, nhi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for(int k = 0; k < n; ++k)
+    {
+        const int c = cand[k];
+        const float* b = c < 0 ? leaf_boxes + 6 * (size_t)(~c) : inner_boxes + 6 * (size_t)c;
+        for(int a = 0; a < 3; ++a)
+        {
+            clo[k][a] = b[a] - eps;
+            chi[k][a] = b[3 + a] + eps;
+            nlo[a] = fminf(nlo[a], clo[k][a]);
+            nhi[a] = fmaxf(nhi[a], chi[k][a]);
+        }
+    }
+    // greedy slot assignment: maximise dot(child centre - node centre, sign(slot))
+    int slot_child[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+    bool assigned[8] = {false, false, false, false, false, false, false, false};
+    for(int it = 0; it < n; ++it)
+    {
+        float best = -FLT_MAX;
+        int bc = -1, bs = -1;
+        for(int k = 0; k < n; ++k)
+        {
+            if(assigned[k]) continue;
+            const float cx = 0.5f * (clo[k][0] + chi[k][0]) - 0.5f * (nlo[0] + nhi[0]);
+            const float cy = 0.5f * (clo[k][1] + chi[k][1]) - 0.5f * (nlo[1] + nhi[1]);
+            const float cz = 0.5f * (clo[k][2] + chi[k][2]) - 0.5f * (nlo[2] + nhi[2]);
+            for(int s = 0; s < 8; ++s)
+            {
+                if(slot_child[s] >= 0) continue;
+                const float cost = ((s & 4) ? cx : -cx) + ((s & 2) ? cy : -cy) + ((s & 1) ? cz : -cz);
+                if(cost > best) { best = cost; bc = k; bs = s; }
+            }
+        }
+        assigned[bc] = true;
+        slot_child[bs] = bc;
+    }
+    // leaf children: triangles become contiguous from tri_base; inner children: contiguous nodes
+    uint32_t tri_total = 0, inner_total = 0;
+    for(int k = 0; k < n; ++k)
+    {
+        const int c = cand[k];
+        if(c < 0 || range_size(ranges, c) <= TR_BVH_LEAF_TRIS) tri_total += (uint32_t)range_size(ranges, c);
+        else inner_total++;
+    }
+    const uint32_t tri_base = tri_total ? atomicAdd(tri_counter, tri_total) : 0u;
+    const int inner_base = inner_total ? atomicAdd(next_count, (int)inner_total) : 0;
+    uint32_t meta_of_child[8];
+    uint32_t imask = 0, tri_off = 0, inner_off = 0;
+    for(int s = 0; s < 8; ++s)
+    {
+        const int k = slot_child[s];
+        if(k < 0) continue;
+        const int c = cand[k];
+        const int cnt = range_size(ranges, c);
+        if(c < 0 || cnt <= TR_BVH_LEAF_TRIS)
+        {
+            const int first = c < 0 ? ~c : ranges[c].x;
+            for(int t = 0; t < cnt; ++t)
+                for(int w = 0; w < 3; ++w)
+                    tris_out[3 * (size_t)(tri_base + tri_off + t) + w] = tris_sorted[3 * (size_t)(first + t) + w];
+            meta_of_child[k] = (((1u << cnt) - 1u) << 5) | tri_off;
+            tri_off += (uint32_t)cnt;
         }
         else
         {
-            const int2 rg = ranges[child];
-            box = inner_boxes + 6 * (size_t)child;
-            if(is_leaf_range(rg)) ref[c] = ~((rg.x << 3) | (rg.y - rg.x));
-            else
-            {
-                int slot = atomicAdd(next_count, 1);
-                next_frontier[slot] = child;
-                ref[c] = next_out_base + slot;
-            }
+            next_frontier[inner_base + (int)inner_off] = c;
+            inner_off++;
+            imask |= 1u << s;
+            meta_of_child[k] = (1u << 5) | (24u + (uint32_t)s);
         }
-#pragma unroll
-        for(int k = 0; k < 3; ++k) { lo[c][k] = box[k] - eps; hi[c][k] = box[3 + k] + eps; }
     }
-    float4* o = nodes + 4 * (size_t)(out_base + i);
-    o[0] = make_float4(lo[0][0], hi[0][0], lo[0][1], hi[0][1]);
-    o[1] = make_float4(lo[1][0], hi[1][0], lo[1][1], hi[1][1]);
-    o[2] = make_float4(lo[0][2], hi[0][2], lo[1][2], hi[1][2]);
-    o[3] = make_float4(__int_as_float(ref[0]), __int_as_float(ref[1]), 0.0f, 0.0f);
+    write_wide_node(nodes + 5 * (size_t)(out_base + i), nlo, nhi, n, clo, chi, slot_child, meta_of_child, imask,
+                    (uint32_t)(next_out_base + inner_base), tri_base);
 }
 
-__global__ void k_emit_single_leaf(int n, const float* __restrict__ leaf_boxes, const float* __restrict__ inner_boxes,
-                                   float eps, float4* __restrict__ nodes)
+// Whole scene fits one leaf child (n <= TR_BVH_LEAF_TRIS), or is empty (n == 0).
+__global__ void k_wide_single(int n, const float* __restrict__ leaf_boxes, const float* __restrict__ inner_boxes, float eps,
+                              const float4* __restrict__ tris_sorted, float4* __restrict__ nodes, float4* __restrict__ tris_out)
 {
-    // whole scene fits one leaf: root = { leaf(0, n), absent }
-    const float* box = n == 1 ? leaf_boxes : inner_boxes;
-    const float inf = __uint_as_float(0x7F800000u);
-    nodes[0] = make_float4(box[0] - eps, box[3] + eps, box[1] - eps, box[4] + eps);
-    nodes[1] = make_float4(inf, -inf, inf, -inf);
-    nodes[2] = make_float4(box[2] - eps, box[5] + eps, inf, -inf);
-    nodes[3] = make_float4(__int_as_float(~((0 << 3) | (n - 1))), __int_as_float(~0), 0.0f, 0.0f);
+    float clo[8][3], chi[8][3], nlo[3] = {0, 0, 0}, nhi[3] = {1, 1, 1};
+    int slot_child[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+    uint32_t meta_of_child[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if(n > 0)
+    {
+        const float* box = n == 1 ? leaf_boxes : inner_boxes;
+        for(int a = 0; a < 3; ++a)
+        {
+            clo[0][a] = nlo[a] = box[a] - eps;
+            chi[0][a] = nhi[a] = box[3 + a] + eps;
+        }
+        slot_child[0] = 0;
+        meta_of_child[0] = (((1u << n) - 1u) << 5) | 0u;
+        for(int t = 0; t < 3 * n; ++t) tris_out[t] = tris_sorted[t];
+    }
+    write_wide_node(nodes, nlo, nhi, n > 0 ? 1 : 0, clo, chi, slot_child, meta_of_child, 0u, 0u, 0u);
 }
 
 __global__ void k_reorder_tris(const float4* __restrict__ tris, const uint32_t* __restrict__ order, uint32_t n, float4* __restrict__ out)
@@ -491,7 +612,7 @@ cudaError_t tr_build_bvh(cudaStream_t stream, const tr_build_input& in, tr_build
     // node count upper bound: n - 1 inner nodes (+1 for the degenerate root)
     float4* nodes = nullptr;
     const size_t max_nodes = std::max<size_t>(n, 2);
-    cudaError_t e = cudaMalloc((void**)&nodes, max_nodes * 4 * sizeof(float4));
+    cudaError_t e = cudaMalloc((void**)&nodes, max_nodes * 5 * sizeof(float4));
     if(e != cudaSuccess) { cudaFree(tris_sorted); return e; }
     auto fail = [&](cudaError_t err) { cudaFree(tris_sorted); cudaFree(nodes); return err; };
 #define CUDA_OK2(x) do { cudaError_t e2_ = (x); if(e2_ != cudaSuccess) return fail(e2_); } while(0)
@@ -513,13 +634,9 @@ cudaError_t tr_build_bvh(cudaStream_t stream, const tr_build_input& in, tr_build
 
     if(n == 0)
     {
-        // empty scene: a root whose children are both absent
-        const float inf = INFINITY;
-        float4 h[4] = {make_float4(inf, -inf, inf, -inf), make_float4(inf, -inf, inf, -inf), make_float4(inf, -inf, inf, -inf),
-                       make_float4(0, 0, 0, 0)};
-        int r = ~0;
-        memcpy(&h[3].x, &r, 4); memcpy(&h[3].y, &r, 4);
-        CUDA_OK2(cudaMemcpyAsync(nodes, h, sizeof(h), cudaMemcpyHostToDevice, stream));
+        // empty scene: one node without children
+        k_wide_single<<<1, 1, 0, stream>>>(0, nullptr, nullptr, eps, tris_sorted, nodes, tris_sorted);
+        CUDA_OK2(cudaGetLastError());
         CUDA_OK2(cudaStreamSynchronize(stream));
         out->nodes = nodes; out->tris = tris_sorted; out->node_count = 1; out->depth = 1;
         return cudaSuccess;
@@ -556,29 +673,37 @@ cudaError_t tr_build_bvh(cudaStream_t stream, const tr_build_input& in, tr_build
     CUDA_OK2(cudaGetLastError());
 
     uint32_t node_count = 0, depth = 0;
-    if(n <= TR_BVH_MAX_LEAF)
+    // tris_sorted holds the Morton order; the wide emission re-packs triangles per node into tris_final
+    float4* tris_final = nullptr;
+    CUDA_OK2(cudaMalloc((void**)&tris_final, std::max<size_t>(3 * (size_t)n, 1) * sizeof(float4)));
+    auto fail2 = [&](cudaError_t err) { cudaFree(tris_final); return fail(err); };
+#define CUDA_OK3(x) do { cudaError_t e3_ = (x); if(e3_ != cudaSuccess) return fail2(e3_); } while(0)
+    if(n <= TR_BVH_LEAF_TRIS)
     {
-        k_emit_single_leaf<<<1, 1, 0, stream>>>((int)n, leaf_boxes, inner_boxes, eps, nodes);
+        k_wide_single<<<1, 1, 0, stream>>>((int)n, leaf_boxes, inner_boxes, eps, tris_sorted, nodes, tris_final);
         node_count = 1; depth = 1;
     }
     else
     {
         int *frontier_a = nullptr, *frontier_b = nullptr, *next_count = nullptr;
-        CUDA_OK2(tmp.alloc(&frontier_a, n)); CUDA_OK2(tmp.alloc(&frontier_b, n)); CUDA_OK2(tmp.alloc(&next_count, 1));
+        uint32_t* tri_counter = nullptr;
+        CUDA_OK3(tmp.alloc(&frontier_a, n)); CUDA_OK3(tmp.alloc(&frontier_b, n)); CUDA_OK3(tmp.alloc(&next_count, 1));
+        CUDA_OK3(tmp.alloc(&tri_counter, 1));
         int zero = 0;
-        CUDA_OK2(cudaMemcpyAsync(frontier_a, &zero, sizeof(int), cudaMemcpyHostToDevice, stream));
+        CUDA_OK3(cudaMemcpyAsync(frontier_a, &zero, sizeof(int), cudaMemcpyHostToDevice, stream));
+        CUDA_OK3(cudaMemsetAsync(tri_counter, 0, sizeof(uint32_t), stream));
         int frontier_size = 1;
         int out_base = 0;
         while(frontier_size > 0)
         {
-            CUDA_OK2(cudaMemsetAsync(next_count, 0, sizeof(int), stream));
+            CUDA_OK3(cudaMemsetAsync(next_count, 0, sizeof(int), stream));
             const int next_out_base = out_base + frontier_size;
-            k_emit_level<<<div_up((uint32_t)frontier_size, 256), 256, 0, stream>>>(
-                frontier_a, frontier_size, out_base, children, ranges, leaf_boxes, inner_boxes, eps, nodes,
-                frontier_b, next_count, next_out_base);
+            k_wide_level<<<div_up((uint32_t)frontier_size, 128), 128, 0, stream>>>(
+                frontier_a, frontier_size, out_base, children, ranges, leaf_boxes, inner_boxes, eps, tris_sorted, nodes,
+                tris_final, frontier_b, next_count, next_out_base, tri_counter);
             int next_size = 0;
-            CUDA_OK2(cudaMemcpyAsync(&next_size, next_count, sizeof(int), cudaMemcpyDeviceToHost, stream));
-            CUDA_OK2(cudaStreamSynchronize(stream));
+            CUDA_OK3(cudaMemcpyAsync(&next_size, next_count, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            CUDA_OK3(cudaStreamSynchronize(stream));
             out_base = next_out_base;
             frontier_size = next_size;
             std::swap(frontier_a, frontier_b);
@@ -586,6 +711,9 @@ cudaError_t tr_build_bvh(cudaStream_t stream, const tr_build_input& in, tr_build
         }
         node_count = (uint32_t)out_base;
     }
+    CUDA_OK3(cudaStreamSynchronize(stream));
+    cudaFree(tris_sorted);
+    tris_sorted = tris_final;
     CUDA_OK2(cudaStreamSynchronize(stream));
     out->nodes = nodes;
     out->tris = tris_sorted;

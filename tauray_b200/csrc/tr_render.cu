@@ -146,20 +146,18 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_generate(const RenderParams P, 
 }
 
 // ---- persistent-threads traversal kernel ---------------------------------------------------------
-// One kernel for both ray kinds (ANY = shadow rays). Structure after Aila & Laine's persistent
-// "speculative while-while" tracer, re-tuned for sm_100a:
+// One kernel for both ray kinds (ANY = shadow rays):
 //   * the grid is SM count x resident blocks; every warp fetches rays from the queue with ONE
 //     atomicAdd per refill (ballot of the idle lanes) and refills as soon as fewer than
 //     FETCH_THRESHOLD lanes are still traversing, so warps stay dense while rays of very different
 //     length retire (measured: the naive one-ray-per-thread loop ran at 5-11 of 32 lanes);
-//   * inner-node loop and leaf loop are separate, a found leaf is postponed until no lane of the
-//     warp can make inner-node progress any more;
-//   * the traversal stack lives in shared memory as a short stack ([entry][thread], conflict-free),
-//     entries beyond SHORT_STACK spill to a per-thread local array;
-//   * nodes (4 x float4) and triangles (3 x float4) are fetched with 128-bit read-only loads.
-constexpr int SHORT_STACK = 16;
+//   * 8-wide compressed BVH (tr_scene.cuh): one node visit = five 128-bit loads and eight quantised
+//     slab tests; the traversal stack holds 64-bit node groups (child base + hit bits) in a
+//     shared-memory short stack ([entry][thread]), entries beyond SHORT_STACK spill to local memory;
+//   * node phase and triangle phase are separate loops; a lane with triangle hits waits for the warp's
+//     node phase only while other lanes still look for their first triangle group.
+constexpr int SHORT_STACK = 8;
 constexpr int FETCH_THRESHOLD = 20;
-constexpr int SENTINEL = 0x76543210;
 constexpr int MAX_FACTORS = 6;
 
 template<bool ANY, bool STATS>
@@ -167,8 +165,8 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_trace(const RenderParams P, con
                                                         const uint32_t* __restrict__ queue, const uint32_t* __restrict__ count,
                                                         uint32_t* __restrict__ work_counter)
 {
-    __shared__ int s_stack[SHORT_STACK * WF_BLOCK];
-    int lstack[TR_BVH_STACK - SHORT_STACK];
+    __shared__ uint2 s_stack[SHORT_STACK * WF_BLOCK];
+    uint2 lstack[TR_BVH_STACK - SHORT_STACK];
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const uint32_t n = *count;
@@ -182,12 +180,14 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_trace(const RenderParams P, con
     unsigned long long rays = 0;
 
     // per-lane ray + traversal state
-    int node = SENTINEL, leaf = 0, sp = 0;
-    bool has_ray = false, exhausted = false;
+    uint2 G = make_uint2(0u, 0u), Gt = make_uint2(0u, 0u);
+    int sp = 0;
+    bool has_ray = false, exhausted = false, done = true;
     uint32_t id = 0, seed = 0;
     vec3 org = V3(0), dir = V3(0);
     float tmin = 0.0f, tmax = 0.0f, best_t = 0.0f;
-    float idx = 0, idy = 0, idz = 0, oodx = 0, oody = 0, oodz = 0;
+    RaySlab rs;
+    rs.idx = rs.idy = rs.idz = 0; rs.ox = rs.oy = rs.oz = 0; rs.octinv = 0;
     RayPre rp;
     rp.kx = rp.ky = rp.kz = 0; rp.Sx = rp.Sy = rp.Sz = 0; rp.org = V3(0);
     Hit best;
@@ -200,12 +200,12 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_trace(const RenderParams P, con
     float overflow = 1.0f;
 
 #define PUSH(v) do { if(sp < SHORT_STACK) s_stack[sp * WF_BLOCK + tid] = (v); else lstack[sp - SHORT_STACK] = (v); sp++; } while(0)
-#define POP(dst) do { if(sp == 0) dst = SENTINEL; else { sp--; dst = sp < SHORT_STACK ? s_stack[sp * WF_BLOCK + tid] : lstack[sp - SHORT_STACK]; } } while(0)
+#define POP(dst) do { sp--; dst = sp < SHORT_STACK ? s_stack[sp * WF_BLOCK + tid] : lstack[sp - SHORT_STACK]; } while(0)
 
     for(;;)
     {
         // ---- retire finished rays --------------------------------------------------------------
-        if(has_ray && node == SENTINEL)
+        if(has_ray && done)
         {
             bool retire = true;
             if(!ANY)
@@ -244,7 +244,10 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_trace(const RenderParams P, con
                         tmin = best.t;
                         best_t = tmax;
                         found = false;
-                        node = 0; leaf = 0; sp = 0;
+                        sp = 0;
+                        if(STATS) st.nodes++;
+                        intersect_node8(nodes, 0, rs, tmin, best_t, G, Gt);
+                        done = false;
                         retire = false;
                     }
                 }
@@ -316,13 +319,15 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_trace(const RenderParams P, con
                         tmin = ray_tmin;
                         best_t = tmax;
                         rp = precompute_ray(org, dir);
-                        idx = safe_inv(dir.x); idy = safe_inv(dir.y); idz = safe_inv(dir.z);
-                        oodx = org.x * idx; oody = org.y * idy; oodz = org.z * idz;
-                        node = 0; leaf = 0; sp = 0;
+                        rs = make_ray_slab(org, dir);
+                        sp = 0;
                         found = false;
                         nf = 0; overflow = 1.0f;
                         has_ray = true;
+                        done = false;
                         rays++;
+                        if(STATS) st.nodes++;
+                        intersect_node8(nodes, 0, rs, tmin, best_t, G, Gt);
                     }
                     else exhausted = true;
                 }
@@ -331,83 +336,58 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_trace(const RenderParams P, con
         }
 
         // ---- traverse ---------------------------------------------------------------------------
-        while(node != SENTINEL)
+        while(!done)
         {
-            // inner nodes, until every lane that can has found a leaf
-            while((unsigned)node < (unsigned)SENTINEL)
+            // node phase: descend until this lane has triangles to test (or runs out of nodes)
+            while(Gt.y == 0u)
             {
+                if((G.y & 0xFF000000u) == 0u)
+                {
+                    if(sp == 0) { done = true; break; }
+                    POP(G);
+                }
+                const uint32_t bit = 31u - (uint32_t)__clz((int)G.y);
+                G.y &= ~(1u << bit);
+                const uint32_t child = child_of_bit(G, bit, rs.octinv);
+                if(G.y & 0xFF000000u) PUSH(G);
                 if(STATS) st.nodes++;
-                const float4 n0 = __ldg(nodes + 4 * node + 0);
-                const float4 n1 = __ldg(nodes + 4 * node + 1);
-                const float4 n2 = __ldg(nodes + 4 * node + 2);
-                const float4 n3 = __ldg(nodes + 4 * node + 3);
-                float c0min, c0max, c1min, c1max;
-                TR_SLAB(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, tmin, best_t, c0min, c0max);
-                TR_SLAB(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, tmin, best_t, c1min, c1max);
-                const bool h0 = c0min <= c0max;
-                const bool h1 = c1min <= c1max;
-                int r0 = __float_as_int(n3.x), r1 = __float_as_int(n3.y);
-                if(!h0 && !h1) POP(node);
-                else
-                {
-                    node = h0 ? r0 : r1;
-                    if(h0 && h1)
-                    {
-                        if(c1min < c0min) { node = r1; r1 = r0; }
-                        PUSH(r1);
-                    }
-                }
-                // first leaf: postpone it and keep traversing
-                if(node < 0 && leaf >= 0)
-                {
-                    leaf = node;
-                    POP(node);
-                }
-                if(!__any_sync(__activemask(), leaf >= 0)) break;
+                intersect_node8(nodes, child, rs, tmin, best_t, G, Gt);
             }
 
-            // postponed leaves
-            while(leaf < 0)
+            // triangle phase
+            while(Gt.y != 0u)
             {
-                const uint32_t lf = (uint32_t)~leaf;
-                const uint32_t first = lf >> 3;
-                const uint32_t cnt = (lf & 7u) + 1u;
-                for(uint32_t i = 0; i < cnt; ++i)
+                const uint32_t bit = 31u - (uint32_t)__clz((int)Gt.y);
+                Gt.y &= ~(1u << bit);
+                if(STATS) st.tris++;
+                const float4* tp = tris + 3 * (size_t)(Gt.x + bit);
+                const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+                float t, u, v;
+                if(!intersect_triangle(rp, f3(t0), f3(t1), f3(t2), tmin, tmax, t, u, v)) continue;
+                const int inst = __float_as_int(t0.w), prim = __float_as_int(t1.w);
+                const uint32_t flags = __float_as_uint(t2.w);
+                if(ANY)
                 {
-                    if(STATS) st.tris++;
-                    const float4 t0 = __ldg(tris + 3 * (first + i) + 0);
-                    const float4 t1 = __ldg(tris + 3 * (first + i) + 1);
-                    const float4 t2 = __ldg(tris + 3 * (first + i) + 2);
-                    float t, u, v;
-                    if(!intersect_triangle(rp, f3(t0), f3(t1), f3(t2), tmin, tmax, t, u, v)) continue;
-                    const int inst = __float_as_int(t0.w), prim = __float_as_int(t1.w);
-                    const uint32_t flags = __float_as_uint(t2.w);
-                    if(ANY)
+                    if(flags & TR_TRI_FLAG_OPAQUE)
                     {
-                        if(flags & TR_TRI_FLAG_OPAQUE)
-                        {
-                            found = true;
-                            node = SENTINEL; sp = 0;   // terminate on the first opaque hit
-                            break;
-                        }
-                        const float f = 1.0f - hit_alpha(P.scene, inst, prim, u, v);
-                        if(nf < MAX_FACTORS) { ft[nf] = t; ff[nf] = f; fi[nf] = inst; fp[nf] = prim; nf++; }
-                        else overflow *= f;
-                        continue;
+                        found = true;          // terminate on the first opaque hit
+                        done = true;
+                        Gt.y = 0u;
+                        break;
                     }
-                    const bool better = !found || t < best.t ||
-                        (t == best.t && (inst < best.instance_id || (inst == best.instance_id && prim < best.primitive_id)));
-                    if(better)
-                    {
-                        found = true;
-                        best.instance_id = inst; best.primitive_id = prim; best.u = u; best.v = v; best.t = t; best.flags = flags;
-                        best_t = t;
-                    }
+                    const float f = 1.0f - hit_alpha(P.scene, inst, prim, u, v);
+                    if(nf < MAX_FACTORS) { ft[nf] = t; ff[nf] = f; fi[nf] = inst; fp[nf] = prim; nf++; }
+                    else overflow *= f;
+                    continue;
                 }
-                // another leaf may have been found while this one was postponed
-                leaf = node;
-                if(node < 0) POP(node);
-                if(ANY && found) { leaf = 0; node = SENTINEL; }
+                const bool better = !found || t < best.t ||
+                    (t == best.t && (inst < best.instance_id || (inst == best.instance_id && prim < best.primitive_id)));
+                if(better)
+                {
+                    found = true;
+                    best.instance_id = inst; best.primitive_id = prim; best.u = u; best.v = v; best.t = t; best.flags = flags;
+                    best_t = t;
+                }
             }
 
             // too few lanes left busy: go refill

@@ -7,18 +7,24 @@
 namespace trd {
 
 // ---- BVH layout in HBM -----------------------------------------------------
-// Node = 4 x float4 = 64 B, one 128-bit load each (Aila/Laine layout):
-//   n0 = (c0.lo.x, c0.hi.x, c0.lo.y, c0.hi.y)
-//   n1 = (c1.lo.x, c1.hi.x, c1.lo.y, c1.hi.y)
-//   n2 = (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z)
-//   n3 = (ref0, ref1, -, -) as int bits
-// ref >= 0: inner node index; ref < 0: leaf, ~ref = (first_triangle << 3) | (count - 1), count <= 8.
-// An absent child has an inverted box (lo = +inf, hi = -inf) and is never entered.
-// Triangle = 3 x float4 = 48 B in leaf (Morton) order:
+// 8-wide compressed node = 5 x float4 = 80 B (after Ylitie, Karras, Laine 2017), five 128-bit loads:
+//   n0 = (p.x, p.y, p.z, [ex | ey<<8 | ez<<16 | imask<<24])      p = box origin, e* = exponent byte of
+//                                                                  the per-axis scale 2^e, imask = slots
+//                                                                  holding inner children
+//   n1 = (child_base, triangle_base, meta[0..3], meta[4..7])     meta per slot: 0 = empty;
+//                                                                  inner  = 001|(24 + slot);
+//                                                                  leaf   = unary(count 1..3)<<5 | first
+//                                                                  triangle offset (< 24)
+//   n2 = (qlo_x[0..3], qlo_x[4..7], qlo_y[0..3], qlo_y[4..7])     quantised child boxes, one byte per
+//   n3 = (qlo_z[0..3], qlo_z[4..7], qhi_x[0..3], qhi_x[4..7])     slot and bound: lo = p + q * 2^e,
+//   n4 = (qhi_y[0..3], qhi_y[4..7], qhi_z[0..3], qhi_z[4..7])     rounded outwards
+// The j-th inner child (in slot order) is node child_base + j. Children sit in slots chosen per octant
+// so that visiting (slot ^ octinv) from high to low is roughly front to back.
+// Triangle = 3 x float4 = 48 B, the triangles of one node are contiguous from triangle_base:
 //   t0 = (v0.xyz, instance_id bits), t1 = (v1.xyz, primitive_id bits), t2 = (v2.xyz, flags bits)
 // flags bit0 = opaque geometry (VK_GEOMETRY_OPAQUE_BIT, src/scene_stage.cc:1410).
-#define TR_BVH_MAX_LEAF 4
-#define TR_BVH_STACK 96
+#define TR_BVH_LEAF_TRIS 3
+#define TR_BVH_STACK 48
 #define TR_TRI_FLAG_OPAQUE 1u
 
 struct DeviceBvh

@@ -97,98 +97,148 @@ TRD float safe_inv(float d)
     return 1.0f / a;
 }
 
-#define TR_SLAB(n0x, n0y, n0z, n0w, n2lo, n2hi, tmin_, tmax_, cmin, cmax)              \
-    {                                                                                      \
-        float lox = fma_(n0x, idx, -oodx), hix = fma_(n0y, idx, -oodx);                    \
-        float loy = fma_(n0z, idy, -oody), hiy = fma_(n0w, idy, -oody);                    \
-        float loz = fma_(n2lo, idz, -oodz), hiz = fma_(n2hi, idz, -oodz);                  \
-        cmin = fmaxf(fmaxf(fminf(lox, hix), fminf(loy, hiy)), fmaxf(fminf(loz, hiz), tmin_)); \
-        cmax = fminf(fminf(fmaxf(lox, hix), fmaxf(loy, hiy)), fminf(fmaxf(loz, hiz), tmax_)); \
-    }
+// Per-ray constants of the wide-node slab test.
+struct RaySlab
+{
+    float idx, idy, idz;     // 1 / dir (clamped away from 0)
+    float ox, oy, oz;        // ray origin
+    uint32_t octinv;         // bit k set when the direction component is >= 0 (x = 4, y = 2, z = 1)
+};
 
-// Closest hit in (tmin, tmax). `ANY`: return at the first OPAQUE hit (shadow rays); non-opaque
-// hits are reported through `on_transparent` and traversal continues.
+TRD RaySlab make_ray_slab(vec3 org, vec3 dir)
+{
+    RaySlab r;
+    r.idx = safe_inv(dir.x); r.idy = safe_inv(dir.y); r.idz = safe_inv(dir.z);
+    r.ox = org.x; r.oy = org.y; r.oz = org.z;
+    r.octinv = (dir.x >= 0.0f ? 4u : 0u) | (dir.y >= 0.0f ? 2u : 0u) | (dir.z >= 0.0f ? 1u : 0u);
+    return r;
+}
+
+TRD float byte_to_float(uint32_t w, int k) { return (float)((w >> (8 * k)) & 0xFFu); }
+
+// One 80-byte compressed wide node (tr_scene.cuh): five 128-bit loads, eight quantised child boxes.
+// Returns the node group G = (child_base, inner-hit bits [31:24] | imask [7:0]) and the triangle
+// group Gt = (triangle_base, triangle-hit bits [23:0]). Inner-child bits are placed at
+// 24 + (slot ^ octinv): the build assigns near-to-far slots per octant, so taking the highest set
+// bit first visits children roughly front to back without sorting.
+TRD void intersect_node8(const float4* __restrict__ nodes, uint32_t node_index, const RaySlab& r,
+                         float tmin, float tmax, uint2& G, uint2& Gt)
+{
+    const float4* n = nodes + 5 * (size_t)node_index;
+    const float4 n0 = __ldg(n + 0);
+    const float4 n1 = __ldg(n + 1);
+    const float4 n2 = __ldg(n + 2);
+    const float4 n3 = __ldg(n + 3);
+    const float4 n4 = __ldg(n + 4);
+    const uint32_t e = __float_as_uint(n0.w);
+    const float sx = __uint_as_float((e & 0xFFu) << 23);
+    const float sy = __uint_as_float(((e >> 8) & 0xFFu) << 23);
+    const float sz = __uint_as_float(((e >> 16) & 0xFFu) << 23);
+    const uint32_t imask = e >> 24;
+    const float ax = sx * r.idx, ay = sy * r.idy, az = sz * r.idz;
+    const float bx = (n0.x - r.ox) * r.idx, by = (n0.y - r.oy) * r.idy, bz = (n0.z - r.oz) * r.idz;
+    uint32_t hitmask = 0;
+#pragma unroll
+    for(int half = 0; half < 2; ++half)
+    {
+        const uint32_t meta4 = __float_as_uint(half ? n1.w : n1.z);
+        const uint32_t qlox = __float_as_uint(half ? n2.y : n2.x), qloy = __float_as_uint(half ? n2.w : n2.z);
+        const uint32_t qloz = __float_as_uint(half ? n3.y : n3.x), qhix = __float_as_uint(half ? n3.w : n3.z);
+        const uint32_t qhiy = __float_as_uint(half ? n4.y : n4.x), qhiz = __float_as_uint(half ? n4.w : n4.z);
+        const uint32_t nx = r.idx < 0.0f ? qhix : qlox, fx = r.idx < 0.0f ? qlox : qhix;
+        const uint32_t ny = r.idy < 0.0f ? qhiy : qloy, fy = r.idy < 0.0f ? qloy : qhiy;
+        const uint32_t nz = r.idz < 0.0f ? qhiz : qloz, fz = r.idz < 0.0f ? qloz : qhiz;
+#pragma unroll
+        for(int k = 0; k < 4; ++k)
+        {
+            const uint32_t meta = (meta4 >> (8 * k)) & 0xFFu;
+            const float tnx = fma_(byte_to_float(nx, k), ax, bx), tfx = fma_(byte_to_float(fx, k), ax, bx);
+            const float tny = fma_(byte_to_float(ny, k), ay, by), tfy = fma_(byte_to_float(fy, k), ay, by);
+            const float tnz = fma_(byte_to_float(nz, k), az, bz), tfz = fma_(byte_to_float(fz, k), az, bz);
+            const float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
+            const float cmax = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
+            if(meta != 0u && cmin <= cmax)
+            {
+                const uint32_t low = meta & 31u;
+                const uint32_t bit = low >= 24u ? (low ^ r.octinv) : low;
+                hitmask |= (meta >> 5) << bit;
+            }
+        }
+    }
+    G.x = __float_as_uint(n1.x);
+    G.y = (hitmask & 0xFF000000u) | imask;
+    Gt.x = __float_as_uint(n1.y);
+    Gt.y = hitmask & 0x00FFFFFFu;
+}
+
+// Index of the inner child behind hit bit `bit` (24..31) of group G.
+TRD uint32_t child_of_bit(const uint2& G, uint32_t bit, uint32_t octinv)
+{
+    const uint32_t slot = (bit - 24u) ^ octinv;
+    return G.x + __popc(G.y & 0xFFu & ((1u << slot) - 1u));
+}
+
+// Straightforward per-thread traversal (megakernel, feature tracer, test hook): closest hit in
+// (tmin, tmax). `ANY`: return at the first OPAQUE hit (shadow rays); non-opaque hits are reported
+// through `on_transparent` and traversal continues. The persistent wavefront kernel (tr_render.cu)
+// runs the same node/triangle code with dynamic ray fetch.
 template<bool ANY, bool STATS, typename F>
 TRD bool traverse(const DeviceBvh& bvh, vec3 org, vec3 dir, float tmin, float tmax, Hit& best,
                   TraceStats& st, F&& on_transparent)
 {
     const RayPre rp = precompute_ray(org, dir);
-    const float idx = safe_inv(dir.x), idy = safe_inv(dir.y), idz = safe_inv(dir.z);
-    const float oodx = org.x * idx, oody = org.y * idy, oodz = org.z * idz;
+    const RaySlab rs = make_ray_slab(org, dir);
     float best_t = tmax;
     bool found = false;
-    int stack[TR_BVH_STACK];
+    uint2 stack[TR_BVH_STACK];
     int sp = 0;
-    int node = 0;
-    const float4* __restrict__ nodes = bvh.nodes;
     const float4* __restrict__ tris = bvh.tris;
-
+    uint2 G, Gt;
+    if(STATS) st.nodes++;
+    intersect_node8(bvh.nodes, 0, rs, tmin, best_t, G, Gt);
     for(;;)
     {
-        if(node >= 0)
+        while(Gt.y != 0u)
         {
-            if(STATS) st.nodes++;
-            const float4 n0 = __ldg(nodes + 4 * node + 0);
-            const float4 n1 = __ldg(nodes + 4 * node + 1);
-            const float4 n2 = __ldg(nodes + 4 * node + 2);
-            const float4 n3 = __ldg(nodes + 4 * node + 3);
-            float c0min, c0max, c1min, c1max;
-            TR_SLAB(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, tmin, best_t, c0min, c0max);
-            TR_SLAB(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, tmin, best_t, c1min, c1max);
-            const bool h0 = c0min <= c0max;
-            const bool h1 = c1min <= c1max;
-            int r0 = __float_as_int(n3.x), r1 = __float_as_int(n3.y);
-            if(h0 && h1)
+            const uint32_t bit = 31u - (uint32_t)__clz((int)Gt.y);
+            Gt.y &= ~(1u << bit);
+            if(STATS) st.tris++;
+            const float4* tp = tris + 3 * (size_t)(Gt.x + bit);
+            const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+            float t, u, v;
+            if(!intersect_triangle(rp, f3(t0), f3(t1), f3(t2), tmin, tmax, t, u, v)) continue;
+            const int inst = __float_as_int(t0.w), prim = __float_as_int(t1.w);
+            const uint32_t flags = __float_as_uint(t2.w);
+            if(ANY)
             {
-                if(c1min < c0min) { int t = r0; r0 = r1; r1 = t; }
-                stack[sp++] = r1;
-                node = r0;
-            }
-            else if(h0) node = r0;
-            else if(h1) node = r1;
-            else
-            {
-                if(sp == 0) break;
-                node = stack[--sp];
-            }
-        }
-        else
-        {
-            const uint32_t leaf = (uint32_t)~node;
-            const uint32_t first = leaf >> 3;
-            const uint32_t count = (leaf & 7u) + 1u;
-            for(uint32_t i = 0; i < count; ++i)
-            {
-                if(STATS) st.tris++;
-                const float4 t0 = __ldg(tris + 3 * (first + i) + 0);
-                const float4 t1 = __ldg(tris + 3 * (first + i) + 1);
-                const float4 t2 = __ldg(tris + 3 * (first + i) + 2);
-                float t, u, v;
-                if(!intersect_triangle(rp, f3(t0), f3(t1), f3(t2), tmin, tmax, t, u, v)) continue;
-                const int inst = __float_as_int(t0.w), prim = __float_as_int(t1.w);
-                const uint32_t flags = __float_as_uint(t2.w);
-                if(ANY)
+                if(flags & TR_TRI_FLAG_OPAQUE)
                 {
-                    if(flags & TR_TRI_FLAG_OPAQUE)
-                    {
-                        best.instance_id = inst; best.primitive_id = prim; best.u = u; best.v = v; best.t = t; best.flags = flags;
-                        return true;
-                    }
-                    on_transparent(inst, prim, u, v, t);
-                    continue;
-                }
-                const bool better = !found || t < best.t ||
-                    (t == best.t && (inst < best.instance_id || (inst == best.instance_id && prim < best.primitive_id)));
-                if(better)
-                {
-                    found = true;
                     best.instance_id = inst; best.primitive_id = prim; best.u = u; best.v = v; best.t = t; best.flags = flags;
-                    best_t = t;
+                    return true;
                 }
+                on_transparent(inst, prim, u, v, t);
+                continue;
             }
-            if(sp == 0) break;
-            node = stack[--sp];
+            const bool better = !found || t < best.t ||
+                (t == best.t && (inst < best.instance_id || (inst == best.instance_id && prim < best.primitive_id)));
+            if(better)
+            {
+                found = true;
+                best.instance_id = inst; best.primitive_id = prim; best.u = u; best.v = v; best.t = t; best.flags = flags;
+                best_t = t;
+            }
         }
+        if((G.y & 0xFF000000u) == 0u)
+        {
+            if(sp == 0) break;
+            G = stack[--sp];
+        }
+        const uint32_t bit = 31u - (uint32_t)__clz((int)G.y);
+        G.y &= ~(1u << bit);
+        const uint32_t child = child_of_bit(G, bit, rs.octinv);
+        if(G.y & 0xFF000000u) stack[sp++] = G;
+        if(STATS) st.nodes++;
+        intersect_node8(bvh.nodes, child, rs, tmin, best_t, G, Gt);
     }
     return found;
 }
