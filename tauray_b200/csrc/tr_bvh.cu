@@ -365,19 +365,23 @@ __device__ __forceinline__ void write_wide_node(float4* __restrict__ out, const 
                                                 const float (*clo)[3], const float (*chi)[3], const int* slot_child,
                                                 const uint32_t* meta_of_child, uint32_t imask, uint32_t child_base, uint32_t tri_base)
 {
-    // per-axis scale 2^e with 255 * 2^e >= extent (one step of margin for the outward rounding)
+    // per-axis quantum 2^e with 127 * 2^e >= extent (one step of margin for the outward rounding);
+    // 7-bit quanta, stored as 0x80 | q so the traversal can build 1 + q/128 with one PRMT. The
+    // exponent byte holds e + 7 (+127 bias): the traversal's scale is 128 * 2^e.
     uint32_t ebyte[3];
     float scale[3];
     for(int a = 0; a < 3; ++a)
     {
         float ext = fmaxf(nhi[a] - nlo[a], 1e-30f);
         int e;
-        frexpf(ext / 254.0f, &e);          // ext/254 = m * 2^e, m in [0.5, 1)  =>  2^e >= ext/254
-        e = max(-126, min(127, e));
-        ebyte[a] = (uint32_t)(e + 127);
-        scale[a] = __uint_as_float(ebyte[a] << 23);
+        frexpf(ext / 126.0f, &e);          // ext/126 = m * 2^e, m in [0.5, 1)  =>  2^e >= ext/126
+        e = max(-126, min(120, e));
+        ebyte[a] = (uint32_t)(e + 7 + 127);
+        scale[a] = __uint_as_float((uint32_t)(e + 127) << 23);
     }
-    uint32_t q[6][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}};   // qlo xyz, qhi xyz; two words of 4 slots
+    // empty slots: inverted box (lo = 127, hi = 0) -> never hit
+    uint32_t q[6][2] = {{0xFFFFFFFFu, 0xFFFFFFFFu}, {0xFFFFFFFFu, 0xFFFFFFFFu}, {0xFFFFFFFFu, 0xFFFFFFFFu},
+                        {0x80808080u, 0x80808080u}, {0x80808080u, 0x80808080u}, {0x80808080u, 0x80808080u}};
     uint32_t meta[2] = {0, 0};
     for(int s = 0; s < 8; ++s)
     {
@@ -388,12 +392,13 @@ __device__ __forceinline__ void write_wide_node(float4* __restrict__ out, const 
         {
             float fl = floorf((clo[c][a] - nlo[a]) / scale[a]);
             float fh = ceilf((chi[c][a] - nlo[a]) / scale[a]);
-            int ql = max(0, min(255, (int)fl));
-            int qh = max(0, min(255, (int)fh));
+            int ql = max(0, min(127, (int)fl));
+            int qh = max(0, min(127, (int)fh));
             while(ql > 0 && nlo[a] + (float)ql * scale[a] > clo[c][a]) ql--;
-            while(qh < 255 && nlo[a] + (float)qh * scale[a] < chi[c][a]) qh++;
-            q[a][s >> 2] |= (uint32_t)ql << (8 * (s & 3));
-            q[3 + a][s >> 2] |= (uint32_t)qh << (8 * (s & 3));
+            while(qh < 127 && nlo[a] + (float)qh * scale[a] < chi[c][a]) qh++;
+            const int sh = 8 * (s & 3);
+            q[a][s >> 2] = (q[a][s >> 2] & ~(0xFFu << sh)) | ((0x80u | (uint32_t)ql) << sh);
+            q[3 + a][s >> 2] = (q[3 + a][s >> 2] & ~(0xFFu << sh)) | ((0x80u | (uint32_t)qh) << sh);
         }
     }
     const uint32_t e4 = ebyte[0] | (ebyte[1] << 8) | (ebyte[2] << 16) | (imask << 24);

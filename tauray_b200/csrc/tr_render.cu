@@ -245,8 +245,8 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_trace(const RenderParams P, con
                         best_t = tmax;
                         found = false;
                         sp = 0;
-                        if(STATS) st.nodes++;
-                        intersect_node8(nodes, 0, rs, tmin, best_t, G, Gt);
+                        G = make_uint2(0u, (0x01000000u << rs.octinv) | 1u);   // the root as a one-child group
+                        Gt = make_uint2(0u, 0u);
                         done = false;
                         retire = false;
                     }
@@ -326,8 +326,8 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_trace(const RenderParams P, con
                         has_ray = true;
                         done = false;
                         rays++;
-                        if(STATS) st.nodes++;
-                        intersect_node8(nodes, 0, rs, tmin, best_t, G, Gt);
+                        G = make_uint2(0u, (0x01000000u << rs.octinv) | 1u);   // the root as a one-child group
+                        Gt = make_uint2(0u, 0u);
                     }
                     else exhausted = true;
                 }
@@ -336,16 +336,13 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_trace(const RenderParams P, con
         }
 
         // ---- traverse ---------------------------------------------------------------------------
+        // One node step per iteration for the lanes that have an open node group; lanes that popped a
+        // (postponed) triangle group take it over. Triangle tests run right after, unless fewer than
+        // 1/5 of the lanes of this iteration have any -- then the group is pushed and traversal goes on.
         while(!done)
         {
-            // node phase: descend until this lane has triangles to test (or runs out of nodes)
-            while(Gt.y == 0u)
+            if(G.y & 0xFF000000u)
             {
-                if((G.y & 0xFF000000u) == 0u)
-                {
-                    if(sp == 0) { done = true; break; }
-                    POP(G);
-                }
                 const uint32_t bit = 31u - (uint32_t)__clz((int)G.y);
                 G.y &= ~(1u << bit);
                 const uint32_t child = child_of_bit(G, bit, rs.octinv);
@@ -353,10 +350,21 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_trace(const RenderParams P, con
                 if(STATS) st.nodes++;
                 intersect_node8(nodes, child, rs, tmin, best_t, G, Gt);
             }
+            else
+            {
+                Gt = G;
+                G = make_uint2(0u, 0u);
+            }
 
-            // triangle phase
+            const int active = __popc(__activemask());
             while(Gt.y != 0u)
             {
+                if(__popc(__activemask()) * 5 < active)
+                {
+                    PUSH(Gt);
+                    Gt.y = 0u;
+                    break;
+                }
                 const uint32_t bit = 31u - (uint32_t)__clz((int)Gt.y);
                 Gt.y &= ~(1u << bit);
                 if(STATS) st.tris++;
@@ -388,6 +396,13 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_trace(const RenderParams P, con
                     best.instance_id = inst; best.primitive_id = prim; best.u = u; best.v = v; best.t = t; best.flags = flags;
                     best_t = t;
                 }
+            }
+            if(done) break;
+
+            if((G.y & 0xFF000000u) == 0u)
+            {
+                if(sp == 0) { done = true; break; }
+                POP(G);
             }
 
             // too few lanes left busy: go refill

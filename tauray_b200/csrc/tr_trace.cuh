@@ -114,13 +114,20 @@ TRD RaySlab make_ray_slab(vec3 org, vec3 dir)
     return r;
 }
 
-TRD float byte_to_float(uint32_t w, int k) { return (float)((w >> (8 * k)) & 0xFFu); }
+// Quantised bounds are stored as 0x80 | q with q in [0, 127]: one PRMT drops the byte into bits
+// 16..23 of 0x3F000000, giving the float 1 + q/128 exactly -- no integer->float conversion (I2F runs
+// at a fraction of the FMA rate). The slab then is t = (1 + q/128) * (128 a) + (b - 128 a).
+template<int K> TRD float qbyte_to_float(uint32_t w)
+{
+    return __uint_as_float(__byte_perm(w, 0x3F000000u, 0x7044u | (K << 8)));
+}
 
 // One 80-byte compressed wide node (tr_scene.cuh): five 128-bit loads, eight quantised child boxes.
 // Returns the node group G = (child_base, inner-hit bits [31:24] | imask [7:0]) and the triangle
 // group Gt = (triangle_base, triangle-hit bits [23:0]). Inner-child bits are placed at
 // 24 + (slot ^ octinv): the build assigns near-to-far slots per octant, so taking the highest set
-// bit first visits children roughly front to back without sorting.
+// bit first visits children roughly front to back without sorting. Empty slots carry an inverted
+// box and can never be hit.
 TRD void intersect_node8(const float4* __restrict__ nodes, uint32_t node_index, const RaySlab& r,
                          float tmin, float tmax, uint2& G, uint2& Gt)
 {
@@ -131,39 +138,41 @@ TRD void intersect_node8(const float4* __restrict__ nodes, uint32_t node_index, 
     const float4 n3 = __ldg(n + 3);
     const float4 n4 = __ldg(n + 4);
     const uint32_t e = __float_as_uint(n0.w);
+    // 128 * 2^e: the exponent byte already includes the factor (tr_bvh.cu writes e + 7)
     const float sx = __uint_as_float((e & 0xFFu) << 23);
     const float sy = __uint_as_float(((e >> 8) & 0xFFu) << 23);
     const float sz = __uint_as_float(((e >> 16) & 0xFFu) << 23);
     const uint32_t imask = e >> 24;
     const float ax = sx * r.idx, ay = sy * r.idy, az = sz * r.idz;
-    const float bx = (n0.x - r.ox) * r.idx, by = (n0.y - r.oy) * r.idy, bz = (n0.z - r.oz) * r.idz;
+    const float bx = (n0.x - r.ox) * r.idx - ax, by = (n0.y - r.oy) * r.idy - ay, bz = (n0.z - r.oz) * r.idz - az;
+    const uint32_t octinv4 = r.octinv * 0x01010101u;
     uint32_t hitmask = 0;
 #pragma unroll
     for(int half = 0; half < 2; ++half)
     {
         const uint32_t meta4 = __float_as_uint(half ? n1.w : n1.z);
+        // byte-parallel: inner children (low 5 bits >= 24) get their slot XORed with octinv
+        const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+        const uint32_t bit_index4 = (meta4 ^ (octinv4 & ((is_inner4 >> 4) * 7u))) & 0x1F1F1F1Fu;
+        const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
         const uint32_t qlox = __float_as_uint(half ? n2.y : n2.x), qloy = __float_as_uint(half ? n2.w : n2.z);
         const uint32_t qloz = __float_as_uint(half ? n3.y : n3.x), qhix = __float_as_uint(half ? n3.w : n3.z);
         const uint32_t qhiy = __float_as_uint(half ? n4.y : n4.x), qhiz = __float_as_uint(half ? n4.w : n4.z);
         const uint32_t nx = r.idx < 0.0f ? qhix : qlox, fx = r.idx < 0.0f ? qlox : qhix;
         const uint32_t ny = r.idy < 0.0f ? qhiy : qloy, fy = r.idy < 0.0f ? qloy : qhiy;
         const uint32_t nz = r.idz < 0.0f ? qhiz : qloz, fz = r.idz < 0.0f ? qloz : qhiz;
-#pragma unroll
-        for(int k = 0; k < 4; ++k)
-        {
-            const uint32_t meta = (meta4 >> (8 * k)) & 0xFFu;
-            const float tnx = fma_(byte_to_float(nx, k), ax, bx), tfx = fma_(byte_to_float(fx, k), ax, bx);
-            const float tny = fma_(byte_to_float(ny, k), ay, by), tfy = fma_(byte_to_float(fy, k), ay, by);
-            const float tnz = fma_(byte_to_float(nz, k), az, bz), tfz = fma_(byte_to_float(fz, k), az, bz);
-            const float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
-            const float cmax = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
-            if(meta != 0u && cmin <= cmax)
-            {
-                const uint32_t low = meta & 31u;
-                const uint32_t bit = low >= 24u ? (low ^ r.octinv) : low;
-                hitmask |= (meta >> 5) << bit;
-            }
+#define TR_CHILD(K)                                                                                        \
+        {                                                                                                  \
+            const float tnx = fma_(qbyte_to_float<K>(nx), ax, bx), tfx = fma_(qbyte_to_float<K>(fx), ax, bx); \
+            const float tny = fma_(qbyte_to_float<K>(ny), ay, by), tfy = fma_(qbyte_to_float<K>(fy), ay, by); \
+            const float tnz = fma_(qbyte_to_float<K>(nz), az, bz), tfz = fma_(qbyte_to_float<K>(fz), az, bz); \
+            const float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));                                   \
+            const float cmax = fminf(fminf(tfx, tfy), fminf(tfz, tmax));                                   \
+            if(cmin <= cmax)                                                                               \
+                hitmask |= ((child_bits4 >> (8 * K)) & 0xFFu) << ((bit_index4 >> (8 * K)) & 0xFFu);        \
         }
+        TR_CHILD(0) TR_CHILD(1) TR_CHILD(2) TR_CHILD(3)
+#undef TR_CHILD
     }
     G.x = __float_as_uint(n1.x);
     G.y = (hitmask & 0xFF000000u) | imask;
