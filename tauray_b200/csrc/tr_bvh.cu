@@ -22,6 +22,7 @@
 #include <cstdio>
 #include <cstring>
 #include <vector>
+#include <cstdlib>
 
 namespace trd {
 
@@ -410,7 +411,7 @@ __device__ __forceinline__ void write_wide_node(float4* __restrict__ out, const 
     (void)n;
 }
 
-__global__ void k_wide_level(const int* __restrict__ frontier, int frontier_size, int out_base,
+__global__ void k_wide_level(int leaf_tris, const int* __restrict__ frontier, int frontier_size, int out_base,
                              const int2* __restrict__ children, const int2* __restrict__ ranges,
                              const float* __restrict__ leaf_boxes, const float* __restrict__ inner_boxes, float eps,
                              const float4* __restrict__ tris_sorted, float4* __restrict__ nodes, float4* __restrict__ tris_out,
@@ -431,7 +432,7 @@ __global__ void k_wide_level(const int* __restrict__ frontier, int frontier_size
         for(int k = 0; k < n; ++k)
         {
             const int c = cand[k];
-            if(c < 0 || range_size(ranges, c) <= TR_BVH_LEAF_TRIS) continue;
+            if(c < 0 || range_size(ranges, c) <= leaf_tris) continue;
             const float* b = inner_boxes + 6 * (size_t)c;
             const float dx = b[3] - b[0], dy = b[4] - b[1], dz = b[5] - b[2];
             const float area = dx * dy + dy * dz + dz * dx;
@@ -484,7 +485,7 @@ __global__ void k_wide_level(const int* __restrict__ frontier, int frontier_size
     for(int k = 0; k < n; ++k)
     {
         const int c = cand[k];
-        if(c < 0 || range_size(ranges, c) <= TR_BVH_LEAF_TRIS) tri_total += (uint32_t)range_size(ranges, c);
+        if(c < 0 || range_size(ranges, c) <= leaf_tris) tri_total += (uint32_t)range_size(ranges, c);
         else inner_total++;
     }
     const uint32_t tri_base = tri_total ? atomicAdd(tri_counter, tri_total) : 0u;
@@ -497,7 +498,7 @@ __global__ void k_wide_level(const int* __restrict__ frontier, int frontier_size
         if(k < 0) continue;
         const int c = cand[k];
         const int cnt = range_size(ranges, c);
-        if(c < 0 || cnt <= TR_BVH_LEAF_TRIS)
+        if(c < 0 || cnt <= leaf_tris)
         {
             const int first = c < 0 ? ~c : ranges[c].x;
             for(int t = 0; t < cnt; ++t)
@@ -677,13 +678,15 @@ cudaError_t tr_build_bvh(cudaStream_t stream, const tr_build_input& in, tr_build
     k_refit<<<div_up(n, 256), 256, 0, stream>>>(tris_unsorted, vals_a, (int)n, children, inner_parent, leaf_parent, leaf_boxes, inner_boxes, flags);
     CUDA_OK2(cudaGetLastError());
 
+    static const int leaf_tris_env = getenv("TR_TUNE_LEAF") ? atoi(getenv("TR_TUNE_LEAF")) : TR_BVH_LEAF_TRIS;
+    const int leaf_tris = std::max(1, std::min(3, leaf_tris_env));
     uint32_t node_count = 0, depth = 0;
     // tris_sorted holds the Morton order; the wide emission re-packs triangles per node into tris_final
     float4* tris_final = nullptr;
     CUDA_OK2(cudaMalloc((void**)&tris_final, std::max<size_t>(3 * (size_t)n, 1) * sizeof(float4)));
     auto fail2 = [&](cudaError_t err) { cudaFree(tris_final); return fail(err); };
 #define CUDA_OK3(x) do { cudaError_t e3_ = (x); if(e3_ != cudaSuccess) return fail2(e3_); } while(0)
-    if(n <= TR_BVH_LEAF_TRIS)
+    if(n <= (uint32_t)leaf_tris)
     {
         k_wide_single<<<1, 1, 0, stream>>>((int)n, leaf_boxes, inner_boxes, eps, tris_sorted, nodes, tris_final);
         node_count = 1; depth = 1;
@@ -704,7 +707,7 @@ cudaError_t tr_build_bvh(cudaStream_t stream, const tr_build_input& in, tr_build
             CUDA_OK3(cudaMemsetAsync(next_count, 0, sizeof(int), stream));
             const int next_out_base = out_base + frontier_size;
             k_wide_level<<<div_up((uint32_t)frontier_size, 128), 128, 0, stream>>>(
-                frontier_a, frontier_size, out_base, children, ranges, leaf_boxes, inner_boxes, eps, tris_sorted, nodes,
+                leaf_tris, frontier_a, frontier_size, out_base, children, ranges, leaf_boxes, inner_boxes, eps, tris_sorted, nodes,
                 tris_final, frontier_b, next_count, next_out_base, tri_counter);
             int next_size = 0;
             CUDA_OK3(cudaMemcpyAsync(&next_size, next_count, sizeof(int), cudaMemcpyDeviceToHost, stream));

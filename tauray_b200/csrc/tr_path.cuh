@@ -28,6 +28,9 @@ struct RenderParams
     float4* peers[8];
     int peer_count;
     int last_pass;
+    // traversal tuning (defaults in tr_render.cu; TR_TUNE_* environment overrides for experiments)
+    int tune_fetch_threshold;
+    int tune_postpone_div;
 };
 
 // Path state carried from bounce to bounce (evaluate_ray's locals).

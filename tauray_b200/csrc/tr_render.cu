@@ -15,6 +15,7 @@
 // registers); it exists as the A/B baseline for the wavefront numbers.
 #include "tr_path.cuh"
 #include "tr_render.h"
+#include <cstdlib>
 
 namespace trd {
 
@@ -359,7 +360,7 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_trace(const RenderParams P, con
             const int active = __popc(__activemask());
             while(Gt.y != 0u)
             {
-                if(__popc(__activemask()) * 5 < active)
+                if(__popc(__activemask()) * P.tune_postpone_div < active)
                 {
                     PUSH(Gt);
                     Gt.y = 0u;
@@ -406,7 +407,7 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_trace(const RenderParams P, con
             }
 
             // too few lanes left busy: go refill
-            if(__popc(__activemask()) < FETCH_THRESHOLD) break;
+            if(__popc(__activemask()) < P.tune_fetch_threshold) break;
         }
     }
 #undef PUSH
@@ -644,16 +645,28 @@ static int grid_for(int sm_count, int blocks_per_sm, uint32_t work)
     return (int)(g < 1 ? 1 : g);
 }
 
-cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const RenderParams& P, const tr_wavefront& wf, int sm_count, uint64_t* launches,
+static int env_int(const char* name, int dflt)
+{
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const RenderParams& P_in, const tr_wavefront& wf, int sm_count, uint64_t* launches,
                                      tr_launch_timer* timer)
 {
+    RenderParams P = P_in;
+    static const int k_fetch = env_int("TR_TUNE_FETCH", FETCH_THRESHOLD);
+    static const int k_postpone = env_int("TR_TUNE_POSTPONE", 5);
+    static const int k_blocks = env_int("TR_TUNE_BLOCKS", TRACE_BLOCKS_PER_SM);
+    P.tune_fetch_threshold = k_fetch;
+    P.tune_postpone_div = k_postpone;
 #define MARK(cls) do { if(timer) timer->mark(stream, cls); } while(0)
     const uint32_t total = P.frame.ray_count_x * P.frame.ray_count_y * P.frame.views;
     if(total == 0) return cudaSuccess;
     const uint32_t D = (uint32_t)P.opt.max_ray_depth;
     const uint32_t spp = (uint32_t)P.opt.samples_per_pass;
     const int grid_full = grid_for(sm_count, 16, total);
-    const int grid_persist = sm_count * TRACE_BLOCKS_PER_SM;
+    const int grid_persist = sm_count * k_blocks;
     for(uint32_t i = 0; i < spp; ++i)
     {
         cudaError_t e = cudaMemsetAsync(wf.counts, 0, sizeof(uint32_t) * (4 * D + 2), stream);

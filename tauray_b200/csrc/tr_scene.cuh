@@ -23,7 +23,7 @@ namespace trd {
 // Triangle = 3 x float4 = 48 B, the triangles of one node are contiguous from triangle_base:
 //   t0 = (v0.xyz, instance_id bits), t1 = (v1.xyz, primitive_id bits), t2 = (v2.xyz, flags bits)
 // flags bit0 = opaque geometry (VK_GEOMETRY_OPAQUE_BIT, src/scene_stage.cc:1410).
-#define TR_BVH_LEAF_TRIS 3
+#define TR_BVH_LEAF_TRIS 2
 #define TR_BVH_STACK 48
 #define TR_TRI_FLAG_OPAQUE 1u
 
