@@ -1,0 +1,62 @@
+"""world_size-N NCCL worker for tests/test_gpu_multi.py: real PathTracers, one per GPU, both stitch modes; every rank
+checks that its stitched full image equals a single-device render bit for bit."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as td  # noqa: E402
+
+from tauray_b200 import abi, distribution, synthetic  # noqa: E402
+from tauray_b200.library import PathTracer  # noqa: E402
+from tauray_b200.renderer import RtRenderer  # noqa: E402
+
+
+def main():
+    rank = int(os.environ["RANK"])
+    world = int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    td.init_process_group("nccl", device_id=torch.device("cuda", local))
+    size = (640, 360)
+    opt = abi.default_options(max_ray_depth=4, samples_per_pixel=2, local_sampler=abi.SAMPLER_SOBOL_OWEN)
+    scene = synthetic.atrium(60000)
+    cams = synthetic.atrium_cameras(16 / 9)
+    cams = np.concatenate([cams, cams])
+    with PathTracer(opt, device=local) as single:
+        single.set_scene(scene)
+        single.set_cameras(cams)
+        single.set_distribution(distribution.make_distribution(
+            size, abi.DISTRIBUTION_SHUFFLED_STRIPS, 0, distribution.calculate_shuffled_strips_pixels_per_device(size, 1.0), True))
+        single.render()
+        single.sync()
+        want = single.read_color()
+    stream = torch.cuda.Stream(device=local)
+    torch.cuda.set_stream(stream)
+    ok = True
+    for stitch, workloads in (("peer", None), ("nccl", None), ("peer", [0.7] + [0.3 / (world - 1)] * (world - 1))):
+        ren = RtRenderer(opt, size, rank=rank, world=world, device=local, stitch=stitch)
+        ren.set_scene(scene, cams)
+        if workloads:
+            ren.set_device_workloads(workloads)
+        for _ in range(2):                      # second frame: accumulation reset + re-stitch over the same buffers
+            ren.reset_accumulation()
+            ren.render(stream.cuda_stream)
+        torch.cuda.synchronize(local)
+        td.barrier()
+        got = ren.image()
+        same = got.tobytes() == want.tobytes()
+        print("rank %d stitch %s workloads %s: %s" % (rank, stitch, workloads, "identical" if same else "DIFFERENT"), flush=True)
+        ok = ok and same
+        td.barrier()
+        ren.close()
+    td.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
