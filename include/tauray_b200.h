@@ -260,6 +260,9 @@ typedef struct tr_pt_stats {
     uint64_t shadow_node_visits;
     uint64_t shadow_triangle_tests;
     uint64_t kernel_launches;           /* kernels launched by the last tr_pt_render */
+    uint64_t culled_shadow_rays;        /* NEE shadow rays NOT traced because the sample's BSDF weight is exactly 0
+                                           (the result cannot depend on visibility); shadow_rays + culled = the
+                                           reference's shadow-ray count */
     float render_ms;                    /* CUDA-event time of the last tr_pt_render */
     float closest_ms;                   /* TR_INSTRUMENT_TIMING: summed over launches of the class */
     float shadow_ms;

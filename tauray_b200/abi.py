@@ -118,7 +118,7 @@ class Stats(C.Structure):
     _fields_ = [("closest_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("paths", C.c_uint64),
                 ("closest_node_visits", C.c_uint64), ("closest_triangle_tests", C.c_uint64),
                 ("shadow_node_visits", C.c_uint64), ("shadow_triangle_tests", C.c_uint64),
-                ("kernel_launches", C.c_uint64),
+                ("kernel_launches", C.c_uint64), ("culled_shadow_rays", C.c_uint64),
                 ("render_ms", C.c_float), ("closest_ms", C.c_float), ("shadow_ms", C.c_float),
                 ("shade_ms", C.c_float), ("other_ms", C.c_float),
                 ("closest_launches", C.c_uint32), ("shadow_launches", C.c_uint32), ("shade_launches", C.c_uint32),

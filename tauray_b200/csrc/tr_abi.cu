@@ -640,6 +640,7 @@ int tr_pt_get_stats(tr_pt_ctx* c, tr_pt_stats* stats)
         c->stats.closest_triangle_tests = h.closest_tris;
         c->stats.shadow_node_visits = h.shadow_nodes;
         c->stats.shadow_triangle_tests = h.shadow_tris;
+        c->stats.culled_shadow_rays = h.culled_shadow_rays;
         c->stats.closest_ms = c->stats.shadow_ms = c->stats.shade_ms = c->stats.other_ms = 0.0f;
         c->stats.closest_launches = c->stats.shadow_launches = c->stats.shade_launches = 0;
         if(c->timer && c->timer->used > 1)

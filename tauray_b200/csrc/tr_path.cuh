@@ -810,6 +810,23 @@ TRD void nee_finish(const RenderParams& P, const NeeJob& job, float visibility, 
     add_demodulated(s, radiance, job.w_diffuse, job.w_reflection);
 }
 
+// A pending NEE sample whose shadow ray cannot change the image: every lobe weight that multiplies the
+// radiance is exactly 0 and the radiance itself is finite for visibility 1 (then it is finite -- namely
+// 0 -- for visibility 0 as well), so the reference would add +-0 whatever the ray returns. Such rays are
+// not traced (counted in culled_shadow_rays); the result is bit-identical.
+TRD bool nee_shadow_ray_is_moot(const NeeJob& job)
+{
+    if(!job.needs_shadow_ray) return false;
+    const bool zero_weight = job.bounce != 0 ?
+        ((job.modulate.x == 0.0f && job.modulate.y == 0.0f && job.modulate.z == 0.0f) ||
+         (job.w_diffuse == 0.0f && job.w_reflection == 0.0f)) :
+        (job.w_diffuse == 0.0f && job.w_reflection == 0.0f);
+    if(!zero_weight) return false;
+    const vec3 r = job.attenuation * (job.contrib / job.mis_pdf);
+    const float big = 1e30f;   // finite with room for the remaining (zero) multiplications
+    return fabsf(r.x) < big && fabsf(r.y) < big && fabsf(r.z) < big;
+}
+
 // path_tracer.rgen:108-117
 TRD vec3 path_color(const RenderParams& P, const PathState& s)
 {

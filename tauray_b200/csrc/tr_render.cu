@@ -423,6 +423,7 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_shade(const RenderParams P, con
     const uint32_t n = *count;
     const uint32_t rounded = (n + 31u) & ~31u;
     const uint32_t stride = gridDim.x * blockDim.x;
+    unsigned long long culled = 0;
     for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += stride)
     {
         bool alive = false, shadow = false;
@@ -451,7 +452,8 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_shade(const RenderParams P, con
             alive = shade_bounce(P, bounce, h, s, ls.ss_seed, rs, job);
             if(job.bounce >= 0)
             {
-                if(job.needs_shadow_ray) { store_job(wf, id, job); shadow = true; }
+                if(nee_shadow_ray_is_moot(job)) culled++;
+                else if(job.needs_shadow_ray) { store_job(wf, id, job); shadow = true; }
                 else nee_finish(P, job, 1.0f, s);
             }
             store_state(wf, id, s);
@@ -461,6 +463,8 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_shade(const RenderParams P, con
         warp_push(next_queue, next_count, alive, id);
         warp_push(shadow_queue, shadow_count, shadow, id);
     }
+    for(int off = 16; off > 0; off >>= 1) culled += __shfl_xor_sync(0xFFFFFFFFu, culled, off);
+    if((threadIdx.x & 31) == 0 && culled) atomicAdd(&P.counters->culled_shadow_rays, culled);
 }
 
 __global__ void __launch_bounds__(WF_BLOCK) k_wf_finish(const RenderParams P, const tr_wavefront wf, uint32_t sample_in_pass, uint32_t total_slots)
@@ -498,7 +502,7 @@ __global__ void __launch_bounds__(WF_BLOCK) k_megakernel(const RenderParams P, u
     const uint32_t stride = gridDim.x * blockDim.x;
     TraceStats st; st.nodes = 0; st.tris = 0;
     TraceStats sst; sst.nodes = 0; sst.tris = 0;
-    unsigned long long closest = 0, shadow = 0, paths = 0;
+    unsigned long long closest = 0, shadow = 0, paths = 0, culled = 0;
     const uint32_t spp = (uint32_t)P.opt.samples_per_pass;
     for(uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < total_slots; slot += stride)
     {
@@ -520,7 +524,8 @@ __global__ void __launch_bounds__(WF_BLOCK) k_megakernel(const RenderParams P, u
                 closest++;
                 NeeJob job;
                 const bool alive = shade_bounce(P, bounce, h, s, ss, rs, job);
-                if(job.bounce >= 0)
+                if(job.bounce >= 0 && nee_shadow_ray_is_moot(job)) culled++;
+                else if(job.bounce >= 0)
                 {
                     float vis = 1.0f;
                     if(job.needs_shadow_ray)
@@ -540,6 +545,8 @@ __global__ void __launch_bounds__(WF_BLOCK) k_megakernel(const RenderParams P, u
     }
     flush_counters(P.counters, closest, shadow, paths, st.nodes, st.tris, 0);
     flush_counters(P.counters, 0, 0, 0, sst.nodes, sst.tris, 1);
+    for(int off = 16; off > 0; off >>= 1) culled += __shfl_xor_sync(0xFFFFFFFFu, culled, off);
+    if((threadIdx.x & 31) == 0 && culled) atomicAdd(&P.counters->culled_shadow_rays, culled);
 }
 
 // ---- feature (AOV) tracer: shader/rt_feature.rgen:18-47, rt_feature.rahit, rt_feature.rchit ------

@@ -99,6 +99,7 @@ struct Counters
 {
     unsigned long long closest_rays, shadow_rays, paths;
     unsigned long long closest_nodes, closest_tris, shadow_nodes, shadow_tris;
+    unsigned long long culled_shadow_rays;
 };
 
 } // namespace trd

@@ -89,7 +89,8 @@ def test_config3_atrium_reduced_resolution_vs_oracle(atrium_scene):
         img = run(pt, atrium_scene, cams, full_dist(size))
         sg = pt.stats()
     assert assert_parity(img, ref, "atrium 240x135")
-    assert (sg["closest_rays"], sg["shadow_rays"], sg["paths"]) == (so["closest_rays"], so["shadow_rays"], so["paths"])
+    assert (sg["closest_rays"], sg["shadow_rays"] + sg["culled_shadow_rays"], sg["paths"]) == (so["closest_rays"], so["shadow_rays"], so["paths"])
+    assert sg["culled_shadow_rays"] > 0     # zero-weight NEE samples are not traced
     assert sg["triangle_count"] == 1_500_000 and sg["tri_light_count"] == 64
 
 
@@ -104,7 +105,7 @@ def test_config3_full_size_properties(atrium_scene):
         st = pt.stats()
         assert not np.isnan(full).any()
         assert st["paths"] == 1920 * 1080 * 4
-        assert st["paths"] < st["closest_rays"] <= 4 * st["paths"] and st["shadow_rays"] <= 3 * st["paths"]
+        assert st["paths"] < st["closest_rays"] <= 4 * st["paths"] and st["shadow_rays"] + st["culled_shadow_rays"] <= 3 * st["paths"]
         # (2) strips: 8 "devices" rendered one after the other on this GPU, gathered by tr_pt_unshuffle
         import torch
         stitched = torch.zeros((1, 1080, 1920, 4), dtype=torch.float32, device="cuda")

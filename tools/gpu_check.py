@@ -41,7 +41,7 @@ def main():
             sg = g.stats()
             compare("sampler %d mode %d" % (sampler, mode), img, ref)
             print("   rays gpu %d+%d oracle %d+%d  gpu ms %.3f launches %d oracle s %.2f" % (
-                sg["closest_rays"], sg["shadow_rays"], so["closest_rays"], so["shadow_rays"], sg["render_ms"], sg["kernel_launches"], t_or))
+                sg["closest_rays"], sg["shadow_rays"] + sg["culled_shadow_rays"], so["closest_rays"], so["shadow_rays"], sg["render_ms"], sg["kernel_launches"], t_or))
             if mode == abi.KERNEL_WAVEFRONT:
                 rays = np.random.RandomState(1).randn(4096, 8).astype(np.float32)
                 rays[:, 3] = 0; rays[:, 7] = np.inf
