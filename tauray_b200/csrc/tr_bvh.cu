@@ -321,7 +321,7 @@ __global__ void k_hierarchy(const unsigned long long* __restrict__ keys, int n, 
 __global__ void k_refit(const float4* __restrict__ tris, const uint32_t* __restrict__ order, int n,
                         const int2* __restrict__ children, const int* __restrict__ inner_parent,
                         const int* __restrict__ leaf_parent, float* __restrict__ leaf_boxes /* n*6 */,
-                        float* __restrict__ inner_boxes /* (n-1)*6 */, int* __restrict__ flags)
+                        float* __restrict__ inner_boxes /* (n-1)*6 */, int* __restrict__ flags, int climb)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if(i >= n) return;
@@ -332,7 +332,7 @@ __global__ void k_refit(const float4* __restrict__ tris, const uint32_t* __restr
         fmaxf(fmaxf(a.x, b.x), c.x), fmaxf(fmaxf(a.y, b.y), c.y), fmaxf(fmaxf(a.z, b.z), c.z)};
 #pragma unroll
     for(int k = 0; k < 6; ++k) leaf_boxes[6 * (size_t)i + k] = box[k];
-    if(n == 1) return;
+    if(n == 1 || !climb) return;
     int node = leaf_parent[i];
     while(node >= 0)
     {
@@ -353,6 +353,122 @@ __global__ void k_refit(const float4* __restrict__ tris, const uint32_t* __restr
 }
 
 // ---------------------------------------------------------------------------------------------
+// 6b. PLOC hierarchy (Meister & Bittner 2018, "Parallel Locally-Ordered Clustering"): optional.
+// Clusters start as the Morton-sorted triangles; every round each cluster finds, within +-PLOC_RADIUS
+// positions, the neighbour whose merged box has the smallest surface area; mutual nearest
+// neighbours merge into a new binary node; survivors are compacted in order. Selected with
+// TR_TUNE_BUILDER=ploc; on the benchmark scene it traces shadow rays ~9% faster and closest-hit rays ~8%
+// slower than the radix tree of section 6 (measured, profiles/), so the radix tree stays the default.
+// ---------------------------------------------------------------------------------------------
+constexpr int PLOC_RADIUS = 16;
+constexpr int PLOC_BLOCK = 256;
+
+__global__ void k_ploc_init(int n, const float* __restrict__ leaf_boxes, float4* __restrict__ lo, float4* __restrict__ hi,
+                            int* __restrict__ cl_node)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    const float* b = leaf_boxes + 6 * (size_t)i;
+    lo[i] = make_float4(b[0], b[1], b[2], 0.0f);
+    hi[i] = make_float4(b[3], b[4], b[5], 0.0f);
+    cl_node[i] = ~i;
+}
+
+__global__ void __launch_bounds__(PLOC_BLOCK) k_ploc_nn(int n, const float4* __restrict__ lo, const float4* __restrict__ hi, int* __restrict__ nn)
+{
+    __shared__ float4 s_lo[PLOC_BLOCK + 2 * PLOC_RADIUS], s_hi[PLOC_BLOCK + 2 * PLOC_RADIUS];
+    const int base = blockIdx.x * PLOC_BLOCK - PLOC_RADIUS;
+    for(int k = threadIdx.x; k < PLOC_BLOCK + 2 * PLOC_RADIUS; k += PLOC_BLOCK)
+    {
+        const int g = base + k;
+        if(g >= 0 && g < n) { s_lo[k] = lo[g]; s_hi[k] = hi[g]; }
+    }
+    __syncthreads();
+    const int i = blockIdx.x * PLOC_BLOCK + threadIdx.x;
+    if(i >= n) return;
+    const float4 al = s_lo[threadIdx.x + PLOC_RADIUS], ah = s_hi[threadIdx.x + PLOC_RADIUS];
+    float best = FLT_MAX;
+    int best_j = -1;
+    for(int d = -PLOC_RADIUS; d <= PLOC_RADIUS; ++d)
+    {
+        const int j = i + d;
+        if(d == 0 || j < 0 || j >= n) continue;
+        const float4 bl = s_lo[threadIdx.x + PLOC_RADIUS + d], bh = s_hi[threadIdx.x + PLOC_RADIUS + d];
+        const float dx = fmaxf(ah.x, bh.x) - fminf(al.x, bl.x);
+        const float dy = fmaxf(ah.y, bh.y) - fminf(al.y, bl.y);
+        const float dz = fmaxf(ah.z, bh.z) - fminf(al.z, bl.z);
+        const float area = dx * dy + dy * dz + dz * dx;
+        if(area < best) { best = area; best_j = j; }
+    }
+    nn[i] = best_j;
+}
+
+__global__ void k_ploc_merge(int n, const int* __restrict__ nn, int* __restrict__ cl_node, float4* __restrict__ lo, float4* __restrict__ hi,
+                             int2* __restrict__ children, float* __restrict__ inner_boxes, int* __restrict__ counts,
+                             int* __restrict__ node_counter, int* __restrict__ valid)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    const int j = nn[i];
+    if(j < 0 || nn[j] != i) { valid[i] = 1; return; }
+    if(i > j) { valid[i] = 0; return; }
+    // i < j: merge j into i
+    const int id = atomicAdd(node_counter, 1);
+    const int a = cl_node[i], b = cl_node[j];
+    children[id] = make_int2(a, b);
+    counts[id] = (a < 0 ? 1 : counts[a]) + (b < 0 ? 1 : counts[b]);
+    const float4 al = lo[i], ah = hi[i], bl = lo[j], bh = hi[j];
+    const float4 l = make_float4(fminf(al.x, bl.x), fminf(al.y, bl.y), fminf(al.z, bl.z), 0.0f);
+    const float4 h = make_float4(fmaxf(ah.x, bh.x), fmaxf(ah.y, bh.y), fmaxf(ah.z, bh.z), 0.0f);
+    float* o = inner_boxes + 6 * (size_t)id;
+    o[0] = l.x; o[1] = l.y; o[2] = l.z; o[3] = h.x; o[4] = h.y; o[5] = h.z;
+    lo[i] = l; hi[i] = h;
+    cl_node[i] = id;
+    valid[i] = 1;
+}
+
+__global__ void __launch_bounds__(PLOC_BLOCK) k_ploc_count(int n, const int* __restrict__ valid, uint32_t* __restrict__ block_sums)
+{
+    const int i = blockIdx.x * PLOC_BLOCK + threadIdx.x;
+    const int v = i < n ? valid[i] : 0;
+    const int c = __syncthreads_count(v);
+    if(threadIdx.x == 0) block_sums[blockIdx.x] = (uint32_t)c;
+    if(threadIdx.x == 0 && blockIdx.x == 0) block_sums[gridDim.x] = 0u;   // becomes the total after the exclusive scan
+}
+
+__global__ void __launch_bounds__(PLOC_BLOCK) k_ploc_compact(int n, const int* __restrict__ valid, const uint32_t* __restrict__ block_offsets,
+                                                              const int* __restrict__ node_in, const float4* __restrict__ lo_in, const float4* __restrict__ hi_in,
+                                                              int* __restrict__ node_out, float4* __restrict__ lo_out, float4* __restrict__ hi_out)
+{
+    __shared__ uint32_t warp_base[PLOC_BLOCK / 32];
+    const int i = blockIdx.x * PLOC_BLOCK + threadIdx.x;
+    const int v = i < n ? valid[i] : 0;
+    const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if(lane == 0) warp_base[warp] = __popc(ballot);
+    __syncthreads();
+    if(threadIdx.x == 0)
+    {
+        uint32_t run = 0;
+        for(int w = 0; w < PLOC_BLOCK / 32; ++w) { uint32_t c = warp_base[w]; warp_base[w] = run; run += c; }
+    }
+    __syncthreads();
+    if(v)
+    {
+        const uint32_t dst = block_offsets[blockIdx.x] + warp_base[warp] + __popc(ballot & ((1u << lane) - 1u));
+        node_out[dst] = node_in[i];
+        lo_out[dst] = lo_in[i];
+        hi_out[dst] = hi_in[i];
+    }
+}
+
+__global__ void k_counts_from_ranges(int n_inner, const int2* __restrict__ ranges, int* __restrict__ counts)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i < n_inner) counts[i] = ranges[i].y - ranges[i].x + 1;
+}
+
+// ---------------------------------------------------------------------------------------------
 // 8. breadth-first emission of the 8-wide compressed BVH
 // ---------------------------------------------------------------------------------------------
 // One thread per wide node. The node's subtree root is a Karras inner node; its child set starts
@@ -360,7 +476,22 @@ __global__ void k_refit(const float4* __restrict__ tris, const uint32_t* __restr
 // its two children) until there are 8 or nothing can be opened. A binary subtree with
 // <= TR_BVH_LEAF_TRIS triangles becomes a leaf child. Children are assigned to slots per octant
 // (greedy on dot(centroid offset, slot sign)), boxes are quantised to 8 bits outwards.
-__device__ __forceinline__ int range_size(const int2* __restrict__ ranges, int c) { return c < 0 ? 1 : ranges[c].y - ranges[c].x + 1; }
+__device__ __forceinline__ int range_size(const int* __restrict__ counts, int c) { return c < 0 ? 1 : counts[c]; }
+
+// Sorted-triangle positions of the (<= 3) leaves below binary node c.
+__device__ __forceinline__ int collect_leaves(const int2* __restrict__ children, int c, int* out)
+{
+    if(c < 0) { out[0] = ~c; return 1; }
+    int stack[4], sp = 0, n = 0;
+    stack[sp++] = c;
+    while(sp)
+    {
+        const int2 ch = children[stack[--sp]];
+        if(ch.y < 0) { if(n < 3) out[n] = ~ch.y; n++; } else stack[sp++] = ch.y;
+        if(ch.x < 0) { if(n < 3) out[n] = ~ch.x; n++; } else stack[sp++] = ch.x;
+    }
+    return n < 3 ? n : 3;
+}
 
 __device__ __forceinline__ void write_wide_node(float4* __restrict__ out, const float* nlo, const float* nhi, int n,
                                                 const float (*clo)[3], const float (*chi)[3], const int* slot_child,
@@ -412,7 +543,7 @@ __device__ __forceinline__ void write_wide_node(float4* __restrict__ out, const 
 }
 
 __global__ void k_wide_level(int leaf_tris, const int* __restrict__ frontier, int frontier_size, int out_base,
-                             const int2* __restrict__ children, const int2* __restrict__ ranges,
+                             const int2* __restrict__ children, const int* __restrict__ ranges,
                              const float* __restrict__ leaf_boxes, const float* __restrict__ inner_boxes, float eps,
                              const float4* __restrict__ tris_sorted, float4* __restrict__ nodes, float4* __restrict__ tris_out,
                              int* __restrict__ next_frontier, int* __restrict__ next_count, int next_out_base,
@@ -500,10 +631,11 @@ __global__ void k_wide_level(int leaf_tris, const int* __restrict__ frontier, in
         const int cnt = range_size(ranges, c);
         if(c < 0 || cnt <= leaf_tris)
         {
-            const int first = c < 0 ? ~c : ranges[c].x;
-            for(int t = 0; t < cnt; ++t)
+            int leaves[3];
+            const int got = collect_leaves(children, c, leaves);
+            for(int t = 0; t < got; ++t)
                 for(int w = 0; w < 3; ++w)
-                    tris_out[3 * (size_t)(tri_base + tri_off + t) + w] = tris_sorted[3 * (size_t)(first + t) + w];
+                    tris_out[3 * (size_t)(tri_base + tri_off + t) + w] = tris_sorted[3 * (size_t)leaves[t] + w];
             meta_of_child[k] = (((1u << cnt) - 1u) << 5) | tri_off;
             tri_off += (uint32_t)cnt;
         }
@@ -674,9 +806,49 @@ cudaError_t tr_build_bvh(cudaStream_t stream, const tr_build_input& in, tr_build
     CUDA_OK2(tmp.alloc(&inner_parent, n)); CUDA_OK2(tmp.alloc(&leaf_parent, n)); CUDA_OK2(tmp.alloc(&flags, n));
     CUDA_OK2(tmp.alloc(&leaf_boxes, 6 * (size_t)n)); CUDA_OK2(tmp.alloc(&inner_boxes, 6 * (size_t)n));
     CUDA_OK2(cudaMemsetAsync(flags, 0, sizeof(int) * n, stream));
-    if(n > 1) k_hierarchy<<<div_up(n - 1, 256), 256, 0, stream>>>(keys_a, (int)n, children, ranges, inner_parent, leaf_parent);
-    k_refit<<<div_up(n, 256), 256, 0, stream>>>(tris_unsorted, vals_a, (int)n, children, inner_parent, leaf_parent, leaf_boxes, inner_boxes, flags);
-    CUDA_OK2(cudaGetLastError());
+    static const bool use_karras = !(getenv("TR_TUNE_BUILDER") && std::strcmp(getenv("TR_TUNE_BUILDER"), "ploc") == 0);
+    int* counts = nullptr;
+    CUDA_OK2(tmp.alloc(&counts, n));
+    int root_node = 0;
+    if(use_karras || n < 2)
+    {
+        if(n > 1) k_hierarchy<<<div_up(n - 1, 256), 256, 0, stream>>>(keys_a, (int)n, children, ranges, inner_parent, leaf_parent);
+        k_refit<<<div_up(n, 256), 256, 0, stream>>>(tris_unsorted, vals_a, (int)n, children, inner_parent, leaf_parent, leaf_boxes, inner_boxes, flags, 1);
+        if(n > 1) k_counts_from_ranges<<<div_up(n - 1, 256), 256, 0, stream>>>((int)n - 1, ranges, counts);
+        CUDA_OK2(cudaGetLastError());
+    }
+    else
+    {
+        k_refit<<<div_up(n, 256), 256, 0, stream>>>(tris_unsorted, vals_a, (int)n, children, inner_parent, leaf_parent, leaf_boxes, inner_boxes, flags, 0);
+        float4 *lo_a = nullptr, *hi_a = nullptr, *lo_b = nullptr, *hi_b = nullptr;
+        int *node_a = nullptr, *node_b = nullptr, *nn = nullptr, *valid = nullptr, *node_counter = nullptr;
+        uint32_t* block_sums = nullptr;
+        CUDA_OK2(tmp.alloc(&lo_a, n)); CUDA_OK2(tmp.alloc(&hi_a, n)); CUDA_OK2(tmp.alloc(&lo_b, n)); CUDA_OK2(tmp.alloc(&hi_b, n));
+        CUDA_OK2(tmp.alloc(&node_a, n)); CUDA_OK2(tmp.alloc(&node_b, n)); CUDA_OK2(tmp.alloc(&nn, n)); CUDA_OK2(tmp.alloc(&valid, n));
+        CUDA_OK2(tmp.alloc(&node_counter, 1)); CUDA_OK2(tmp.alloc(&block_sums, div_up(n, PLOC_BLOCK) + 1));
+        CUDA_OK2(cudaMemsetAsync(node_counter, 0, sizeof(int), stream));
+        k_ploc_init<<<div_up(n, 256), 256, 0, stream>>>((int)n, leaf_boxes, lo_a, hi_a, node_a);
+        uint32_t m = n;
+        int rounds = 0;
+        while(m > 1)
+        {
+            const uint32_t blocks = div_up(m, PLOC_BLOCK);
+            k_ploc_nn<<<blocks, PLOC_BLOCK, 0, stream>>>((int)m, lo_a, hi_a, nn);
+            k_ploc_merge<<<blocks, PLOC_BLOCK, 0, stream>>>((int)m, nn, node_a, lo_a, hi_a, children, inner_boxes, counts, node_counter, valid);
+            k_ploc_count<<<blocks, PLOC_BLOCK, 0, stream>>>((int)m, valid, block_sums);
+            k_sort_scan<<<1, 1024, 0, stream>>>(block_sums, blocks + 1);
+            k_ploc_compact<<<blocks, PLOC_BLOCK, 0, stream>>>((int)m, valid, block_sums, node_a, lo_a, hi_a, node_b, lo_b, hi_b);
+            uint32_t next_m = 0;
+            CUDA_OK2(cudaMemcpyAsync(&next_m, block_sums + blocks, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+            CUDA_OK2(cudaStreamSynchronize(stream));
+            if(next_m == 0 || next_m >= m) return fail(cudaErrorUnknown);   // cannot happen: the closest pair always merges
+            m = next_m;
+            std::swap(node_a, node_b); std::swap(lo_a, lo_b); std::swap(hi_a, hi_b);
+            if(++rounds > 4096) return fail(cudaErrorUnknown);
+        }
+        CUDA_OK2(cudaMemcpyAsync(&root_node, node_a, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CUDA_OK2(cudaStreamSynchronize(stream));
+    }
 
     static const int leaf_tris_env = getenv("TR_TUNE_LEAF") ? atoi(getenv("TR_TUNE_LEAF")) : TR_BVH_LEAF_TRIS;
     const int leaf_tris = std::max(1, std::min(3, leaf_tris_env));
@@ -697,8 +869,7 @@ cudaError_t tr_build_bvh(cudaStream_t stream, const tr_build_input& in, tr_build
         uint32_t* tri_counter = nullptr;
         CUDA_OK3(tmp.alloc(&frontier_a, n)); CUDA_OK3(tmp.alloc(&frontier_b, n)); CUDA_OK3(tmp.alloc(&next_count, 1));
         CUDA_OK3(tmp.alloc(&tri_counter, 1));
-        int zero = 0;
-        CUDA_OK3(cudaMemcpyAsync(frontier_a, &zero, sizeof(int), cudaMemcpyHostToDevice, stream));
+        CUDA_OK3(cudaMemcpyAsync(frontier_a, &root_node, sizeof(int), cudaMemcpyHostToDevice, stream));
         CUDA_OK3(cudaMemsetAsync(tri_counter, 0, sizeof(uint32_t), stream));
         int frontier_size = 1;
         int out_base = 0;
@@ -707,7 +878,7 @@ cudaError_t tr_build_bvh(cudaStream_t stream, const tr_build_input& in, tr_build
             CUDA_OK3(cudaMemsetAsync(next_count, 0, sizeof(int), stream));
             const int next_out_base = out_base + frontier_size;
             k_wide_level<<<div_up((uint32_t)frontier_size, 128), 128, 0, stream>>>(
-                leaf_tris, frontier_a, frontier_size, out_base, children, ranges, leaf_boxes, inner_boxes, eps, tris_sorted, nodes,
+                leaf_tris, frontier_a, frontier_size, out_base, children, counts, leaf_boxes, inner_boxes, eps, tris_sorted, nodes,
                 tris_final, frontier_b, next_count, next_out_base, tri_counter);
             int next_size = 0;
             CUDA_OK3(cudaMemcpyAsync(&next_size, next_count, sizeof(int), cudaMemcpyDeviceToHost, stream));
