@@ -35,6 +35,23 @@ def bench_options(abi, spp=SPP):
                                mis_mode=abi.MIS_POWER_HEURISTIC, tri_light_mode=abi.TRI_LIGHT_SOLID_ANGLE)
 
 
+def ncu_traffic_per_launch(kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture (profiles/r1_ncu_full_top_kernels.csv; same command line as this bench)."""
+    path = os.path.join(ROOT, "profiles", "r1_ncu_full_top_kernels.csv")
+    try:
+        import csv
+        rows = list(csv.reader(open(path)))
+        hdr, units = rows[0], rows[1]
+        k, r, w = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+        vals = [float(x[r]) * scale.get(units[r], 1.0) + float(x[w]) * scale.get(units[w], 1.0)
+                for x in rows[2:] if kernel_substr in x[k]]
+        return sum(vals) / len(vals) if vals else None
+    except Exception:
+        return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -110,8 +127,8 @@ def run_reference(args):
     size = (WIDTH, HEIGHT)
     slots = distribution.calculate_shuffled_strips_pixels_per_device(size, 1.0)
     ora.set_distribution(distribution.make_distribution(size, abi.DISTRIBUTION_SHUFFLED_STRIPS, 0, slots, True))
-    # a step = 1 spp over the first 1/16 of the shuffled-strip slots (a uniform sample of the image)
-    sample_slots = slots // 16
+    # a step = 1 spp over the whole image = 1/4 of the 4-spp frame
+    sample_slots = slots
     for _ in range(args.warmup):
         ora.render(sample_slots)
     rays = 0
@@ -122,7 +139,7 @@ def run_reference(args):
         rays += st["closest_rays"] + st["shadow_rays"]
     dt = time.perf_counter() - t0
     value = rays / dt / 1e6
-    sample = "per step: 1 spp over 1/16 of the 1920x1080 shuffled-strip slots (%d paths) of the same scene/options" % sample_slots
+    sample = "per step: 1 spp over all 1920x1080 shuffled-strip slots (%d paths = 1/4 of the 4-spp frame), same scene/options" % sample_slots
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
@@ -301,13 +318,19 @@ def main():
     roofline = {
         "bound": "hbm", "kernel": {"closest": "k_wf_trace_closest", "shadow": "k_wf_trace_shadow", "shade": "k_wf_shade"}[dominant],
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_kind,
+        "note": "achieved = ALGORITHMIC bytes (DESIGN.md section 6) / CUDA-event time; most node/triangle fetches hit L1/L2, so real "
+                "DRAM traffic (`traffic`, bytes per launch from ncu) is far smaller: the kernel is bound by issue slots and warp divergence",
         "launches_per_frame": cls_n.get(dominant), "avg_launch_ms": dom_ms / max(cls_n.get(dominant, 1), 1),
         "bytes_per_ray": {"closest": b_closest, "shadow": b_shadow}, "nodes_per_ray": {"closest": nodes_c, "shadow": nodes_s},
         "tris_per_ray": {"closest": tris_c, "shadow": tris_s},
         "class_ms_per_frame": cls_ms,
     }
+    ncu_name = {"closest": "k_wf_trace<0", "shadow": "k_wf_trace<1", "shade": "k_wf_shade"}[dominant]
+    roofline["traffic"] = ncu_traffic_per_launch(ncu_name) if world == 1 else None
+    roofline["algorithmic_bytes_per_launch"] = per_frame_bytes[dominant] / max(cls_n.get(dominant, 1), 1)
     if args.kernel != "wavefront":
         roofline["kernel"] = "k_megakernel"
+        roofline["traffic"] = None
 
     # ---- cpu_baseline (rank 0, N = 1 only): the oracle on a bounded sample ----
     cpu_baseline = None
@@ -333,6 +356,9 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "triangles": args.triangles, "sampler": "sobol-owen", "kernel": args.kernel,
+                       "rays_definition": "traversal queries actually traced (closest + shadow); NEE shadow rays whose BSDF weight is "
+                                          "exactly 0 are proven moot and not traced",
+                       "culled_shadow_rays_per_frame": sum_over_ranks(float(st["culled_shadow_rays"])),
                        "distribution": "shuffled-strips", "stitch": ren.stitch, "rays_per_frame": rays_all / args.steps,
                        "l2": "inputs exceed L2: BVH+triangles+vertices ~%.0f MB, wavefront state ~%.0f MB per rank" % (
                            (st["bvh_node_count"] * 64 + st["triangle_count"] * 48 * 2 + st["triangle_count"] * 12) / 1e6,
