@@ -257,6 +257,7 @@ def main():
     launches = st["kernel_launches"] * args.steps
     ms_max = max_over_ranks(ms_total)
     rays_all = sum_over_ranks(float(rays_total))
+    culled_all = sum_over_ranks(float(st["culled_shadow_rays"]))
     value = rays_all / (ms_max * 1e-3) / 1e6
     ms_per_step = ms_max / args.steps
     for k in cls_ms:
@@ -358,7 +359,7 @@ def main():
             "config": {"workload": WORKLOAD, "triangles": args.triangles, "sampler": "sobol-owen", "kernel": args.kernel,
                        "rays_definition": "traversal queries actually traced (closest + shadow); NEE shadow rays whose BSDF weight is "
                                           "exactly 0 are proven moot and not traced",
-                       "culled_shadow_rays_per_frame": sum_over_ranks(float(st["culled_shadow_rays"])),
+                       "culled_shadow_rays_per_frame": culled_all,
                        "distribution": "shuffled-strips", "stitch": ren.stitch, "rays_per_frame": rays_all / args.steps,
                        "l2": "inputs exceed L2: BVH+triangles+vertices ~%.0f MB, wavefront state ~%.0f MB per rank" % (
                            (st["bvh_node_count"] * 64 + st["triangle_count"] * 48 * 2 + st["triangle_count"] * 12) / 1e6,

@@ -159,6 +159,7 @@ void fill_params(const tr_pt_ctx* c, RenderParams& P)
     P.cameras = c->cameras;
     P.color = c->color;
     P.counters = c->counters;
+    P.sobol_chunks = tr_render_sobol_chunks();
     P.stats = (c->instrumentation & TR_INSTRUMENT_VISITS) ? 1 : 0;
     for(int i = 0; i < c->peer_count; ++i) P.peers[i] = c->peers[i];
     P.peer_count = c->peer_count;
@@ -794,6 +795,7 @@ int tr_pt_sample_test(tr_pt_ctx* c, const uint32_t* coords, uint32_t n, int draw
     P.frame.sample_counter = c->frame_counter * (uint32_t)c->opt.samples_per_pixel;
     P.frame.rng_seed = c->opt.rng_seed != 0 ? host_pcg((uint32_t)c->opt.rng_seed) : 0;
     P.frame.max_sobol_bounces = (uint32_t)(c->opt.max_ray_depth > 8 ? 8 : c->opt.max_ray_depth);
+    P.sobol_chunks = tr_render_sobol_chunks();
     TRY_CUDA(c, tr_render_sample_test(c->stream, P, d_in, n, draw_index, d_out));
     TRY_CUDA(c, cudaMemcpyAsync(out, d_out, 16 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
     TRY_CUDA(c, cudaStreamSynchronize(c->stream));

@@ -23,6 +23,7 @@ struct RenderParams
     const tr_camera_pair* cameras;
     float4* color;              // colour target of this device
     Counters* counters;
+    const uint4* sobol_chunks;  // g_sobol_chunks (global memory)
     int stats;                  // count node visits / triangle tests
     // fused stitch: full images of the peer GPUs (NVLink-mapped), written by the last pass
     float4* peers[8];
@@ -524,10 +525,10 @@ TRD vec3 sample_explicit_light(const RenderParams& P, uvec4 rand_uint, vec3 pos,
     return V3(0);
 }
 
-TRD uvec4 generate_ray_sample_uint(const RenderParams& P, const uvec4& ss_seed, uvec4& rs_seed, uint32_t bounce_index)
+TRD uvec4 generate_ray_sample_uint(const RenderParams& P, const SobolTables& tables, const uvec4& ss_seed, uvec4& rs_seed, uint32_t bounce_index)
 {
     if(P.opt.local_sampler == TR_SAMPLER_SOBOL_OWEN)
-        return get_shuffled_scrambled_sobol_pt_uint(ss_seed, bounce_index, P.frame.max_sobol_bounces);
+        return get_shuffled_scrambled_sobol_pt_uint(tables, ss_seed, bounce_index, P.frame.max_sobol_bounces);
     return pcg4d(rs_seed);
 }
 
@@ -619,7 +620,7 @@ TRD void add_demodulated(PathState& s, vec3 light_color, float w_diffuse, float 
 // Returns true when the path continues (s.pos / s.view hold the next ray); `job.bounce >= 0`
 // when an NEE sample was drawn (finish it with nee_finish, after tracing the shadow ray if
 // job.needs_shadow_ray).
-TRD bool shade_bounce(const RenderParams& P, uint32_t bounce, const Hit& h, PathState& s,
+TRD bool shade_bounce(const RenderParams& P, const SobolTables& tables, uint32_t bounce, const Hit& h, PathState& s,
                       const uvec4& ss_seed, uvec4& rs_seed, NeeJob& job)
 {
     job.bounce = -1;
@@ -725,7 +726,7 @@ TRD bool shade_bounce(const RenderParams& P, uint32_t bounce, const Hit& h, Path
     // ---- next event estimation up to the shadow ray, :302-339 and :449-456
     // The NEE draw is an argument of next_event_estimation(): it is evaluated (and advances the PCG
     // stream) even when no light class is enabled.
-    const uvec4 nee_rand = generate_ray_sample_uint(P, ss_seed, rs_seed, bounce * 2);
+    const uvec4 nee_rand = generate_ray_sample_uint(P, tables, ss_seed, rs_seed, bounce * 2);
     if(nee_enabled(P))
     {
         vec3 out_dir;
@@ -775,7 +776,7 @@ TRD bool shade_bounce(const RenderParams& P, uint32_t bounce, const Hit& h, Path
 
     // ---- sample the BSDF for the next ray, :476-497
     bsdf_lobes lobes = LOBES(0, 0, 0, 0);
-    vec4 ray_sample = to_unit(generate_ray_sample_uint(P, ss_seed, rs_seed, bounce * 2 + 1));
+    vec4 ray_sample = to_unit(generate_ray_sample_uint(P, tables, ss_seed, rs_seed, bounce * 2 + 1));
     vec3 out_dir;
     float pdf;
     material_bsdf_sample(P.opt.bounce_mode, ray_sample, shading_view, mat, out_dir, lobes, pdf);

@@ -16,6 +16,7 @@
 #include "tr_path.cuh"
 #include "tr_render.h"
 #include <cstdlib>
+#include <vector>
 
 namespace trd {
 
@@ -420,6 +421,18 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_shade(const RenderParams P, con
                                                         uint32_t* __restrict__ next_queue, uint32_t* __restrict__ next_count,
                                                         uint32_t* __restrict__ shadow_queue, uint32_t* __restrict__ shadow_count)
 {
+    // Sobol byte-chunk tables of this bounce's two dimension groups (2b: NEE, 2b+1: BSDF) in shared memory
+    __shared__ uint4 s_chunks[2 * 1024];
+    SobolTables tables;
+    tables.base = P.sobol_chunks;
+    tables.first_group = 0;
+    if(P.opt.local_sampler == TR_SAMPLER_SOBOL_OWEN && 2 * bounce + 1 < P.frame.max_sobol_bounces)
+    {
+        for(int k = threadIdx.x; k < 2 * 1024; k += blockDim.x) s_chunks[k] = P.sobol_chunks[(size_t)2 * bounce * 1024 + k];
+        tables.base = s_chunks;
+        tables.first_group = 2 * bounce;
+    }
+    __syncthreads();
     const uint32_t n = *count;
     const uint32_t rounded = (n + 31u) & ~31u;
     const uint32_t stride = gridDim.x * blockDim.x;
@@ -449,7 +462,7 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_shade(const RenderParams P, con
             }
             else rs = ls.rs_seed;
             NeeJob job;
-            alive = shade_bounce(P, bounce, h, s, ls.ss_seed, rs, job);
+            alive = shade_bounce(P, tables, bounce, h, s, ls.ss_seed, rs, job);
             if(job.bounce >= 0)
             {
                 if(nee_shadow_ray_is_moot(job)) culled++;
@@ -503,6 +516,9 @@ __global__ void __launch_bounds__(WF_BLOCK) k_megakernel(const RenderParams P, u
     TraceStats st; st.nodes = 0; st.tris = 0;
     TraceStats sst; sst.nodes = 0; sst.tris = 0;
     unsigned long long closest = 0, shadow = 0, paths = 0, culled = 0;
+    SobolTables tables;
+    tables.base = P.sobol_chunks;
+    tables.first_group = 0;
     const uint32_t spp = (uint32_t)P.opt.samples_per_pass;
     for(uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < total_slots; slot += stride)
     {
@@ -523,7 +539,7 @@ __global__ void __launch_bounds__(WF_BLOCK) k_megakernel(const RenderParams P, u
                                    !(P.opt.hide_lights && bounce == 0), s.random_seed, h, st);
                 closest++;
                 NeeJob job;
-                const bool alive = shade_bounce(P, bounce, h, s, ss, rs, job);
+                const bool alive = shade_bounce(P, tables, bounce, h, s, ss, rs, job);
                 if(job.bounce >= 0 && nee_shadow_ray_is_moot(job)) culled++;
                 else if(job.bounce >= 0)
                 {
@@ -620,7 +636,13 @@ __global__ void k_sample_test(const RenderParams P, const uint32_t* __restrict__
                                           P.frame.sample_counter, P.frame.rng_seed);
     uvec4 r;
     if(draw_index < 0) r = pcg4d(ls.rs_seed);
-    else r = generate_ray_sample_uint(P, ls.ss_seed, ls.rs_seed, (uint32_t)draw_index);
+    else
+    {
+        SobolTables tables;
+        tables.base = P.sobol_chunks;
+        tables.first_group = 0;
+        r = generate_ray_sample_uint(P, tables, ls.ss_seed, ls.rs_seed, (uint32_t)draw_index);
+    }
     out[4 * i] = r.x; out[4 * i + 1] = r.y; out[4 * i + 2] = r.z; out[4 * i + 3] = r.w;
 }
 
@@ -641,7 +663,27 @@ using namespace trd;
 
 cudaError_t tr_render_init_constants()
 {
-    return cudaMemcpyToSymbol(c_sobol_table, TR_SOBOL_TABLE, sizeof(TR_SOBOL_TABLE));
+    std::vector<uint4> chunks(8 * 4 * 256);
+    for(int g = 0; g < 8; ++g)
+        for(int c = 0; c < 4; ++c)
+            for(int v = 0; v < 256; ++v)
+            {
+                uint4 x = make_uint4(0, 0, 0, 0);
+                for(int j = 0; j < 8; ++j)
+                    if((v >> j) & 1)
+                    {
+                        const unsigned int* row = TR_SOBOL_TABLE[g * 32 + c * 8 + j];
+                        x.x ^= row[0]; x.y ^= row[1]; x.z ^= row[2]; x.w ^= row[3];
+                    }
+                chunks[(size_t)(g * 4 + c) * 256 + v] = x;
+            }
+    return cudaMemcpyToSymbol(g_sobol_chunks, chunks.data(), chunks.size() * sizeof(uint4));
+}
+
+const uint4* tr_render_sobol_chunks()
+{
+    void* p = nullptr;
+    return cudaGetSymbolAddress(&p, g_sobol_chunks) == cudaSuccess ? (const uint4*)p : nullptr;
 }
 
 static int grid_for(int sm_count, int blocks_per_sm, uint32_t work)

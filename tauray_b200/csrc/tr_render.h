@@ -56,6 +56,7 @@ struct tr_launch_timer
 };
 
 cudaError_t tr_render_init_constants();
+const uint4* tr_render_sobol_chunks();
 // One pass (= samples_per_pass samples of every slot) of path_tracer.rgen.
 cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const trd::RenderParams& P, const tr_wavefront& wf,
                                      int sm_count, uint64_t* launches, tr_launch_timer* timer);

@@ -174,3 +174,28 @@ def test_errors_are_reported_not_swallowed():
         pt.set_scene(testscenes.cornell())
         with pytest.raises(TaurayB200Error):
             pt.render()      # cameras / distribution missing
+
+
+@pytest.mark.parametrize("env", [{"TR_TUNE_BUILDER": "ploc"}, {"TR_TUNE_LEAF": "1"}, {"TR_TUNE_LEAF": "3", "TR_TUNE_BUILDER": "ploc"},
+                                 {"TR_TUNE_FETCH": "32", "TR_TUNE_POSTPONE": "2"}])
+def test_image_does_not_depend_on_the_tree_or_the_schedule(env):
+    """The predicate, not the acceleration structure, defines the image: the optional PLOC hierarchy, other leaf sizes
+    and other traversal schedules (refill / postponement thresholds) must all give the oracle's image bit for bit."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from tauray_b200 import abi, testscenes\n"
+        "from tauray_b200.library import PathTracer\n"
+        "from oracle.oracle_py import Oracle\n"
+        "from helpers import full_dist, run, bits_equal\n"
+        "opt = abi.default_options(max_ray_depth=4, samples_per_pixel=2, local_sampler=abi.SAMPLER_SOBOL_OWEN)\n"
+        "sc = testscenes.cornell(subdiv=8); cams = testscenes.cornell_cameras(4 / 3); d = full_dist((96, 72))\n"
+        "ref = run(Oracle(opt), sc, cams, d)\n"
+        "pt = PathTracer(opt); img = run(pt, sc, cams, d)\n"
+        "print('EXACT' if bits_equal(img, ref) else 'DIFFERENT')\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, **env), timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "EXACT" in r.stdout, (env, r.stdout)
