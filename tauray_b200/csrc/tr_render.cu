@@ -138,7 +138,10 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_generate(const RenderParams P, 
                 path_begin(P, px, py, view, sample_in_pass, s, ss, rs);
                 store_state(wf, slot, s);
                 store_first_hit(wf, slot, s);
-                wf.rs_seed[slot] = make_uint4(rs.x, rs.y, rs.z, rs.w);
+                // one 16-byte sampler record per slot: the PCG stream state (uniform-random sampler) or the
+                // constant Sobol-Owen seed (sobol-owen sampler)
+                if(P.opt.local_sampler == TR_SAMPLER_SOBOL_OWEN) wf.rs_seed[slot] = make_uint4(ss.x, ss.y, ss.z, ss.w);
+                else wf.rs_seed[slot] = make_uint4(rs.x, rs.y, rs.z, rs.w);
                 paths++;
             }
         }
@@ -449,20 +452,12 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_shade(const RenderParams P, con
             const int4 hr = wf.hits[id];
             Hit h;
             h.instance_id = hr.x; h.primitive_id = hr.y; h.u = __int_as_float(hr.z); h.v = __int_as_float(hr.w); h.t = h.u; h.flags = 0;
-            uint32_t px, py, view, widx;
-            map_slot(P.frame, id, px, py, view, widx);
-            // the Sobol state is a pure function of the sample coordinate: recompute, do not store
-            local_sampler ls = init_local_sampler(px, py, view, P.frame.previous_samples + sample_in_pass,
-                                                  P.frame.sample_counter, P.frame.rng_seed);
-            uvec4 rs;
-            if(P.opt.local_sampler != TR_SAMPLER_SOBOL_OWEN)
-            {
-                const uint4 r = wf.rs_seed[id];
-                rs.x = r.x; rs.y = r.y; rs.z = r.z; rs.w = r.w;
-            }
-            else rs = ls.rs_seed;
+            const uint4 sr = wf.rs_seed[id];
+            uvec4 ss, rs;
+            ss.x = sr.x; ss.y = sr.y; ss.z = sr.z; ss.w = sr.w;
+            rs = ss;
             NeeJob job;
-            alive = shade_bounce(P, tables, bounce, h, s, ls.ss_seed, rs, job);
+            alive = shade_bounce(P, tables, bounce, h, s, ss, rs, job);
             if(job.bounce >= 0)
             {
                 if(nee_shadow_ray_is_moot(job)) culled++;
@@ -716,6 +711,8 @@ cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const RenderParams& P_
     const uint32_t spp = (uint32_t)P.opt.samples_per_pass;
     const int grid_full = grid_for(sm_count, 16, total);
     const int grid_persist = sm_count * k_blocks;
+    static const int k_shade_blocks = env_int("TR_TUNE_SHADE_BLOCKS", 4);
+    const int grid_shade = sm_count * k_shade_blocks;   // 128 registers/thread: 4 resident blocks per SM
     for(uint32_t i = 0; i < spp; ++i)
     {
         cudaError_t e = cudaMemsetAsync(wf.counts, 0, sizeof(uint32_t) * (4 * D + 2), stream);
@@ -734,7 +731,7 @@ cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const RenderParams& P_
             if(P.stats) k_wf_trace<false, true><<<grid_persist, WF_BLOCK, 0, stream>>>(P, wf, b, q_in, active_counts + b, work_counters + 2 * b);
             else k_wf_trace<false, false><<<grid_persist, WF_BLOCK, 0, stream>>>(P, wf, b, q_in, active_counts + b, work_counters + 2 * b);
             MARK(TR_KCLASS_SHADE);
-            k_wf_shade<<<grid_persist, WF_BLOCK, 0, stream>>>(P, wf, b, i, q_in, active_counts + b, q_out, active_counts + b + 1,
+            k_wf_shade<<<grid_shade, WF_BLOCK, 0, stream>>>(P, wf, b, i, q_in, active_counts + b, q_out, active_counts + b + 1,
                                                               wf.shadow_queue, shadow_counts + b);
             *launches += 2;
             if(b + 1 < D)
