@@ -52,6 +52,7 @@ struct tr_pt_ctx
     uint32_t frame_counter = 0;
     int accumulated_samples = 0;
     int instrumentation = 0;
+    uint32_t pass_batch = 1;
     tr_pt_stats stats{};
     bool rendered = false;
     float4* peers[8] = {};
@@ -193,7 +194,17 @@ int prepare_targets(tr_pt_ctx* c)
     }
     const uint64_t slots64 = (uint64_t)f.ray_count_x * f.ray_count_y * f.views;
     if(slots64 >= (1ull << 31)) return fail(c, TR_ERR_UNSUPPORTED, "more than 2^31 launch slots per pass");
-    const uint32_t slots = (uint32_t)slots64;
+    // passes of one sample each are traced `pass_batch` at a time (more rays in flight per launch)
+    const uint32_t pass_count = (uint32_t)(c->opt.samples_per_pixel / c->opt.samples_per_pass);
+    uint32_t batch = 1;
+    if(c->opt.samples_per_pass == 1 && slots64 > 0)
+    {
+        const uint64_t budget = 16ull << 20;   // <= 16 Mi slots (~4 GB of state) in flight
+        batch = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint64_t>(pass_count, 8), budget / slots64));
+    }
+    c->pass_batch = batch;
+    const uint32_t slots = (uint32_t)(slots64 * batch);
+    if(slots64 * batch >= (1ull << 31)) return fail(c, TR_ERR_UNSUPPORTED, "more than 2^31 launch slots in flight");
     if(c->opt.kernel_mode == TR_KERNEL_WAVEFRONT && (c->wf.capacity < slots || !c->wf.counts))
     {
         free_list(c->wf_allocs);
@@ -525,14 +536,17 @@ int tr_pt_render(tr_pt_ctx* c, void* cuda_stream)
     }
     else if(c->timer) c->timer->reset();
     const uint32_t pass_count = (uint32_t)(c->opt.samples_per_pixel / c->opt.samples_per_pass); // path_tracer_stage.cc:37
-    for(uint32_t pass = 0; pass < pass_count; ++pass)
+    for(uint32_t pass = 0; pass < pass_count;)
     {
+        const bool wavefront = c->opt.kernel_mode == TR_KERNEL_WAVEFRONT;
+        const uint32_t batch = wavefront ? std::min(c->pass_batch, pass_count - pass) : 1u;
         P.frame.previous_samples = pass * (uint32_t)c->opt.samples_per_pass; // path_tracer_stage.cc:141
-        P.last_pass = pass + 1 == pass_count;
-        cudaError_t e = c->opt.kernel_mode == TR_KERNEL_WAVEFRONT ?
-            tr_render_pass_wavefront(st, P, c->wf, c->sm_count, &launches, timer) :
+        P.last_pass = pass + batch == pass_count;
+        cudaError_t e = wavefront ?
+            tr_render_pass_wavefront(st, P, c->wf, c->sm_count, &launches, timer, batch) :
             tr_render_pass_megakernel(st, P, c->sm_count, &launches, timer);
         if(e != cudaSuccess) return fail_cuda(c, e, "render pass launch");
+        pass += batch;
     }
     TRY_CUDA(c, cudaEventRecord(c->ev_end, st));
     c->last_stream = st;

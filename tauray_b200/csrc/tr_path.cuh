@@ -836,10 +836,10 @@ TRD vec3 path_color(const RenderParams& P, const PathState& s)
 }
 
 // write_all_outputs (path_tracer.glsl:535-576) + accumulate_gbuffer_color (gbuffer.glsl:18-28)
-TRD float4 accumulate(const RenderParams& P, vec3 color, float alpha, uint32_t write_index)
+TRD float4 accumulate(const RenderParams& P, vec3 color, float alpha, uint32_t write_index, uint32_t pass_offset = 0)
 {
     const uint32_t samples = (uint32_t)P.opt.samples_per_pass;
-    const uint32_t prev_samples = P.frame.samples_accumulated + P.frame.previous_samples;
+    const uint32_t prev_samples = P.frame.samples_accumulated + P.frame.previous_samples + pass_offset * samples;
     vec4 out = V4(color, alpha);
     if(prev_samples != 0)
     {

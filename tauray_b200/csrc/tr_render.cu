@@ -118,8 +118,11 @@ TRD void flush_counters(Counters* c, unsigned long long closest, unsigned long l
 }
 
 // ---- wavefront kernels ---------------------------------------------------------------------------
+// `batch` passes of one sample each are traced together (slot = pass * base_slots + base slot): the samples
+// of different passes are independent, only their accumulation order matters, and k_wf_finish keeps it.
 __global__ void __launch_bounds__(WF_BLOCK) k_wf_generate(const RenderParams P, const tr_wavefront wf, uint32_t sample_in_pass,
-                                                           uint32_t total_slots, uint32_t* __restrict__ queue, uint32_t* __restrict__ count)
+                                                           uint32_t base_slots, uint32_t total_slots,
+                                                           uint32_t* __restrict__ queue, uint32_t* __restrict__ count)
 {
     unsigned long long paths = 0;
     const uint32_t stride = gridDim.x * blockDim.x;
@@ -130,12 +133,13 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_generate(const RenderParams P, 
         if(slot < total_slots)
         {
             uint32_t px, py, view, widx;
-            valid = map_slot(P.frame, slot, px, py, view, widx);
+            const uint32_t pass = slot / base_slots;
+            valid = map_slot(P.frame, slot - pass * base_slots, px, py, view, widx);
             if(valid)
             {
                 PathState s;
                 uvec4 ss, rs;
-                path_begin(P, px, py, view, sample_in_pass, s, ss, rs);
+                path_begin(P, px, py, view, sample_in_pass + pass * (uint32_t)P.opt.samples_per_pass, s, ss, rs);
                 store_state(wf, slot, s);
                 store_first_hit(wf, slot, s);
                 // one 16-byte sampler record per slot: the PCG stream state (uniform-random sampler) or the
@@ -475,30 +479,38 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_shade(const RenderParams P, con
     if((threadIdx.x & 31) == 0 && culled) atomicAdd(&P.counters->culled_shadow_rays, culled);
 }
 
-__global__ void __launch_bounds__(WF_BLOCK) k_wf_finish(const RenderParams P, const tr_wavefront wf, uint32_t sample_in_pass, uint32_t total_slots)
+__global__ void __launch_bounds__(WF_BLOCK) k_wf_finish(const RenderParams P, const tr_wavefront wf, uint32_t sample_in_pass,
+                                                         uint32_t base_slots, uint32_t batch)
 {
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t spp = (uint32_t)P.opt.samples_per_pass;
-    for(uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < total_slots; slot += stride)
+    for(uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < base_slots; slot += stride)
     {
         uint32_t px, py, view, widx;
         if(!map_slot(P.frame, slot, px, py, view, widx)) continue;
-        PathState s;
-        const float4 e = wf.diffuse[slot], f = wf.reflection[slot];
-        s.diffuse = V3(e.x, e.y, e.z);
-        s.reflection = V3(f.x, f.y, f.z);
-        load_first_hit(wf, slot, s);
-        vec3 c = path_color(P, s);
-        if(spp > 1)
+        float4 o = make_float4(0, 0, 0, 0);
+        // accumulate the batched passes in pass order (gbuffer.glsl:18-28 is an order-dependent running mean)
+        for(uint32_t pass = 0; pass < batch; ++pass)
         {
-            vec3 sum = V3(0);
-            if(sample_in_pass != 0) { const float4 q = wf.sum_color[slot]; sum = V3(q.x, q.y, q.z); }
-            sum += c;
-            if(sample_in_pass + 1 < spp) { wf.sum_color[slot] = make_float4(sum.x, sum.y, sum.z, 0.0f); continue; }
-            c = sum / (float)spp;
+            const uint32_t id = pass * base_slots + slot;
+            PathState s;
+            const float4 e = wf.diffuse[id], f = wf.reflection[id];
+            s.diffuse = V3(e.x, e.y, e.z);
+            s.reflection = V3(f.x, f.y, f.z);
+            load_first_hit(wf, id, s);
+            vec3 c = path_color(P, s);
+            if(spp > 1)   // batch == 1 here: the samples of one pass are summed first (path_tracer.rgen:81-126)
+            {
+                vec3 sum = V3(0);
+                if(sample_in_pass != 0) { const float4 q = wf.sum_color[slot]; sum = V3(q.x, q.y, q.z); }
+                sum += c;
+                if(sample_in_pass + 1 < spp) { wf.sum_color[slot] = make_float4(sum.x, sum.y, sum.z, 0.0f); continue; }
+                c = sum / (float)spp;
+            }
+            const float alpha = P.opt.transparent_background ? s.fh_albedo.w : 1.0f;
+            o = accumulate(P, c, alpha, widx, pass);
         }
-        const float alpha = P.opt.transparent_background ? s.fh_albedo.w : 1.0f;
-        const float4 o = accumulate(P, c, alpha, widx);
+        if(spp > 1 && sample_in_pass + 1 < spp) continue;
         store_to_peers(P, o, px, py, view);
     }
 }
@@ -696,7 +708,7 @@ static int env_int(const char* name, int dflt)
 }
 
 cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const RenderParams& P_in, const tr_wavefront& wf, int sm_count, uint64_t* launches,
-                                     tr_launch_timer* timer)
+                                     tr_launch_timer* timer, uint32_t batch)
 {
     RenderParams P = P_in;
     static const int k_fetch = env_int("TR_TUNE_FETCH", FETCH_THRESHOLD);
@@ -705,11 +717,14 @@ cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const RenderParams& P_
     P.tune_fetch_threshold = k_fetch;
     P.tune_postpone_div = k_postpone;
 #define MARK(cls) do { if(timer) timer->mark(stream, cls); } while(0)
-    const uint32_t total = P.frame.ray_count_x * P.frame.ray_count_y * P.frame.views;
-    if(total == 0) return cudaSuccess;
+    const uint32_t base = P.frame.ray_count_x * P.frame.ray_count_y * P.frame.views;
+    if(base == 0) return cudaSuccess;
     const uint32_t D = (uint32_t)P.opt.max_ray_depth;
     const uint32_t spp = (uint32_t)P.opt.samples_per_pass;
+    if(spp > 1) batch = 1;
+    const uint32_t total = base * batch;
     const int grid_full = grid_for(sm_count, 16, total);
+    const int grid_finish = grid_for(sm_count, 16, base);
     const int grid_persist = sm_count * k_blocks;
     static const int k_shade_blocks = env_int("TR_TUNE_SHADE_BLOCKS", 4);
     const int grid_shade = sm_count * k_shade_blocks;   // 128 registers/thread: 4 resident blocks per SM
@@ -721,7 +736,7 @@ cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const RenderParams& P_
         uint32_t* shadow_counts = wf.counts + D + 1;   // [D]
         uint32_t* work_counters = wf.counts + 2 * D + 1; // [2 D] dynamic-fetch cursors
         MARK(TR_KCLASS_OTHER);
-        k_wf_generate<<<grid_full, WF_BLOCK, 0, stream>>>(P, wf, i, total, wf.queue[0], active_counts);
+        k_wf_generate<<<grid_full, WF_BLOCK, 0, stream>>>(P, wf, i, base, total, wf.queue[0], active_counts);
         ++*launches;
         for(uint32_t b = 0; b < D; ++b)
         {
@@ -743,7 +758,7 @@ cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const RenderParams& P_
             }
         }
         MARK(TR_KCLASS_OTHER);
-        k_wf_finish<<<grid_full, WF_BLOCK, 0, stream>>>(P, wf, i, total);
+        k_wf_finish<<<grid_finish, WF_BLOCK, 0, stream>>>(P, wf, i, base, batch);
         ++*launches;
     }
     MARK(TR_KCLASS_END);

@@ -59,7 +59,7 @@ cudaError_t tr_render_init_constants();
 const uint4* tr_render_sobol_chunks();
 // One pass (= samples_per_pass samples of every slot) of path_tracer.rgen.
 cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const trd::RenderParams& P, const tr_wavefront& wf,
-                                     int sm_count, uint64_t* launches, tr_launch_timer* timer);
+                                     int sm_count, uint64_t* launches, tr_launch_timer* timer, uint32_t batch);
 cudaError_t tr_render_pass_megakernel(cudaStream_t stream, const trd::RenderParams& P, int sm_count, uint64_t* launches,
                                       tr_launch_timer* timer);
 cudaError_t tr_render_feature(cudaStream_t stream, const trd::RenderParams& P, int feature, const float default_value[4]);
