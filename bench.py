@@ -362,8 +362,8 @@ def main():
                        "culled_shadow_rays_per_frame": culled_all,
                        "distribution": "shuffled-strips", "stitch": ren.stitch, "rays_per_frame": rays_all / args.steps,
                        "l2": "inputs exceed L2: BVH+triangles+vertices ~%.0f MB, wavefront state ~%.0f MB per rank" % (
-                           (st["bvh_node_count"] * 64 + st["triangle_count"] * 48 * 2 + st["triangle_count"] * 12) / 1e6,
-                           WIDTH * HEIGHT / world * 276 / 1e6),
+                           (st["bvh_node_count"] * 80 + st["triangle_count"] * 48 * 2 + st["triangle_count"] * 12) / 1e6,
+                           WIDTH * HEIGHT / world * SPP * 236 / 1e6),
                        "bvh_build_ms": st["bvh_build_ms"], "bvh_nodes": st["bvh_node_count"], "bvh_depth": st["bvh_depth"],
                        "scene_upload_s": t_scene, "scene_generate_s": t_gen, "wall_s_timed": wall},
             "roofline": roofline,
