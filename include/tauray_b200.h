@@ -63,7 +63,9 @@ enum { TR_FEATURE_ALBEDO = 0, TR_FEATURE_WORLD_NORMAL = 1, TR_FEATURE_VIEW_NORMA
 /* kernel organisation of the hot loop (ours) */
 enum { TR_KERNEL_WAVEFRONT = 0, TR_KERNEL_MEGAKERNEL = 1 };
 /* texture formats accepted in tr_texture */
-enum { TR_TEXTURE_RGBA8_UNORM = 0, TR_TEXTURE_RGBA32F = 1 };
+enum { TR_TEXTURE_RGBA8_UNORM = 0, TR_TEXTURE_RGBA32F = 1, TR_TEXTURE_RGBA16F = 2 };
+/* environment_map::projection, src/environment_map.hh:12-15 */
+enum { TR_ENVMAP_NONE = -1, TR_ENVMAP_LAT_LONG = 0 };
 
 /* ---- scene tables ------------------------------------------------------------------ */
 /* mesh::vertex, src/mesh.hh:19-25 == shader/scene.glsl:14-20 */
@@ -193,8 +195,14 @@ typedef struct tr_pt_scene_desc {
     const tr_directional_light* directional_lights;
     const tr_texture* textures;
     float environment_factor[4];        /* scene_metadata.environment_factor */
-    int32_t environment_proj;           /* -1: no environment map (the only supported value) */
+    int32_t environment_proj;           /* TR_ENVMAP_NONE (-1) or TR_ENVMAP_LAT_LONG */
     uint32_t reserved;
+    /* Texels of the environment map when environment_proj >= 0 (RGBA16F like the reference's .hdr
+     * textures, src/texture.cc:498-510, or RGBA32F); sampled bilinearly with repeat in x and
+     * clamp-to-edge in y (envmap_sampler, src/scene_stage.cc:259-265). The importance-sampling
+     * alias table (environment_map::generate_alias_table, src/environment_map.cc:39-140 +
+     * shader/alias_table_importance.comp) is built by tr_pt_set_scene. NULL otherwise. */
+    const tr_texture* environment_map;
 } tr_pt_scene_desc;
 
 /* ---- options: field names and meaning follow path_tracer_stage::options
@@ -362,6 +370,9 @@ int tr_pt_set_instrumentation(tr_pt_ctx* ctx, int flags);
 
 /* Test hooks (device results copied to the host). */
 int tr_pt_read_tri_lights(tr_pt_ctx* ctx, tr_tri_light* out, uint32_t capacity);
+/* The environment map's alias table (width * height entries, row-major); returns the number of
+ * entries written, or a negative error. */
+int tr_pt_read_alias_table(tr_pt_ctx* ctx, tr_alias_table_entry* out, uint32_t capacity);
 /* Traces `n` rays (origin.xyz,tmin / dir.xyz,tmax as 8 floats each) through the LBVH with the
  * closest-hit kernel; out = n * {int instance_id, int primitive_id, float u, float v, float t}. */
 int tr_pt_trace_rays(tr_pt_ctx* ctx, const float* rays, uint32_t n, void* hits_out);

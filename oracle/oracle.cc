@@ -100,6 +100,8 @@ struct orc_ctx
     std::vector<texture_data> textures;
     vec4 environment_factor = V4(0, 0, 0, 0);
     int environment_proj = -1;
+    texture_data envmap;
+    std::vector<tr_alias_table_entry> alias_table;
     bool any_non_opaque = false;
     bvh accel;
 
@@ -194,8 +196,147 @@ struct orc_ctx
             const float* f = reinterpret_cast<const float*>(t.bytes.data());
             return V4(f[i], f[i + 1], f[i + 2], f[i + 3]);
         }
+        if(t.format == TR_TEXTURE_RGBA16F)
+        {
+            const uint16_t* hf = reinterpret_cast<const uint16_t*>(t.bytes.data());
+            return V4(half_to_float_(hf[i]), half_to_float_(hf[i + 1]), half_to_float_(hf[i + 2]), half_to_float_(hf[i + 3]));
+        }
         const uint8_t* b = t.bytes.data();
         return V4((float)b[i] / 255.0f, (float)b[i + 1] / 255.0f, (float)b[i + 2] / 255.0f, (float)b[i + 3] / 255.0f);
+    }
+    // envmap_sampler (src/scene_stage.cc:259-265): linear, repeat in x, clamp-to-edge in y, LOD 0
+    vec4 sample_envmap_texture(vec2 uv) const
+    {
+        const texture_data& t = envmap;
+        float x = uv.x * (float)t.w - 0.5f;
+        float y = uv.y * (float)t.h - 0.5f;
+        if(!(fabsf(x) < 1e9f)) x = 0.0f;
+        if(!(fabsf(y) < 1e9f)) y = 0.0f;
+        float fx0 = floorf(x), fy0 = floorf(y);
+        float fx = x - fx0, fy = y - fy0;
+        int w = (int)t.w, h = (int)t.h;
+        int x0 = (int)fx0 % w; if(x0 < 0) x0 += w;
+        int x1 = x0 + 1 == w ? 0 : x0 + 1;
+        int y0 = std::min(std::max((int)fy0, 0), h - 1);
+        int y1 = std::min(std::max((int)fy0 + 1, 0), h - 1);
+        vec4 top = mix_(texel(t, x0, y0), texel(t, x1, y0), fx);
+        vec4 bot = mix_(texel(t, x0, y1), texel(t, x1, y1), fx);
+        return mix_(top, bot, fy);
+    }
+
+    // ------------------------------------------------------------------------------------
+    // shader/alias_table.glsl:23-37, shader/rt.glsl:251-300
+    // ------------------------------------------------------------------------------------
+    static int latlong_direction_to_pixel_id(vec3 dir, int sx, int sy)
+    {
+        vec2 uv = V2(atan2_(dir.z, dir.x) * 0.5f / TR_PI + 0.5f, asin_(-dir.y) / TR_PI + 0.5f);
+        int px = (int)(uv.x * (float)sx + 0.5f);
+        int py = (int)(uv.y * (float)sy + 0.5f);
+        return px + py * sx;
+    }
+    static vec3 uv_to_latlong_direction(vec2 uv)
+    {
+        float ux = (uv.x - 0.5f) * TR_PI, uy = (uv.y - 0.5f) * TR_PI;
+        vec3 dir = V3(cos_(2.0f * ux), -sin_(uy), sin_(2.0f * ux));
+        float r = sqrtf(1.0f - dir.y * dir.y);
+        dir.x *= r; dir.z *= r;
+        return dir;
+    }
+    // out-of-range ids read as zero (robust buffer access); see DESIGN.md
+    tr_alias_table_entry alias_entry(int64_t i) const
+    {
+        if(i < 0 || i >= (int64_t)alias_table.size()) return tr_alias_table_entry{0u, 0u, 0.0f, 0.0f};
+        return alias_table[(size_t)i];
+    }
+    vec3 sample_environment_map(uvec4 rand, vec3& dir, float& length, float& pdf) const
+    {
+        vec3 color = xyz(environment_factor);
+        const uint32_t sx = envmap.w, sy = envmap.h;
+        const uint32_t pixel_count = sx * sy;
+        uint32_t ipx = std::min(rand.x / (0xFFFFFFFFu / sx), sx - 1u);
+        uint32_t ipy = std::min(rand.y / (0xFFFFFFFFu / sy), sy - 1u);
+        int i = (int)(ipx + ipy * sx);
+        tr_alias_table_entry at = alias_entry(i);
+        pdf = at.pdf;
+        if(rand.z > at.probability)
+        {
+            i = (int)at.alias_id;
+            pdf = at.alias_pdf;
+        }
+        const uint32_t px = (uint32_t)i % sx, py = (uint32_t)i / sx;
+        vec2 off = V2((float)(uint32_t)(rand.x * pixel_count) * TR_INV_UINT32_MAX, (float)(uint32_t)(rand.y * pixel_count) * TR_INV_UINT32_MAX);
+        vec2 uv = V2(((float)(int)px + off.x) / (float)sx, ((float)(int)py + off.y) / (float)sy);
+        dir = uv_to_latlong_direction(uv);
+        color = color * xyz(sample_envmap_texture(uv));
+        length = INFINITY; // RAY_MAX_DIST = float(1e39), shader/rt.glsl:25
+        return color;
+    }
+    float sample_environment_map_pdf(vec3 dir) const
+    {
+        return alias_entry(latlong_direction_to_pixel_id(dir, (int)envmap.w, (int)envmap.h)).pdf;
+    }
+    // environment_map::generate_alias_table (src/environment_map.cc:39-140) with the importances of
+    // shader/alias_table_importance.comp:19-31
+    void generate_alias_table()
+    {
+        const int sx = (int)envmap.w, sy = (int)envmap.h;
+        const unsigned pixel_count = (unsigned)(sx * sy);
+        std::vector<float> importance(pixel_count);
+        for(int y = 0; y < sy; ++y)
+        {
+            float y0 = (float)y / (float)sy, y1 = (float)(y + 1) / (float)sy;
+            float solid_angle = 2.0f * TR_PI * (cos_(TR_PI * y0) - cos_(TR_PI * y1)) / (float)sx;
+            for(int x = 0; x < sx; ++x)
+            {
+                vec4 c = texel(envmap, x, y);
+                importance[(size_t)y * sx + x] = dot(xyz(c), V3(0.2126f, 0.7152f, 0.0722f)) * solid_angle;
+            }
+        }
+        double sum_importance = 0;
+        for(unsigned i = 0; i < pixel_count; ++i) sum_importance += importance[i];
+        double average = sum_importance / double(pixel_count);
+        float inv_average = (float)(1.0 / average);
+        for(unsigned i = 0; i < pixel_count; ++i) importance[i] *= inv_average;
+
+        auto to_prob = [](float v) { return (uint32_t)(int64_t)ldexpf(v, 32); }; // x86-64 float->unsigned: via 64 bits, truncated
+        alias_table.assign(pixel_count, tr_alias_table_entry{0u, 0xFFFFFFFFu, 1.0f, 1.0f});
+        for(unsigned i = 0; i < pixel_count; ++i) alias_table[i].alias_id = i;
+        unsigned i = 0, j = 0; // i: light items, j: heavy items
+        while(i < pixel_count && importance[i] > 1.0f) ++i;
+        while(j < pixel_count && importance[j] <= 1.0f) ++j;
+        float weight = j < pixel_count ? importance[j] : 0.0f;
+        while(j < pixel_count)
+        {
+            if(weight > 1.0f)
+            {
+                if(i >= pixel_count) break; // (the reference tests i > pixel_count and would write one past the end)
+                alias_table[i].probability = to_prob(importance[i]);
+                alias_table[i].alias_id = j;
+                weight = (weight + importance[i]) - 1.0f;
+                ++i;
+                while(i < pixel_count && importance[i] > 1.0f) ++i;
+            }
+            else
+            {
+                alias_table[j].probability = to_prob(weight);
+                unsigned old_j = j;
+                ++j;
+                while(j < pixel_count && importance[j] <= 1.0f) ++j;
+                if(j < pixel_count)
+                {
+                    alias_table[old_j].alias_id = j;
+                    weight = (weight + importance[j]) - 1.0f;
+                }
+            }
+        }
+        std::vector<float> sin_theta((size_t)sy);
+        for(int y = 0; y < sy; ++y) sin_theta[(size_t)y] = (float)sin(((float)y + 0.5f) / (float)sy * M_PI);
+        for(unsigned k = 0; k < pixel_count; ++k)
+        {
+            unsigned a = alias_table[k].alias_id;
+            alias_table[k].pdf = (float)(importance[k] / (2.0f * M_PI * M_PI * sin_theta[k / (unsigned)sx]));
+            alias_table[k].alias_pdf = (float)(importance[a] / (2.0f * M_PI * M_PI * sin_theta[a / (unsigned)sx]));
+        }
     }
     vec4 sample_texture(int id, vec2 uv) const
     {
@@ -526,6 +667,14 @@ struct orc_ctx
         else
         {
             vec4 color = environment_factor;
+            if(environment_proj >= 0)
+            {
+                vec2 uv;
+                uv.y = asin_(-view.y) / TR_PI + 0.5f;
+                uv.x = atan2_(view.z, view.x) / (2.0f * TR_PI) + 0.5f;
+                vec3 t = xyz(sample_envmap_texture(uv));
+                color.x *= t.x; color.y *= t.y; color.z *= t.z;
+            }
             mat.emission = V3(0);
             light = V3(0);
             for(size_t i = 0; i < directional_lights.size(); ++i)
@@ -550,7 +699,7 @@ struct orc_ctx
             if(opt.sampling_weight_envmap > 0)
             {
                 light += xyz(color);
-                nee_pdf.envmap_pdf = environment_proj >= 0 ? 0.0f /* envmap unsupported */ : 0.0f;
+                nee_pdf.envmap_pdf = environment_proj >= 0 ? sample_environment_map_pdf(view) : 0.0f;
             }
             else mat.emission += xyz(color);
             return false;
@@ -608,13 +757,9 @@ struct orc_ctx
         }
         else if(opt.sampling_weight_envmap > 0 && (u.w -= envmap_prob) < 0)
         {
-            // Environment maps are outside this round's scope; envmap_prob is
-            // 0 because set_scene rejects environment_proj >= 0, so this is only reachable
-            // through rounding of u.w and contributes nothing, like the fall-through below.
-            pdf = 1.0f;
-            out_dir = V3(0);
-            out_length = 0.0f;
-            return V3(0);
+            vec3 color = sample_environment_map(rand_uint, out_dir, out_length, pdf);
+            pdf *= envmap_prob;
+            return color;
         }
         else if(opt.sampling_weight_directional_lights > 0 && (u.w -= dir_prob) < 0)
         {
@@ -983,7 +1128,9 @@ void orc_destroy(orc_ctx* ctx) { delete ctx; }
 int orc_set_scene(orc_ctx* ctx, const tr_pt_scene_desc* s)
 {
     if(!ctx || !s) return fail(ctx, TR_ERR_INVALID_ARGUMENT, "null argument");
-    if(s->environment_proj >= 0) return fail(ctx, TR_ERR_UNSUPPORTED, "environment maps are outside the hot-path scope");
+    if(s->environment_proj > TR_ENVMAP_LAT_LONG) return fail(ctx, TR_ERR_UNSUPPORTED, "unknown environment map projection");
+    if(s->environment_proj >= 0 && (!s->environment_map || !s->environment_map->data || !s->environment_map->width || !s->environment_map->height))
+        return fail(ctx, TR_ERR_INVALID_ARGUMENT, "environment_proj >= 0 needs environment_map texels");
     ctx->instances.assign(s->instances, s->instances + s->instance_count);
     ctx->vertices.assign(s->instance_count, {});
     ctx->indices.assign(s->instance_count, {});
@@ -995,12 +1142,24 @@ int orc_set_scene(orc_ctx* ctx, const tr_pt_scene_desc* s)
     {
         texture_data t;
         t.w = s->textures[i].width; t.h = s->textures[i].height; t.format = s->textures[i].format;
-        size_t bytes = (size_t)t.w * t.h * (t.format == TR_TEXTURE_RGBA32F ? 16 : 4);
+        size_t bytes = (size_t)t.w * t.h * (t.format == TR_TEXTURE_RGBA32F ? 16 : t.format == TR_TEXTURE_RGBA16F ? 8 : 4);
         t.bytes.assign((const uint8_t*)s->textures[i].data, (const uint8_t*)s->textures[i].data + bytes);
         ctx->textures.push_back(std::move(t));
     }
     ctx->environment_factor = V4(s->environment_factor[0], s->environment_factor[1], s->environment_factor[2], s->environment_factor[3]);
     ctx->environment_proj = s->environment_proj;
+    ctx->envmap = texture_data();
+    ctx->alias_table.clear();
+    if(s->environment_proj >= 0)
+    {
+        const tr_texture& e = *s->environment_map;
+        if(e.format != TR_TEXTURE_RGBA16F && e.format != TR_TEXTURE_RGBA32F)
+            return fail(ctx, TR_ERR_INVALID_ARGUMENT, "environment map must be RGBA16F or RGBA32F");
+        ctx->envmap.w = e.width; ctx->envmap.h = e.height; ctx->envmap.format = e.format;
+        size_t bytes = (size_t)e.width * e.height * (e.format == TR_TEXTURE_RGBA32F ? 16 : 8);
+        ctx->envmap.bytes.assign((const uint8_t*)e.data, (const uint8_t*)e.data + bytes);
+        ctx->generate_alias_table();
+    }
     ctx->any_non_opaque = false;
 
     std::vector<tri_record> tris;
@@ -1225,6 +1384,14 @@ int orc_read_tri_lights(orc_ctx* ctx, tr_tri_light* out, uint32_t capacity)
     uint32_t n = (uint32_t)std::min<size_t>(capacity, ctx->tri_lights.size());
     if(out && n) memcpy(out, ctx->tri_lights.data(), n * sizeof(tr_tri_light));
     return (int)ctx->tri_lights.size();
+}
+
+int orc_read_alias_table(orc_ctx* ctx, tr_alias_table_entry* out, uint32_t capacity)
+{
+    if(!ctx) return TR_ERR_INVALID_ARGUMENT;
+    uint32_t n = (uint32_t)std::min<size_t>(capacity, ctx->alias_table.size());
+    if(out && n) memcpy(out, ctx->alias_table.data(), n * sizeof(tr_alias_table_entry));
+    return (int)ctx->alias_table.size();
 }
 
 int orc_trace_rays(orc_ctx* ctx, const float* rays, uint32_t n, void* hits_out)

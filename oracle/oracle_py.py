@@ -43,6 +43,7 @@ def lib():
         l.orc_read_color.argtypes = [vp, vp, C.c_size_t]
         l.orc_get_stats.argtypes = [vp, C.POINTER(abi.Stats)]
         l.orc_read_tri_lights.argtypes = [vp, vp, C.c_uint32]
+        l.orc_read_alias_table.argtypes = [vp, vp, C.c_uint32]
         l.orc_trace_rays.argtypes = [vp, vp, C.c_uint32, vp]
         l.orc_sample_test.argtypes = [vp, vp, C.c_uint32, C.c_int, vp]
         l.orc_unshuffle.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp]
@@ -125,6 +126,12 @@ class Oracle:
         n = self._check(self._l.orc_read_tri_lights(self._ctx, None, 0), "orc_read_tri_lights")
         out = np.zeros(max(n, 1), dtype=abi.TRI_LIGHT)
         self._l.orc_read_tri_lights(self._ctx, out.ctypes.data, n)
+        return out[:n]
+
+    def alias_table(self):
+        n = self._check(self._l.orc_read_alias_table(self._ctx, None, 0), "orc_read_alias_table")
+        out = np.zeros(max(n, 1), dtype=abi.ALIAS_TABLE_ENTRY)
+        self._l.orc_read_alias_table(self._ctx, out.ctypes.data, n)
         return out[:n]
 
     def trace_rays(self, rays):

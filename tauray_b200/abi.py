@@ -25,7 +25,8 @@ FEATURE_ALBEDO, FEATURE_WORLD_NORMAL, FEATURE_VIEW_NORMAL, FEATURE_WORLD_POS, FE
 FEATURE_INSTANCE_ID = 9
 KERNEL_WAVEFRONT, KERNEL_MEGAKERNEL = range(2)
 INSTRUMENT_VISITS, INSTRUMENT_TIMING = 1, 2
-TEXTURE_RGBA8_UNORM, TEXTURE_RGBA32F = range(2)
+TEXTURE_RGBA8_UNORM, TEXTURE_RGBA32F, TEXTURE_RGBA16F = range(3)
+ENVMAP_NONE, ENVMAP_LAT_LONG = -1, 0
 
 OK = 0
 ERR_INVALID_ARGUMENT, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED, ERR_NO_SCENE, ERR_OUT_OF_MEMORY = -1, -2, -3, -4, -5, -6
@@ -60,6 +61,7 @@ CAMERA_DATA = np.dtype([
 ])
 CAMERA_PAIR = np.dtype([("current", CAMERA_DATA), ("previous", CAMERA_DATA)])
 HIT = np.dtype([("instance_id", "<i4"), ("primitive_id", "<i4"), ("u", "<f4"), ("v", "<f4"), ("t", "<f4")])
+ALIAS_TABLE_ENTRY = np.dtype([("alias_id", "<u4"), ("probability", "<u4"), ("pdf", "<f4"), ("alias_pdf", "<f4")])
 
 assert VERTEX.itemsize == 48 and MATERIAL.itemsize == 80 and INSTANCE.itemsize == 288
 assert DIRECTIONAL_LIGHT.itemsize == 32 and POINT_LIGHT.itemsize == 64 and TRI_LIGHT.itemsize == 64
@@ -88,7 +90,7 @@ class SceneDesc(C.Structure):
                 ("instances", C.c_void_p), ("meshes", C.POINTER(MeshRef)), ("point_lights", C.c_void_p),
                 ("directional_lights", C.c_void_p), ("textures", C.POINTER(Texture)),
                 ("environment_factor", C.c_float * 4), ("environment_proj", C.c_int32),
-                ("reserved", C.c_uint32)]
+                ("reserved", C.c_uint32), ("environment_map", C.POINTER(Texture))]
 
 
 class Options(C.Structure):

@@ -11,6 +11,7 @@
 #include "tr_render.h"
 #include "tr_build.h"
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -322,10 +323,71 @@ void tr_pt_destroy(tr_pt_ctx* c)
     delete c;
 }
 
+// The host half of environment_map::generate_alias_table (src/environment_map.cc:63-120): normalise the
+// importances to mean 1, one sweep pairing under-full ("light") with over-full ("heavy") texels
+// (arXiv:1903.00227), then the per-texel solid-angle pdfs. `imp` is normalised in place.
+static void build_alias_table(std::vector<float>& imp, uint32_t width, uint32_t height, std::vector<tr_alias_table_entry>& table)
+{
+    const uint32_t n = width * height;
+    double total = 0.0;
+    for(float v: imp) total += v;
+    const float inv_mean = (float)(1.0 / (total / (double)n));
+    for(float& v: imp) v *= inv_mean;
+
+    table.resize(n);
+    for(uint32_t k = 0; k < n; ++k) table[k] = tr_alias_table_entry{k, 0xFFFFFFFFu, 1.0f, 1.0f};
+    // 2^32 * v as the x86-64 build of the reference converts it: through 64 bits, truncated to 32
+    auto fixed32 = [](float v) { return (uint32_t)(long long)std::ldexp(v, 32); };
+    auto next_light = [&](uint32_t k) { while(k < n && imp[k] > 1.0f) ++k; return k; };
+    auto next_heavy = [&](uint32_t k) { while(k < n && imp[k] <= 1.0f) ++k; return k; };
+    uint32_t light = next_light(0), heavy = next_heavy(0);
+    float carry = heavy < n ? imp[heavy] : 0.0f;   // what is left of the current heavy texel
+    while(heavy < n)
+    {
+        if(carry > 1.0f)
+        {
+            // top a light texel up from the heavy one
+            if(light >= n) break;   // the reference tests `>` and would write one entry past the end
+            table[light].probability = fixed32(imp[light]);
+            table[light].alias_id = heavy;
+            carry = (carry + imp[light]) - 1.0f;
+            light = next_light(light + 1);
+        }
+        else
+        {
+            // the heavy texel has become light itself: it is topped up by the next heavy one
+            const uint32_t done = heavy;
+            table[done].probability = fixed32(carry);
+            heavy = next_heavy(heavy + 1);
+            if(heavy < n)
+            {
+                table[done].alias_id = heavy;
+                carry = (carry + imp[heavy]) - 1.0f;
+            }
+        }
+    }
+    std::vector<float> row_sin(height);
+    for(uint32_t y = 0; y < height; ++y) row_sin[y] = (float)std::sin(((float)y + 0.5f) / (float)height * M_PI);
+    for(uint32_t k = 0; k < n; ++k)
+    {
+        const uint32_t a = table[k].alias_id;
+        table[k].pdf = (float)(imp[k] / (2.0f * M_PI * M_PI * row_sin[k / width]));
+        table[k].alias_pdf = (float)(imp[a] / (2.0f * M_PI * M_PI * row_sin[a / width]));
+    }
+}
+
 int tr_pt_set_scene(tr_pt_ctx* c, const tr_pt_scene_desc* s)
 {
     if(!c || !s) return fail(c, TR_ERR_INVALID_ARGUMENT, "null argument");
-    if(s->environment_proj >= 0) return fail(c, TR_ERR_UNSUPPORTED, "environment maps are outside the hot-path scope");
+    if(s->environment_proj > TR_ENVMAP_LAT_LONG) return fail(c, TR_ERR_UNSUPPORTED, "unknown environment map projection");
+    if(s->environment_proj >= 0)
+    {
+        const tr_texture* e = s->environment_map;
+        if(!e || !e->data || !e->width || !e->height) return fail(c, TR_ERR_INVALID_ARGUMENT, "environment_proj >= 0 needs environment_map texels");
+        if(e->format != TR_TEXTURE_RGBA16F && e->format != TR_TEXTURE_RGBA32F)
+            return fail(c, TR_ERR_INVALID_ARGUMENT, "environment map must be RGBA16F or RGBA32F");
+        if((uint64_t)e->width * e->height >= (1ull << 31)) return fail(c, TR_ERR_UNSUPPORTED, "environment map too large");
+    }
     if(s->instance_count && (!s->instances || !s->meshes)) return fail(c, TR_ERR_INVALID_ARGUMENT, "null instance tables");
     DeviceGuard guard(c->device);
     TRY_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -407,8 +469,8 @@ int tr_pt_set_scene(tr_pt_ctx* c, const tr_pt_scene_desc* s)
     for(uint32_t i = 0; i < s->texture_count; ++i)
     {
         const tr_texture& t = s->textures[i];
-        if(!t.data || t.width == 0 || t.height == 0 || t.format > TR_TEXTURE_RGBA32F) return fail(c, TR_ERR_INVALID_ARGUMENT, "bad texture");
-        const size_t bytes = (size_t)t.width * t.height * (t.format == TR_TEXTURE_RGBA32F ? 16 : 4);
+        if(!t.data || t.width == 0 || t.height == 0 || t.format > TR_TEXTURE_RGBA16F) return fail(c, TR_ERR_INVALID_ARGUMENT, "bad texture");
+        const size_t bytes = (size_t)t.width * t.height * (t.format == TR_TEXTURE_RGBA32F ? 16 : t.format == TR_TEXTURE_RGBA16F ? 8 : 4);
         uint8_t* d = nullptr;
         TRY_CUDA(c, dev_alloc(A, &d, bytes));
         TRY_CUDA(c, cudaMemcpyAsync(d, t.data, bytes, cudaMemcpyHostToDevice, st));
@@ -417,6 +479,33 @@ int tr_pt_set_scene(tr_pt_ctx* c, const tr_pt_scene_desc* s)
     DeviceTexture* d_tex = nullptr;
     TRY_CUDA(c, dev_alloc(A, &d_tex, s->texture_count));
     if(s->texture_count) TRY_CUDA(c, cudaMemcpyAsync(d_tex, htex.data(), sizeof(DeviceTexture) * htex.size(), cudaMemcpyHostToDevice, st));
+
+    // ---- environment map + alias table (environment_map::generate_alias_table, src/environment_map.cc:39-140)
+    DeviceTexture env_tex{};
+    tr_alias_table_entry* d_alias = nullptr;
+    if(s->environment_proj >= 0)
+    {
+        const tr_texture& e = *s->environment_map;
+        const size_t texels = (size_t)e.width * e.height;
+        const size_t bytes = texels * (e.format == TR_TEXTURE_RGBA32F ? 16 : 8);
+        uint8_t* d = nullptr;
+        float* d_importance = nullptr;
+        TRY_CUDA(c, dev_alloc(A, &d, bytes));
+        TRY_CUDA(c, dev_alloc(A, &d_alias, texels));
+        TRY_CUDA(c, cudaMalloc(&d_importance, sizeof(float) * texels));
+        std::vector<float> importance(texels);
+        cudaError_t e1 = cudaMemcpyAsync(d, e.data, bytes, cudaMemcpyHostToDevice, st);
+        if(e1 == cudaSuccess) e1 = tr_build_envmap_importance(st, d, e.format, e.width, e.height, d_importance);
+        if(e1 == cudaSuccess) e1 = cudaMemcpyAsync(importance.data(), d_importance, sizeof(float) * texels, cudaMemcpyDeviceToHost, st);
+        if(e1 == cudaSuccess) e1 = cudaStreamSynchronize(st);
+        cudaFree(d_importance);
+        if(e1 != cudaSuccess) return fail_cuda(c, e1, "environment map importances");
+        std::vector<tr_alias_table_entry> table;
+        build_alias_table(importance, e.width, e.height, table);
+        TRY_CUDA(c, cudaMemcpyAsync(d_alias, table.data(), sizeof(tr_alias_table_entry) * texels, cudaMemcpyHostToDevice, st));
+        TRY_CUDA(c, cudaStreamSynchronize(st));   // `table` is pageable host memory
+        env_tex.data = d; env_tex.width = e.width; env_tex.height = e.height; env_tex.format = e.format; env_tex.pad = 0;
+    }
 
     // ---- extract_tri_lights.comp
     tr_tri_light* d_tl = nullptr;
@@ -458,6 +547,8 @@ int tr_pt_set_scene(tr_pt_ctx* c, const tr_pt_scene_desc* s)
     memcpy(ds.environment_factor, s->environment_factor, 16);
     ds.environment_proj = s->environment_proj;
     ds.any_non_opaque = any_non_opaque ? 1u : 0u;
+    ds.envmap = env_tex;
+    ds.alias_table = d_alias;
     c->has_scene = true;
     c->stats.bvh_build_ms = build_ms;
     c->stats.bvh_node_count = bout.node_count;
@@ -767,6 +858,17 @@ int tr_pt_read_tri_lights(tr_pt_ctx* c, tr_tri_light* out, uint32_t capacity)
     const uint32_t n = std::min(capacity, c->scene.tri_light_count);
     if(out && n) TRY_CUDA(c, cudaMemcpy(out, c->scene.tri_lights, sizeof(tr_tri_light) * n, cudaMemcpyDeviceToHost));
     return (int)c->scene.tri_light_count;
+}
+
+int tr_pt_read_alias_table(tr_pt_ctx* c, tr_alias_table_entry* out, uint32_t capacity)
+{
+    if(!c) return TR_ERR_INVALID_ARGUMENT;
+    if(!c->has_scene) return fail(c, TR_ERR_NO_SCENE, "no scene");
+    DeviceGuard guard(c->device);
+    const uint32_t total = c->scene.environment_proj >= 0 ? c->scene.envmap.width * c->scene.envmap.height : 0u;
+    const uint32_t n = std::min(capacity, total);
+    if(out && n) TRY_CUDA(c, cudaMemcpy(out, c->scene.alias_table, sizeof(tr_alias_table_entry) * n, cudaMemcpyDeviceToHost));
+    return (int)total;
 }
 
 int tr_pt_trace_rays(tr_pt_ctx* c, const float* rays, uint32_t n, void* hits_out)

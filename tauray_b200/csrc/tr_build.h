@@ -36,4 +36,7 @@ cudaError_t tr_build_pre_transform(cudaStream_t stream, const tr_vertex* in, tr_
 cudaError_t tr_build_extract_tri_lights(cudaStream_t stream, const tr_vertex* verts, const uint32_t* indices,
                                         uint32_t triangle_count, uint32_t instance_id, int32_t light_base_id,
                                         const float emission[3], int32_t emission_tex_id, tr_tri_light* out);
+// importance = luminance * texel solid angle of a lat-long environment map (RGBA16F / RGBA32F texels on the device)
+cudaError_t tr_build_envmap_importance(cudaStream_t stream, const void* texels, uint32_t format, uint32_t width, uint32_t height,
+                                       float* importance_dev);
 cudaError_t tr_build_bvh(cudaStream_t stream, const tr_build_input& in, tr_build_output* out);

@@ -725,6 +725,40 @@ cudaError_t tr_build_extract_tri_lights(cudaStream_t stream, const tr_vertex* ve
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------
+// environment map importances: shader/alias_table_importance.comp:19-31 with
+// latlong_texel_solid_angle (shader/alias_table.glsl:15-20)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_envmap_importance(const void* __restrict__ texels, uint32_t format, int sx, int sy, float* __restrict__ importance)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if(x >= sx || y >= sy) return;
+    const size_t i = (size_t)y * sx + x;
+    vec3 c;
+    if(format == TR_TEXTURE_RGBA32F)
+    {
+        const float4 f = reinterpret_cast<const float4*>(texels)[i];
+        c = V3(f.x, f.y, f.z);
+    }
+    else
+    {
+        const uint2 h = reinterpret_cast<const uint2*>(texels)[i];
+        c = V3(half_to_float_(h.x & 0xFFFFu), half_to_float_(h.x >> 16), half_to_float_(h.y & 0xFFFFu));
+    }
+    const float y0 = (float)y / (float)sy, y1 = (float)(y + 1) / (float)sy;
+    const float solid_angle = 2.0f * TR_PI * (cos_(TR_PI * y0) - cos_(TR_PI * y1)) / (float)sx;
+    importance[i] = dot(c, V3(0.2126f, 0.7152f, 0.0722f)) * solid_angle;
+}
+
+cudaError_t tr_build_envmap_importance(cudaStream_t stream, const void* texels, uint32_t format, uint32_t width, uint32_t height,
+                                       float* importance_dev)
+{
+    dim3 block(16, 16), grid(div_up(width, 16), div_up(height, 16));
+    k_envmap_importance<<<grid, block, 0, stream>>>(texels, format, (int)width, (int)height, importance_dev);
+    return cudaGetLastError();
+}
+
 cudaError_t tr_build_bvh(cudaStream_t stream, const tr_build_input& in, tr_build_output* out)
 {
     const uint32_t n = in.triangle_count;

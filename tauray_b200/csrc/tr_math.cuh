@@ -73,6 +73,8 @@ TRD float atan2_(float y, float x)
     if(x < 0.0f) r = 3.1415927410125732f - r;
     return y < 0.0f ? -r : r;
 }
+TRD float sin_(float x) { float s, c; sincos_(x, &s, &c); return s; }
+TRD float cos_(float x) { float s, c; sincos_(x, &s, &c); return c; }
 TRD float asin_(float x) { return atan2_(x, sqrtf((1.0f - x) * (1.0f + x))); }
 TRD float acos_(float x) { return atan2_(sqrtf((1.0f - x) * (1.0f + x)), x); }
 

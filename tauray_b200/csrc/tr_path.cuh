@@ -118,6 +118,11 @@ TRD vec4 texel(const DeviceTexture& t, int x, int y)
         float4 f = __ldg(reinterpret_cast<const float4*>(t.data) + i);
         return V4(f.x, f.y, f.z, f.w);
     }
+    if(t.format == TR_TEXTURE_RGBA16F)
+    {
+        uint2 h = __ldg(reinterpret_cast<const uint2*>(t.data) + i);
+        return V4(half_to_float_(h.x & 0xFFFFu), half_to_float_(h.x >> 16), half_to_float_(h.y & 0xFFFFu), half_to_float_(h.y >> 16));
+    }
     uchar4 b = __ldg(reinterpret_cast<const uchar4*>(t.data) + i);
     return V4((float)b.x / 255.0f, (float)b.y / 255.0f, (float)b.z / 255.0f, (float)b.w / 255.0f);
 }
@@ -138,6 +143,91 @@ TRD vec4 sample_texture(const DeviceScene& s, int id, vec2 uv)
     vec4 top = mix_(texel(t, x0, y0), texel(t, x1, y0), fx);
     vec4 bot = mix_(texel(t, x0, y1), texel(t, x1, y1), fx);
     return mix_(top, bot, fy);
+}
+
+// envmap_sampler (src/scene_stage.cc:259-265): linear, repeat in x, clamp-to-edge in y, LOD 0
+TRD vec4 sample_envmap_texture(const DeviceScene& s, vec2 uv)
+{
+    const DeviceTexture t = s.envmap;
+    float x = uv.x * (float)t.width - 0.5f;
+    float y = uv.y * (float)t.height - 0.5f;
+    if(!(fabsf(x) < 1e9f)) x = 0.0f;
+    if(!(fabsf(y) < 1e9f)) y = 0.0f;
+    float fx0 = floorf(x), fy0 = floorf(y);
+    float fx = x - fx0, fy = y - fy0;
+    int w = (int)t.width, h = (int)t.height;
+    int x0 = (int)fx0 % w; if(x0 < 0) x0 += w;
+    int x1 = x0 + 1 == w ? 0 : x0 + 1;
+    int y0 = min(max((int)fy0, 0), h - 1);
+    int y1 = min(max((int)fy0 + 1, 0), h - 1);
+    vec4 top = mix_(texel(t, x0, y0), texel(t, x1, y0), fx);
+    vec4 bot = mix_(texel(t, x0, y1), texel(t, x1, y1), fx);
+    return mix_(top, bot, fy);
+}
+
+// ---------------------------------------------------------------------------------------------
+// environment map importance sampling: shader/alias_table.glsl:23-37, shader/rt.glsl:251-300
+// ---------------------------------------------------------------------------------------------
+// ids outside the table read as zero (Vulkan robust buffer access): the rounding in
+// latlong_direction_to_pixel_id can produce row == height.
+TRD tr_alias_table_entry alias_entry(const DeviceScene& s, int i)
+{
+    tr_alias_table_entry e;
+    e.alias_id = 0u; e.probability = 0u; e.pdf = 0.0f; e.alias_pdf = 0.0f;
+    if(i >= 0 && (uint32_t)i < s.envmap.width * s.envmap.height)
+    {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(s.alias_table) + i);
+        e.alias_id = q.x; e.probability = q.y; e.pdf = __uint_as_float(q.z); e.alias_pdf = __uint_as_float(q.w);
+    }
+    return e;
+}
+
+TRD int latlong_direction_to_pixel_id(vec3 dir, int sx, int sy)
+{
+    const float u = atan2_(dir.z, dir.x) * 0.5f / TR_PI + 0.5f;
+    const float v = asin_(-dir.y) / TR_PI + 0.5f;
+    const int px = (int)(u * (float)sx + 0.5f);
+    const int py = (int)(v * (float)sy + 0.5f);
+    return px + py * sx;
+}
+
+TRD vec3 uv_to_latlong_direction(vec2 uv)
+{
+    const float ux = (uv.x - 0.5f) * TR_PI, uy = (uv.y - 0.5f) * TR_PI;
+    vec3 dir = V3(cos_(2.0f * ux), -sin_(uy), sin_(2.0f * ux));
+    const float r = sqrtf(1.0f - dir.y * dir.y);
+    dir.x *= r; dir.z *= r;
+    return dir;
+}
+
+TRD vec3 sample_environment_map(const DeviceScene& s, uvec4 rand, vec3& dir, float& length, float& pdf)
+{
+    vec3 color = V3(s.environment_factor[0], s.environment_factor[1], s.environment_factor[2]);
+    const uint32_t sx = s.envmap.width, sy = s.envmap.height;
+    const uint32_t pixel_count = sx * sy;
+    const uint32_t ipx = min(rand.x / (0xFFFFFFFFu / sx), sx - 1u);
+    const uint32_t ipy = min(rand.y / (0xFFFFFFFFu / sy), sy - 1u);
+    int i = (int)(ipx + ipy * sx);
+    const tr_alias_table_entry at = alias_entry(s, i);
+    pdf = at.pdf;
+    if(rand.z > at.probability)
+    {
+        i = (int)at.alias_id;
+        pdf = at.alias_pdf;
+    }
+    const uint32_t px = (uint32_t)i % sx, py = (uint32_t)i / sx;
+    const float offx = (float)(rand.x * pixel_count) * TR_INV_UINT32_MAX;
+    const float offy = (float)(rand.y * pixel_count) * TR_INV_UINT32_MAX;
+    const vec2 uv = V2(((float)(int)px + offx) / (float)sx, ((float)(int)py + offy) / (float)sy);
+    dir = uv_to_latlong_direction(uv);
+    color = color * xyz(sample_envmap_texture(s, uv));
+    length = inf_();   // RAY_MAX_DIST = float(1e39), shader/rt.glsl:25
+    return color;
+}
+
+TRD float sample_environment_map_pdf(const DeviceScene& s, vec3 dir)
+{
+    return alias_entry(s, latlong_direction_to_pixel_id(dir, (int)s.envmap.width, (int)s.envmap.height)).pdf;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -503,10 +593,9 @@ TRD vec3 sample_explicit_light(const RenderParams& P, uvec4 rand_uint, vec3 pos,
     }
     else if(P.opt.sampling_weight_envmap > 0 && (u.w -= pr.envmap) < 0)
     {
-        pdf = 1.0f;
-        out_dir = V3(0);
-        out_length = 0.0f;
-        return V3(0);
+        vec3 color = sample_environment_map(P.scene, rand_uint, out_dir, out_length, pdf);
+        pdf *= pr.envmap;
+        return color;
     }
     else if(P.opt.sampling_weight_directional_lights > 0 && (u.w -= pr.directional) < 0)
     {
@@ -670,7 +759,14 @@ TRD bool shade_bounce(const RenderParams& P, const SobolTables& tables, uint32_t
     }
     else
     {
-        const vec3 env = V3(P.scene.environment_factor[0], P.scene.environment_factor[1], P.scene.environment_factor[2]);
+        vec3 env = V3(P.scene.environment_factor[0], P.scene.environment_factor[1], P.scene.environment_factor[2]);
+        if(P.scene.environment_proj >= 0)
+        {
+            vec2 uv;
+            uv.y = asin_(-view.y) / TR_PI + 0.5f;
+            uv.x = atan2_(view.z, view.x) / (2.0f * TR_PI) + 0.5f;
+            env = env * xyz(sample_envmap_texture(P.scene, uv));
+        }
         for(uint32_t i = 0; i < P.scene.directional_light_count; ++i)
         {
             const tr_directional_light dl = P.scene.directional_lights[i];
@@ -686,7 +782,11 @@ TRD bool shade_bounce(const RenderParams& P, const SobolTables& tables, uint32_t
         }
         v_pos = origin;
         v_mapped = -view;
-        if(P.opt.sampling_weight_envmap > 0) light += env;
+        if(P.opt.sampling_weight_envmap > 0)
+        {
+            light += env;
+            nee_pdf.envmap_pdf = P.scene.environment_proj >= 0 ? sample_environment_map_pdf(P.scene, view) : 0.0f;
+        }
         else mat.emission += env;
         surface = false;
     }

@@ -72,6 +72,8 @@ struct DeviceScene
     float environment_factor[4];
     int32_t environment_proj;
     uint32_t any_non_opaque;
+    DeviceTexture envmap;                          // lat-long texels (environment_proj >= 0)
+    const tr_alias_table_entry* alias_table;       // envmap.width * envmap.height entries
 };
 
 // distribution UBO (src/rt_camera_stage.cc:17-24) + push constants (src/path_tracer_stage.cc:10-20)

@@ -22,7 +22,7 @@ EXPORTS = [
     "tr_pt_default_options", "tr_pt_create", "tr_pt_destroy", "tr_pt_set_scene", "tr_pt_set_cameras",
     "tr_pt_set_distribution", "tr_pt_reset_accumulation", "tr_pt_render", "tr_pt_render_feature", "tr_pt_sync",
     "tr_pt_get_color_buffer", "tr_pt_read_color", "tr_pt_unshuffle", "tr_pt_set_peer_images", "tr_pt_get_stats",
-    "tr_pt_set_instrumentation", "tr_pt_read_tri_lights", "tr_pt_trace_rays", "tr_pt_sample_test",
+    "tr_pt_set_instrumentation", "tr_pt_read_tri_lights", "tr_pt_read_alias_table", "tr_pt_trace_rays", "tr_pt_sample_test",
     "tr_pt_last_error", "tr_pt_abi_version", "tr_pt_alloc_full_image", "tr_pt_ipc_get_handle",
     "tr_pt_ipc_open_handle", "tr_pt_ipc_close_handle", "tr_pt_set_color_buffer", "tr_pt_read_full_image", "tr_pt_enable_peer_access",
 ]
@@ -63,6 +63,7 @@ def lib():
     l.tr_pt_get_stats.argtypes = [vp, C.POINTER(abi.Stats)]
     l.tr_pt_set_instrumentation.argtypes = [vp, C.c_int]
     l.tr_pt_read_tri_lights.argtypes = [vp, vp, C.c_uint32]
+    l.tr_pt_read_alias_table.argtypes = [vp, vp, C.c_uint32]
     l.tr_pt_trace_rays.argtypes = [vp, vp, C.c_uint32, vp]
     l.tr_pt_sample_test.argtypes = [vp, vp, C.c_uint32, C.c_int, vp]
     l.tr_pt_alloc_full_image.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
@@ -217,6 +218,12 @@ class PathTracer:
         n = self._check(self._l.tr_pt_read_tri_lights(self._ctx, None, 0), "tr_pt_read_tri_lights")
         out = np.zeros(max(n, 1), dtype=abi.TRI_LIGHT)
         self._check(self._l.tr_pt_read_tri_lights(self._ctx, out.ctypes.data, n), "tr_pt_read_tri_lights")
+        return out[:n]
+
+    def alias_table(self):
+        n = self._check(self._l.tr_pt_read_alias_table(self._ctx, None, 0), "tr_pt_read_alias_table")
+        out = np.zeros(max(n, 1), dtype=abi.ALIAS_TABLE_ENTRY)
+        self._check(self._l.tr_pt_read_alias_table(self._ctx, out.ctypes.data, n), "tr_pt_read_alias_table")
         return out[:n]
 
     def trace_rays(self, rays):

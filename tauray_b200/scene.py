@@ -49,9 +49,22 @@ class Scene:
         self.textures = []        # (H, W, 4) uint8 or float32
         self.environment_factor = (0.0, 0.0, 0.0, 0.0)
         self.environment_proj = -1
+        self.environment_map = None   # (H, W, 4) float16 / float32 lat-long texels
         self._keep = None
 
     # -- building -------------------------------------------------------------------------
+    def set_environment_map(self, texels, factor=(1.0, 1.0, 1.0)):
+        """environment_map(path, LAT_LONG, factor): texels (H, W, 3|4) -> RGBA16F like the reference's
+        .hdr textures (src/texture.cc:498-510); scene_metadata gets vec4(factor, 1) (scene_stage.cc:1345)."""
+        t = np.asarray(texels)
+        if t.shape[2] == 3:
+            t = np.concatenate([t, np.ones(t.shape[:2] + (1,), dtype=t.dtype)], axis=2)
+        if t.dtype != np.float32:
+            t = t.astype(np.float16)
+        self.environment_map = np.ascontiguousarray(t)
+        self.environment_factor = (float(factor[0]), float(factor[1]), float(factor[2]), 1.0)
+        self.environment_proj = abi.ENVMAP_LAT_LONG
+
     def add_instance(self, vertices, indices, material, transform=None, opaque=None):
         vertices = np.ascontiguousarray(vertices, dtype=abi.VERTEX)
         indices = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1)
@@ -164,7 +177,8 @@ class Scene:
             texs[i].data = t.ctypes.data
             texs[i].width = t.shape[1]
             texs[i].height = t.shape[0]
-            texs[i].format = abi.TEXTURE_RGBA8_UNORM if t.dtype == np.uint8 else abi.TEXTURE_RGBA32F
+            texs[i].format = {np.dtype(np.uint8): abi.TEXTURE_RGBA8_UNORM, np.dtype(np.float16): abi.TEXTURE_RGBA16F,
+                              np.dtype(np.float32): abi.TEXTURE_RGBA32F}[t.dtype]
         d = abi.SceneDesc()
         d.instance_count = n
         d.point_light_count = self.point_lights.shape[0]
@@ -177,7 +191,18 @@ class Scene:
         d.textures = texs
         d.environment_factor = (C.c_float * 4)(*self.environment_factor)
         d.environment_proj = self.environment_proj
-        d._keep = (inst, mesh_refs, texs, self)
+        env = None
+        if self.environment_proj >= 0:
+            e = self.environment_map
+            assert e is not None and e.ndim == 3 and e.shape[2] == 4 and e.dtype in (np.float16, np.float32)
+            e = np.ascontiguousarray(e)
+            env = abi.Texture()
+            env.data = e.ctypes.data
+            env.width, env.height = e.shape[1], e.shape[0]
+            env.format = abi.TEXTURE_RGBA16F if e.dtype == np.float16 else abi.TEXTURE_RGBA32F
+            d.environment_map = C.pointer(env)
+            env = (env, e)
+        d._keep = (inst, mesh_refs, texs, self, env)
         return d
 
 

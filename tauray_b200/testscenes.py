@@ -147,3 +147,62 @@ def cornell_camera(aspect=1.0, fov_deg=45.0):
 
 def cornell_cameras(aspect=1.0):
     return camera_pairs([cornell_camera(aspect)])
+
+
+def sky_texels(width=64, height=32, sun=True, seed=11):
+    """Procedural lat-long HDR sky (H, W, 4) float16: gradient + noise + a small very bright sun
+    patch, i.e. an importance distribution with light and heavy texels for the alias table."""
+    rng = np.random.RandomState(seed)
+    v = (np.arange(height) + 0.5) / height
+    u = (np.arange(width) + 0.5) / width
+    uu, vv = np.meshgrid(u, v)
+    up = np.clip(1.0 - 2.0 * vv, 0.0, 1.0)           # v = 0 is straight up (dir.y = +1)
+    rgb = np.stack([0.25 + 0.3 * up, 0.35 + 0.45 * up, 0.5 + 0.9 * up], axis=-1)
+    rgb[vv > 0.5] = (0.12, 0.1, 0.08)                # ground
+    rgb *= 0.75 + 0.5 * rng.rand(height, width, 1)
+    if sun:
+        d = np.hypot((uu - 0.62) * 2.0, vv - 0.22)
+        rgb += np.exp(-(d / 0.035) ** 2)[..., None] * np.array([260.0, 230.0, 180.0])
+    out = np.ones((height, width, 4), dtype=np.float16)
+    out[..., :3] = rgb.astype(np.float16)
+    return out
+
+
+def courtyard(subdiv=3, envmap=True, sun_in_sky=True, directional=False, emissive=False, env_size=(64, 32)):
+    """Open scene lit by an environment map: ground plane, a metal and a diffuse block, a glass
+    block and an alpha-textured card. Camera rays also see the sky directly."""
+    s = Scene()
+    ground = make_material(albedo=(0.7, 0.68, 0.6, 1), roughness=0.9)
+    s.add_instance(*quad((-6, -1, 6), (6, -1, 6), (6, -1, -6), (-6, -1, -6), subdiv * 2), ground)
+    bv, bi = box((-0.6, -0.6, -0.6), (0.6, 0.6, 0.6), subdiv)
+    metal = make_material(albedo=(0.9, 0.6, 0.2, 1), metallic=1.0, roughness=0.15)
+    t = np.eye(4)
+    a = 0.6
+    t[:3, :3] = [[np.cos(a), 0, np.sin(a)], [0, 1.5, 0], [-np.sin(a), 0, np.cos(a)]]
+    t[:3, 3] = (-1.1, -0.1, -0.5)
+    s.add_instance(bv, bi, metal, transform=t)
+    diffuse = make_material(albedo=(0.2, 0.5, 0.8, 1), roughness=0.6)
+    t2 = np.eye(4)
+    t2[:3, 3] = (0.9, -0.4, 0.3)
+    s.add_instance(bv, bi, diffuse, transform=t2)
+    glass = make_material(albedo=(0.9, 0.95, 0.9, 1), roughness=0.05, transmittance=1.0)
+    t3 = np.eye(4)
+    t3[0, 0] = t3[1, 1] = t3[2, 2] = 0.6
+    t3[:3, 3] = (0.0, -0.64, 1.6)
+    s.add_instance(bv, bi, glass, transform=t3)
+    tid = s.add_texture(checker_texture())
+    card = make_material(albedo=(1, 1, 1, 1), albedo_tex=tid, roughness=0.6)
+    s.add_instance(*quad((-2.4, -1.0, 0.8), (-1.2, -1.0, 1.4), (-1.2, 0.3, 1.4), (-2.4, 0.3, 0.8), 1), card)
+    if emissive:
+        em = make_material(albedo=(0, 0, 0, 1), emission=(6.0, 3.0, 1.0))
+        s.add_instance(*quad((1.6, -0.99, 1.8), (2.4, -0.99, 1.8), (2.4, -0.99, 1.0), (1.6, -0.99, 1.0), 1), em)
+    if directional:
+        s.add_directional_light((2.0, 1.8, 1.5), (-0.4, -1.0, -0.3), angle_deg=1.0)
+    if envmap:
+        s.set_environment_map(sky_texels(env_size[0], env_size[1], sun=sun_in_sky), factor=(1.0, 0.9, 0.8))
+    return s
+
+
+def courtyard_cameras(aspect=1.0, fov_deg=55.0):
+    cam = perspective_camera(look_at_transform((0.3, 0.6, 5.0), (0, -0.1, 0)), fov_deg, aspect, 0.1, 100.0)
+    return camera_pairs([cam])

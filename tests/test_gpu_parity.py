@@ -166,11 +166,15 @@ def test_errors_are_reported_not_swallowed():
         with pytest.raises(TaurayB200Error) as e:
             pt.render()
         assert e.value.code == abi.ERR_NO_SCENE
-        sc = testscenes.cornell()
-        sc.environment_proj = 0
+        d = testscenes.cornell().desc()
+        d.environment_proj = 1       # only LAT_LONG (0) exists, src/environment_map.hh:12-15
         with pytest.raises(TaurayB200Error) as e:
-            pt.set_scene(sc)
+            pt.set_scene(d)
         assert e.value.code == abi.ERR_UNSUPPORTED
+        d.environment_proj = 0       # an environment map without texels
+        with pytest.raises(TaurayB200Error) as e:
+            pt.set_scene(d)
+        assert e.value.code == abi.ERR_INVALID_ARGUMENT
         pt.set_scene(testscenes.cornell())
         with pytest.raises(TaurayB200Error):
             pt.render()      # cameras / distribution missing
