@@ -64,6 +64,20 @@ enum { TR_FEATURE_ALBEDO = 0, TR_FEATURE_WORLD_NORMAL = 1, TR_FEATURE_VIEW_NORMA
 enum { TR_KERNEL_WAVEFRONT = 0, TR_KERNEL_MEGAKERNEL = 1 };
 /* texture formats accepted in tr_texture */
 enum { TR_TEXTURE_RGBA8_UNORM = 0, TR_TEXTURE_RGBA32F = 1, TR_TEXTURE_RGBA16F = 2 };
+/* Layers of gbuffer_target the path tracer writes (TR_GBUFFER_ENTRIES, src/gbuffer.hh:18-51;
+ * write_all_outputs, shader/path_tracer.glsl:535-576). Texel formats are the reference's. */
+enum {
+    TR_GBUFFER_COLOR = 0,               /* rgba32f (src/rt_renderer.cc:189-190); always present */
+    TR_GBUFFER_DIFFUSE = 1,             /* rgba16f; demodulated diffuse light, a = 1/second-hit distance; running mean */
+    TR_GBUFFER_REFLECTION = 2,          /* rgba16f; demodulated reflected light; running mean */
+    TR_GBUFFER_ALBEDO = 3,              /* rgba16f; written by the first sample only, like all layers below */
+    TR_GBUFFER_MATERIAL = 4,            /* rgba8 unorm: metallic, roughness, ior/4, transmittance (gbuffer.glsl:256-260) */
+    TR_GBUFFER_NORMAL = 5,              /* rg16 snorm: octahedral mapped normal (math.glsl:480-485) */
+    TR_GBUFFER_POS = 6,                 /* rgba32f world position */
+    TR_GBUFFER_SCREEN_MOTION = 7,       /* rgba32f: previous-frame uv + depth (camera.glsl:61-67) */
+    TR_GBUFFER_INSTANCE_ID = 8,         /* r32 sint */
+    TR_GBUFFER_LAYER_COUNT = 9
+};
 /* environment_map::projection, src/environment_map.hh:12-15 */
 enum { TR_ENVMAP_NONE = -1, TR_ENVMAP_LAT_LONG = 0 };
 
@@ -364,6 +378,16 @@ int tr_pt_ipc_close_handle(tr_pt_ctx* ctx, void* device_ptr);
  * library's own colour target; NULL restores the internal target. `bytes` must equal the size
  * tr_pt_get_color_buffer reports for the current cameras/distribution. */
 int tr_pt_set_color_buffer(tr_pt_ctx* ctx, void* device_ptr, size_t bytes);
+
+/* Auxiliary G-buffer layers (gbuffer_target entries other than colour): `layer_mask` has bit
+ * (1 << TR_GBUFFER_x) set for every layer the target has; the library allocates them with the
+ * colour target's layout (views x layer pixels; full image on the primary device, strip otherwise).
+ * They are written by tr_pt_render exactly as write_all_outputs does (shader/path_tracer.glsl:
+ * 547-574): diffuse/reflection are running means in rgba16f, the others are written when no sample
+ * has been accumulated yet. Default: none. Multi-GPU stitching covers the colour layer only. */
+int tr_pt_set_gbuffer_layers(tr_pt_ctx* ctx, uint32_t layer_mask);
+int tr_pt_get_gbuffer_layer(tr_pt_ctx* ctx, int layer, void** device_ptr, size_t* bytes);
+int tr_pt_read_gbuffer_layer(tr_pt_ctx* ctx, int layer, void* host_dst, size_t bytes);
 
 int tr_pt_get_stats(tr_pt_ctx* ctx, tr_pt_stats* stats);
 int tr_pt_set_instrumentation(tr_pt_ctx* ctx, int flags);

@@ -111,6 +111,9 @@ struct orc_ctx
     uint32_t frame_counter = 0;
     int accumulated_samples = 0;
     std::vector<float> color; // float4 per slot
+    uint32_t gbuffer_mask = 0;                                   // aux layers of gbuffer_target
+    std::vector<uint8_t> layers[TR_GBUFFER_LAYER_COUNT];
+    std::vector<mat4> prev_from_world;                           // model_prev * inverse(model) per instance
     tr_pt_stats stats{};
 
     // ------------------------------------------------------------------------------------
@@ -1005,6 +1008,84 @@ struct orc_ctx
     }
 
     // ------------------------------------------------------------------------------------
+    // aux G-buffer stores: write_all_outputs (shader/path_tracer.glsl:547-574), texel formats of
+    // src/gbuffer.hh:18-51
+    // ------------------------------------------------------------------------------------
+    static size_t layer_texel_bytes(int layer)
+    {
+        static const size_t b[TR_GBUFFER_LAYER_COUNT] = {16, 8, 8, 8, 4, 4, 16, 16, 4};
+        return b[layer];
+    }
+    bool has_layer(int layer) const { return (gbuffer_mask >> layer) & 1u; }
+    static void store_rgba16f(uint8_t* dst, vec4 v)
+    {
+        uint16_t h[4] = {(uint16_t)float_to_half_(v.x), (uint16_t)float_to_half_(v.y), (uint16_t)float_to_half_(v.z), (uint16_t)float_to_half_(v.w)};
+        memcpy(dst, h, 8);
+    }
+    static vec4 load_rgba16f(const uint8_t* src)
+    {
+        uint16_t h[4];
+        memcpy(h, src, 8);
+        return V4(half_to_float_(h[0]), half_to_float_(h[1]), half_to_float_(h[2]), half_to_float_(h[3]));
+    }
+    // accumulate_gbuffer_diffuse / _reflection (shader/gbuffer.glsl:68-78,118-128) on an rgba16f image
+    static void accumulate_rgba16f(uint8_t* dst, vec4 v, uint32_t samples, uint32_t previous_samples)
+    {
+        if(previous_samples != 0)
+        {
+            vec4 prev = load_rgba16f(dst);
+            uint32_t tot = samples + previous_samples;
+            v = mix_(v, prev, (float)previous_samples / (float)tot);
+        }
+        store_rgba16f(dst, v);
+    }
+    static vec2 octahedral_pack(vec3 n) // shader/math.glsl:480-485
+    {
+        n = n / (fabsf(n.x) + fabsf(n.y) + fabsf(n.z));
+        if(n.z >= 0.0f) return V2(n.x, n.y);
+        return V2((1.0f - fabsf(n.y)) * (step_(0.0f, n.x) * 2.0f - 1.0f), (1.0f - fabsf(n.x)) * (step_(0.0f, n.y) * 2.0f - 1.0f));
+    }
+    void write_first_sample_layers(size_t texel, uint32_t view, const pt_vertex_data& v, const sampled_material& m)
+    {
+        if(has_layer(TR_GBUFFER_ALBEDO)) store_rgba16f(&layers[TR_GBUFFER_ALBEDO][texel * 8], m.albedo);
+        if(has_layer(TR_GBUFFER_MATERIAL))
+        {
+            // pack_gbuffer_material, shader/gbuffer.glsl:256-260
+            float ior = m.ior_out / m.ior_in;
+            uint8_t* d = &layers[TR_GBUFFER_MATERIAL][texel * 4];
+            d[0] = (uint8_t)float_to_unorm8_(m.metallic); d[1] = (uint8_t)float_to_unorm8_(m.roughness);
+            d[2] = (uint8_t)float_to_unorm8_(ior * 0.25f); d[3] = (uint8_t)float_to_unorm8_(m.transmittance);
+        }
+        if(has_layer(TR_GBUFFER_NORMAL))
+        {
+            vec2 o = octahedral_pack(v.mapped_normal);
+            uint16_t q[2] = {(uint16_t)float_to_snorm16_(o.x), (uint16_t)float_to_snorm16_(o.y)};
+            memcpy(&layers[TR_GBUFFER_NORMAL][texel * 4], q, 4);
+        }
+        if(has_layer(TR_GBUFFER_POS))
+        {
+            float q[4] = {v.pos.x, v.pos.y, v.pos.z, 0.0f};
+            memcpy(&layers[TR_GBUFFER_POS][texel * 16], q, 16);
+        }
+        if(has_layer(TR_GBUFFER_SCREEN_MOTION))
+        {
+            // prev_pos (shader/rt.glsl:73-79, PRE_TRANSFORMED_VERTICES) + get_camera_projection (camera.glsl:61-67)
+            vec3 prev_pos = v.pos;
+            if(v.instance_id >= 0) prev_pos = xyz(mul(prev_from_world[(size_t)v.instance_id], V4(v.pos, 1.0f)));
+            mat4 view_proj;
+            memcpy(view_proj.m, cameras[view].previous.view_proj, 64);
+            vec4 pp = mul(view_proj, V4(prev_pos, 1.0f));
+            float q[4] = {pp.x / pp.w * 0.5f + 0.5f, pp.y / pp.w * 0.5f + 0.5f, pp.w, 0.0f};
+            memcpy(&layers[TR_GBUFFER_SCREEN_MOTION][texel * 16], q, 16);
+        }
+        if(has_layer(TR_GBUFFER_INSTANCE_ID))
+        {
+            int32_t id = v.instance_id;
+            memcpy(&layers[TR_GBUFFER_INSTANCE_ID][texel * 4], &id, 4);
+        }
+    }
+
+    // ------------------------------------------------------------------------------------
     // one pass of path_tracer.rgen over this device's launch ids
     // ------------------------------------------------------------------------------------
     void render_pass(uint32_t pass_index, uint32_t sample_counter, uint32_t rng_seed, uint32_t samples_accumulated,
@@ -1042,6 +1123,7 @@ struct orc_ctx
                     pt_vertex_data first_hit_vertex{};
                     sampled_material first_hit_material{};
                     vec3 sum_color = V3(0);
+                    vec4 sum_diffuse = V4(0, 0, 0, 0), sum_reflection = V4(0, 0, 0, 0);
                     for(uint32_t i = 0; i < spp_pass; ++i)
                     {
                         local_sampler ls = init_local_sampler(
@@ -1057,6 +1139,8 @@ struct orc_ctx
                             m.albedo.x = 1; m.albedo.y = 1; m.albedo.z = 1;
                         }
                         sum_color += first_hit_material.emission + modulate_color(m, xyz(diffuse), xyz(reflection));
+                        sum_diffuse = sum_diffuse + diffuse;
+                        sum_reflection = sum_reflection + reflection;
                     }
                     vec3 col = sum_color / (float)spp_pass;
                     // write_all_outputs (path_tracer.glsl:535-576) + accumulate_gbuffer_color (gbuffer.glsl:18-28)
@@ -1071,6 +1155,15 @@ struct orc_ctx
                         out = mix_(out, prev, (float)prev_samples / (float)tot);
                     }
                     dst[0] = out.x; dst[1] = out.y; dst[2] = out.z; dst[3] = out.w;
+                    if(gbuffer_mask)
+                    {
+                        const size_t texel = (size_t)view * layer + write_index;
+                        if(prev_samples == 0) write_first_sample_layers(texel, view, first_hit_vertex, first_hit_material);
+                        if(has_layer(TR_GBUFFER_DIFFUSE))
+                            accumulate_rgba16f(&layers[TR_GBUFFER_DIFFUSE][texel * 8], sum_diffuse / (float)spp_pass, spp_pass, prev_samples);
+                        if(has_layer(TR_GBUFFER_REFLECTION))
+                            accumulate_rgba16f(&layers[TR_GBUFFER_REFLECTION][texel * 8], sum_reflection / (float)spp_pass, spp_pass, prev_samples);
+                    }
                 }
             }
         };
@@ -1125,6 +1218,38 @@ int orc_create(orc_ctx** out, const tr_pt_options* opt, int threads)
 
 void orc_destroy(orc_ctx* ctx) { delete ctx; }
 
+// model_prev * inverse(model) (shader/rt.glsl:75, PRE_TRANSFORMED_VERTICES): GLSL leaves the precision of
+// inverse() open; defined here as the adjugate/determinant formula and the product in double precision,
+// rounded once to fp32 (column-major, like the wire format).
+static void prev_from_world_matrix(const float model[16], const float model_prev[16], float out[16])
+{
+    double a[4][4], inv[4][4];
+    for(int c = 0; c < 4; ++c) for(int r = 0; r < 4; ++r) a[r][c] = model[c * 4 + r];
+    auto minor3 = [&](int r0, int r1, int r2, int c0, int c1, int c2) {
+        return a[r0][c0] * (a[r1][c1] * a[r2][c2] - a[r1][c2] * a[r2][c1])
+             - a[r0][c1] * (a[r1][c0] * a[r2][c2] - a[r1][c2] * a[r2][c0])
+             + a[r0][c2] * (a[r1][c0] * a[r2][c1] - a[r1][c1] * a[r2][c0]);
+    };
+    double cof[4][4];
+    for(int r = 0; r < 4; ++r)
+        for(int c = 0; c < 4; ++c)
+        {
+            int rr[3], cc[3], k = 0, l = 0;
+            for(int i = 0; i < 4; ++i) { if(i != r) rr[k++] = i; if(i != c) cc[l++] = i; }
+            double m = minor3(rr[0], rr[1], rr[2], cc[0], cc[1], cc[2]);
+            cof[r][c] = ((r + c) & 1) ? -m : m;
+        }
+    double det = a[0][0] * cof[0][0] + a[0][1] * cof[0][1] + a[0][2] * cof[0][2] + a[0][3] * cof[0][3];
+    for(int r = 0; r < 4; ++r) for(int c = 0; c < 4; ++c) inv[r][c] = cof[c][r] / det;
+    for(int c = 0; c < 4; ++c)
+        for(int r = 0; r < 4; ++r)
+        {
+            double acc = 0.0;
+            for(int k = 0; k < 4; ++k) acc += (double)model_prev[k * 4 + r] * inv[k][c];
+            out[c * 4 + r] = (float)acc;
+        }
+}
+
 int orc_set_scene(orc_ctx* ctx, const tr_pt_scene_desc* s)
 {
     if(!ctx || !s) return fail(ctx, TR_ERR_INVALID_ARGUMENT, "null argument");
@@ -1135,6 +1260,9 @@ int orc_set_scene(orc_ctx* ctx, const tr_pt_scene_desc* s)
     ctx->vertices.assign(s->instance_count, {});
     ctx->indices.assign(s->instance_count, {});
     ctx->opaque.assign(s->instance_count, 1);
+    ctx->prev_from_world.assign(s->instance_count, mat4{});
+    for(uint32_t i = 0; i < s->instance_count; ++i)
+        prev_from_world_matrix(s->instances[i].model, s->instances[i].model_prev, ctx->prev_from_world[i].m);
     ctx->point_lights.assign(s->point_lights, s->point_lights + s->point_light_count);
     ctx->directional_lights.assign(s->directional_lights, s->directional_lights + s->directional_light_count);
     ctx->textures.clear();
@@ -1267,6 +1395,34 @@ static int prepare_target(orc_ctx* ctx)
     if(ctx->cameras.empty() || ctx->dist.size[0] == 0) return fail(ctx, TR_ERR_INVALID_ARGUMENT, "cameras/distribution not set");
     size_t need = ctx->layer_size() * ctx->views() * 4;
     if(ctx->color.size() != need) ctx->color.assign(need, 0.0f);
+    for(int l = 1; l < TR_GBUFFER_LAYER_COUNT; ++l)
+    {
+        size_t bytes = ctx->has_layer(l) ? ctx->layer_size() * ctx->views() * orc_ctx::layer_texel_bytes(l) : 0;
+        if(ctx->layers[l].size() != bytes) ctx->layers[l].assign(bytes, 0);
+    }
+    return TR_OK;
+}
+
+int orc_set_gbuffer_layers(orc_ctx* ctx, uint32_t mask)
+{
+    if(!ctx) return TR_ERR_INVALID_ARGUMENT;
+    if(mask >> TR_GBUFFER_LAYER_COUNT) return fail(ctx, TR_ERR_INVALID_ARGUMENT, "unknown G-buffer layer");
+    ctx->gbuffer_mask = mask & ~1u;
+    return TR_OK;
+}
+
+int orc_read_gbuffer_layer(orc_ctx* ctx, int layer, void* out, size_t bytes)
+{
+    if(!ctx || !out || layer < 0 || layer >= TR_GBUFFER_LAYER_COUNT) return TR_ERR_INVALID_ARGUMENT;
+    if(layer == TR_GBUFFER_COLOR)
+    {
+        if(bytes != ctx->color.size() * 4) return fail(ctx, TR_ERR_INVALID_ARGUMENT, "size mismatch");
+        memcpy(out, ctx->color.data(), bytes);
+        return TR_OK;
+    }
+    if(!ctx->has_layer(layer)) return fail(ctx, TR_ERR_INVALID_ARGUMENT, "layer not enabled");
+    if(bytes != ctx->layers[layer].size()) return fail(ctx, TR_ERR_INVALID_ARGUMENT, "size mismatch: layer has " + std::to_string(ctx->layers[layer].size()) + " bytes");
+    memcpy(out, ctx->layers[layer].data(), bytes);
     return TR_OK;
 }
 

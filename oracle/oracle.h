@@ -28,6 +28,8 @@ int orc_render_feature(orc_ctx* ctx, int feature, const float default_value[4]);
 int orc_read_color(orc_ctx* ctx, float* rgba32f, size_t bytes);
 int orc_get_stats(orc_ctx* ctx, tr_pt_stats* stats);
 int orc_read_tri_lights(orc_ctx* ctx, tr_tri_light* out, uint32_t capacity);
+int orc_set_gbuffer_layers(orc_ctx* ctx, uint32_t layer_mask);
+int orc_read_gbuffer_layer(orc_ctx* ctx, int layer, void* out, size_t bytes);
 int orc_read_alias_table(orc_ctx* ctx, tr_alias_table_entry* out, uint32_t capacity);
 int orc_trace_rays(orc_ctx* ctx, const float* rays, uint32_t n, void* hits_out);
 int orc_sample_test(orc_ctx* ctx, const uint32_t* coords, uint32_t n, int draw_index, uint32_t* out);

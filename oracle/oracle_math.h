@@ -160,6 +160,19 @@ static inline uint32_t float_to_half_(float f)
     if(rem > 0x1000u || (rem == 0x1000u && (h & 1u))) h++;
     return sign | h;
 }
+// image-store conversions (Vulkan format conversion rules: clamp, scale, round to nearest even; NaN -> 0)
+static inline uint32_t float_to_unorm8_(float v)
+{
+    if(!(v > 0.0f)) return 0u;
+    if(v >= 1.0f) return 255u;
+    return (uint32_t)(int)rintf(v * 255.0f);
+}
+static inline uint32_t float_to_snorm16_(float v)
+{
+    if(isnan_(v)) return 0u;
+    float c = v < -1.0f ? -1.0f : (v > 1.0f ? 1.0f : v);
+    return (uint32_t)(int)rintf(c * 32767.0f) & 0xFFFFu;
+}
 static inline float half_to_float_(uint32_t h)
 {
     uint32_t sign = (h & 0x8000u) << 16;

@@ -44,6 +44,8 @@ def lib():
         l.orc_get_stats.argtypes = [vp, C.POINTER(abi.Stats)]
         l.orc_read_tri_lights.argtypes = [vp, vp, C.c_uint32]
         l.orc_read_alias_table.argtypes = [vp, vp, C.c_uint32]
+        l.orc_set_gbuffer_layers.argtypes = [vp, C.c_uint32]
+        l.orc_read_gbuffer_layer.argtypes = [vp, C.c_int, vp, C.c_size_t]
         l.orc_trace_rays.argtypes = [vp, vp, C.c_uint32, vp]
         l.orc_sample_test.argtypes = [vp, vp, C.c_uint32, C.c_int, vp]
         l.orc_unshuffle.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp]
@@ -127,6 +129,19 @@ class Oracle:
         out = np.zeros(max(n, 1), dtype=abi.TRI_LIGHT)
         self._l.orc_read_tri_lights(self._ctx, out.ctypes.data, n)
         return out[:n]
+
+    def set_gbuffer_layers(self, layers):
+        mask = 0
+        for l in layers:
+            mask |= 1 << int(l)
+        self._check(self._l.orc_set_gbuffer_layers(self._ctx, mask), "orc_set_gbuffer_layers")
+
+    def read_gbuffer_layer(self, layer):
+        dt, ch = abi.GBUFFER_TEXEL[int(layer)]
+        texels = self.read_color().size // 4
+        out = np.zeros(texels * ch, dtype=dt)
+        self._check(self._l.orc_read_gbuffer_layer(self._ctx, int(layer), out.ctypes.data, out.nbytes), "orc_read_gbuffer_layer")
+        return out.reshape(self._views, -1, ch)
 
     def alias_table(self):
         n = self._check(self._l.orc_read_alias_table(self._ctx, None, 0), "orc_read_alias_table")

@@ -27,6 +27,15 @@ KERNEL_WAVEFRONT, KERNEL_MEGAKERNEL = range(2)
 INSTRUMENT_VISITS, INSTRUMENT_TIMING = 1, 2
 TEXTURE_RGBA8_UNORM, TEXTURE_RGBA32F, TEXTURE_RGBA16F = range(3)
 ENVMAP_NONE, ENVMAP_LAT_LONG = -1, 0
+(GBUFFER_COLOR, GBUFFER_DIFFUSE, GBUFFER_REFLECTION, GBUFFER_ALBEDO, GBUFFER_MATERIAL, GBUFFER_NORMAL, GBUFFER_POS,
+ GBUFFER_SCREEN_MOTION, GBUFFER_INSTANCE_ID) = range(9)
+GBUFFER_LAYER_COUNT = 9
+# numpy view of one texel of each layer (src/gbuffer.hh:18-51)
+GBUFFER_TEXEL = {
+    GBUFFER_COLOR: ("<f4", 4), GBUFFER_DIFFUSE: ("<f2", 4), GBUFFER_REFLECTION: ("<f2", 4), GBUFFER_ALBEDO: ("<f2", 4),
+    GBUFFER_MATERIAL: ("u1", 4), GBUFFER_NORMAL: ("<i2", 2), GBUFFER_POS: ("<f4", 4), GBUFFER_SCREEN_MOTION: ("<f4", 4),
+    GBUFFER_INSTANCE_ID: ("<i4", 1),
+}
 
 OK = 0
 ERR_INVALID_ARGUMENT, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED, ERR_NO_SCENE, ERR_OUT_OF_MEMORY = -1, -2, -3, -4, -5, -6

@@ -40,6 +40,10 @@ struct tr_pt_ctx
     bool has_dist = false;
     float4* color = nullptr;        // the target in use (own_color or an external buffer)
     float4* own_color = nullptr;
+    uint32_t gbuffer_mask = 0;                              // aux layers of gbuffer_target (tr_pt_set_gbuffer_layers)
+    void* gbuffer[TR_GBUFFER_LAYER_COUNT] = {};
+    size_t gbuffer_pixels = 0;
+    float* prev_from_world = nullptr;                       // scene allocation: 16 floats per instance
     float4* external_color = nullptr;
     size_t external_bytes = 0;
     size_t color_pixels = 0;
@@ -166,6 +170,21 @@ void fill_params(const tr_pt_ctx* c, RenderParams& P)
     for(int i = 0; i < c->peer_count; ++i) P.peers[i] = c->peers[i];
     P.peer_count = c->peer_count;
     P.last_pass = 0;
+    for(int l = 1; l < TR_GBUFFER_LAYER_COUNT; ++l) P.gbuffer[l] = ((c->gbuffer_mask >> l) & 1u) ? c->gbuffer[l] : nullptr;
+    P.gbuffer_mask = c->gbuffer_mask;
+    P.prev_from_world = c->prev_from_world;
+}
+
+const size_t k_layer_texel_bytes[TR_GBUFFER_LAYER_COUNT] = {16, 8, 8, 8, 4, 4, 16, 16, 4};
+
+void free_gbuffer(tr_pt_ctx* c)
+{
+    for(int l = 1; l < TR_GBUFFER_LAYER_COUNT; ++l)
+    {
+        if(c->gbuffer[l]) cudaFree(c->gbuffer[l]);
+        c->gbuffer[l] = nullptr;
+    }
+    c->gbuffer_pixels = 0;
 }
 
 // (re)allocates the colour target and the wavefront buffers for the current cameras/distribution
@@ -187,12 +206,27 @@ int prepare_targets(tr_pt_ctx* c)
     else if(pixels != c->color_pixels || !c->own_color || c->color != c->own_color)
     {
         if(c->own_color) cudaFree(c->own_color);
+    free_gbuffer(c);
         c->own_color = nullptr;
         TRY_CUDA(c, cudaMalloc((void**)&c->own_color, std::max<size_t>(pixels, 1) * sizeof(float4)));
         TRY_CUDA(c, cudaMemsetAsync(c->own_color, 0, std::max<size_t>(pixels, 1) * sizeof(float4), c->stream));
         c->color = c->own_color;
         c->color_pixels = pixels;
     }
+    // aux G-buffer layers share the colour target's layout
+    if(c->gbuffer_pixels != pixels) free_gbuffer(c);
+    for(int l = 1; l < TR_GBUFFER_LAYER_COUNT; ++l)
+    {
+        const bool want = (c->gbuffer_mask >> l) & 1u;
+        if(want && !c->gbuffer[l])
+        {
+            const size_t bytes = std::max<size_t>(pixels, 1) * k_layer_texel_bytes[l];
+            TRY_CUDA(c, cudaMalloc(&c->gbuffer[l], bytes));
+            TRY_CUDA(c, cudaMemsetAsync(c->gbuffer[l], 0, bytes, c->stream));
+        }
+        else if(!want && c->gbuffer[l]) { cudaFree(c->gbuffer[l]); c->gbuffer[l] = nullptr; }
+    }
+    c->gbuffer_pixels = pixels;
     const uint64_t slots64 = (uint64_t)f.ray_count_x * f.ray_count_y * f.views;
     if(slots64 >= (1ull << 31)) return fail(c, TR_ERR_UNSUPPORTED, "more than 2^31 launch slots per pass");
     // passes of one sample each are traced `pass_batch` at a time (more rays in flight per launch)
@@ -223,7 +257,7 @@ int prepare_targets(tr_pt_ctx* c)
         TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.rs_seed, n));
         TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.hits, n));
         TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.nee, 4 * n));
-        TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.sum_color, c->opt.samples_per_pass > 1 ? n : 1));
+        TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.sum_color, c->opt.samples_per_pass > 1 ? 3 * n : 1));   // colour, diffuse, reflection sums
         TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.queue[0], n));
         TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.queue[1], n));
         TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.shadow_queue, n));
@@ -236,6 +270,7 @@ int prepare_targets(tr_pt_ctx* c)
 void free_scene(tr_pt_ctx* c)
 {
     free_list(c->scene_allocs);
+    c->prev_from_world = nullptr;
     memset(&c->scene, 0, sizeof(c->scene));
     c->has_scene = false;
 }
@@ -321,6 +356,37 @@ void tr_pt_destroy(tr_pt_ctx* c)
     if(c->ev_end) cudaEventDestroy(c->ev_end);
     if(c->stream) cudaStreamDestroy(c->stream);
     delete c;
+}
+
+// M = model_prev * inverse(model) (column-major wire matrices): what `prev_pos = model_prev * inverse(model) *
+// model_pos` (rt.glsl:75) applies to a pre-transformed vertex. GLSL does not pin inverse(); defined here as
+// inverse = adjugate / determinant and the product, all in double, rounded once to fp32.
+static void previous_from_world(const float model[16], const float model_prev[16], float out[16])
+{
+    auto at = [&](int row, int col) { return (double)model[col * 4 + row]; };
+    auto det3 = [&](const int r[3], const int c[3]) {
+        return at(r[0], c[0]) * (at(r[1], c[1]) * at(r[2], c[2]) - at(r[1], c[2]) * at(r[2], c[1]))
+             - at(r[0], c[1]) * (at(r[1], c[0]) * at(r[2], c[2]) - at(r[1], c[2]) * at(r[2], c[0]))
+             + at(r[0], c[2]) * (at(r[1], c[0]) * at(r[2], c[1]) - at(r[1], c[1]) * at(r[2], c[0]));
+    };
+    double cofactor[4][4];
+    for(int row = 0; row < 4; ++row)
+        for(int col = 0; col < 4; ++col)
+        {
+            int r[3], cidx[3];
+            for(int i = 0, k = 0; i < 4; ++i) if(i != row) r[k++] = i;
+            for(int i = 0, k = 0; i < 4; ++i) if(i != col) cidx[k++] = i;
+            const double m = det3(r, cidx);
+            cofactor[row][col] = ((row + col) & 1) ? -m : m;
+        }
+    const double det = at(0, 0) * cofactor[0][0] + at(0, 1) * cofactor[0][1] + at(0, 2) * cofactor[0][2] + at(0, 3) * cofactor[0][3];
+    for(int col = 0; col < 4; ++col)
+        for(int row = 0; row < 4; ++row)
+        {
+            double acc = 0.0;
+            for(int k = 0; k < 4; ++k) acc += (double)model_prev[k * 4 + row] * (cofactor[col][k] / det);   // inverse[k][col]
+            out[col * 4 + row] = (float)acc;
+        }
 }
 
 // The host half of environment_map::generate_alias_table (src/environment_map.cc:63-120): normalise the
@@ -458,6 +524,18 @@ int tr_pt_set_scene(tr_pt_ctx* c, const tr_pt_scene_desc* s)
     DeviceInstance* d_instances = nullptr;
     TRY_CUDA(c, dev_alloc(A, &d_instances, s->instance_count));
     if(s->instance_count) TRY_CUDA(c, cudaMemcpyAsync(d_instances, dinst.data(), sizeof(DeviceInstance) * dinst.size(), cudaMemcpyHostToDevice, st));
+    // model_prev * inverse(model) per instance, for the screen-motion layer (rt.glsl:73-79)
+    float* d_prev = nullptr;
+    {
+        std::vector<float> prev((size_t)s->instance_count * 16);
+        for(uint32_t i = 0; i < s->instance_count; ++i) previous_from_world(s->instances[i].model, s->instances[i].model_prev, &prev[(size_t)i * 16]);
+        TRY_CUDA(c, dev_alloc(A, &d_prev, prev.size()));
+        if(!prev.empty())
+        {
+            TRY_CUDA(c, cudaMemcpyAsync(d_prev, prev.data(), sizeof(float) * prev.size(), cudaMemcpyHostToDevice, st));
+            TRY_CUDA(c, cudaStreamSynchronize(st));   // `prev` is a local
+        }
+    }
     tr_point_light* d_pl = nullptr;
     tr_directional_light* d_dl = nullptr;
     TRY_CUDA(c, dev_alloc(A, &d_pl, s->point_light_count));
@@ -549,6 +627,7 @@ int tr_pt_set_scene(tr_pt_ctx* c, const tr_pt_scene_desc* s)
     ds.any_non_opaque = any_non_opaque ? 1u : 0u;
     ds.envmap = env_tex;
     ds.alias_table = d_alias;
+    c->prev_from_world = d_prev;
     c->has_scene = true;
     c->stats.bvh_build_ms = build_ms;
     c->stats.bvh_node_count = bout.node_count;
@@ -690,6 +769,45 @@ int tr_pt_read_color(tr_pt_ctx* c, float* out, size_t bytes)
         return fail(c, TR_ERR_INVALID_ARGUMENT, "size mismatch: target has " + std::to_string(c->color_pixels * sizeof(float4)) + " bytes");
     cudaStream_t st = c->last_stream ? c->last_stream : c->stream;
     TRY_CUDA(c, cudaMemcpyAsync(out, c->color, bytes, cudaMemcpyDeviceToHost, st));
+    TRY_CUDA(c, cudaStreamSynchronize(st));
+    return TR_OK;
+}
+
+int tr_pt_set_gbuffer_layers(tr_pt_ctx* c, uint32_t layer_mask)
+{
+    if(!c) return TR_ERR_INVALID_ARGUMENT;
+    if(layer_mask >> TR_GBUFFER_LAYER_COUNT) return fail(c, TR_ERR_INVALID_ARGUMENT, "unknown G-buffer layer");
+    DeviceGuard guard(c->device);
+    cudaStream_t st = c->last_stream ? c->last_stream : c->stream;
+    TRY_CUDA(c, cudaStreamSynchronize(st));
+    c->gbuffer_mask = layer_mask & ~(1u << TR_GBUFFER_COLOR);
+    if(c->has_scene && c->has_dist && c->views) return prepare_targets(c);
+    return TR_OK;
+}
+
+int tr_pt_get_gbuffer_layer(tr_pt_ctx* c, int layer, void** device_ptr, size_t* bytes)
+{
+    if(!c || layer < 0 || layer >= TR_GBUFFER_LAYER_COUNT) return TR_ERR_INVALID_ARGUMENT;
+    if(layer == TR_GBUFFER_COLOR) return tr_pt_get_color_buffer(c, device_ptr, bytes);
+    if(!((c->gbuffer_mask >> layer) & 1u)) return fail(c, TR_ERR_INVALID_ARGUMENT, "G-buffer layer not enabled");
+    DeviceGuard guard(c->device);
+    int rc = prepare_targets(c);
+    if(rc) return rc;
+    if(device_ptr) *device_ptr = c->gbuffer[layer];
+    if(bytes) *bytes = c->gbuffer_pixels * k_layer_texel_bytes[layer];
+    return TR_OK;
+}
+
+int tr_pt_read_gbuffer_layer(tr_pt_ctx* c, int layer, void* out, size_t bytes)
+{
+    if(!c || !out || layer < 0 || layer >= TR_GBUFFER_LAYER_COUNT) return TR_ERR_INVALID_ARGUMENT;
+    if(layer == TR_GBUFFER_COLOR) return tr_pt_read_color(c, (float*)out, bytes);
+    if(!((c->gbuffer_mask >> layer) & 1u) || !c->gbuffer[layer]) return fail(c, TR_ERR_INVALID_ARGUMENT, "G-buffer layer not enabled or nothing rendered yet");
+    DeviceGuard guard(c->device);
+    const size_t have = c->gbuffer_pixels * k_layer_texel_bytes[layer];
+    if(bytes != have) return fail(c, TR_ERR_INVALID_ARGUMENT, "size mismatch: layer has " + std::to_string(have) + " bytes");
+    cudaStream_t st = c->last_stream ? c->last_stream : c->stream;
+    TRY_CUDA(c, cudaMemcpyAsync(out, c->gbuffer[layer], bytes, cudaMemcpyDeviceToHost, st));
     TRY_CUDA(c, cudaStreamSynchronize(st));
     return TR_OK;
 }

@@ -196,6 +196,7 @@ TRD vec3& operator+=(vec3& a, vec3 b) { a = a + b; return a; }
 TRD vec3& operator*=(vec3& a, vec3 b) { a = a * b; return a; }
 TRD vec3& operator*=(vec3& a, float s) { a = a * s; return a; }
 TRD vec3& operator/=(vec3& a, float s) { a = a / s; return a; }
+TRD vec4 operator/(vec4 a, float s) { return V4(a.x / s, a.y / s, a.z / s, a.w / s); }
 
 TRD vec4 operator+(vec4 a, vec4 b) { return V4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 TRD vec4 operator*(vec4 a, float s) { return V4(a.x * s, a.y * s, a.z * s, a.w * s); }

@@ -29,6 +29,10 @@ struct RenderParams
     float4* peers[8];
     int peer_count;
     int last_pass;
+    // aux G-buffer layers (NULL when absent), texel formats of src/gbuffer.hh:18-51
+    void* gbuffer[TR_GBUFFER_LAYER_COUNT];
+    uint32_t gbuffer_mask;
+    const float* prev_from_world;   // 16 floats per instance: model_prev * inverse(model), column-major
     // traversal tuning (defaults in tr_render.cu; TR_TUNE_* environment overrides for experiments)
     int tune_fetch_threshold;
     int tune_postpone_div;
@@ -45,6 +49,7 @@ struct PathState
     bsdf_lobes primary_lobes;
     vec3 diffuse;
     vec3 reflection;
+    float aux_alpha;            // diffuse.a = reflection.a (1 / distance to the second hit)
     uint32_t random_seed;       // payload.random_seed
     // first hit (first_hit_material.{emission, albedo, metallic})
     vec3 fh_emission;
@@ -688,6 +693,7 @@ TRD void path_begin(const RenderParams& P, uint32_t px, uint32_t py, uint32_t vi
     s.attenuation = V3(1);
     s.diffuse = V3(0);
     s.reflection = V3(0);
+    s.aux_alpha = 0.0f;
     s.regularization = 1.0f;
     s.bsdf_pdf = 0.0f;
     s.primary_lobes = LOBES(0, 0, 0, 1);
@@ -705,19 +711,19 @@ TRD void add_demodulated(PathState& s, vec3 light_color, float w_diffuse, float 
     s.reflection += light_color * w_reflection;
 }
 
-// The body of evaluate_ray's bounce loop (path_tracer.glsl:405-497) for a hit record `h`.
-// Returns true when the path continues (s.pos / s.view hold the next ray); `job.bounce >= 0`
-// when an NEE sample was drawn (finish it with nee_finish, after tracing the shadow ray if
-// job.needs_shadow_ray).
-TRD bool shade_bounce(const RenderParams& P, const SobolTables& tables, uint32_t bounce, const Hit& h, PathState& s,
-                      const uvec4& ss_seed, uvec4& rs_seed, NeeJob& job)
+// get_intersection_info (path_tracer.glsl:91-201) for a hit record `h` of the ray (origin, view).
+struct HitInfo
 {
-    job.bounce = -1;
-    const uint32_t max_bounces = (uint32_t)P.opt.max_ray_depth;
-    const vec3 origin = s.pos;
-    const vec3 view = s.view;
+    IntersectionPdf nee_pdf;
+    sampled_material mat;
+    vec3 light;
+    vec3 pos, hard_normal, mapped_normal;
+    int instance_id;
+    bool surface;
+};
 
-    // ---- get_intersection_info, path_tracer.glsl:91-201
+TRD void get_intersection_info(const RenderParams& P, const Hit& h, vec3 origin, vec3 view, HitInfo& out)
+{
     IntersectionPdf nee_pdf;
     nee_pdf.point_light_pdf = 0; nee_pdf.directional_light_pdf = 0; nee_pdf.tri_light_pdf = 0; nee_pdf.envmap_pdf = 0;
     sampled_material mat;
@@ -790,6 +796,31 @@ TRD bool shade_bounce(const RenderParams& P, const SobolTables& tables, uint32_t
         else mat.emission += env;
         surface = false;
     }
+    out.nee_pdf = nee_pdf; out.mat = mat; out.light = light;
+    out.pos = v_pos; out.hard_normal = v_hard; out.mapped_normal = v_mapped;
+    out.instance_id = surface ? h.instance_id : -1;
+    out.surface = surface;
+}
+
+// The body of evaluate_ray's bounce loop (path_tracer.glsl:405-497) for a hit record `h`.
+// Returns true when the path continues (s.pos / s.view hold the next ray); `job.bounce >= 0`
+// when an NEE sample was drawn (finish it with nee_finish, after tracing the shadow ray if
+// job.needs_shadow_ray).
+TRD bool shade_bounce(const RenderParams& P, const SobolTables& tables, uint32_t bounce, const Hit& h, PathState& s,
+                      const uvec4& ss_seed, uvec4& rs_seed, NeeJob& job)
+{
+    job.bounce = -1;
+    const uint32_t max_bounces = (uint32_t)P.opt.max_ray_depth;
+    const vec3 origin = s.pos;
+    const vec3 view = s.view;
+
+    HitInfo hi;
+    get_intersection_info(P, h, origin, view, hi);
+    const IntersectionPdf nee_pdf = hi.nee_pdf;
+    sampled_material mat = hi.mat;
+    vec3 light = hi.light;
+    const vec3 v_pos = hi.pos, v_hard = hi.hard_normal, v_mapped = hi.mapped_normal;
+    const bool surface = hi.surface;
     const bool terminal = !surface || bounce == max_bounces - 1;
 
     // ---- MIS-weighted emission, path_tracer.glsl:411-435
@@ -819,6 +850,7 @@ TRD bool shade_bounce(const RenderParams& P, const SobolTables& tables, uint32_t
         mat.roughness = 1.0f - ((1.0f - mat.roughness) * s.regularization);
     }
     if(terminal) return false;
+    if(bounce == 1) s.aux_alpha = 1.0f / length(v_pos - origin);   // diffuse.a = reflection.a, path_tracer.glsl:470-471
 
     const mat3 tbn = create_tangent_space(v_mapped);
     const vec3 shading_view = view_to_tangent_space(view, tbn);
@@ -933,6 +965,77 @@ TRD vec3 path_color(const RenderParams& P, const PathState& s)
 {
     vec3 albedo = P.opt.use_white_albedo_on_first_bounce ? V3(1) : xyz(s.fh_albedo);
     return s.fh_emission + modulate_color(albedo, s.fh_metallic, s.diffuse, s.reflection);
+}
+
+// ---------------------------------------------------------------------------------------------
+// aux G-buffer stores of write_all_outputs (path_tracer.glsl:547-574); texel formats src/gbuffer.hh:18-51
+// ---------------------------------------------------------------------------------------------
+TRD uint2 pack_rgba16f(vec4 v)
+{
+    return make_uint2(float_to_half_(v.x) | (float_to_half_(v.y) << 16), float_to_half_(v.z) | (float_to_half_(v.w) << 16));
+}
+TRD vec4 unpack_rgba16f(uint2 q)
+{
+    return V4(half_to_float_(q.x & 0xFFFFu), half_to_float_(q.x >> 16), half_to_float_(q.y & 0xFFFFu), half_to_float_(q.y >> 16));
+}
+// accumulate_gbuffer_diffuse / _reflection (gbuffer.glsl:68-78,118-128) on an rgba16f layer
+TRD void accumulate_rgba16f(uint2* __restrict__ layer, uint32_t index, vec4 v, uint32_t samples, uint32_t previous_samples)
+{
+    if(previous_samples != 0)
+    {
+        const vec4 prev = unpack_rgba16f(layer[index]);
+        const uint32_t tot = samples + previous_samples;
+        v = mix_(v, prev, (float)previous_samples / (float)tot);
+    }
+    layer[index] = pack_rgba16f(v);
+}
+// image-store conversions: clamp, scale, round to nearest even; NaN -> 0
+TRD uint32_t float_to_unorm8_(float v)
+{
+    if(!(v > 0.0f)) return 0u;
+    if(v >= 1.0f) return 255u;
+    return (uint32_t)__float2int_rn(v * 255.0f);
+}
+TRD uint32_t float_to_snorm16_(float v)
+{
+    if(isnan_(v)) return 0u;
+    const float c = v < -1.0f ? -1.0f : (v > 1.0f ? 1.0f : v);
+    return (uint32_t)__float2int_rn(c * 32767.0f) & 0xFFFFu;
+}
+TRD vec2 octahedral_pack(vec3 n) // math.glsl:480-485
+{
+    n = n / (fabsf(n.x) + fabsf(n.y) + fabsf(n.z));
+    if(n.z >= 0.0f) return V2(n.x, n.y);
+    return V2((1.0f - fabsf(n.y)) * (step_(0.0f, n.x) * 2.0f - 1.0f), (1.0f - fabsf(n.x)) * (step_(0.0f, n.y) * 2.0f - 1.0f));
+}
+// The layers written by the first sample only (prev_samples == 0), from the first hit of the path.
+TRD void write_first_sample_layers(const RenderParams& P, uint32_t texel, uint32_t view, const HitInfo& hi)
+{
+    if(P.gbuffer[TR_GBUFFER_ALBEDO]) reinterpret_cast<uint2*>(P.gbuffer[TR_GBUFFER_ALBEDO])[texel] = pack_rgba16f(hi.mat.albedo);
+    if(P.gbuffer[TR_GBUFFER_MATERIAL])
+    {
+        const float ior = hi.mat.ior_out / hi.mat.ior_in;   // pack_gbuffer_material, gbuffer.glsl:256-260
+        reinterpret_cast<uint32_t*>(P.gbuffer[TR_GBUFFER_MATERIAL])[texel] =
+            float_to_unorm8_(hi.mat.metallic) | (float_to_unorm8_(hi.mat.roughness) << 8) |
+            (float_to_unorm8_(ior * 0.25f) << 16) | (float_to_unorm8_(hi.mat.transmittance) << 24);
+    }
+    if(P.gbuffer[TR_GBUFFER_NORMAL])
+    {
+        const vec2 o = octahedral_pack(hi.mapped_normal);
+        reinterpret_cast<uint32_t*>(P.gbuffer[TR_GBUFFER_NORMAL])[texel] = float_to_snorm16_(o.x) | (float_to_snorm16_(o.y) << 16);
+    }
+    if(P.gbuffer[TR_GBUFFER_POS])
+        reinterpret_cast<float4*>(P.gbuffer[TR_GBUFFER_POS])[texel] = make_float4(hi.pos.x, hi.pos.y, hi.pos.z, 0.0f);
+    if(P.gbuffer[TR_GBUFFER_SCREEN_MOTION])
+    {
+        // prev_pos (rt.glsl:73-79, PRE_TRANSFORMED_VERTICES) + get_camera_projection (camera.glsl:61-67)
+        vec3 prev_pos = hi.pos;
+        if(hi.instance_id >= 0) prev_pos = xyz(mul4(P.prev_from_world + 16 * (size_t)hi.instance_id, V4(hi.pos, 1.0f)));
+        const vec4 pp = mul4(P.cameras[view].previous.view_proj, V4(prev_pos, 1.0f));
+        reinterpret_cast<float4*>(P.gbuffer[TR_GBUFFER_SCREEN_MOTION])[texel] =
+            make_float4(pp.x / pp.w * 0.5f + 0.5f, pp.y / pp.w * 0.5f + 0.5f, pp.w, 0.0f);
+    }
+    if(P.gbuffer[TR_GBUFFER_INSTANCE_ID]) reinterpret_cast<int32_t*>(P.gbuffer[TR_GBUFFER_INSTANCE_ID])[texel] = hi.instance_id;
 }
 
 // write_all_outputs (path_tracer.glsl:535-576) + accumulate_gbuffer_color (gbuffer.glsl:18-28)

@@ -35,7 +35,7 @@ TRD void store_state(const tr_wavefront& wf, uint32_t id, const PathState& s)
     wf.atten_reg[id] = make_float4(s.attenuation.x, s.attenuation.y, s.attenuation.z, s.regularization);
     wf.lobes[id] = make_float4(s.primary_lobes.transmission, s.primary_lobes.diffuse,
                                s.primary_lobes.dielectric_reflection, s.primary_lobes.metallic_reflection);
-    wf.diffuse[id] = make_float4(s.diffuse.x, s.diffuse.y, s.diffuse.z, 0.0f);
+    wf.diffuse[id] = make_float4(s.diffuse.x, s.diffuse.y, s.diffuse.z, s.aux_alpha);
     wf.reflection[id] = make_float4(s.reflection.x, s.reflection.y, s.reflection.z, 0.0f);
 }
 TRD void store_first_hit(const tr_wavefront& wf, uint32_t id, const PathState& s)
@@ -53,6 +53,7 @@ TRD void load_state(const tr_wavefront& wf, uint32_t id, PathState& s)
     s.primary_lobes = LOBES(d.x, d.y, d.z, d.w);
     s.diffuse = V3(e.x, e.y, e.z);
     s.reflection = V3(f.x, f.y, f.z);
+    s.aux_alpha = e.w;
 }
 TRD void load_first_hit(const tr_wavefront& wf, uint32_t id, PathState& s)
 {
@@ -288,7 +289,7 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_trace(const RenderParams P, con
                 s.diffuse = V3(e.x, e.y, e.z);
                 s.reflection = V3(f.x, f.y, f.z);
                 nee_finish(P, job, visibility, s);
-                wf.diffuse[id] = make_float4(s.diffuse.x, s.diffuse.y, s.diffuse.z, 0.0f);
+                wf.diffuse[id] = make_float4(s.diffuse.x, s.diffuse.y, s.diffuse.z, e.w);
                 wf.reflection[id] = make_float4(s.reflection.x, s.reflection.y, s.reflection.z, 0.0f);
             }
             if(retire) has_ray = false;
@@ -484,6 +485,9 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_finish(const RenderParams P, co
 {
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t spp = (uint32_t)P.opt.samples_per_pass;
+    uint2* const diffuse_layer = reinterpret_cast<uint2*>(P.gbuffer[TR_GBUFFER_DIFFUSE]);
+    uint2* const reflection_layer = reinterpret_cast<uint2*>(P.gbuffer[TR_GBUFFER_REFLECTION]);
+    const bool light_layers = diffuse_layer || reflection_layer;
     for(uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < base_slots; slot += stride)
     {
         uint32_t px, py, view, widx;
@@ -499,19 +503,67 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_finish(const RenderParams P, co
             s.reflection = V3(f.x, f.y, f.z);
             load_first_hit(wf, id, s);
             vec3 c = path_color(P, s);
+            vec4 dif = V4(s.diffuse, e.w), ref = V4(s.reflection, e.w);
             if(spp > 1)   // batch == 1 here: the samples of one pass are summed first (path_tracer.rgen:81-126)
             {
                 vec3 sum = V3(0);
-                if(sample_in_pass != 0) { const float4 q = wf.sum_color[slot]; sum = V3(q.x, q.y, q.z); }
+                vec4 sum_d = V4(0, 0, 0, 0), sum_r = V4(0, 0, 0, 0);
+                if(sample_in_pass != 0)
+                {
+                    const float4 q = wf.sum_color[slot];
+                    sum = V3(q.x, q.y, q.z);
+                    if(light_layers)
+                    {
+                        const float4 qd = wf.sum_color[base_slots + slot], qr = wf.sum_color[2 * base_slots + slot];
+                        sum_d = V4(qd.x, qd.y, qd.z, qd.w); sum_r = V4(qr.x, qr.y, qr.z, qr.w);
+                    }
+                }
                 sum += c;
-                if(sample_in_pass + 1 < spp) { wf.sum_color[slot] = make_float4(sum.x, sum.y, sum.z, 0.0f); continue; }
+                sum_d = sum_d + dif; sum_r = sum_r + ref;
+                if(sample_in_pass + 1 < spp)
+                {
+                    wf.sum_color[slot] = make_float4(sum.x, sum.y, sum.z, 0.0f);
+                    if(light_layers)
+                    {
+                        wf.sum_color[base_slots + slot] = make_float4(sum_d.x, sum_d.y, sum_d.z, sum_d.w);
+                        wf.sum_color[2 * base_slots + slot] = make_float4(sum_r.x, sum_r.y, sum_r.z, sum_r.w);
+                    }
+                    continue;
+                }
                 c = sum / (float)spp;
+                dif = sum_d / (float)spp; ref = sum_r / (float)spp;
             }
             const float alpha = P.opt.transparent_background ? s.fh_albedo.w : 1.0f;
             o = accumulate(P, c, alpha, widx, pass);
+            if(light_layers)
+            {
+                const uint32_t prev_samples = P.frame.samples_accumulated + P.frame.previous_samples + pass * spp;
+                if(diffuse_layer) accumulate_rgba16f(diffuse_layer, widx, dif, spp, prev_samples);
+                if(reflection_layer) accumulate_rgba16f(reflection_layer, widx, ref, spp, prev_samples);
+            }
         }
         if(spp > 1 && sample_in_pass + 1 < spp) continue;
         store_to_peers(P, o, px, py, view);
+    }
+}
+
+// The G-buffer layers only the first sample writes (write_all_outputs, path_tracer.glsl:547-563): recomputed
+// from the bounce-0 hit records, between the bounce-0 traversal and its shade pass (which overwrites the ray).
+// Launched only while no sample has been accumulated and a layer is present -- never on the steady-state path.
+__global__ void __launch_bounds__(WF_BLOCK) k_wf_first_sample_layers(const RenderParams P, const tr_wavefront wf, uint32_t base_slots)
+{
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for(uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < base_slots; slot += stride)
+    {
+        uint32_t px, py, view, widx;
+        if(!map_slot(P.frame, slot, px, py, view, widx)) continue;
+        const float4 o = wf.pos_pdf[slot], d = wf.dir_seed[slot];
+        const int4 hr = wf.hits[slot];
+        Hit h;
+        h.instance_id = hr.x; h.primitive_id = hr.y; h.u = __int_as_float(hr.z); h.v = __int_as_float(hr.w); h.t = h.u; h.flags = 0;
+        HitInfo hi;
+        get_intersection_info(P, h, V3(o.x, o.y, o.z), V3(d.x, d.y, d.z), hi);
+        write_first_sample_layers(P, widx, view, hi);
     }
 }
 
@@ -527,12 +579,15 @@ __global__ void __launch_bounds__(WF_BLOCK) k_megakernel(const RenderParams P, u
     tables.base = P.sobol_chunks;
     tables.first_group = 0;
     const uint32_t spp = (uint32_t)P.opt.samples_per_pass;
+    const bool first_layers = (P.gbuffer_mask & ~((1u << TR_GBUFFER_COLOR) | (1u << TR_GBUFFER_DIFFUSE) | (1u << TR_GBUFFER_REFLECTION))) != 0;
     for(uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < total_slots; slot += stride)
     {
         uint32_t px, py, view, widx;
         if(!map_slot(P.frame, slot, px, py, view, widx)) continue;
         vec3 sum = V3(0);
+        vec4 sum_d = V4(0, 0, 0, 0), sum_r = V4(0, 0, 0, 0);
         float alpha = 1.0f;
+        const uint32_t prev_samples = P.frame.samples_accumulated + P.frame.previous_samples;
         for(uint32_t i = 0; i < spp; ++i)
         {
             PathState s;
@@ -545,6 +600,12 @@ __global__ void __launch_bounds__(WF_BLOCK) k_megakernel(const RenderParams P, u
                 closest_hit<STATS>(P, s.pos, bounce == 0 ? 0.0f : P.opt.min_ray_dist, s.view,
                                    !(P.opt.hide_lights && bounce == 0), s.random_seed, h, st);
                 closest++;
+                if(bounce == 0 && first_layers && prev_samples == 0 && i + 1 == spp)
+                {
+                    HitInfo hi;
+                    get_intersection_info(P, h, s.pos, s.view, hi);
+                    write_first_sample_layers(P, widx, view, hi);
+                }
                 NeeJob job;
                 const bool alive = shade_bounce(P, tables, bounce, h, s, ss, rs, job);
                 if(job.bounce >= 0 && nee_shadow_ray_is_moot(job)) culled++;
@@ -561,9 +622,15 @@ __global__ void __launch_bounds__(WF_BLOCK) k_megakernel(const RenderParams P, u
                 if(!alive) break;
             }
             sum += path_color(P, s);
+            sum_d = sum_d + V4(s.diffuse, s.aux_alpha);
+            sum_r = sum_r + V4(s.reflection, s.aux_alpha);
             alpha = P.opt.transparent_background ? s.fh_albedo.w : 1.0f;
         }
         const float4 o = accumulate(P, sum / (float)spp, alpha, widx);
+        if(P.gbuffer[TR_GBUFFER_DIFFUSE])
+            accumulate_rgba16f(reinterpret_cast<uint2*>(P.gbuffer[TR_GBUFFER_DIFFUSE]), widx, sum_d / (float)spp, spp, prev_samples);
+        if(P.gbuffer[TR_GBUFFER_REFLECTION])
+            accumulate_rgba16f(reinterpret_cast<uint2*>(P.gbuffer[TR_GBUFFER_REFLECTION]), widx, sum_r / (float)spp, spp, prev_samples);
         store_to_peers(P, o, px, py, view);
     }
     flush_counters(P.counters, closest, shadow, paths, st.nodes, st.tris, 0);
@@ -728,6 +795,9 @@ cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const RenderParams& P_
     const int grid_persist = sm_count * k_blocks;
     static const int k_shade_blocks = env_int("TR_TUNE_SHADE_BLOCKS", 4);
     const int grid_shade = sm_count * k_shade_blocks;   // 128 registers/thread: 4 resident blocks per SM
+    // layers written only while prev_samples == 0 (pass 0 = the first `base` slots of a batch)
+    const bool first_sample_layers = (P.gbuffer_mask & ~((1u << TR_GBUFFER_COLOR) | (1u << TR_GBUFFER_DIFFUSE) | (1u << TR_GBUFFER_REFLECTION))) != 0 &&
+                                     P.frame.samples_accumulated + P.frame.previous_samples == 0;
     for(uint32_t i = 0; i < spp; ++i)
     {
         cudaError_t e = cudaMemsetAsync(wf.counts, 0, sizeof(uint32_t) * (4 * D + 2), stream);
@@ -745,6 +815,12 @@ cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const RenderParams& P_
             MARK(TR_KCLASS_CLOSEST);
             if(P.stats) k_wf_trace<false, true><<<grid_persist, WF_BLOCK, 0, stream>>>(P, wf, b, q_in, active_counts + b, work_counters + 2 * b);
             else k_wf_trace<false, false><<<grid_persist, WF_BLOCK, 0, stream>>>(P, wf, b, q_in, active_counts + b, work_counters + 2 * b);
+            if(b == 0 && first_sample_layers && i + 1 == spp)
+            {
+                MARK(TR_KCLASS_OTHER);
+                k_wf_first_sample_layers<<<grid_finish, WF_BLOCK, 0, stream>>>(P, wf, base);
+                ++*launches;
+            }
             MARK(TR_KCLASS_SHADE);
             k_wf_shade<<<grid_shade, WF_BLOCK, 0, stream>>>(P, wf, b, i, q_in, active_counts + b, q_out, active_counts + b + 1,
                                                               wf.shadow_queue, shadow_counts + b);

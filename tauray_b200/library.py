@@ -22,6 +22,7 @@ EXPORTS = [
     "tr_pt_default_options", "tr_pt_create", "tr_pt_destroy", "tr_pt_set_scene", "tr_pt_set_cameras",
     "tr_pt_set_distribution", "tr_pt_reset_accumulation", "tr_pt_render", "tr_pt_render_feature", "tr_pt_sync",
     "tr_pt_get_color_buffer", "tr_pt_read_color", "tr_pt_unshuffle", "tr_pt_set_peer_images", "tr_pt_get_stats",
+    "tr_pt_set_gbuffer_layers", "tr_pt_get_gbuffer_layer", "tr_pt_read_gbuffer_layer",
     "tr_pt_set_instrumentation", "tr_pt_read_tri_lights", "tr_pt_read_alias_table", "tr_pt_trace_rays", "tr_pt_sample_test",
     "tr_pt_last_error", "tr_pt_abi_version", "tr_pt_alloc_full_image", "tr_pt_ipc_get_handle",
     "tr_pt_ipc_open_handle", "tr_pt_ipc_close_handle", "tr_pt_set_color_buffer", "tr_pt_read_full_image", "tr_pt_enable_peer_access",
@@ -63,6 +64,9 @@ def lib():
     l.tr_pt_get_stats.argtypes = [vp, C.POINTER(abi.Stats)]
     l.tr_pt_set_instrumentation.argtypes = [vp, C.c_int]
     l.tr_pt_read_tri_lights.argtypes = [vp, vp, C.c_uint32]
+    l.tr_pt_set_gbuffer_layers.argtypes = [vp, C.c_uint32]
+    l.tr_pt_get_gbuffer_layer.argtypes = [vp, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    l.tr_pt_read_gbuffer_layer.argtypes = [vp, C.c_int, vp, C.c_size_t]
     l.tr_pt_read_alias_table.argtypes = [vp, vp, C.c_uint32]
     l.tr_pt_trace_rays.argtypes = [vp, vp, C.c_uint32, vp]
     l.tr_pt_sample_test.argtypes = [vp, vp, C.c_uint32, C.c_int, vp]
@@ -209,6 +213,26 @@ class PathTracer:
         s = abi.Stats()
         self._check(self._l.tr_pt_get_stats(self._ctx, C.byref(s)), "tr_pt_get_stats")
         return s.as_dict()
+
+    def set_gbuffer_layers(self, layers):
+        """Enable aux G-buffer layers (iterable of abi.GBUFFER_* ids)."""
+        mask = 0
+        for l in layers:
+            mask |= 1 << int(l)
+        self._check(self._l.tr_pt_set_gbuffer_layers(self._ctx, mask), "tr_pt_set_gbuffer_layers")
+
+    def gbuffer_layer_ptr(self, layer):
+        ptr, n = C.c_void_p(), C.c_size_t()
+        self._check(self._l.tr_pt_get_gbuffer_layer(self._ctx, int(layer), C.byref(ptr), C.byref(n)), "tr_pt_get_gbuffer_layer")
+        return ptr.value, n.value
+
+    def read_gbuffer_layer(self, layer):
+        """Layer texels as (views, layer pixels, channels) in the layer's own format (abi.GBUFFER_TEXEL)."""
+        _, nbytes = self.gbuffer_layer_ptr(layer)
+        dt, ch = abi.GBUFFER_TEXEL[int(layer)]
+        out = np.zeros(nbytes // np.dtype(dt).itemsize, dtype=dt)
+        self._check(self._l.tr_pt_read_gbuffer_layer(self._ctx, int(layer), out.ctypes.data, nbytes), "tr_pt_read_gbuffer_layer")
+        return out.reshape(self._views, -1, ch)
 
     def set_instrumentation(self, flags):
         self._check(self._l.tr_pt_set_instrumentation(self._ctx, int(flags)), "tr_pt_set_instrumentation")

@@ -42,6 +42,7 @@ class Scene:
     def __init__(self):
         self.materials = []
         self.transforms = []
+        self.prev_transforms = {}  # instance index -> previous-frame transform (default: the current one)
         self.meshes = []          # (vertices[VERTEX], indices[u32])
         self.opaque = []
         self.point_lights = np.zeros(0, dtype=abi.POINT_LIGHT)
@@ -157,7 +158,7 @@ class Scene:
             m = self.transforms[i].astype(np.float64)
             inst[i]["model"] = abi.mat_to_wire(m)
             inst[i]["model_normal"] = abi.mat_to_wire(np.linalg.inv(m).T)
-            inst[i]["model_prev"] = abi.mat_to_wire(m)
+            inst[i]["model_prev"] = abi.mat_to_wire(np.asarray(self.prev_transforms.get(i, m), dtype=np.float64))
             inst[i]["mat"] = mat
         return inst
 
