@@ -351,15 +351,21 @@ int tr_pt_read_color(tr_pt_ctx* ctx, float* rgba32f_host, size_t bytes);
 
 /* == stitch_shuffled_strips.comp:21-63 / stitch_scanline.comp for ONE source strip: scatters
  * `strip` (count*views float4, device memory, e.g. one slice of an all-gather result) of the
- * device that rendered [index, index+count) into `full_image` (size.x*size.y*views float4). */
+ * device that rendered [index, index+count) into `full_image` (size.x*size.y*views float4).
+ * blend_ratio < 1 mixes with the image's previous content, mix(old, new, blend_ratio)
+ * (stitch_shuffled_strips.comp:50-57; stitch_stage::set_blend_ratio, src/stitch_stage.cc:112). */
 int tr_pt_unshuffle(tr_pt_ctx* ctx, const void* strip_device, uint32_t index, uint32_t count,
-                    void* full_image_device, void* cuda_stream);
+                    void* full_image_device, float blend_ratio, void* cuda_stream);
 
 /* Fused render->stitch over NVLink peer memory: the last accumulation pass of tr_pt_render
  * also stores every finished pixel into each registered peer image (device pointers mapped
  * into this process, e.g. with cudaIpcOpenMemHandle) at its un-shuffled position, so no
  * separate gather/stitch pass runs. Pass n = 0 to disable. */
 int tr_pt_set_peer_images(tr_pt_ctx* ctx, void* const* full_image_device_ptrs, int n);
+/* The fused stitch's blend ratio for the NEXT frames (stitch_stage::set_blend_ratio): the reference sets
+ * 1/(accumulated_frames+1) for the frame after a workload change under accumulation and 1 again after
+ * it (src/rt_renderer.cc:124-128,178-182). Default 1 (plain store). */
+int tr_pt_set_stitch_blend(tr_pt_ctx* ctx, float blend_ratio);
 
 /* Cross-process exchange of full images for tr_pt_set_peer_images (one process per GPU):
  * tr_pt_alloc_full_image allocates (or returns) a library-owned size.x*size.y*views float4 image,

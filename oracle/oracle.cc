@@ -1527,6 +1527,18 @@ int orc_read_color(orc_ctx* ctx, float* out, size_t bytes)
     return TR_OK;
 }
 
+// Test hook for the multi-device emulation: overwrite the colour target (the primary device's target IS the
+// stitched image in the reference, so other devices' strips land in it between frames).
+int orc_write_color(orc_ctx* ctx, const float* in, size_t bytes)
+{
+    if(!ctx || !in) return TR_ERR_INVALID_ARGUMENT;
+    int rc = prepare_target(ctx);
+    if(rc) return rc;
+    if(bytes != ctx->color.size() * 4) return fail(ctx, TR_ERR_INVALID_ARGUMENT, "size mismatch");
+    memcpy(ctx->color.data(), in, bytes);
+    return TR_OK;
+}
+
 int orc_get_stats(orc_ctx* ctx, tr_pt_stats* stats)
 {
     if(!ctx || !stats) return TR_ERR_INVALID_ARGUMENT;
@@ -1596,7 +1608,7 @@ int orc_sample_test(orc_ctx* ctx, const uint32_t* coords, uint32_t n, int draw_i
     return TR_OK;
 }
 
-int orc_unshuffle(orc_ctx* ctx, const float* strip, uint32_t index, uint32_t count, float* full_image)
+int orc_unshuffle(orc_ctx* ctx, const float* strip, uint32_t index, uint32_t count, float* full_image, float blend_ratio)
 {
     if(!ctx || !strip || !full_image) return TR_ERR_INVALID_ARGUMENT;
     const uint32_t W = ctx->dist.size[0], H = ctx->dist.size[1];
@@ -1608,7 +1620,11 @@ int orc_unshuffle(orc_ctx* ctx, const float* strip, uint32_t index, uint32_t cou
             if(ctx->dist.strategy == TR_DISTRIBUTION_SHUFFLED_STRIPS) j = ctx->permute_region_id(index + i);
             else return fail(ctx, TR_ERR_UNSUPPORTED, "unshuffle: shuffled strips only");
             if(j >= W * H) continue;
-            memcpy(full_image + ((size_t)view * W * H + j) * 4, strip + ((size_t)view * count + i) * 4, 16);
+            float* dst = full_image + ((size_t)view * W * H + j) * 4;
+            const float* src = strip + ((size_t)view * count + i) * 4;
+            vec4 out = V4(src[0], src[1], src[2], src[3]);
+            if(blend_ratio < 1.0f) out = mix_(V4(dst[0], dst[1], dst[2], dst[3]), out, blend_ratio); // stitch_shuffled_strips.comp:50-57
+            dst[0] = out.x; dst[1] = out.y; dst[2] = out.z; dst[3] = out.w;
         }
     return TR_OK;
 }

@@ -27,6 +27,7 @@ int orc_render(orc_ctx* ctx, uint64_t max_slots);
 int orc_render_feature(orc_ctx* ctx, int feature, const float default_value[4]);
 int orc_read_color(orc_ctx* ctx, float* rgba32f, size_t bytes);
 int orc_get_stats(orc_ctx* ctx, tr_pt_stats* stats);
+int orc_write_color(orc_ctx* ctx, const float* in, size_t bytes);
 int orc_read_tri_lights(orc_ctx* ctx, tr_tri_light* out, uint32_t capacity);
 int orc_set_gbuffer_layers(orc_ctx* ctx, uint32_t layer_mask);
 int orc_read_gbuffer_layer(orc_ctx* ctx, int layer, void* out, size_t bytes);
@@ -34,7 +35,7 @@ int orc_read_alias_table(orc_ctx* ctx, tr_alias_table_entry* out, uint32_t capac
 int orc_trace_rays(orc_ctx* ctx, const float* rays, uint32_t n, void* hits_out);
 int orc_sample_test(orc_ctx* ctx, const uint32_t* coords, uint32_t n, int draw_index, uint32_t* out);
 /* scatter one strip into a full image on the host (stitch_shuffled_strips.comp:21-63) */
-int orc_unshuffle(orc_ctx* ctx, const float* strip, uint32_t index, uint32_t count, float* full_image);
+int orc_unshuffle(orc_ctx* ctx, const float* strip, uint32_t index, uint32_t count, float* full_image, float blend_ratio);
 /* elementary functions of "TR math", for unit tests: op 0 sin,1 cos,2 atan2(a,b),3 pow(a,b),4 log2,5 exp2,
  * 6 asin, 7 acos */
 int orc_math(int op, const float* a, const float* b, float* out, uint32_t n);

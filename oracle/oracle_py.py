@@ -41,6 +41,7 @@ def lib():
         l.orc_render.argtypes = [vp, C.c_uint64]
         l.orc_render_feature.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
         l.orc_read_color.argtypes = [vp, vp, C.c_size_t]
+        l.orc_write_color.argtypes = [vp, vp, C.c_size_t]
         l.orc_get_stats.argtypes = [vp, C.POINTER(abi.Stats)]
         l.orc_read_tri_lights.argtypes = [vp, vp, C.c_uint32]
         l.orc_read_alias_table.argtypes = [vp, vp, C.c_uint32]
@@ -48,7 +49,7 @@ def lib():
         l.orc_read_gbuffer_layer.argtypes = [vp, C.c_int, vp, C.c_size_t]
         l.orc_trace_rays.argtypes = [vp, vp, C.c_uint32, vp]
         l.orc_sample_test.argtypes = [vp, vp, C.c_uint32, C.c_int, vp]
-        l.orc_unshuffle.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp]
+        l.orc_unshuffle.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, C.c_float]
         l.orc_math.argtypes = [C.c_int, vp, vp, vp, C.c_uint32]
         l.orc_last_error.argtypes = [vp]
         l.orc_last_error.restype = C.c_char_p
@@ -119,6 +120,10 @@ class Oracle:
         self._check(self._l.orc_read_color(self._ctx, out.ctypes.data, out.nbytes), "orc_read_color")
         return out
 
+    def write_color(self, img):
+        img = np.ascontiguousarray(img, dtype=np.float32)
+        self._check(self._l.orc_write_color(self._ctx, img.ctypes.data, img.nbytes), "orc_write_color")
+
     def stats(self):
         s = abi.Stats()
         self._check(self._l.orc_get_stats(self._ctx, C.byref(s)), "orc_get_stats")
@@ -161,9 +166,9 @@ class Oracle:
         self._check(self._l.orc_sample_test(self._ctx, coords.ctypes.data, coords.shape[0], draw_index, out.ctypes.data), "orc_sample_test")
         return out
 
-    def unshuffle(self, strip, index, count, full_image):
+    def unshuffle(self, strip, index, count, full_image, blend_ratio=1.0):
         strip = np.ascontiguousarray(strip, dtype=np.float32)
-        self._check(self._l.orc_unshuffle(self._ctx, strip.ctypes.data, index, count, full_image.ctypes.data), "orc_unshuffle")
+        self._check(self._l.orc_unshuffle(self._ctx, strip.ctypes.data, index, count, full_image.ctypes.data, blend_ratio), "orc_unshuffle")
 
 
 def math_op(op, a, b=None):

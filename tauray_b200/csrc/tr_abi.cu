@@ -40,6 +40,7 @@ struct tr_pt_ctx
     bool has_dist = false;
     float4* color = nullptr;        // the target in use (own_color or an external buffer)
     float4* own_color = nullptr;
+    float stitch_blend = 1.0f;
     uint32_t gbuffer_mask = 0;                              // aux layers of gbuffer_target (tr_pt_set_gbuffer_layers)
     void* gbuffer[TR_GBUFFER_LAYER_COUNT] = {};
     size_t gbuffer_pixels = 0;
@@ -170,6 +171,7 @@ void fill_params(const tr_pt_ctx* c, RenderParams& P)
     for(int i = 0; i < c->peer_count; ++i) P.peers[i] = c->peers[i];
     P.peer_count = c->peer_count;
     P.last_pass = 0;
+    P.stitch_blend = c->stitch_blend;
     for(int l = 1; l < TR_GBUFFER_LAYER_COUNT; ++l) P.gbuffer[l] = ((c->gbuffer_mask >> l) & 1u) ? c->gbuffer[l] : nullptr;
     P.gbuffer_mask = c->gbuffer_mask;
     P.prev_from_world = c->prev_from_world;
@@ -824,7 +826,8 @@ int tr_pt_read_full_image(tr_pt_ctx* c, float* out, size_t bytes)
     return TR_OK;
 }
 
-int tr_pt_unshuffle(tr_pt_ctx* c, const void* strip_device, uint32_t index, uint32_t count, void* full_image_device, void* cuda_stream)
+int tr_pt_unshuffle(tr_pt_ctx* c, const void* strip_device, uint32_t index, uint32_t count, void* full_image_device, float blend_ratio,
+                    void* cuda_stream)
 {
     if(!c || !strip_device || !full_image_device) return TR_ERR_INVALID_ARGUMENT;
     if(!c->has_dist || c->views == 0) return fail(c, TR_ERR_INVALID_ARGUMENT, "cameras / distribution not set");
@@ -833,7 +836,7 @@ int tr_pt_unshuffle(tr_pt_ctx* c, const void* strip_device, uint32_t index, uint
     FrameParams f;
     fill_frame(c, f);
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
-    TRY_CUDA(c, tr_render_unshuffle(st, f, (const float4*)strip_device, index, count, (float4*)full_image_device));
+    TRY_CUDA(c, tr_render_unshuffle(st, f, (const float4*)strip_device, index, count, (float4*)full_image_device, blend_ratio));
     return TR_OK;
 }
 
@@ -842,6 +845,14 @@ int tr_pt_set_peer_images(tr_pt_ctx* c, void* const* ptrs, int n)
     if(!c || n < 0 || n > 8 || (n > 0 && !ptrs)) return fail(c, TR_ERR_INVALID_ARGUMENT, "0..8 peer images");
     for(int i = 0; i < n; ++i) c->peers[i] = (float4*)ptrs[i];
     c->peer_count = n;
+    return TR_OK;
+}
+
+int tr_pt_set_stitch_blend(tr_pt_ctx* c, float blend_ratio)
+{
+    if(!c) return TR_ERR_INVALID_ARGUMENT;
+    if(!(blend_ratio >= 0.0f && blend_ratio <= 1.0f)) return fail(c, TR_ERR_INVALID_ARGUMENT, "blend ratio must be in [0, 1]");
+    c->stitch_blend = blend_ratio;
     return TR_OK;
 }
 

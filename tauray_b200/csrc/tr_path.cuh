@@ -29,6 +29,7 @@ struct RenderParams
     float4* peers[8];
     int peer_count;
     int last_pass;
+    float stitch_blend;         // stitch_stage blend_ratio; 1 = plain store
     // aux G-buffer layers (NULL when absent), texel formats of src/gbuffer.hh:18-51
     void* gbuffer[TR_GBUFFER_LAYER_COUNT];
     uint32_t gbuffer_mask;
@@ -1061,6 +1062,17 @@ TRD void store_to_peers(const RenderParams& P, float4 o, uint32_t px, uint32_t p
 {
     if(P.peer_count == 0 || !P.last_pass) return;
     const size_t dst = (size_t)view * P.frame.size_x * P.frame.size_y + (size_t)py * P.frame.size_x + px;
+    if(P.stitch_blend < 1.0f)
+    {
+        // stitch_shuffled_strips.comp:50-57: every image holds the same previous content, so all stay identical
+        for(int k = 0; k < P.peer_count; ++k)
+        {
+            const float4 q = P.peers[k][dst];
+            const vec4 m = mix_(V4(q.x, q.y, q.z, q.w), V4(o.x, o.y, o.z, o.w), P.stitch_blend);
+            P.peers[k][dst] = make_float4(m.x, m.y, m.z, m.w);
+        }
+        return;
+    }
     for(int k = 0; k < P.peer_count; ++k) P.peers[k][dst] = o;
 }
 

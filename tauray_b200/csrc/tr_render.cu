@@ -720,15 +720,24 @@ __global__ void k_sample_test(const RenderParams P, const uint32_t* __restrict__
     out[4 * i] = r.x; out[4 * i + 1] = r.y; out[4 * i + 2] = r.z; out[4 * i + 3] = r.w;
 }
 
-// stitch_shuffled_strips.comp:21-63 for one source strip (blend_ratio = 1)
-__global__ void k_unshuffle(const FrameParams f, const float4* __restrict__ strip, uint32_t index, uint32_t count, float4* __restrict__ full)
+// stitch_shuffled_strips.comp:21-63 for one source strip
+__global__ void k_unshuffle(const FrameParams f, const float4* __restrict__ strip, uint32_t index, uint32_t count, float4* __restrict__ full,
+                            float blend_ratio)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t view = blockIdx.y;
     if(i >= count) return;
     const uint32_t j = permute_region_id(f, index + i);
     if(j >= f.size_x * f.size_y) return;
-    full[(size_t)view * f.size_x * f.size_y + j] = strip[(size_t)view * count + i];
+    float4 o = strip[(size_t)view * count + i];
+    float4* dst = full + (size_t)view * f.size_x * f.size_y + j;
+    if(blend_ratio < 1.0f)
+    {
+        const float4 q = *dst;
+        const vec4 m = mix_(V4(q.x, q.y, q.z, q.w), V4(o.x, o.y, o.z, o.w), blend_ratio);
+        o = make_float4(m.x, m.y, m.z, m.w);
+    }
+    *dst = o;
 }
 
 } // namespace trd
@@ -878,10 +887,11 @@ cudaError_t tr_render_sample_test(cudaStream_t stream, const RenderParams& P, co
     return cudaGetLastError();
 }
 
-cudaError_t tr_render_unshuffle(cudaStream_t stream, const FrameParams& f, const float4* strip, uint32_t index, uint32_t count, float4* full_image)
+cudaError_t tr_render_unshuffle(cudaStream_t stream, const FrameParams& f, const float4* strip, uint32_t index, uint32_t count, float4* full_image,
+                                float blend_ratio)
 {
     if(count == 0 || f.views == 0) return cudaSuccess;
     dim3 grid((count + 255) / 256, f.views);
-    k_unshuffle<<<grid, 256, 0, stream>>>(f, strip, index, count, full_image);
+    k_unshuffle<<<grid, 256, 0, stream>>>(f, strip, index, count, full_image, blend_ratio);
     return cudaGetLastError();
 }

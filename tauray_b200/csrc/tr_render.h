@@ -67,4 +67,4 @@ cudaError_t tr_render_trace_rays(cudaStream_t stream, const trd::RenderParams& P
 cudaError_t tr_render_sample_test(cudaStream_t stream, const trd::RenderParams& P, const uint32_t* coords_dev, uint32_t n,
                                   int draw_index, uint32_t* out_dev);
 cudaError_t tr_render_unshuffle(cudaStream_t stream, const trd::FrameParams& f, const float4* strip, uint32_t index,
-                                uint32_t count, float4* full_image);
+                                uint32_t count, float4* full_image, float blend_ratio);

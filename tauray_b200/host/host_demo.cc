@@ -65,10 +65,21 @@ int main(int argc, char** argv)
         if(const char* fake = std::getenv("TR_FAKE_DEVICES")) { devices.assign((size_t)std::atoi(fake), 0); }
 
         uvec2 size{(unsigned)std::atoi(argv[3]), (unsigned)std::atoi(argv[4])};
+        const bool rebalance = argc > 8 && std::string(argv[8]) == "rebalance";
+        opt.accumulate = rebalance;
         rt_renderer rr(devices, size, opt);
         rr.set_scene(desc, cams.data(), nv);
         rr.reset_accumulation();
         rr.render();
+        if(rebalance)
+        {
+            // a workload change under accumulation (src/rt_renderer.cc:136-183): 2 frames, new strips, 1 frame
+            rr.render();
+            std::vector<double> w(rr.device_count(), rr.device_count() > 1 ? 0.7 / (double)(rr.device_count() - 1) : 1.0);
+            if(rr.device_count() > 1) w[0] = 0.3;
+            rr.set_device_workloads(w);
+            rr.render();
+        }
         std::vector<float> img = rr.read_image();
         std::ofstream o(argv[2], std::ios::binary);
         o.write(reinterpret_cast<const char*>(img.data()), img.size() * sizeof(float));

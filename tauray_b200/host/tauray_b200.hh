@@ -278,6 +278,7 @@ public:
     struct options: path_tracer_stage::options
     {
         distribution_strategy strategy = DISTRIBUTION_SHUFFLED_STRIPS;
+        bool accumulate = false;    // rt_renderer::options::accumulate
     };
 
     rt_renderer(const std::vector<int>& cuda_devices, uvec2 size, const options& opt)
@@ -296,17 +297,20 @@ public:
         }
         if(devices.size() > 1)
         {
-            // display device = device 0 (src/context.cc); every stage stores its finished pixels straight
-            // into the display image over NVLink (replaces device_transfer + stitch_stage)
+            // display device = device 0 (src/context.cc): it renders in place into the display image
+            // (primary distribution); every other stage stores its finished pixels straight into that image
+            // over NVLink (replaces device_transfer + stitch_stage)
             void* full = nullptr; size_t bytes = 0;
             check(tr_pt_alloc_full_image(stages[0]->handle(), &full, &bytes), stages[0]->handle(), "tr_pt_alloc_full_image");
-            for(size_t i = 0; i < devices.size(); ++i)
+            check(tr_pt_set_color_buffer(stages[0]->handle(), full, bytes), stages[0]->handle(), "tr_pt_set_color_buffer");
+            for(size_t i = 1; i < devices.size(); ++i)
             {
                 check(tr_pt_enable_peer_access(stages[i]->handle(), devices[0]), stages[i]->handle(), "tr_pt_enable_peer_access");
                 void* peers[1] = {full};
                 check(tr_pt_set_peer_images(stages[i]->handle(), peers, 1), stages[i]->handle(), "tr_pt_set_peer_images");
             }
         }
+        accumulated_frames = 0;
     }
     // renderer::reset_accumulation (src/rt_renderer.cc:67-81)
     void reset_accumulation(bool reset_sample_counter = true)
@@ -316,18 +320,36 @@ public:
             s->reset_accumulated_samples();
             if(reset_sample_counter) s->reset_sample_counter();
         }
+        accumulated_frames = 0;
+        set_blend_ratio(1.0f);
     }
     // renderer::render (src/rt_renderer.cc:84-133)
     void render()
     {
+        // every stage touches only the pixels of its own strip, in the display image too: no ordering between stages
         for(auto& s: stages) s->run();
         for(auto& s: stages) s->sync();
+        if(blend_ratio < 1.0f) set_blend_ratio(1.0f);   // "Reset temporary blending from stitching", :126-127
+        accumulated_frames++;
     }
     // renderer::set_device_workloads (src/rt_renderer.cc:136-183)
     void set_device_workloads(const std::vector<double>& ratios)
     {
-        workloads = ratios;
-        for(size_t i = 0; i < stages.size(); ++i) stages[i]->reset_distribution_params(device_params(i));
+        if(opt.strategy != DISTRIBUTION_SHUFFLED_STRIPS) return;
+        double cumulative = 0;
+        workloads.resize(ratios.size());
+        for(size_t i = 0; i < ratios.size(); ++i)
+        {
+            workloads[i] = std::min(std::max(ratios[i], 0.0), 1.0 - cumulative);
+            cumulative += workloads[i];
+        }
+        for(size_t i = 0; i < stages.size(); ++i)
+        {
+            stages[i]->reset_distribution_params(device_params(i));
+            // only the primary device renders in place and can keep accumulating (:165-175)
+            if(i != 0 && stages.size() > 1) stages[i]->reset_accumulated_samples();
+        }
+        if(opt.accumulate && stages.size() > 1) set_blend_ratio(1.0f / (float)(accumulated_frames + 1));
     }
     // the stitched image on the display device (headless staging copy, src/headless.cc:125-171)
     std::vector<float> read_image()
@@ -358,7 +380,14 @@ private:
         }
         double offset = 0;
         for(size_t k = 0; k < i; ++k) offset += workloads[k];
-        return get_device_distribution_params(size, opt.strategy, offset, workloads[i], (unsigned)i, (unsigned)devices.size(), false);
+        return get_device_distribution_params(size, opt.strategy, offset, workloads[i], (unsigned)i, (unsigned)devices.size(), i == 0);
+    }
+    // stitch_stage::set_blend_ratio for the fused stitch of the non-primary stages
+    void set_blend_ratio(float r)
+    {
+        blend_ratio = r;
+        for(size_t i = 1; i < stages.size(); ++i)
+            check(tr_pt_set_stitch_blend(stages[i]->handle(), r), stages[i]->handle(), "tr_pt_set_stitch_blend");
     }
 
     std::vector<int> devices;
@@ -367,6 +396,8 @@ private:
     std::vector<double> workloads;
     std::vector<std::unique_ptr<path_tracer_stage>> stages;
     uint32_t views = 0;
+    uint32_t accumulated_frames = 0;
+    float blend_ratio = 1.0f;
 };
 
 } // namespace tr_b200

@@ -21,7 +21,7 @@ _lib = None
 EXPORTS = [
     "tr_pt_default_options", "tr_pt_create", "tr_pt_destroy", "tr_pt_set_scene", "tr_pt_set_cameras",
     "tr_pt_set_distribution", "tr_pt_reset_accumulation", "tr_pt_render", "tr_pt_render_feature", "tr_pt_sync",
-    "tr_pt_get_color_buffer", "tr_pt_read_color", "tr_pt_unshuffle", "tr_pt_set_peer_images", "tr_pt_get_stats",
+    "tr_pt_get_color_buffer", "tr_pt_read_color", "tr_pt_unshuffle", "tr_pt_set_peer_images", "tr_pt_set_stitch_blend", "tr_pt_get_stats",
     "tr_pt_set_gbuffer_layers", "tr_pt_get_gbuffer_layer", "tr_pt_read_gbuffer_layer",
     "tr_pt_set_instrumentation", "tr_pt_read_tri_lights", "tr_pt_read_alias_table", "tr_pt_trace_rays", "tr_pt_sample_test",
     "tr_pt_last_error", "tr_pt_abi_version", "tr_pt_alloc_full_image", "tr_pt_ipc_get_handle",
@@ -59,7 +59,8 @@ def lib():
     l.tr_pt_sync.argtypes = [vp]
     l.tr_pt_get_color_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     l.tr_pt_read_color.argtypes = [vp, vp, C.c_size_t]
-    l.tr_pt_unshuffle.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, vp]
+    l.tr_pt_unshuffle.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, C.c_float, vp]
+    l.tr_pt_set_stitch_blend.argtypes = [vp, C.c_float]
     l.tr_pt_set_peer_images.argtypes = [vp, C.POINTER(vp), C.c_int]
     l.tr_pt_get_stats.argtypes = [vp, C.POINTER(abi.Stats)]
     l.tr_pt_set_instrumentation.argtypes = [vp, C.c_int]
@@ -176,8 +177,11 @@ class PathTracer:
         self._check(self._l.tr_pt_get_color_buffer(self._ctx, C.byref(p), C.byref(n)), "tr_pt_get_color_buffer")
         return p.value, n.value
 
-    def unshuffle(self, strip_ptr, index, count, full_image_ptr, stream=None):
-        self._check(self._l.tr_pt_unshuffle(self._ctx, strip_ptr, index, count, full_image_ptr, stream), "tr_pt_unshuffle")
+    def unshuffle(self, strip_ptr, index, count, full_image_ptr, stream=None, blend_ratio=1.0):
+        self._check(self._l.tr_pt_unshuffle(self._ctx, strip_ptr, index, count, full_image_ptr, blend_ratio, stream), "tr_pt_unshuffle")
+
+    def set_stitch_blend(self, blend_ratio):
+        self._check(self._l.tr_pt_set_stitch_blend(self._ctx, float(blend_ratio)), "tr_pt_set_stitch_blend")
 
     def set_peer_images(self, ptrs):
         arr = (C.c_void_p * max(len(ptrs), 1))(*ptrs)

@@ -50,7 +50,7 @@ class RtRenderer:
 
     def __init__(self, options, size, rank=0, world=1, device=0, stitch=None,
                  strategy=abi.DISTRIBUTION_SHUFFLED_STRIPS, tracer_factory=None, process_group=None,
-                 backend_is_cuda=True):
+                 backend_is_cuda=True, primary=None, accumulate=False):
         self.options = abi.copy_options(options)
         self.size = (int(size[0]), int(size[1]))
         self.rank, self.world, self.device = rank, world, device
@@ -64,6 +64,13 @@ class RtRenderer:
         if world > 1 and strategy != abi.DISTRIBUTION_SHUFFLED_STRIPS:
             raise NotImplementedError("multi-device stitching implements shuffled strips (the reference's default)")
         self.stitch = stitch
+        # `primary`: the rank that plays the reference's display device -- it renders in place into its full
+        # image and keeps accumulating across workload changes (src/rt_renderer.cc:165-175). None: no rank does
+        # (headless; every rank renders a strip). `accumulate` = rt_renderer::options::accumulate.
+        self.primary = primary if world > 1 else None
+        self.accumulate = bool(accumulate)
+        self.accumulated_frames = 0
+        self._blend = 1.0
         if tracer_factory is None:
             from .library import PathTracer
             tracer_factory = lambda opt: PathTracer(opt, device=device)  # noqa: E731
@@ -86,13 +93,36 @@ class RtRenderer:
         self._apply_distribution()
 
     def reset_accumulation(self, reset_sample_counter=True):
+        """rt_renderer::reset_accumulation (src/rt_renderer.cc:66-81)."""
         self.tracer.reset_accumulation(reset_sample_counter)
+        self.accumulated_frames = 0
+        self._set_blend(1.0)
 
     def set_device_workloads(self, ratios):
-        """rt_renderer::set_device_workloads (src/rt_renderer.cc:136-183)."""
+        """rt_renderer::set_device_workloads (src/rt_renderer.cc:136-183): new strips for everyone; only the
+        primary device renders in place, so every other device restarts its accumulation and its next strip is
+        blended into the stitched image with 1/(accumulated_frames+1) instead."""
         assert len(ratios) == self.world
-        self.workloads = list(ratios)
+        if self.strategy != abi.DISTRIBUTION_SHUFFLED_STRIPS:
+            return
+        cumulative, clamped = 0.0, []
+        for r in ratios:
+            r = min(max(float(r), 0.0), 1.0 - cumulative)
+            clamped.append(r)
+            cumulative += r
+        self.workloads = clamped
         self._apply_distribution()
+        if self.world > 1:
+            if self.rank != self.primary:
+                self.tracer.reset_accumulation(False)
+            if self.accumulate:
+                self._set_blend(1.0 / (self.accumulated_frames + 1))
+
+    def _set_blend(self, ratio):
+        self._blend = float(ratio)
+        if self.world > 1 and self.stitch == "peer" and hasattr(self.tracer, "set_stitch_blend"):
+            # the primary's pixels are written in place and never blended (stitch_stage.cc:160: img_idx != primary_index)
+            self.tracer.set_stitch_blend(1.0 if self.rank == self.primary else self._blend)
 
     # -- distribution / buffers ------------------------------------------------------------
     def _apply_distribution(self):
@@ -101,7 +131,7 @@ class RtRenderer:
                 if self.strategy == abi.DISTRIBUTION_SHUFFLED_STRIPS else 1
             self.dists = [dist_mod.make_distribution(self.size, self.strategy, 0, count, True)]
         else:
-            self.dists = dist_mod.device_distributions(self.size, self.strategy, self.workloads, primary_device=None)
+            self.dists = dist_mod.device_distributions(self.size, self.strategy, self.workloads, primary_device=self.primary)
         self.tracer.set_distribution(self.dists[self.rank])
         if self.world > 1 and self.views:
             self._alloc_stitch_buffers()
@@ -112,34 +142,43 @@ class RtRenderer:
         W, H = self.size
         self.max_count = max(d.count for d in self.dists)
         my = self.dists[self.rank]
-        if self.cuda:
+        in_place = self.rank == self.primary          # the display device renders straight into the stitched image
+        if self.cuda and not in_place:
             # strip target: caller-owned torch memory so NCCL can gather straight out of it
             self._strip = torch.zeros((self.views, my.count, 4), dtype=torch.float32, device=dev)
             self.tracer.set_color_buffer(self._strip.data_ptr(), self._strip.numel() * 4)
         if self.stitch == "nccl":
             self._send = torch.zeros((self.views, self.max_count, 4), dtype=torch.float32, device=dev)
             self._gathered = torch.zeros((self.world, self.views, self.max_count, 4), dtype=torch.float32, device=dev)
-            self._full = torch.zeros((self.views, H, W, 4), dtype=torch.float32, device=dev)
+            if self._full is None or tuple(self._full.shape) != (self.views, H, W, 4):
+                self._full = torch.zeros((self.views, H, W, 4), dtype=torch.float32, device=dev)
             self._full_ptr = self._full.data_ptr() if self.cuda else None
+            if self.cuda and in_place:
+                self.tracer.set_color_buffer(self._full_ptr, self._full.numel() * 4)
         elif self.stitch == "peer":
             import torch.distributed as td
             ptr, nbytes = self.tracer.alloc_full_image()
-            self._full_ptr, self._full_bytes = ptr, nbytes
-            handles = [None] * self.world
-            td.all_gather_object(handles, self.tracer.ipc_get_handle(), group=self.pg)
-            for p in self._peer_ptrs:
-                self.tracer.ipc_close_handle(p)
-            self._peer_ptrs = []
-            ptrs = []
-            for r, h in enumerate(handles):
-                if r == self.rank:
-                    ptrs.append(ptr)
-                else:
-                    p = self.tracer.ipc_open_handle(h)
-                    self._peer_ptrs.append(p)
-                    ptrs.append(p)
-            self.tracer.set_peer_images(ptrs)
-            self._flag = torch.zeros(1, dtype=torch.float32, device=dev)
+            # same size => the library returns the same allocation on every rank: the (collective) handle
+            # exchange is needed only when the size changed
+            if nbytes != getattr(self, "_full_bytes", None):
+                self._full_ptr, self._full_bytes = ptr, nbytes
+                handles = [None] * self.world
+                td.all_gather_object(handles, self.tracer.ipc_get_handle(), group=self.pg)
+                for p in self._peer_ptrs:
+                    self.tracer.ipc_close_handle(p)
+                self._peer_ptrs = []
+                ptrs = []
+                for r, h in enumerate(handles):
+                    if r == self.rank:
+                        ptrs.append(ptr)
+                    else:
+                        p = self.tracer.ipc_open_handle(h)
+                        self._peer_ptrs.append(p)
+                        ptrs.append(p)
+                self.tracer.set_peer_images(ptrs)
+                self._flag = torch.zeros(1, dtype=torch.float32, device=dev)
+            if in_place:
+                self.tracer.set_color_buffer(ptr, nbytes)
 
     # -- frame -----------------------------------------------------------------------------
     def render(self, stream=None):
@@ -147,9 +186,19 @@ class RtRenderer:
         if stream is None and self.cuda and self.world > 1:
             import torch
             stream = torch.cuda.current_stream(self.device).cuda_stream  # order with the NCCL ops
+        in_place = self.world > 1 and self.rank == self.primary
+        if in_place and not self.cuda and hasattr(self.tracer, "write_color"):
+            self.tracer.write_color(self._full.numpy())      # CPU stand-in for "the target is the stitched image"
         self.tracer.render(stream)
-        if self.world == 1 or self.stitch == "none":
-            return
+        if self.world > 1 and self.stitch != "none":
+            self._stitch(stream, in_place)
+            # "Reset temporary blending from stitching" (src/rt_renderer.cc:126-127)
+            if self._blend != 1.0:
+                self._set_blend(1.0)
+        self.accumulated_frames += 1
+
+    def _stitch(self, stream, in_place):
+        import torch
         import torch.distributed as td
         if self.stitch == "peer":
             # all peers' stores into my image are complete once every rank's kernels finished:
@@ -157,27 +206,47 @@ class RtRenderer:
             td.all_reduce(self._flag, group=self.pg)
             return
         my = self.dists[self.rank]
-        if self.cuda:
-            self._send[:, :my.count].copy_(self._strip)
-        else:
-            import torch
-            self._send[:, :my.count].copy_(torch.from_numpy(self.tracer.read_color()))
+        if not in_place:
+            if self.cuda:
+                self._send[:, :my.count].copy_(self._strip)
+            else:
+                self._send[:, :my.count].copy_(torch.from_numpy(self.tracer.read_color()))
+        elif not self.cuda:
+            # the primary's pixels, rendered in place in the tracer's own full-size target
+            img = torch.from_numpy(self.tracer.read_color()).reshape(self.views, -1, 4)
+            j = dist_mod.permute_region_id(np.arange(my.index, my.index + my.count, dtype=np.uint64), self.size)
+            j = torch.from_numpy(j[j < self.size[0] * self.size[1]].astype(np.int64))
+            self._full.view(self.views, -1, 4)[:, j] = img[:, j]
         # concatenated-along-dim-0 form: accepted by both NCCL and gloo
         td.all_gather_into_tensor(self._gathered.view(self.world * self.views, self.max_count, 4), self._send, group=self.pg)
-        for r, d in enumerate(self.dists):
-            src = self._gathered[r, :, :d.count].contiguous() if d.count != self.max_count else self._gathered[r]
-            if self.cuda:
-                self.tracer.unshuffle(src.data_ptr(), d.index, d.count, self._full_ptr, stream)
-            else:
-                self._unshuffle_host(src.numpy(), d.index, d.count)
+        if self.primary is None or in_place:
+            for r, d in enumerate(self.dists):
+                if r == self.primary:
+                    continue                              # in place already, never blended (stitch_stage.cc:160)
+                src = self._gathered[r, :, :d.count].contiguous() if d.count != self.max_count else self._gathered[r]
+                if self.cuda:
+                    self.tracer.unshuffle(src.data_ptr(), d.index, d.count, self._full_ptr, stream, self._blend)
+                else:
+                    self._unshuffle_host(src.numpy(), d.index, d.count, self._blend)
+        if self.primary is not None:
+            # only the display device stitches in the reference; every rank gets the image here
+            td.broadcast(self._full, src=self.primary, group=self.pg)
 
-    def _unshuffle_host(self, strip, index, count):
+    def _unshuffle_host(self, strip, index, count, blend=1.0):
         """stitch_shuffled_strips.comp:21-63 on the host (gloo tests)."""
         W, H = self.size
         j = dist_mod.permute_region_id(np.arange(index, index + count, dtype=np.uint64), self.size)
         ok = j < W * H
+        jj = j[ok].astype(np.int64)
         full = self._full.numpy().reshape(self.views, W * H, 4)
-        full[:, j[ok].astype(np.int64)] = strip[:, ok]
+        new = strip[:, ok]
+        if blend < 1.0:
+            # mix(old, new, a) = fma(new, a, old * (1 - a)) in fp32 (TR math); the product new*a is exact in fp64
+            a = np.float32(blend)
+            old = full[:, jj]
+            t = (old * (np.float32(1.0) - a)).astype(np.float32)
+            new = (new.astype(np.float64) * np.float64(a) + t.astype(np.float64)).astype(np.float32)
+        full[:, jj] = new
 
     # -- results ---------------------------------------------------------------------------
     def image(self):

@@ -31,10 +31,47 @@ class OracleTracer:
         self.o.close()
 
 
+def rebalance(out_dir, primary):
+    """Workload change under accumulation (src/rt_renderer.cc:136-183) against single-device expectations."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _rebalance_common as rc
+    from helpers import full_dist
+    rank, world = td.get_rank(), td.get_world_size()
+    size = (64, 36)
+    f1 = 2
+    opt = abi.default_options(max_ray_depth=2, samples_per_pixel=2, local_sampler=abi.SAMPLER_SOBOL_OWEN)
+    scene = testscenes.cornell()
+    cams = testscenes.cornell_cameras(size[0] / size[1])
+    ren = RtRenderer(opt, size, rank=rank, world=world, stitch="nccl", tracer_factory=OracleTracer, backend_is_cuda=False,
+                     primary=primary, accumulate=True)
+    ren.set_scene(scene, cams)
+    for _ in range(f1):
+        ren.render()
+    before = ren.image().copy()
+    ren.set_device_workloads([0.25, 0.75] if world == 2 else [0.2, 0.5, 0.3])
+    ren.render()
+    img_a = ren.image().copy()
+    ren.render()
+    img_b = ren.image().copy()
+    single = Oracle(opt, threads=2)
+    single.set_scene(scene)
+    single.set_cameras(cams)
+    m_f1, a_pri, a_oth, b_pri, b_oth = rc.expected_images(single, full_dist(size), f1)
+    mask = rc.primary_mask(size, ren.dists, primary)
+    bad = [rc.mismatches(before, m_f1), rc.mismatches(img_a, rc.compose(mask, a_pri, a_oth)),
+           rc.mismatches(img_b, rc.compose(mask, b_pri, b_oth))]
+    np.save(os.path.join(out_dir, "rebalance_rank%d.npy" % rank), np.asarray(bad + [int(mask.sum())]))
+    ren.close()
+
+
 def main():
     out_dir = sys.argv[1]
-    workloads = [float(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 and sys.argv[2] else None
     td.init_process_group("gloo")
+    if len(sys.argv) > 2 and sys.argv[2].startswith("rebalance"):
+        rebalance(out_dir, 0 if sys.argv[2].endswith("primary0") else None)
+        td.destroy_process_group()
+        return
+    workloads = [float(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 and sys.argv[2] else None
     rank, world = td.get_rank(), td.get_world_size()
     size = (96, 54)
     opt = abi.default_options(max_ray_depth=3, samples_per_pixel=2, local_sampler=abi.SAMPLER_SOBOL_OWEN)

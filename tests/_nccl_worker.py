@@ -54,6 +54,44 @@ def main():
         ok = ok and same
         td.barrier()
         ren.close()
+    # ---- workload change under accumulation (src/rt_renderer.cc:136-183, stitch_shuffled_strips.comp:50-57)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _rebalance_common as rc
+    f1 = 2
+    size2 = (320, 180)
+    full = distribution.make_distribution(size2, abi.DISTRIBUTION_SHUFFLED_STRIPS, 0,
+                                          distribution.calculate_shuffled_strips_pixels_per_device(size2, 1.0), True)
+    with PathTracer(opt, device=local) as single:
+        single.set_scene(scene)
+        single.set_cameras(cams)
+        m_f1, a_pri, a_oth, b_pri, b_oth = rc.expected_images(single, full, f1)
+    for stitch in ("peer", "nccl"):
+        for primary in (0, None):
+            ren = RtRenderer(opt, size2, rank=rank, world=world, device=local, stitch=stitch, primary=primary, accumulate=True)
+            ren.set_scene(scene, cams)
+            for _ in range(f1):
+                ren.render(stream.cuda_stream)
+            torch.cuda.synchronize(local)
+            td.barrier()
+            before = ren.image().copy()
+            ren.set_device_workloads([0.3] + [0.7 / (world - 1)] * (world - 1))
+            ren.render(stream.cuda_stream)
+            torch.cuda.synchronize(local)
+            td.barrier()
+            img_a = ren.image().copy()
+            ren.render(stream.cuda_stream)
+            torch.cuda.synchronize(local)
+            td.barrier()
+            img_b = ren.image().copy()
+            mask = rc.primary_mask(size2, ren.dists, primary)
+            bad = [rc.mismatches(before, m_f1), rc.mismatches(img_a, rc.compose(mask, a_pri, a_oth)),
+                   rc.mismatches(img_b, rc.compose(mask, b_pri, b_oth))]
+            # the expected blend emulates the fp32 fma through fp64 (double rounding: at most a stray value)
+            same = bad[0] == 0 and bad[1] <= 2 and bad[2] == 0
+            print("rank %d rebalance stitch %s primary %s: %s %s" % (rank, stitch, primary, "identical" if same else "DIFFERENT", bad), flush=True)
+            ok = ok and same
+            td.barrier()
+            ren.close()
     td.destroy_process_group()
     sys.exit(0 if ok else 1)
 

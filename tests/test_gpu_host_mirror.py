@@ -59,6 +59,33 @@ def test_cpp_host_mirror_matches_python(tmp_path, fake_devices):
 
 
 @pytest.mark.gpu
+def test_cpp_rt_renderer_rebalances_like_the_reference(tmp_path):
+    """rt_renderer::set_device_workloads under accumulation through the C++ mirror (2 stages on this GPU): device 0
+    is the display device and keeps accumulating in place, device 1 restarts and its strip is blended with 1/3."""
+    import _rebalance_common as rc
+    from tauray_b200 import distribution
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tauray_b200", "host")], check=True)
+    size = (160, 90)
+    scene = testscenes.cornell(alpha_card=False)
+    cams = testscenes.cornell_cameras(size[0] / size[1])
+    dump_scene(tmp_path / "scene.bin", scene, cams)
+    env = dict(os.environ, TR_FAKE_DEVICES="2")
+    r = subprocess.run([DEMO, str(tmp_path / "scene.bin"), str(tmp_path / "out.raw"), str(size[0]), str(size[1]), "2", "4", "1", "rebalance"],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr
+    got = np.fromfile(tmp_path / "out.raw", dtype=np.float32).reshape(1, size[1], size[0], 4)
+    opt = abi.default_options(max_ray_depth=4, samples_per_pixel=2, local_sampler=abi.SAMPLER_SOBOL_OWEN)
+    with PathTracer(opt) as pt:
+        pt.set_scene(scene)
+        pt.set_cameras(cams)
+        _, a_pri, a_oth, _, _ = rc.expected_images(pt, full_dist(size), 2)
+    dists = distribution.device_distributions(size, abi.DISTRIBUTION_SHUFFLED_STRIPS, [0.3, 0.7], primary_device=0)
+    mask = rc.primary_mask(size, dists, 0)
+    assert 0 < mask.sum() < mask.size
+    assert rc.mismatches(got, rc.compose(mask, a_pri, a_oth)) <= 2
+
+
+@pytest.mark.gpu
 def test_cpp_errors_surface_as_runtime_error(tmp_path):
     r = subprocess.run([DEMO, str(tmp_path / "missing.bin"), str(tmp_path / "o.raw"), "8", "8", "1", "1", "1"],
                        capture_output=True, text=True)

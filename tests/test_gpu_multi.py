@@ -1,5 +1,6 @@
 """N>1 on real GPUs (needs >= 2 devices; skipped otherwise): one process per GPU over NCCL, fused NVLink peer-store
-stitch and the all-gather baseline, equal and unequal workloads -- every rank's image == the single-device image."""
+stitch and the all-gather baseline, equal and unequal workloads -- every rank's image == the single-device image; plus a workload change under
+accumulation (blend-on-rebalance) for both stitch modes, with and without a primary (display) rank."""
 import os
 import socket
 import subprocess
@@ -31,4 +32,4 @@ def test_two_ranks_nccl_and_peer_stitch():
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "_nccl_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-3000:])
-    assert r.stdout.count("identical") == 3 * world and "DIFFERENT" not in r.stdout
+    assert r.stdout.count("identical") == (3 + 4) * world and "DIFFERENT" not in r.stdout, r.stdout[-3000:]

@@ -44,3 +44,20 @@ def test_multi_rank_stitch_equals_single_device(tmp_path, oracle_lib, world, wor
         got = np.load(os.path.join(tmp_path, "rank%d.npy" % rank))
         assert got.shape == want.shape
         assert got.tobytes() == want.tobytes(), "rank %d image differs from the single-device image" % rank
+
+
+@pytest.mark.parametrize("world,mode", [(2, "rebalance_primary0"), (3, "rebalance_none")])
+def test_workload_change_under_accumulation(tmp_path, oracle_lib, world, mode):
+    """set_device_workloads while accumulating (src/rt_renderer.cc:136-183): non-primary devices restart, the stitch
+    blends their first strip with 1/(accumulated_frames+1) (stitch_shuffled_strips.comp:50-57), the primary keeps
+    accumulating in place. Expected images come from single-device renders only (tests/_rebalance_common.py)."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", str(free_port()),
+           os.path.join(ROOT, "tests", "_gloo_worker.py"), str(tmp_path), mode]
+    env = dict(os.environ, OMP_NUM_THREADS="1", CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    for rank in range(world):
+        bad = np.load(os.path.join(tmp_path, "rebalance_rank%d.npy" % rank))
+        assert list(bad[:3]) == [0, 0, 0], "rank %d: mismatching values before/after/next = %s" % (rank, bad[:3])
+        assert (bad[3] > 0) == mode.endswith("primary0")
