@@ -836,12 +836,22 @@ struct orc_ctx
         return 1;
     }
 
+    int z_curve_dims() const
+    {
+        return opt.local_sampler == TR_SAMPLER_SOBOL_Z_ORDER_2D ? 2 : (opt.local_sampler == TR_SAMPLER_SOBOL_Z_ORDER_3D ? 3 : 0);
+    }
     uvec4 generate_ray_sample_uint(local_sampler& ls, uint32_t bounce_index) const
     {
         if(opt.local_sampler == TR_SAMPLER_SOBOL_OWEN)
         {
             uint32_t msb = (uint32_t)(opt.max_ray_depth > 8 ? 8 : opt.max_ray_depth);
             return get_shuffled_scrambled_sobol_pt_uint(ls.ss_seed, bounce_index, msb);
+        }
+        if(opt.local_sampler == TR_SAMPLER_SOBOL_Z_ORDER_2D || opt.local_sampler == TR_SAMPLER_SOBOL_Z_ORDER_3D)
+        {
+            // get_sobol_z_sample_uint, shader/sobol_z_sampler.glsl:19-22
+            uint32_t msb = (uint32_t)(opt.max_ray_depth > 8 ? 8 : opt.max_ray_depth);
+            return generate_sobol_sample(ls.ss_seed.x, bounce_index, msb);
         }
         return pcg4d(ls.rs_seed);
     }
@@ -1127,7 +1137,7 @@ struct orc_ctx
                     for(uint32_t i = 0; i < spp_pass; ++i)
                     {
                         local_sampler ls = init_local_sampler(
-                            uvec4{(uint32_t)px, (uint32_t)py, view, previous_samples + i}, sample_counter, rng_seed);
+                            uvec4{(uint32_t)px, (uint32_t)py, view, previous_samples + i}, sample_counter, rng_seed, z_curve_dims());
                         vec3 origin, dir;
                         get_world_camera_ray(ls, px, py, view, origin, dir);
                         vec4 diffuse, reflection;
@@ -1194,8 +1204,6 @@ static int check_options(const tr_pt_options* o, std::string& why)
 {
     if(o->max_ray_depth < 1) { why = "max_ray_depth must be >= 1"; return TR_ERR_INVALID_ARGUMENT; }
     if(o->samples_per_pass < 1 || o->samples_per_pixel < o->samples_per_pass) { why = "bad samples_per_pixel/samples_per_pass"; return TR_ERR_INVALID_ARGUMENT; }
-    if(o->local_sampler != TR_SAMPLER_UNIFORM_RANDOM && o->local_sampler != TR_SAMPLER_SOBOL_OWEN)
-    { why = "sobol-z samplers are outside the hot-path scope"; return TR_ERR_UNSUPPORTED; }
     if(o->projection != TR_PROJECTION_PERSPECTIVE && o->projection != TR_PROJECTION_ORTHOGRAPHIC)
     { why = "only matrix cameras are supported"; return TR_ERR_UNSUPPORTED; }
     return TR_OK;
@@ -1599,7 +1607,7 @@ int orc_sample_test(orc_ctx* ctx, const uint32_t* coords, uint32_t n, int draw_i
     for(uint32_t i = 0; i < n; ++i)
     {
         uvec4 c = {coords[4 * i], coords[4 * i + 1], coords[4 * i + 2], coords[4 * i + 3]};
-        local_sampler ls = init_local_sampler(c, sample_counter, rng_seed);
+        local_sampler ls = init_local_sampler(c, sample_counter, rng_seed, ctx->z_curve_dims());
         uvec4 r;
         if(draw_index < 0) r = pcg4d(ls.rs_seed);
         else r = ctx->generate_ray_sample_uint(ls, (uint32_t)draw_index);

@@ -72,14 +72,88 @@ static inline uvec4 get_shuffled_scrambled_sobol_pt_uint(uvec4 seed, uint32_t bo
     return owen_scramble_2d(generate_sobol_sample(shuffled_index, bounce, max_sobol_bounces), yzwx);
 }
 
-// shader/sampling.glsl:32-45 + random_sampler.glsl:11-19 + sobol_owen_sampler.glsl:23-28
-static inline local_sampler init_local_sampler(uvec4 coord, uint32_t sample_counter, uint32_t rng_seed)
+// ---- Z-order Sobol sampler (shader/sobol_z_sampler.glsl) ------------------------------------------
+// shader/math.glsl:85-93 (only .x of the result is used here)
+static inline uint32_t pcg2d_x(uint32_t sx, uint32_t sy)
+{
+    sx = sx * 1664525u + 1013904223u; sy = sy * 1664525u + 1013904223u;
+    uint32_t ox = sx, oy = sy;
+    sx = ox + oy * 1664525u; sy = oy + ox * 1664525u;
+    sx = (sx >> 16) ^ sx; sy = (sy >> 16) ^ sy;
+    ox = sx; oy = sy;
+    sx = ox + oy * 1664525u; sy = oy + ox * 1664525u;
+    sx = (sx >> 16) ^ sx;
+    return sx;
+}
+// shader/math.glsl:155-166
+static inline uint32_t get_permutation_n(int n, uint32_t permutation, uint32_t dimension)
+{
+    uint32_t res = 0;
+    for(int i = n - 1; i >= 0; --i)
+    {
+        uint32_t q = permutation % (uint32_t)(n - i);
+        permutation /= (uint32_t)(n - i);
+        if((uint32_t)i == dimension) res = q;
+        if(dimension > (uint32_t)i) res += (res >= q) ? 1u : 0u;
+    }
+    return res;
+}
+// shader/math.glsl:181-203
+static inline uint32_t owen_scramble_4d(uint32_t x, uint32_t seed)
+{
+    uint32_t result = 0;
+    for(uint32_t i = 0; i < 32; i += 2)
+        result |= get_permutation_n(4, pcg2d_x(seed, x & ((~3u) << i)) % 24u, (x >> i) & 3u) << i;
+    return result;
+}
+static inline uint32_t owen_scramble_8d(uint32_t x, uint32_t seed)
+{
+    uint32_t result = 0;
+    for(uint32_t i = 0; i < 32; i += 3)
+        result |= get_permutation_n(8, pcg2d_x(seed, x & ((~7u) << i)) % 40320u, (x >> i) & 7u) << i;
+    return result;
+}
+// shader/math.glsl:260-278
+static inline uint32_t morton_spread_2d(uint32_t x)
+{
+    x &= 0x0000ffffu;
+    x = (x ^ (x << 8)) & 0x00ff00ffu;
+    x = (x ^ (x << 4)) & 0x0f0f0f0fu;
+    x = (x ^ (x << 2)) & 0x33333333u;
+    x = (x ^ (x << 1)) & 0x55555555u;
+    return x;
+}
+static inline uint32_t morton_2d(uint32_t x, uint32_t y) { return morton_spread_2d(x) + 2u * morton_spread_2d(y); }
+static inline uint32_t morton_spread_3d(uint32_t x)
+{
+    x &= 0x000003ffu;
+    x = (x ^ (x << 16)) & 0xff0000ffu;
+    x = (x ^ (x << 8)) & 0x0300f00fu;
+    x = (x ^ (x << 4)) & 0x030c30c3u;
+    x = (x ^ (x << 2)) & 0x09249249u;
+    return x;
+}
+static inline uint32_t morton_3d(uint32_t x, uint32_t y, uint32_t z)
+{
+    return morton_spread_3d(x) + 2u * morton_spread_3d(y) + 4u * morton_spread_3d(z);
+}
+// shader/sobol_z_sampler.glsl:24-40 (coord.z -- the view -- is not part of the key)
+static inline uint32_t init_sobol_z_index(uvec4 coord, int curve_dims)
+{
+    if(curve_dims == 3) return owen_scramble_8d(morton_3d(coord.x, coord.y, coord.w), coord.w >> 10u);
+    return owen_scramble_4d(morton_2d(coord.x, coord.y), coord.w);
+}
+
+// shader/sampling.glsl:32-45 + random_sampler.glsl:11-19 + sobol_owen_sampler.glsl:23-28;
+// z_curve_dims: 0 = sobol-owen / uniform-random, 2 / 3 = sobol-z2 / sobol-z3 (ss_seed.x = sobol_index)
+static inline local_sampler init_local_sampler(uvec4 coord, uint32_t sample_counter, uint32_t rng_seed, int z_curve_dims = 0)
 {
     local_sampler ls;
     coord.w += sample_counter;
     coord.z += rng_seed;
     uvec4 s = coord;
     ls.ss_seed = pcg4d(s);
+    if(z_curve_dims) ls.ss_seed = uvec4{init_sobol_z_index(coord, z_curve_dims), 0u, 0u, 0u};
     ls.rs_seed = coord;
     ls.rs_seed.y ^= pcg(ls.rs_seed.x);
     ls.rs_seed.z ^= pcg(ls.rs_seed.y);

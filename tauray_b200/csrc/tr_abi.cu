@@ -120,10 +120,9 @@ int check_options(const tr_pt_options* o, std::string& why)
 {
     if(o->max_ray_depth < 1 || o->max_ray_depth > 64) { why = "max_ray_depth must be in [1, 64]"; return TR_ERR_INVALID_ARGUMENT; }
     if(o->samples_per_pass < 1 || o->samples_per_pixel < o->samples_per_pass) { why = "bad samples_per_pixel/samples_per_pass"; return TR_ERR_INVALID_ARGUMENT; }
-    if(o->local_sampler != TR_SAMPLER_UNIFORM_RANDOM && o->local_sampler != TR_SAMPLER_SOBOL_OWEN)
-    { why = "sobol-z samplers are outside the hot-path scope"; return TR_ERR_UNSUPPORTED; }
     if(o->projection != TR_PROJECTION_PERSPECTIVE && o->projection != TR_PROJECTION_ORTHOGRAPHIC)
     { why = "only matrix cameras are supported"; return TR_ERR_UNSUPPORTED; }
+    if(o->local_sampler < 0 || o->local_sampler > TR_SAMPLER_SOBOL_Z_ORDER_3D) { why = "unknown sampler"; return TR_ERR_INVALID_ARGUMENT; }
     if(o->film < 0 || o->film > 2 || o->mis_mode < 0 || o->mis_mode > 2 || o->bounce_mode < 0 || o->bounce_mode > 2 ||
        o->tri_light_mode < 0 || o->tri_light_mode > 2 || o->kernel_mode < 0 || o->kernel_mode > 1)
     { why = "enum option out of range"; return TR_ERR_INVALID_ARGUMENT; }

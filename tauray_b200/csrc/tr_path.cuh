@@ -624,6 +624,8 @@ TRD uvec4 generate_ray_sample_uint(const RenderParams& P, const SobolTables& tab
 {
     if(P.opt.local_sampler == TR_SAMPLER_SOBOL_OWEN)
         return get_shuffled_scrambled_sobol_pt_uint(tables, ss_seed, bounce_index, P.frame.max_sobol_bounces);
+    if(P.opt.local_sampler >= TR_SAMPLER_SOBOL_Z_ORDER_2D)   // get_sobol_z_sample_uint, sobol_z_sampler.glsl:19-22
+        return generate_sobol_sample(tables, ss_seed.x, bounce_index, P.frame.max_sobol_bounces);
     return pcg4d(rs_seed);
 }
 
@@ -675,7 +677,7 @@ TRD void path_begin(const RenderParams& P, uint32_t px, uint32_t py, uint32_t vi
                     PathState& s, uvec4& ss_seed, uvec4& rs_seed)
 {
     local_sampler ls = init_local_sampler(px, py, view, P.frame.previous_samples + sample_in_pass,
-                                          P.frame.sample_counter, P.frame.rng_seed);
+                                          P.frame.sample_counter, P.frame.rng_seed, P.opt.local_sampler);
     vec2 cam_offset = V2(0, 0);
     if(P.opt.film != TR_FILM_POINT)
     {

@@ -144,8 +144,8 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_generate(const RenderParams P, 
                 store_state(wf, slot, s);
                 store_first_hit(wf, slot, s);
                 // one 16-byte sampler record per slot: the PCG stream state (uniform-random sampler) or the
-                // constant Sobol-Owen seed (sobol-owen sampler)
-                if(P.opt.local_sampler == TR_SAMPLER_SOBOL_OWEN) wf.rs_seed[slot] = make_uint4(ss.x, ss.y, ss.z, ss.w);
+                // constant Sobol-Owen seed (sobol-owen sampler) / Sobol index (sobol-z samplers)
+                if(P.opt.local_sampler != TR_SAMPLER_UNIFORM_RANDOM) wf.rs_seed[slot] = make_uint4(ss.x, ss.y, ss.z, ss.w);
                 else wf.rs_seed[slot] = make_uint4(rs.x, rs.y, rs.z, rs.w);
                 paths++;
             }
@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_shade(const RenderParams P, con
     SobolTables tables;
     tables.base = P.sobol_chunks;
     tables.first_group = 0;
-    if(P.opt.local_sampler == TR_SAMPLER_SOBOL_OWEN && 2 * bounce + 1 < P.frame.max_sobol_bounces)
+    if(P.opt.local_sampler != TR_SAMPLER_UNIFORM_RANDOM && 2 * bounce + 1 < P.frame.max_sobol_bounces)
     {
         for(int k = threadIdx.x; k < 2 * 1024; k += blockDim.x) s_chunks[k] = P.sobol_chunks[(size_t)2 * bounce * 1024 + k];
         tables.base = s_chunks;
@@ -707,7 +707,7 @@ __global__ void k_sample_test(const RenderParams P, const uint32_t* __restrict__
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if(i >= n) return;
     local_sampler ls = init_local_sampler(coords[4 * i], coords[4 * i + 1], coords[4 * i + 2], coords[4 * i + 3],
-                                          P.frame.sample_counter, P.frame.rng_seed);
+                                          P.frame.sample_counter, P.frame.rng_seed, P.opt.local_sampler);
     uvec4 r;
     if(draw_index < 0) r = pcg4d(ls.rs_seed);
     else

@@ -59,6 +59,9 @@ OPTION_CASES = {
     "weighted_nee": dict(max_ray_depth=3, sampling_weight_point_lights=2.0, sampling_weight_emissive_triangles=0.5),
     "samples_per_pass_2": dict(max_ray_depth=3, samples_per_pixel=4, samples_per_pass=2, local_sampler=abi.SAMPLER_SOBOL_OWEN),
     "depth_1": dict(max_ray_depth=1),
+    "sobol_z2": dict(max_ray_depth=4, local_sampler=abi.SAMPLER_SOBOL_Z_ORDER_2D, samples_per_pixel=2),
+    "sobol_z3": dict(max_ray_depth=4, local_sampler=abi.SAMPLER_SOBOL_Z_ORDER_3D, samples_per_pixel=2, film=abi.FILM_BOX),
+    "sobol_z3_depth9_pcg_fallback_dims": dict(max_ray_depth=9, local_sampler=abi.SAMPLER_SOBOL_Z_ORDER_3D, rng_seed=5),
 }
 
 
@@ -116,7 +119,7 @@ def test_scene_variants():
 
 def test_device_sampler_is_bit_exact():
     coords = np.random.RandomState(5).randint(0, 5000, size=(4096, 4)).astype(np.uint32)
-    for sampler in (abi.SAMPLER_SOBOL_OWEN, abi.SAMPLER_UNIFORM_RANDOM):
+    for sampler in (abi.SAMPLER_SOBOL_OWEN, abi.SAMPLER_UNIFORM_RANDOM, abi.SAMPLER_SOBOL_Z_ORDER_2D, abi.SAMPLER_SOBOL_Z_ORDER_3D):
         for depth in (2, 4, 12):
             opt = abi.default_options(max_ray_depth=depth, local_sampler=sampler, rng_seed=99)
             o = Oracle(opt)
