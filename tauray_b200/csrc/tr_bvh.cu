@@ -695,15 +695,63 @@ using namespace trd;
 
 static inline uint32_t div_up(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 
+// Build temporaries: one arena (a single cudaMalloc / cudaFree -- both synchronise the device and dominated
+// the build time when every array had its own) with a bump pointer; anything that does not fit falls back to
+// its own allocation.
 struct ScopedFree
 {
     std::vector<void*> ptrs;
-    ~ScopedFree() { for(void* p: ptrs) cudaFree(p); }
+    char* arena = nullptr;
+    size_t arena_size = 0, arena_used = 0;
+    ~ScopedFree() { for(void* p: ptrs) cudaFree(p); if(arena) cudaFree(arena); }
+    cudaError_t reserve(size_t bytes)
+    {
+        cudaError_t e = cudaMalloc((void**)&arena, bytes);
+        if(e != cudaSuccess) { arena = nullptr; cudaGetLastError(); return cudaSuccess; }   // fall back to per-array allocations
+        arena_size = bytes;
+        return cudaSuccess;
+    }
     template<typename T> cudaError_t alloc(T** p, size_t count)
     {
-        cudaError_t e = cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T));
+        const size_t bytes = (std::max<size_t>(count, 1) * sizeof(T) + 255) & ~(size_t)255;
+        if(arena && arena_used + bytes <= arena_size)
+        {
+            *p = reinterpret_cast<T*>(arena + arena_used);
+            arena_used += bytes;
+            return cudaSuccess;
+        }
+        cudaError_t e = cudaMalloc((void**)p, bytes);
         if(e == cudaSuccess) ptrs.push_back(*p);
         return e;
+    }
+};
+
+// optional phase timing of the build (TR_BUILD_TIMING=1 prints to stderr)
+struct PhaseTimer
+{
+    cudaStream_t stream;
+    bool on;
+    std::vector<std::pair<const char*, cudaEvent_t>> marks;
+    explicit PhaseTimer(cudaStream_t s): stream(s), on(getenv("TR_BUILD_TIMING") != nullptr) {}
+    void mark(const char* name)
+    {
+        if(!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, stream);
+        marks.push_back({name, e});
+    }
+    ~PhaseTimer()
+    {
+        if(!on) return;
+        cudaStreamSynchronize(stream);
+        for(size_t i = 1; i < marks.size(); ++i)
+        {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second);
+            fprintf(stderr, "[tr_build] %-12s %.3f ms\n", marks[i - 1].first, ms);
+        }
+        for(auto& m: marks) cudaEventDestroy(m.second);
     }
 };
 
@@ -764,10 +812,17 @@ cudaError_t tr_build_bvh(cudaStream_t stream, const tr_build_input& in, tr_build
     const uint32_t n = in.triangle_count;
     out->nodes = nullptr; out->tris = nullptr; out->node_count = 0; out->depth = 0;
     ScopedFree tmp;
+    PhaseTimer timer(stream);
+    {
+        // 2 x 48 n triangle records, 80 n node upper bound, ~115 n sort/hierarchy arrays (+ ~100 n for PLOC)
+        const bool ploc = getenv("TR_TUNE_BUILDER") && std::strcmp(getenv("TR_TUNE_BUILDER"), "ploc") == 0;
+        CUDA_OK(tmp.reserve((size_t)n * (ploc ? 420 : 300) + (4u << 20)));
+    }
     float4* tris_unsorted = nullptr;
     uint32_t* bounds = nullptr;
     CUDA_OK(tmp.alloc(&tris_unsorted, 3 * (size_t)n));
     CUDA_OK(tmp.alloc(&bounds, 8));
+    timer.mark("gather");
     k_init_bounds<<<1, 32, 0, stream>>>(bounds);
     for(uint32_t i = 0; i < in.instance_count; ++i)
     {
@@ -779,14 +834,14 @@ cudaError_t tr_build_bvh(cudaStream_t stream, const tr_build_input& in, tr_build
     }
     CUDA_OK(cudaGetLastError());
 
+    // Morton-ordered records and the nodes at their upper bound (n - 1 inner nodes, +1 for the degenerate root)
+    // are temporaries; the results are copied into exact-size allocations at the end.
     float4* tris_sorted = nullptr;
-    CUDA_OK(cudaMalloc((void**)&tris_sorted, std::max<size_t>(3 * (size_t)n, 1) * sizeof(float4)));
-    // node count upper bound: n - 1 inner nodes (+1 for the degenerate root)
+    CUDA_OK(tmp.alloc(&tris_sorted, 3 * (size_t)n));
     float4* nodes = nullptr;
     const size_t max_nodes = std::max<size_t>(n, 2);
-    cudaError_t e = cudaMalloc((void**)&nodes, max_nodes * 5 * sizeof(float4));
-    if(e != cudaSuccess) { cudaFree(tris_sorted); return e; }
-    auto fail = [&](cudaError_t err) { cudaFree(tris_sorted); cudaFree(nodes); return err; };
+    CUDA_OK(tmp.alloc(&nodes, max_nodes * 5));
+    auto fail = [&](cudaError_t err) { return err; };
 #define CUDA_OK2(x) do { cudaError_t e2_ = (x); if(e2_ != cudaSuccess) return fail(e2_); } while(0)
 
     uint32_t hb[6];
@@ -807,10 +862,15 @@ cudaError_t tr_build_bvh(cudaStream_t stream, const tr_build_input& in, tr_build
     if(n == 0)
     {
         // empty scene: one node without children
-        k_wide_single<<<1, 1, 0, stream>>>(0, nullptr, nullptr, eps, tris_sorted, nodes, tris_sorted);
-        CUDA_OK2(cudaGetLastError());
-        CUDA_OK2(cudaStreamSynchronize(stream));
-        out->nodes = nodes; out->tris = tris_sorted; out->node_count = 1; out->depth = 1;
+        float4 *nodes_final = nullptr, *tris_empty = nullptr;
+        CUDA_OK2(cudaMalloc((void**)&nodes_final, 5 * sizeof(float4)));
+        cudaError_t e0 = cudaMalloc((void**)&tris_empty, 3 * sizeof(float4));
+        if(e0 != cudaSuccess) { cudaFree(nodes_final); return e0; }
+        k_wide_single<<<1, 1, 0, stream>>>(0, nullptr, nullptr, eps, tris_empty, nodes_final, tris_empty);
+        e0 = cudaGetLastError();
+        if(e0 == cudaSuccess) e0 = cudaStreamSynchronize(stream);
+        if(e0 != cudaSuccess) { cudaFree(nodes_final); cudaFree(tris_empty); return e0; }
+        out->nodes = nodes_final; out->tris = tris_empty; out->node_count = 1; out->depth = 1;
         return cudaSuccess;
     }
 
@@ -820,6 +880,7 @@ cudaError_t tr_build_bvh(cudaStream_t stream, const tr_build_input& in, tr_build
     CUDA_OK2(tmp.alloc(&keys_a, n)); CUDA_OK2(tmp.alloc(&keys_b, n));
     CUDA_OK2(tmp.alloc(&vals_a, n)); CUDA_OK2(tmp.alloc(&vals_b, n));
     CUDA_OK2(tmp.alloc(&hist, 256 * (size_t)tiles));
+    timer.mark("morton+sort");
     k_morton<<<div_up(n, 256), 256, 0, stream>>>(tris_unsorted, n, bounds, keys_a, vals_a);
     for(int pass = 0; pass < 8; ++pass)
     {
@@ -840,6 +901,7 @@ cudaError_t tr_build_bvh(cudaStream_t stream, const tr_build_input& in, tr_build
     CUDA_OK2(tmp.alloc(&inner_parent, n)); CUDA_OK2(tmp.alloc(&leaf_parent, n)); CUDA_OK2(tmp.alloc(&flags, n));
     CUDA_OK2(tmp.alloc(&leaf_boxes, 6 * (size_t)n)); CUDA_OK2(tmp.alloc(&inner_boxes, 6 * (size_t)n));
     CUDA_OK2(cudaMemsetAsync(flags, 0, sizeof(int) * n, stream));
+    timer.mark("hierarchy");
     static const bool use_karras = !(getenv("TR_TUNE_BUILDER") && std::strcmp(getenv("TR_TUNE_BUILDER"), "ploc") == 0);
     int* counts = nullptr;
     CUDA_OK2(tmp.alloc(&counts, n));
@@ -884,6 +946,7 @@ cudaError_t tr_build_bvh(cudaStream_t stream, const tr_build_input& in, tr_build
         CUDA_OK2(cudaStreamSynchronize(stream));
     }
 
+    timer.mark("wide");
     static const int leaf_tris_env = getenv("TR_TUNE_LEAF") ? atoi(getenv("TR_TUNE_LEAF")) : TR_BVH_LEAF_TRIS;
     const int leaf_tris = std::max(1, std::min(3, leaf_tris_env));
     uint32_t node_count = 0, depth = 0;
@@ -924,10 +987,16 @@ cudaError_t tr_build_bvh(cudaStream_t stream, const tr_build_input& in, tr_build
         }
         node_count = (uint32_t)out_base;
     }
-    CUDA_OK3(cudaStreamSynchronize(stream));
-    cudaFree(tris_sorted);
+    timer.mark("finalize");
+    // exact-size node array for the caller (the upper-bound array lives in the arena)
+    float4* nodes_final = nullptr;
+    CUDA_OK3(cudaMalloc((void**)&nodes_final, (size_t)node_count * 5 * sizeof(float4)));
+    cudaError_t ef = cudaMemcpyAsync(nodes_final, nodes, (size_t)node_count * 5 * sizeof(float4), cudaMemcpyDeviceToDevice, stream);
+    if(ef == cudaSuccess) ef = cudaStreamSynchronize(stream);
+    if(ef != cudaSuccess) { cudaFree(nodes_final); return fail2(ef); }
+    timer.mark("end");
+    nodes = nodes_final;
     tris_sorted = tris_final;
-    CUDA_OK2(cudaStreamSynchronize(stream));
     out->nodes = nodes;
     out->tris = tris_sorted;
     out->node_count = node_count;
