@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_trace(const RenderParams P, con
     vec3 org = V3(0), dir = V3(0);
     float tmin = 0.0f, tmax = 0.0f, best_t = 0.0f;
     RaySlab rs;
-    rs.idx = rs.idy = rs.idz = 0; rs.ox = rs.oy = rs.oz = 0; rs.octinv = 0;
+    rs.idx = rs.idy = rs.idz = 0; rs.ox = rs.oy = rs.oz = 0; rs.octinv = 0; rs.k3f = P.k3f;
     RayPre rp;
     rp.kx = rp.ky = rp.kz = 0; rp.Sx = rp.Sy = rp.Sz = 0; rp.org = V3(0);
     Hit best;
@@ -330,6 +330,7 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_trace(const RenderParams P, con
                         best_t = tmax;
                         rp = precompute_ray(org, dir);
                         rs = make_ray_slab(org, dir);
+                        rs.k3f = P.k3f;
                         sp = 0;
                         found = false;
                         nf = 0; overflow = 1.0f;
@@ -790,6 +791,7 @@ cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const RenderParams& P_
     static const int k_fetch = env_int("TR_TUNE_FETCH", FETCH_THRESHOLD);
     static const int k_postpone = env_int("TR_TUNE_POSTPONE", 5);
     static const int k_blocks = env_int("TR_TUNE_BLOCKS", TRACE_BLOCKS_PER_SM);
+    P.k3f = 0x3F000000u;
     P.tune_fetch_threshold = k_fetch;
     P.tune_postpone_div = k_postpone;
 #define MARK(cls) do { if(timer) timer->mark(stream, cls); } while(0)

@@ -103,6 +103,7 @@ struct RaySlab
     float idx, idy, idz;     // 1 / dir (clamped away from 0)
     float ox, oy, oz;        // ray origin
     uint32_t octinv;         // bit k set when the direction component is >= 0 (x = 4, y = 2, z = 1)
+    uint32_t k3f;            // 0x3F000000 held in a register (see qbyte_to_float)
 };
 
 TRD RaySlab make_ray_slab(vec3 org, vec3 dir)
@@ -111,16 +112,22 @@ TRD RaySlab make_ray_slab(vec3 org, vec3 dir)
     r.idx = safe_inv(dir.x); r.idy = safe_inv(dir.y); r.idz = safe_inv(dir.z);
     r.ox = org.x; r.oy = org.y; r.oz = org.z;
     r.octinv = (dir.x >= 0.0f ? 4u : 0u) | (dir.y >= 0.0f ? 2u : 0u) | (dir.z >= 0.0f ? 1u : 0u);
+    r.k3f = 0x3F000000u;
     return r;
 }
 
 // Quantised bounds are stored as 0x80 | q with q in [0, 127]: one PRMT drops the byte into bits
 // 16..23 of 0x3F000000, giving the float 1 + q/128 exactly -- no integer->float conversion (I2F runs
 // at a fraction of the FMA rate). The slab then is t = (1 + q/128) * (128 a) + (b - 128 a).
-template<int K> TRD float qbyte_to_float(uint32_t w)
+// PRMT takes one non-register source: with a literal 0x3F000000 ptxas makes that the immediate and
+// spends a move per PRMT on the selector (measured: 42 of 333 instructions per node step), so the
+// constant comes in through a register the compiler cannot fold (RaySlab::k3f, a kernel parameter).
+template<int K> TRD float qbyte_to_float(uint32_t w, uint32_t k3f)
 {
-    return __uint_as_float(__byte_perm(w, 0x3F000000u, 0x7044u | (K << 8)));
+    return __uint_as_float(__byte_perm(w, k3f, 0x7044u | (K << 8)));
 }
+// byte K of a word of four packed bytes
+template<int K> TRD uint32_t byte_of(uint32_t w) { return __byte_perm(w, 0u, 0x4440u | K); }
 
 // One 80-byte compressed wide node (tr_scene.cuh): five 128-bit loads, eight quantised child boxes.
 // Returns the node group G = (child_base, inner-hit bits [31:24] | imask [7:0]) and the triangle
@@ -146,6 +153,7 @@ TRD void intersect_node8(const float4* __restrict__ nodes, uint32_t node_index, 
     const float ax = sx * r.idx, ay = sy * r.idy, az = sz * r.idz;
     const float bx = (n0.x - r.ox) * r.idx - ax, by = (n0.y - r.oy) * r.idy - ay, bz = (n0.z - r.oz) * r.idz - az;
     const uint32_t octinv4 = r.octinv * 0x01010101u;
+    const uint32_t k3f = r.k3f;
     uint32_t hitmask = 0;
 #pragma unroll
     for(int half = 0; half < 2; ++half)
@@ -163,13 +171,12 @@ TRD void intersect_node8(const float4* __restrict__ nodes, uint32_t node_index, 
         const uint32_t nz = r.idz < 0.0f ? qhiz : qloz, fz = r.idz < 0.0f ? qloz : qhiz;
 #define TR_CHILD(K)                                                                                        \
         {                                                                                                  \
-            const float tnx = fma_(qbyte_to_float<K>(nx), ax, bx), tfx = fma_(qbyte_to_float<K>(fx), ax, bx); \
-            const float tny = fma_(qbyte_to_float<K>(ny), ay, by), tfy = fma_(qbyte_to_float<K>(fy), ay, by); \
-            const float tnz = fma_(qbyte_to_float<K>(nz), az, bz), tfz = fma_(qbyte_to_float<K>(fz), az, bz); \
+            const float tnx = fma_(qbyte_to_float<K>(nx, k3f), ax, bx), tfx = fma_(qbyte_to_float<K>(fx, k3f), ax, bx); \
+            const float tny = fma_(qbyte_to_float<K>(ny, k3f), ay, by), tfy = fma_(qbyte_to_float<K>(fy, k3f), ay, by); \
+            const float tnz = fma_(qbyte_to_float<K>(nz, k3f), az, bz), tfz = fma_(qbyte_to_float<K>(fz, k3f), az, bz); \
             const float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));                                   \
             const float cmax = fminf(fminf(tfx, tfy), fminf(tfz, tmax));                                   \
-            if(cmin <= cmax)                                                                               \
-                hitmask |= ((child_bits4 >> (8 * K)) & 0xFFu) << ((bit_index4 >> (8 * K)) & 0xFFu);        \
+            if(cmin <= cmax) hitmask |= byte_of<K>(child_bits4) << byte_of<K>(bit_index4);                 \
         }
         TR_CHILD(0) TR_CHILD(1) TR_CHILD(2) TR_CHILD(3)
 #undef TR_CHILD
