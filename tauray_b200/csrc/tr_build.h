@@ -24,7 +24,7 @@ struct tr_build_input
 
 struct tr_build_output
 {
-    float4* nodes;            // device, 4 float4 per node, breadth-first order; caller frees
+    float4* nodes;            // device, TR_BVH_NODE_VEC4 float4 per node, breadth-first order; caller frees
     float4* tris;             // device, 3 float4 per triangle in leaf order; caller frees
     uint32_t node_count;
     uint32_t depth;           // number of breadth-first levels

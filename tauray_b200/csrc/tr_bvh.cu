@@ -11,7 +11,7 @@
 //                        (the reference's radix_sort.cc wraps a Vulkan sort it never calls)
 //   6. hierarchy         Karras 2012 binary radix tree over (code, index) keys
 //   7. refit             bottom-up AABBs with one atomic flag per inner node
-//   8. emit              breadth-first collapse into an 8-wide compressed BVH (80-byte nodes, <= 3
+//   8. emit              breadth-first collapse into an 8-wide compressed BVH (80-byte nodes, <= 2
 //                        triangles per leaf slot), boxes inflated by eps = 2^-16 * max|coordinate|
 #include "tr_scene.cuh"
 #include "tr_math.cuh"
@@ -493,9 +493,11 @@ __device__ __forceinline__ int collect_leaves(const int2* __restrict__ children,
     return n < 3 ? n : 3;
 }
 
+// 80-byte node, tr_scene.cuh. `count_of_slot[s]` = triangles of the leaf in slot s (1..2), 0 for inner /
+// empty slots.
 __device__ __forceinline__ void write_wide_node(float4* __restrict__ out, const float* nlo, const float* nhi, int n,
                                                 const float (*clo)[3], const float (*chi)[3], const int* slot_child,
-                                                const uint32_t* meta_of_child, uint32_t imask, uint32_t child_base, uint32_t tri_base)
+                                                const uint32_t* count_of_slot, uint32_t imask, uint32_t child_base, uint32_t tri_base)
 {
     // per-axis quantum 2^e with 127 * 2^e >= extent (one step of margin for the outward rounding);
     // 7-bit quanta, stored as 0x80 | q so the traversal can build 1 + q/128 with one PRMT. The
@@ -514,12 +516,13 @@ __device__ __forceinline__ void write_wide_node(float4* __restrict__ out, const 
     // empty slots: inverted box (lo = 127, hi = 0) -> never hit
     uint32_t q[6][2] = {{0xFFFFFFFFu, 0xFFFFFFFFu}, {0xFFFFFFFFu, 0xFFFFFFFFu}, {0xFFFFFFFFu, 0xFFFFFFFFu},
                         {0x80808080u, 0x80808080u}, {0x80808080u, 0x80808080u}, {0x80808080u, 0x80808080u}};
-    uint32_t meta[2] = {0, 0};
+    uint32_t leaf8 = 0, two8 = 0;
     for(int s = 0; s < 8; ++s)
     {
         const int c = slot_child[s];
         if(c < 0) continue;
-        meta[s >> 2] |= meta_of_child[c] << (8 * (s & 3));
+        if(count_of_slot[s] >= 1u) leaf8 |= 1u << s;
+        if(count_of_slot[s] >= 2u) two8 |= 1u << s;
         for(int a = 0; a < 3; ++a)
         {
             float fl = floorf((clo[c][a] - nlo[a]) / scale[a]);
@@ -533,9 +536,19 @@ __device__ __forceinline__ void write_wide_node(float4* __restrict__ out, const 
             q[3 + a][s >> 2] = (q[3 + a][s >> 2] & ~(0xFFu << sh)) | ((0x80u | (uint32_t)qh) << sh);
         }
     }
-    const uint32_t e4 = ebyte[0] | (ebyte[1] << 8) | (ebyte[2] << 16) | (imask << 24);
+    // the inner-child mask in the visiting order of ray octants 0..3: bit (slot ^ o); octant o >= 4 is the
+    // bit reversal of octant o ^ 7 (tr_trace.cuh)
+    uint32_t perm = 0;
+    for(uint32_t o = 0; o < 4; ++o)
+    {
+        uint32_t m = 0;
+        for(uint32_t s = 0; s < 8; ++s)
+            if(imask & (1u << s)) m |= 1u << (s ^ o);
+        perm |= m << (8 * o);
+    }
+    const uint32_t e4 = ebyte[0] | (ebyte[1] << 8) | (ebyte[2] << 16);
     out[0] = make_float4(nlo[0], nlo[1], nlo[2], __uint_as_float(e4));
-    out[1] = make_float4(__uint_as_float(child_base), __uint_as_float(tri_base), __uint_as_float(meta[0]), __uint_as_float(meta[1]));
+    out[1] = make_float4(__uint_as_float(child_base), __uint_as_float(tri_base), __uint_as_float(perm), __uint_as_float(leaf8 | (two8 << 8)));
     out[2] = make_float4(__uint_as_float(q[0][0]), __uint_as_float(q[0][1]), __uint_as_float(q[1][0]), __uint_as_float(q[1][1]));
     out[3] = make_float4(__uint_as_float(q[2][0]), __uint_as_float(q[2][1]), __uint_as_float(q[3][0]), __uint_as_float(q[3][1]));
     out[4] = make_float4(__uint_as_float(q[4][0]), __uint_as_float(q[4][1]), __uint_as_float(q[5][0]), __uint_as_float(q[5][1]));
@@ -621,7 +634,7 @@ __global__ void k_wide_level(int leaf_tris, const int* __restrict__ frontier, in
     }
     const uint32_t tri_base = tri_total ? atomicAdd(tri_counter, tri_total) : 0u;
     const int inner_base = inner_total ? atomicAdd(next_count, (int)inner_total) : 0;
-    uint32_t meta_of_child[8];
+    uint32_t count_of_slot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint32_t imask = 0, tri_off = 0, inner_off = 0;
     for(int s = 0; s < 8; ++s)
     {
@@ -636,7 +649,7 @@ __global__ void k_wide_level(int leaf_tris, const int* __restrict__ frontier, in
             for(int t = 0; t < got; ++t)
                 for(int w = 0; w < 3; ++w)
                     tris_out[3 * (size_t)(tri_base + tri_off + t) + w] = tris_sorted[3 * (size_t)leaves[t] + w];
-            meta_of_child[k] = (((1u << cnt) - 1u) << 5) | tri_off;
+            count_of_slot[s] = (uint32_t)cnt;
             tri_off += (uint32_t)cnt;
         }
         else
@@ -644,10 +657,9 @@ __global__ void k_wide_level(int leaf_tris, const int* __restrict__ frontier, in
             next_frontier[inner_base + (int)inner_off] = c;
             inner_off++;
             imask |= 1u << s;
-            meta_of_child[k] = (1u << 5) | (24u + (uint32_t)s);
         }
     }
-    write_wide_node(nodes + 5 * (size_t)(out_base + i), nlo, nhi, n, clo, chi, slot_child, meta_of_child, imask,
+    write_wide_node(nodes + TR_BVH_NODE_VEC4 * (size_t)(out_base + i), nlo, nhi, n, clo, chi, slot_child, count_of_slot, imask,
                     (uint32_t)(next_out_base + inner_base), tri_base);
 }
 
@@ -657,7 +669,7 @@ __global__ void k_wide_single(int n, const float* __restrict__ leaf_boxes, const
 {
     float clo[8][3], chi[8][3], nlo[3] = {0, 0, 0}, nhi[3] = {1, 1, 1};
     int slot_child[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
-    uint32_t meta_of_child[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t count_of_slot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if(n > 0)
     {
         const float* box = n == 1 ? leaf_boxes : inner_boxes;
@@ -667,10 +679,10 @@ __global__ void k_wide_single(int n, const float* __restrict__ leaf_boxes, const
             chi[0][a] = nhi[a] = box[3 + a] + eps;
         }
         slot_child[0] = 0;
-        meta_of_child[0] = (((1u << n) - 1u) << 5) | 0u;
+        count_of_slot[0] = (uint32_t)n;
         for(int t = 0; t < 3 * n; ++t) tris_out[t] = tris_sorted[t];
     }
-    write_wide_node(nodes, nlo, nhi, n > 0 ? 1 : 0, clo, chi, slot_child, meta_of_child, 0u, 0u, 0u);
+    write_wide_node(nodes, nlo, nhi, n > 0 ? 1 : 0, clo, chi, slot_child, count_of_slot, 0u, 0u, 0u);
 }
 
 __global__ void k_reorder_tris(const float4* __restrict__ tris, const uint32_t* __restrict__ order, uint32_t n, float4* __restrict__ out)
@@ -840,7 +852,7 @@ cudaError_t tr_build_bvh(cudaStream_t stream, const tr_build_input& in, tr_build
     CUDA_OK(tmp.alloc(&tris_sorted, 3 * (size_t)n));
     float4* nodes = nullptr;
     const size_t max_nodes = std::max<size_t>(n, 2);
-    CUDA_OK(tmp.alloc(&nodes, max_nodes * 5));
+    CUDA_OK(tmp.alloc(&nodes, max_nodes * TR_BVH_NODE_VEC4));
     auto fail = [&](cudaError_t err) { return err; };
 #define CUDA_OK2(x) do { cudaError_t e2_ = (x); if(e2_ != cudaSuccess) return fail(e2_); } while(0)
 
@@ -863,7 +875,7 @@ cudaError_t tr_build_bvh(cudaStream_t stream, const tr_build_input& in, tr_build
     {
         // empty scene: one node without children
         float4 *nodes_final = nullptr, *tris_empty = nullptr;
-        CUDA_OK2(cudaMalloc((void**)&nodes_final, 5 * sizeof(float4)));
+        CUDA_OK2(cudaMalloc((void**)&nodes_final, TR_BVH_NODE_VEC4 * sizeof(float4)));
         cudaError_t e0 = cudaMalloc((void**)&tris_empty, 3 * sizeof(float4));
         if(e0 != cudaSuccess) { cudaFree(nodes_final); return e0; }
         k_wide_single<<<1, 1, 0, stream>>>(0, nullptr, nullptr, eps, tris_empty, nodes_final, tris_empty);
@@ -948,7 +960,7 @@ cudaError_t tr_build_bvh(cudaStream_t stream, const tr_build_input& in, tr_build
 
     timer.mark("wide");
     static const int leaf_tris_env = getenv("TR_TUNE_LEAF") ? atoi(getenv("TR_TUNE_LEAF")) : TR_BVH_LEAF_TRIS;
-    const int leaf_tris = std::max(1, std::min(3, leaf_tris_env));
+    const int leaf_tris = std::max(1, std::min(TR_BVH_LEAF_TRIS, leaf_tris_env));
     uint32_t node_count = 0, depth = 0;
     // tris_sorted holds the Morton order; the wide emission re-packs triangles per node into tris_final
     float4* tris_final = nullptr;
@@ -990,8 +1002,8 @@ cudaError_t tr_build_bvh(cudaStream_t stream, const tr_build_input& in, tr_build
     timer.mark("finalize");
     // exact-size node array for the caller (the upper-bound array lives in the arena)
     float4* nodes_final = nullptr;
-    CUDA_OK3(cudaMalloc((void**)&nodes_final, (size_t)node_count * 5 * sizeof(float4)));
-    cudaError_t ef = cudaMemcpyAsync(nodes_final, nodes, (size_t)node_count * 5 * sizeof(float4), cudaMemcpyDeviceToDevice, stream);
+    CUDA_OK3(cudaMalloc((void**)&nodes_final, (size_t)node_count * TR_BVH_NODE_VEC4 * sizeof(float4)));
+    cudaError_t ef = cudaMemcpyAsync(nodes_final, nodes, (size_t)node_count * TR_BVH_NODE_VEC4 * sizeof(float4), cudaMemcpyDeviceToDevice, stream);
     if(ef == cudaSuccess) ef = cudaStreamSynchronize(stream);
     if(ef != cudaSuccess) { cudaFree(nodes_final); return fail2(ef); }
     timer.mark("end");

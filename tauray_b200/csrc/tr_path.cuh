@@ -37,7 +37,6 @@ struct RenderParams
     // traversal tuning (defaults in tr_render.cu; TR_TUNE_* environment overrides for experiments)
     int tune_fetch_threshold;
     int tune_postpone_div;
-    uint32_t k3f;               // 0x3F000000, passed as data so that it lives in a register (tr_trace.cuh qbyte_to_float)
 };
 
 // Path state carried from bounce to bounce (evaluate_ray's locals).

@@ -22,6 +22,15 @@ namespace trd {
 
 constexpr int WF_BLOCK = 128;
 constexpr int TRACE_BLOCKS_PER_SM = 8;
+#ifndef TRACE_MIN_BLOCKS_CLOSEST
+#define TRACE_MIN_BLOCKS_CLOSEST 8
+#endif
+#ifndef SHADE_MIN_BLOCKS
+#define SHADE_MIN_BLOCKS 4
+#endif
+#ifndef TRACE_MIN_BLOCKS_SHADOW
+#define TRACE_MIN_BLOCKS_SHADOW 8
+#endif
 
 // ---- SoA <-> registers ---------------------------------------------------------------------------
 TRD void store_ray(const tr_wavefront& wf, uint32_t id, const PathState& s)
@@ -171,7 +180,7 @@ constexpr int FETCH_THRESHOLD = 20;
 constexpr int MAX_FACTORS = 6;
 
 template<bool ANY, bool STATS>
-__global__ void __launch_bounds__(WF_BLOCK) k_wf_trace(const RenderParams P, const tr_wavefront wf, uint32_t bounce,
+__global__ void __launch_bounds__(WF_BLOCK, ANY ? TRACE_MIN_BLOCKS_SHADOW : TRACE_MIN_BLOCKS_CLOSEST) k_wf_trace(const RenderParams P, const tr_wavefront wf, uint32_t bounce,
                                                         const uint32_t* __restrict__ queue, const uint32_t* __restrict__ count,
                                                         uint32_t* __restrict__ work_counter)
 {
@@ -197,7 +206,7 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_trace(const RenderParams P, con
     vec3 org = V3(0), dir = V3(0);
     float tmin = 0.0f, tmax = 0.0f, best_t = 0.0f;
     RaySlab rs;
-    rs.idx = rs.idy = rs.idz = 0; rs.ox = rs.oy = rs.oz = 0; rs.octinv = 0; rs.k3f = P.k3f;
+    rs = make_ray_slab(V3(0), V3(0));
     RayPre rp;
     rp.kx = rp.ky = rp.kz = 0; rp.Sx = rp.Sy = rp.Sz = 0; rp.org = V3(0);
     Hit best;
@@ -330,7 +339,6 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_trace(const RenderParams P, con
                         best_t = tmax;
                         rp = precompute_ray(org, dir);
                         rs = make_ray_slab(org, dir);
-                        rs.k3f = P.k3f;
                         sp = 0;
                         found = false;
                         nf = 0; overflow = 1.0f;
@@ -368,7 +376,7 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_trace(const RenderParams P, con
             }
 
             const int active = __popc(__activemask());
-            while(Gt.y != 0u)
+            while(Gt.y & 0xFFu)
             {
                 if(__popc(__activemask()) * P.tune_postpone_div < active)
                 {
@@ -376,10 +384,9 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_trace(const RenderParams P, con
                     Gt.y = 0u;
                     break;
                 }
-                const uint32_t bit = 31u - (uint32_t)__clz((int)Gt.y);
-                Gt.y &= ~(1u << bit);
+                const uint32_t tri_index = pop_triangle(Gt, rs.octinv);
                 if(STATS) st.tris++;
-                const float4* tp = tris + 3 * (size_t)(Gt.x + bit);
+                const float4* tp = tris + 3 * (size_t)tri_index;
                 const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
                 float t, u, v;
                 if(!intersect_triangle(rp, f3(t0), f3(t1), f3(t2), tmin, tmax, t, u, v)) continue;
@@ -425,7 +432,7 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_trace(const RenderParams P, con
     flush_counters(P.counters, ANY ? 0 : rays, ANY ? rays : 0, 0, st.nodes, st.tris, ANY ? 1 : 0);
 }
 
-__global__ void __launch_bounds__(WF_BLOCK) k_wf_shade(const RenderParams P, const tr_wavefront wf, uint32_t bounce, uint32_t sample_in_pass,
+__global__ void __launch_bounds__(WF_BLOCK, SHADE_MIN_BLOCKS) k_wf_shade(const RenderParams P, const tr_wavefront wf, uint32_t bounce, uint32_t sample_in_pass,
                                                         const uint32_t* __restrict__ queue, const uint32_t* __restrict__ count,
                                                         uint32_t* __restrict__ next_queue, uint32_t* __restrict__ next_count,
                                                         uint32_t* __restrict__ shadow_queue, uint32_t* __restrict__ shadow_count)
@@ -791,7 +798,6 @@ cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const RenderParams& P_
     static const int k_fetch = env_int("TR_TUNE_FETCH", FETCH_THRESHOLD);
     static const int k_postpone = env_int("TR_TUNE_POSTPONE", 5);
     static const int k_blocks = env_int("TR_TUNE_BLOCKS", TRACE_BLOCKS_PER_SM);
-    P.k3f = 0x3F000000u;
     P.tune_fetch_threshold = k_fetch;
     P.tune_postpone_div = k_postpone;
 #define MARK(cls) do { if(timer) timer->mark(stream, cls); } while(0)

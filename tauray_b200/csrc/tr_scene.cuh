@@ -8,21 +8,26 @@ namespace trd {
 
 // ---- BVH layout in HBM -----------------------------------------------------
 // 8-wide compressed node = 5 x float4 = 80 B (after Ylitie, Karras, Laine 2017), five 128-bit loads:
-//   n0 = (p.x, p.y, p.z, [ex | ey<<8 | ez<<16 | imask<<24])      p = box origin, e* = exponent byte of
-//                                                                  the per-axis scale 2^e, imask = slots
-//                                                                  holding inner children
-//   n1 = (child_base, triangle_base, meta[0..3], meta[4..7])     meta per slot: 0 = empty;
-//                                                                  inner  = 001|(24 + slot);
-//                                                                  leaf   = unary(count 1..3)<<5 | first
-//                                                                  triangle offset (< 24)
+//   n0 = (p.x, p.y, p.z, [ex | ey<<8 | ez<<16])                   p = box origin, e* = exponent byte of
+//                                                                  the per-axis scale 2^e
+//   n1 = (child_base, triangle_base, imask_oct[0..3], [leaf8 | two8<<8])
+//                                                                  imask_oct[o] = slots holding inner
+//                                                                  children, as bit (slot ^ o): the mask
+//                                                                  in the order a ray of octant o visits
+//                                                                  them (imask_oct[0] = plain slot mask;
+//                                                                  octant o >= 4 = bit reversal of o ^ 7);
+//                                                                  leaf8 = slots holding a leaf, two8 =
+//                                                                  leaf slots with two triangles
 //   n2 = (qlo_x[0..3], qlo_x[4..7], qlo_y[0..3], qlo_y[4..7])     quantised child boxes, one byte per
 //   n3 = (qlo_z[0..3], qlo_z[4..7], qhi_x[0..3], qhi_x[4..7])     slot and bound: lo = p + q * 2^e,
 //   n4 = (qhi_y[0..3], qhi_y[4..7], qhi_z[0..3], qhi_z[4..7])     rounded outwards
 // The j-th inner child (in slot order) is node child_base + j. Children sit in slots chosen per octant
 // so that visiting (slot ^ octinv) from high to low is roughly front to back.
-// Triangle = 3 x float4 = 48 B, the triangles of one node are contiguous from triangle_base:
+// Triangle = 3 x float4 = 48 B; the triangles of one node are contiguous from triangle_base in slot
+// order, one or two per leaf slot:
 //   t0 = (v0.xyz, instance_id bits), t1 = (v1.xyz, primitive_id bits), t2 = (v2.xyz, flags bits)
 // flags bit0 = opaque geometry (VK_GEOMETRY_OPAQUE_BIT, src/scene_stage.cc:1410).
+#define TR_BVH_NODE_VEC4 5
 #define TR_BVH_LEAF_TRIS 2
 #define TR_BVH_STACK 48
 #define TR_TRI_FLAG_OPAQUE 1u

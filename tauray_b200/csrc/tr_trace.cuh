@@ -103,7 +103,7 @@ struct RaySlab
     float idx, idy, idz;     // 1 / dir (clamped away from 0)
     float ox, oy, oz;        // ray origin
     uint32_t octinv;         // bit k set when the direction component is >= 0 (x = 4, y = 2, z = 1)
-    uint32_t k3f;            // 0x3F000000 held in a register (see qbyte_to_float)
+    uint32_t sel0;           // PRMT selector of the child processed first in a half, see qbyte_to_float
 };
 
 TRD RaySlab make_ray_slab(vec3 org, vec3 dir)
@@ -112,33 +112,45 @@ TRD RaySlab make_ray_slab(vec3 org, vec3 dir)
     r.idx = safe_inv(dir.x); r.idy = safe_inv(dir.y); r.idz = safe_inv(dir.z);
     r.ox = org.x; r.oy = org.y; r.oz = org.z;
     r.octinv = (dir.x >= 0.0f ? 4u : 0u) | (dir.y >= 0.0f ? 2u : 0u) | (dir.z >= 0.0f ? 1u : 0u);
-    r.k3f = 0x3F000000u;
+    r.sel0 = 0x7044u | ((r.octinv & 3u) << 8);
     return r;
 }
 
 // Quantised bounds are stored as 0x80 | q with q in [0, 127]: one PRMT drops the byte into bits
 // 16..23 of 0x3F000000, giving the float 1 + q/128 exactly -- no integer->float conversion (I2F runs
 // at a fraction of the FMA rate). The slab then is t = (1 + q/128) * (128 a) + (b - 128 a).
-// PRMT takes one non-register source: with a literal 0x3F000000 ptxas makes that the immediate and
-// spends a move per PRMT on the selector (measured: 42 of 333 instructions per node step), so the
-// constant comes in through a register the compiler cannot fold (RaySlab::k3f, a kernel parameter).
-template<int K> TRD float qbyte_to_float(uint32_t w, uint32_t k3f)
+// The selector is a register: nibble 2 names the byte, and the byte taken for the K-th processed child
+// of a half is K ^ (octinv & 3), so that children are tested in the ray's octant order and the hit bit
+// of the K-th test is the constant 1 << K.
+TRD float qbyte_to_float(uint32_t w, uint32_t sel)
 {
-    return __uint_as_float(__byte_perm(w, k3f, 0x7044u | (K << 8)));
+    return __uint_as_float(__byte_perm(w, 0x3F000000u, sel));
 }
-// byte K of a word of four packed bytes
-template<int K> TRD uint32_t byte_of(uint32_t w) { return __byte_perm(w, 0u, 0x4440u | K); }
+
+// Two independent IEEE fp32 FMAs in one issue slot (Blackwell FFMA2): (d0, d1) = (a0, a1) * b + c.
+// Each half rounds exactly like fmaf, so this changes the instruction count only.
+TRD void fma2_bcast(float& d0, float& d1, float a0, float a1, float b, float c)
+{
+    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\t"
+        "mov.b64 rb, {%4, %4};\n\t"
+        "mov.b64 rc, {%5, %5};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+        "mov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b), "f"(c));
+}
 
 // One 80-byte compressed wide node (tr_scene.cuh): five 128-bit loads, eight quantised child boxes.
 // Returns the node group G = (child_base, inner-hit bits [31:24] | imask [7:0]) and the triangle
-// group Gt = (triangle_base, triangle-hit bits [23:0]). Inner-child bits are placed at
-// 24 + (slot ^ octinv): the build assigns near-to-far slots per octant, so taking the highest set
-// bit first visits children roughly front to back without sorting. Empty slots carry an inverted
-// box and can never be hit.
+// group Gt = (triangle_base, leaf-hit bits [7:0] | leaf slots [15:8] | two-triangle slots [23:16]).
+// Hit bits are in octant order, position (slot ^ octinv): the build assigns near-to-far slots per
+// octant, so taking the highest set bit first visits children roughly front to back without sorting.
+// The node stores its inner-child mask already permuted into that order for octants 0..3; octant o >= 4
+// is the bit reversal of octant o ^ 7. Empty slots carry an inverted box and can never be hit.
 TRD void intersect_node8(const float4* __restrict__ nodes, uint32_t node_index, const RaySlab& r,
                          float tmin, float tmax, uint2& G, uint2& Gt)
 {
-    const float4* n = nodes + 5 * (size_t)node_index;
+    const float4* n = nodes + TR_BVH_NODE_VEC4 * (size_t)node_index;
     const float4 n0 = __ldg(n + 0);
     const float4 n1 = __ldg(n + 1);
     const float4 n2 = __ldg(n + 2);
@@ -149,42 +161,57 @@ TRD void intersect_node8(const float4* __restrict__ nodes, uint32_t node_index, 
     const float sx = __uint_as_float((e & 0xFFu) << 23);
     const float sy = __uint_as_float(((e >> 8) & 0xFFu) << 23);
     const float sz = __uint_as_float(((e >> 16) & 0xFFu) << 23);
-    const uint32_t imask = e >> 24;
     const float ax = sx * r.idx, ay = sy * r.idy, az = sz * r.idz;
     const float bx = (n0.x - r.ox) * r.idx - ax, by = (n0.y - r.oy) * r.idy - ay, bz = (n0.z - r.oz) * r.idz - az;
-    const uint32_t octinv4 = r.octinv * 0x01010101u;
-    const uint32_t k3f = r.k3f;
-    uint32_t hitmask = 0;
+    const uint32_t sel0 = r.sel0, sel1 = sel0 ^ 0x100u, sel2 = sel0 ^ 0x200u, sel3 = sel0 ^ 0x300u;
+    uint32_t acc[2] = {0u, 0u};
 #pragma unroll
     for(int half = 0; half < 2; ++half)
     {
-        const uint32_t meta4 = __float_as_uint(half ? n1.w : n1.z);
-        // byte-parallel: inner children (low 5 bits >= 24) get their slot XORed with octinv
-        const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-        const uint32_t bit_index4 = (meta4 ^ (octinv4 & ((is_inner4 >> 4) * 7u))) & 0x1F1F1F1Fu;
-        const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
         const uint32_t qlox = __float_as_uint(half ? n2.y : n2.x), qloy = __float_as_uint(half ? n2.w : n2.z);
         const uint32_t qloz = __float_as_uint(half ? n3.y : n3.x), qhix = __float_as_uint(half ? n3.w : n3.z);
         const uint32_t qhiy = __float_as_uint(half ? n4.y : n4.x), qhiz = __float_as_uint(half ? n4.w : n4.z);
         const uint32_t nx = r.idx < 0.0f ? qhix : qlox, fx = r.idx < 0.0f ? qlox : qhix;
         const uint32_t ny = r.idy < 0.0f ? qhiy : qloy, fy = r.idy < 0.0f ? qloy : qhiy;
         const uint32_t nz = r.idz < 0.0f ? qhiz : qloz, fz = r.idz < 0.0f ? qloz : qhiz;
-#define TR_CHILD(K)                                                                                        \
+#define TR_CHILD(K, SEL)                                                                                   \
         {                                                                                                  \
-            const float tnx = fma_(qbyte_to_float<K>(nx, k3f), ax, bx), tfx = fma_(qbyte_to_float<K>(fx, k3f), ax, bx); \
-            const float tny = fma_(qbyte_to_float<K>(ny, k3f), ay, by), tfy = fma_(qbyte_to_float<K>(fy, k3f), ay, by); \
-            const float tnz = fma_(qbyte_to_float<K>(nz, k3f), az, bz), tfz = fma_(qbyte_to_float<K>(fz, k3f), az, bz); \
+            float tnx, tfx, tny, tfy, tnz, tfz;                                                            \
+            fma2_bcast(tnx, tfx, qbyte_to_float(nx, SEL), qbyte_to_float(fx, SEL), ax, bx);      \
+            fma2_bcast(tny, tfy, qbyte_to_float(ny, SEL), qbyte_to_float(fy, SEL), ay, by);      \
+            fma2_bcast(tnz, tfz, qbyte_to_float(nz, SEL), qbyte_to_float(fz, SEL), az, bz);      \
             const float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));                                   \
             const float cmax = fminf(fminf(tfx, tfy), fminf(tfz, tmax));                                   \
-            if(cmin <= cmax) hitmask |= byte_of<K>(child_bits4) << byte_of<K>(bit_index4);                 \
+            if(cmin <= cmax) acc[half] |= 1u << K;                                                         \
         }
-        TR_CHILD(0) TR_CHILD(1) TR_CHILD(2) TR_CHILD(3)
+        TR_CHILD(0, sel0) TR_CHILD(1, sel1) TR_CHILD(2, sel2) TR_CHILD(3, sel3)
 #undef TR_CHILD
     }
+    const uint32_t hi_octant = r.octinv & 4u;
+    const uint32_t hits = (acc[0] << hi_octant) | (acc[1] << (4u - hi_octant));
+    const uint32_t perm_word = __float_as_uint(n1.z);
+    uint32_t imask_oct = (perm_word >> (8u * ((hi_octant ? ~r.octinv : r.octinv) & 3u))) & 0xFFu;
+    if(hi_octant) imask_oct = __brev(imask_oct) >> 24;
     G.x = __float_as_uint(n1.x);
-    G.y = (hitmask & 0xFF000000u) | imask;
+    G.y = ((hits & imask_oct) << 24) | (perm_word & 0xFFu);
     Gt.x = __float_as_uint(n1.y);
-    Gt.y = hitmask & 0x00FFFFFFu;
+    Gt.y = (hits & ~imask_oct) | (__float_as_uint(n1.w) << 8);
+}
+
+// Takes the next triangle out of a triangle group: the leaf slot with the highest octant-order hit
+// bit, first triangle first. Triangles of a node are stored in slot order, one or two per leaf
+// slot, so the index of a slot's first triangle is the number of leaf slots below it plus the number of
+// two-triangle slots below it. Bit 31 of Gt.x marks "second triangle of the top slot pending".
+TRD uint32_t pop_triangle(uint2& Gt, uint32_t octinv)
+{
+    const uint32_t p = 31u - (uint32_t)__clz((int)(Gt.y & 0xFFu));
+    const uint32_t s = p ^ octinv;
+    const uint32_t below = ~(0xFFFFFFFFu << s);
+    const uint32_t second = Gt.x >> 31;
+    const uint32_t index = (Gt.x & 0x7FFFFFFFu) + __popc((Gt.y >> 8) & below) + __popc((Gt.y >> 16) & below) + second;
+    if(((Gt.y >> (16u + s)) & 1u) > second) Gt.x |= 0x80000000u;
+    else { Gt.x &= 0x7FFFFFFFu; Gt.y &= ~(1u << p); }
+    return index;
 }
 
 // Index of the inner child behind hit bit `bit` (24..31) of group G.
@@ -214,12 +241,11 @@ TRD bool traverse(const DeviceBvh& bvh, vec3 org, vec3 dir, float tmin, float tm
     intersect_node8(bvh.nodes, 0, rs, tmin, best_t, G, Gt);
     for(;;)
     {
-        while(Gt.y != 0u)
+        while(Gt.y & 0xFFu)
         {
-            const uint32_t bit = 31u - (uint32_t)__clz((int)Gt.y);
-            Gt.y &= ~(1u << bit);
+            const uint32_t tri_index = pop_triangle(Gt, rs.octinv);
             if(STATS) st.tris++;
-            const float4* tp = tris + 3 * (size_t)(Gt.x + bit);
+            const float4* tp = tris + 3 * (size_t)tri_index;
             const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
             float t, u, v;
             if(!intersect_triangle(rp, f3(t0), f3(t1), f3(t2), tmin, tmax, t, u, v)) continue;

@@ -15,7 +15,8 @@ from . import abi
 from .distribution import target_shape
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtauray_b200.so")
+# TAURAY_B200_LIB: development override used to A/B differently tuned builds of the same library
+LIB_PATH = os.environ.get("TAURAY_B200_LIB") or os.path.join(_HERE, "libtauray_b200.so")
 _lib = None
 
 EXPORTS = [
