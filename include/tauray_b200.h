@@ -318,6 +318,18 @@ void tr_pt_destroy(tr_pt_ctx* ctx);
  * tri-lights (extract_tri_lights.comp) and builds the LBVH on the device. */
 int tr_pt_set_scene(tr_pt_ctx* ctx, const tr_pt_scene_desc* scene);
 
+/* == the per-frame part of scene_stage::update for animated scenes: instance-buffer refresh
+ * (src/scene_stage.cc:1066-1116), pre_transform + tri-light re-extraction and the acceleration
+ * structure update (scene_stage::record_as_build / record_tri_light_extraction,
+ * src/scene_stage.cc:1572-1675; top_level_acceleration_structure::rebuild,
+ * src/acceleration_structure.cc:376-443). `instances` replaces the scene's instance records
+ * (transforms, materials; same count, same meshes, same light_base_id layout). Everything runs on
+ * the device from the vertex data tr_pt_set_scene uploaded: world-space vertices, tri lights and a
+ * full LBVH rebuild (a rebuild, not a refit: it costs a few ms and keeps the tree quality). The
+ * result is identical to tr_pt_set_scene with the new records. Accumulation is not reset, as in the
+ * reference (the application calls reset_accumulation). */
+int tr_pt_update_instances(tr_pt_ctx* ctx, const tr_instance* instances, uint32_t instance_count);
+
 /* == camera UBO upload (src/scene_stage.cc:1145-1174); `pairs` = view_count tr_camera_pair. */
 int tr_pt_set_cameras(tr_pt_ctx* ctx, const tr_camera_pair* pairs, uint32_t view_count);
 

@@ -45,6 +45,23 @@ struct tr_pt_ctx
     void* gbuffer[TR_GBUFFER_LAYER_COUNT] = {};
     size_t gbuffer_pixels = 0;
     float* prev_from_world = nullptr;                       // scene allocation: 16 floats per instance
+    // what tr_pt_update_instances needs to redo the transform-dependent part of the scene on the device
+    struct Geometry
+    {
+        tr_vertex* v_raw = nullptr;          // object-space vertices as uploaded (scene allocation)
+        tr_vertex* v_world = nullptr;
+        uint32_t* indices = nullptr;
+        float* matrices = nullptr;           // 32 floats per instance: model, model_normal
+        DeviceInstance* d_instances = nullptr;
+        tr_tri_light* d_tri_lights = nullptr;
+        float4* bvh_nodes = nullptr;         // owned here, replaced by every rebuild
+        float4* bvh_tris = nullptr;
+        std::vector<tr_build_instance> binst;
+        std::vector<DeviceInstance> dinst;
+        std::vector<uint32_t> vertex_counts;
+        uint64_t triangle_total = 0;
+        uint64_t tri_light_count = 0;
+    } geom;
     float4* external_color = nullptr;
     size_t external_bytes = 0;
     size_t color_pixels = 0;
@@ -271,6 +288,9 @@ int prepare_targets(tr_pt_ctx* c)
 void free_scene(tr_pt_ctx* c)
 {
     free_list(c->scene_allocs);
+    if(c->geom.bvh_nodes) cudaFree(c->geom.bvh_nodes);
+    if(c->geom.bvh_tris) cudaFree(c->geom.bvh_tris);
+    c->geom = tr_pt_ctx::Geometry();
     c->prev_from_world = nullptr;
     memset(&c->scene, 0, sizeof(c->scene));
     c->has_scene = false;
@@ -443,6 +463,72 @@ static void build_alias_table(std::vector<float>& imp, uint32_t width, uint32_t 
     }
 }
 
+// The transform-dependent part of the scene, all on the device: pre_transform.comp, instance table,
+// model_prev * inverse(model), extract_tri_lights.comp and the BVH (the reference's per-frame
+// scene_stage::record_as_build / record_tri_light_extraction + instance-buffer refresh,
+// src/scene_stage.cc:1572-1675). Used by tr_pt_set_scene and tr_pt_update_instances.
+static int transform_and_build(tr_pt_ctx* c, const tr_instance* instances, uint32_t instance_count)
+{
+    tr_pt_ctx::Geometry& g = c->geom;
+    cudaStream_t st = c->stream;
+    std::vector<float> hm(32 * (size_t)instance_count);
+    std::vector<float> prev((size_t)instance_count * 16);
+    for(uint32_t i = 0; i < instance_count; ++i)
+    {
+        memcpy(&hm[32 * (size_t)i], instances[i].model, 64);
+        memcpy(&hm[32 * (size_t)i + 16], instances[i].model_normal, 64);
+        // model_prev * inverse(model) per instance, for the screen-motion layer (rt.glsl:73-79)
+        previous_from_world(instances[i].model, instances[i].model_prev, &prev[(size_t)i * 16]);
+        DeviceInstance& d = g.dinst[i];
+        d.mat = instances[i].mat;
+        d.light_base_id = instances[i].light_base_id;
+        d.shadow_terminator_mul = instances[i].shadow_terminator_mul;
+    }
+    if(instance_count)
+    {
+        TRY_CUDA(c, cudaMemcpyAsync(g.matrices, hm.data(), hm.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+        TRY_CUDA(c, cudaMemcpyAsync(g.d_instances, g.dinst.data(), sizeof(DeviceInstance) * g.dinst.size(), cudaMemcpyHostToDevice, st));
+        TRY_CUDA(c, cudaMemcpyAsync(c->prev_from_world, prev.data(), sizeof(float) * prev.size(), cudaMemcpyHostToDevice, st));
+    }
+    for(uint32_t i = 0; i < instance_count; ++i)
+        TRY_CUDA(c, tr_build_pre_transform(st, g.v_raw + g.binst[i].vertex_base, g.v_world + g.binst[i].vertex_base, g.vertex_counts[i],
+                                           g.matrices + 32 * (size_t)i, g.matrices + 32 * (size_t)i + 16));
+    // ---- extract_tri_lights.comp
+    if(g.tri_light_count) TRY_CUDA(c, cudaMemsetAsync(g.d_tri_lights, 0, sizeof(tr_tri_light) * g.tri_light_count, st));
+    for(uint32_t i = 0; i < instance_count; ++i)
+    {
+        if(g.dinst[i].light_base_id < 0) continue;
+        TRY_CUDA(c, tr_build_extract_tri_lights(st, g.v_world + g.binst[i].vertex_base, g.indices + g.binst[i].index_base, g.binst[i].triangle_count,
+                                                i, g.dinst[i].light_base_id, g.dinst[i].mat.emission_factor, g.dinst[i].mat.emission_tex_id, g.d_tri_lights));
+    }
+    // ---- LBVH
+    TRY_CUDA(c, cudaEventRecord(c->ev_begin, st));
+    tr_build_input bin;
+    bin.vertices = g.v_world; bin.indices = g.indices; bin.instances = g.binst.data();
+    bin.instance_count = instance_count; bin.triangle_count = (uint32_t)g.triangle_total;
+    tr_build_output bout;
+    TRY_CUDA(c, tr_build_bvh(st, bin, &bout));
+    TRY_CUDA(c, cudaEventRecord(c->ev_end, st));
+    TRY_CUDA(c, cudaStreamSynchronize(st));   // also covers the host staging vectors above
+    if(g.bvh_nodes) cudaFree(g.bvh_nodes);
+    if(g.bvh_tris) cudaFree(g.bvh_tris);
+    g.bvh_nodes = bout.nodes; g.bvh_tris = bout.tris;
+    float build_ms = 0.0f;
+    cudaEventElapsedTime(&build_ms, c->ev_begin, c->ev_end);
+    if(bout.depth >= TR_BVH_STACK)
+    {
+        free_scene(c);
+        return fail(c, TR_ERR_UNSUPPORTED, "BVH depth " + std::to_string(bout.depth) + " exceeds the traversal stack");
+    }
+    DeviceScene& ds = c->scene;
+    ds.bvh.nodes = bout.nodes; ds.bvh.tris = bout.tris; ds.bvh.node_count = bout.node_count; ds.bvh.tri_count = (uint32_t)g.triangle_total;
+    ds.bvh.top_nodes = 0;
+    c->stats.bvh_build_ms = build_ms;
+    c->stats.bvh_node_count = bout.node_count;
+    c->stats.bvh_depth = bout.depth;
+    return TR_OK;
+}
+
 int tr_pt_set_scene(tr_pt_ctx* c, const tr_pt_scene_desc* s)
 {
     if(!c || !s) return fail(c, TR_ERR_INVALID_ARGUMENT, "null argument");
@@ -463,8 +549,12 @@ int tr_pt_set_scene(tr_pt_ctx* c, const tr_pt_scene_desc* s)
     cudaStream_t st = c->stream;
 
     // ---- layout of the concatenated buffers
-    std::vector<tr_build_instance> binst(s->instance_count);
-    std::vector<DeviceInstance> dinst(s->instance_count);
+    tr_pt_ctx::Geometry& g = c->geom;
+    g.binst.assign(s->instance_count, tr_build_instance());
+    g.dinst.assign(s->instance_count, DeviceInstance());
+    g.vertex_counts.assign(s->instance_count, 0u);
+    std::vector<tr_build_instance>& binst = g.binst;
+    std::vector<DeviceInstance>& dinst = g.dinst;
     uint64_t vtotal = 0, itotal = 0, ttotal = 0;
     uint64_t tri_light_count = 0;
     bool any_non_opaque = false;
@@ -478,65 +568,41 @@ int tr_pt_set_scene(tr_pt_ctx* c, const tr_pt_scene_desc* s)
         binst[i].triangle_base = (uint32_t)ttotal;
         binst[i].triangle_count = m.index_count / 3;
         binst[i].opaque = m.opaque ? 1u : 0u;
+        g.vertex_counts[i] = m.vertex_count;
         if(!m.opaque) any_non_opaque = true;
         DeviceInstance& d = dinst[i];
         memset(&d, 0, sizeof(d));
-        d.mat = s->instances[i].mat;
-        d.light_base_id = s->instances[i].light_base_id;
         d.vertex_base = (uint32_t)vtotal;
         d.index_base = (uint32_t)itotal;
         d.opaque = binst[i].opaque;
-        d.shadow_terminator_mul = s->instances[i].shadow_terminator_mul;
-        const tr_material& mat = d.mat;
+        const tr_material& mat = s->instances[i].mat;
         const int32_t tex_ids[4] = {mat.albedo_tex_id, mat.metallic_roughness_tex_id, mat.normal_tex_id, mat.emission_tex_id};
         for(int32_t t: tex_ids)
             if(t >= (int32_t)s->texture_count) return fail(c, TR_ERR_INVALID_ARGUMENT, "texture id out of range");
-        if(d.light_base_id >= 0) tri_light_count = std::max<uint64_t>(tri_light_count, (uint64_t)d.light_base_id + binst[i].triangle_count);
+        if(s->instances[i].light_base_id >= 0)
+            tri_light_count = std::max<uint64_t>(tri_light_count, (uint64_t)s->instances[i].light_base_id + binst[i].triangle_count);
         vtotal += m.vertex_count; itotal += m.index_count; ttotal += binst[i].triangle_count;
     }
     if(vtotal >= (1ull << 32) || itotal >= (1ull << 32) || ttotal >= (1ull << 28))
         return fail(c, TR_ERR_UNSUPPORTED, "scene too large (>= 2^28 triangles)");
+    g.triangle_total = ttotal;
+    g.tri_light_count = tri_light_count;
 
-    // ---- upload + pre_transform.comp
-    tr_vertex *v_raw = nullptr, *v_world = nullptr;
-    uint32_t* indices = nullptr;
-    float* matrices = nullptr;
-    std::vector<void*> tmp;
-    struct TmpFree { std::vector<void*>& l; ~TmpFree() { free_list(l); } } tmp_free{tmp};
-    TRY_CUDA(c, dev_alloc(tmp, &v_raw, vtotal));
-    TRY_CUDA(c, dev_alloc(tmp, &matrices, 32 * (size_t)s->instance_count));
-    TRY_CUDA(c, dev_alloc(A, &v_world, vtotal));
-    TRY_CUDA(c, dev_alloc(A, &indices, itotal));
-    std::vector<float> hm(32 * (size_t)s->instance_count);
+    // ---- upload (object space; the world-space copy is made by transform_and_build)
+    TRY_CUDA(c, dev_alloc(A, &g.v_raw, vtotal));
+    TRY_CUDA(c, dev_alloc(A, &g.matrices, 32 * (size_t)s->instance_count));
+    TRY_CUDA(c, dev_alloc(A, &g.v_world, vtotal));
+    TRY_CUDA(c, dev_alloc(A, &g.indices, itotal));
+    TRY_CUDA(c, dev_alloc(A, &g.d_instances, s->instance_count));
+    TRY_CUDA(c, dev_alloc(A, &c->prev_from_world, (size_t)s->instance_count * 16));
+    TRY_CUDA(c, dev_alloc(A, &g.d_tri_lights, tri_light_count));
     for(uint32_t i = 0; i < s->instance_count; ++i)
     {
         const tr_mesh_ref& m = s->meshes[i];
-        memcpy(&hm[32 * (size_t)i], s->instances[i].model, 64);
-        memcpy(&hm[32 * (size_t)i + 16], s->instances[i].model_normal, 64);
-        if(m.vertex_count) TRY_CUDA(c, cudaMemcpyAsync(v_raw + binst[i].vertex_base, m.vertices, sizeof(tr_vertex) * (size_t)m.vertex_count, cudaMemcpyHostToDevice, st));
-        if(m.index_count) TRY_CUDA(c, cudaMemcpyAsync(indices + binst[i].index_base, m.indices, sizeof(uint32_t) * (size_t)m.index_count, cudaMemcpyHostToDevice, st));
+        if(m.vertex_count) TRY_CUDA(c, cudaMemcpyAsync(g.v_raw + binst[i].vertex_base, m.vertices, sizeof(tr_vertex) * (size_t)m.vertex_count, cudaMemcpyHostToDevice, st));
+        if(m.index_count) TRY_CUDA(c, cudaMemcpyAsync(g.indices + binst[i].index_base, m.indices, sizeof(uint32_t) * (size_t)m.index_count, cudaMemcpyHostToDevice, st));
     }
-    if(!hm.empty()) TRY_CUDA(c, cudaMemcpyAsync(matrices, hm.data(), hm.size() * sizeof(float), cudaMemcpyHostToDevice, st));
-    for(uint32_t i = 0; i < s->instance_count; ++i)
-        TRY_CUDA(c, tr_build_pre_transform(st, v_raw + binst[i].vertex_base, v_world + binst[i].vertex_base, s->meshes[i].vertex_count,
-                                           matrices + 32 * (size_t)i, matrices + 32 * (size_t)i + 16));
 
-    // ---- tables
-    DeviceInstance* d_instances = nullptr;
-    TRY_CUDA(c, dev_alloc(A, &d_instances, s->instance_count));
-    if(s->instance_count) TRY_CUDA(c, cudaMemcpyAsync(d_instances, dinst.data(), sizeof(DeviceInstance) * dinst.size(), cudaMemcpyHostToDevice, st));
-    // model_prev * inverse(model) per instance, for the screen-motion layer (rt.glsl:73-79)
-    float* d_prev = nullptr;
-    {
-        std::vector<float> prev((size_t)s->instance_count * 16);
-        for(uint32_t i = 0; i < s->instance_count; ++i) previous_from_world(s->instances[i].model, s->instances[i].model_prev, &prev[(size_t)i * 16]);
-        TRY_CUDA(c, dev_alloc(A, &d_prev, prev.size()));
-        if(!prev.empty())
-        {
-            TRY_CUDA(c, cudaMemcpyAsync(d_prev, prev.data(), sizeof(float) * prev.size(), cudaMemcpyHostToDevice, st));
-            TRY_CUDA(c, cudaStreamSynchronize(st));   // `prev` is a local
-        }
-    }
     tr_point_light* d_pl = nullptr;
     tr_directional_light* d_dl = nullptr;
     TRY_CUDA(c, dev_alloc(A, &d_pl, s->point_light_count));
@@ -586,41 +652,14 @@ int tr_pt_set_scene(tr_pt_ctx* c, const tr_pt_scene_desc* s)
         env_tex.data = d; env_tex.width = e.width; env_tex.height = e.height; env_tex.format = e.format; env_tex.pad = 0;
     }
 
-    // ---- extract_tri_lights.comp
-    tr_tri_light* d_tl = nullptr;
-    TRY_CUDA(c, dev_alloc(A, &d_tl, tri_light_count));
-    if(tri_light_count) TRY_CUDA(c, cudaMemsetAsync(d_tl, 0, sizeof(tr_tri_light) * tri_light_count, st));
-    for(uint32_t i = 0; i < s->instance_count; ++i)
+    // ---- transforms, tri lights, BVH
     {
-        if(dinst[i].light_base_id < 0) continue;
-        TRY_CUDA(c, tr_build_extract_tri_lights(st, v_world + binst[i].vertex_base, indices + binst[i].index_base, binst[i].triangle_count,
-                                                i, dinst[i].light_base_id, dinst[i].mat.emission_factor, dinst[i].mat.emission_tex_id, d_tl));
+        const int rc = transform_and_build(c, s->instances, s->instance_count);
+        if(rc != TR_OK) return rc;
     }
-
-    // ---- LBVH
-    TRY_CUDA(c, cudaEventRecord(c->ev_begin, st));
-    tr_build_input bin;
-    bin.vertices = v_world; bin.indices = indices; bin.instances = binst.data();
-    bin.instance_count = s->instance_count; bin.triangle_count = (uint32_t)ttotal;
-    tr_build_output bout;
-    TRY_CUDA(c, tr_build_bvh(st, bin, &bout));
-    A.push_back(bout.nodes);
-    A.push_back(bout.tris);
-    TRY_CUDA(c, cudaEventRecord(c->ev_end, st));
-    TRY_CUDA(c, cudaStreamSynchronize(st));
-    float build_ms = 0.0f;
-    cudaEventElapsedTime(&build_ms, c->ev_begin, c->ev_end);
-    if(bout.depth >= TR_BVH_STACK)
-    {
-        free_scene(c);
-        return fail(c, TR_ERR_UNSUPPORTED, "BVH depth " + std::to_string(bout.depth) + " exceeds the traversal stack");
-    }
-
     DeviceScene& ds = c->scene;
-    ds.bvh.nodes = bout.nodes; ds.bvh.tris = bout.tris; ds.bvh.node_count = bout.node_count; ds.bvh.tri_count = (uint32_t)ttotal;
-    ds.bvh.top_nodes = 0;
-    ds.instances = d_instances; ds.vertices = v_world; ds.indices = indices;
-    ds.point_lights = d_pl; ds.directional_lights = d_dl; ds.tri_lights = d_tl; ds.textures = d_tex;
+    ds.instances = g.d_instances; ds.vertices = g.v_world; ds.indices = g.indices;
+    ds.point_lights = d_pl; ds.directional_lights = d_dl; ds.tri_lights = g.d_tri_lights; ds.textures = d_tex;
     ds.instance_count = s->instance_count; ds.point_light_count = s->point_light_count;
     ds.directional_light_count = s->directional_light_count; ds.tri_light_count = (uint32_t)tri_light_count;
     memcpy(ds.environment_factor, s->environment_factor, 16);
@@ -628,14 +667,27 @@ int tr_pt_set_scene(tr_pt_ctx* c, const tr_pt_scene_desc* s)
     ds.any_non_opaque = any_non_opaque ? 1u : 0u;
     ds.envmap = env_tex;
     ds.alias_table = d_alias;
-    c->prev_from_world = d_prev;
     c->has_scene = true;
-    c->stats.bvh_build_ms = build_ms;
-    c->stats.bvh_node_count = bout.node_count;
-    c->stats.bvh_depth = bout.depth;
     c->stats.triangle_count = (uint32_t)ttotal;
     c->stats.tri_light_count = (uint32_t)tri_light_count;
     return TR_OK;
+}
+
+int tr_pt_update_instances(tr_pt_ctx* c, const tr_instance* instances, uint32_t instance_count)
+{
+    if(!c || (instance_count && !instances)) return fail(c, TR_ERR_INVALID_ARGUMENT, "null argument");
+    if(!c->has_scene) return fail(c, TR_ERR_INVALID_ARGUMENT, "tr_pt_update_instances needs a scene");
+    if(instance_count != c->scene.instance_count) return fail(c, TR_ERR_INVALID_ARGUMENT, "instance count differs from the scene's");
+    const tr_pt_ctx::Geometry& g = c->geom;
+    uint64_t tri_light_count = 0;
+    for(uint32_t i = 0; i < instance_count; ++i)
+        if(instances[i].light_base_id >= 0)
+            tri_light_count = std::max<uint64_t>(tri_light_count, (uint64_t)instances[i].light_base_id + g.binst[i].triangle_count);
+    if(tri_light_count != g.tri_light_count) return fail(c, TR_ERR_INVALID_ARGUMENT, "the tri-light layout (light_base_id) may not change; use tr_pt_set_scene");
+    DeviceGuard guard(c->device);
+    if(c->last_stream && c->last_stream != c->stream) TRY_CUDA(c, cudaStreamSynchronize(c->last_stream));
+    TRY_CUDA(c, cudaStreamSynchronize(c->stream));
+    return transform_and_build(c, instances, instance_count);
 }
 
 int tr_pt_set_cameras(tr_pt_ctx* c, const tr_camera_pair* pairs, uint32_t view_count)

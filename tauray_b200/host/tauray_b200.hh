@@ -196,6 +196,12 @@ public:
     {
         check(tr_pt_set_cameras(ctx, cameras, view_count), ctx, "tr_pt_set_cameras");
     }
+    // the per-frame part of scene_stage::update for animated scenes (src/scene_stage.cc:1572-1675):
+    // new instance records -> world-space vertices, tri lights and the acceleration structure, on the device
+    void update_instances(const tr_instance* instances, uint32_t instance_count)
+    {
+        check(tr_pt_update_instances(ctx, instances, instance_count), ctx, "tr_pt_update_instances");
+    }
     std::vector<float> read_color()
     {
         void* p; size_t bytes;
@@ -283,6 +289,12 @@ public:
 
     rt_renderer(const std::vector<int>& cuda_devices, uvec2 size, const options& opt)
     : devices(cuda_devices), size(size), opt(opt), workloads(cuda_devices.size(), 1.0 / cuda_devices.size()) {}
+
+    // scene_stage::update on every device (the scene is replicated per device like Tauray's per_device<> buffers)
+    void update_instances(const tr_instance* instances, uint32_t instance_count)
+    {
+        for(auto& s: stages) s->update_instances(instances, instance_count);
+    }
 
     // renderer::set_scene (src/rt_renderer.cc:60-65): builds one stage per device
     void set_scene(const tr_pt_scene_desc& scene, const tr_camera_pair* cameras, uint32_t view_count)

@@ -20,7 +20,7 @@ LIB_PATH = os.environ.get("TAURAY_B200_LIB") or os.path.join(_HERE, "libtauray_b
 _lib = None
 
 EXPORTS = [
-    "tr_pt_default_options", "tr_pt_create", "tr_pt_destroy", "tr_pt_set_scene", "tr_pt_set_cameras",
+    "tr_pt_default_options", "tr_pt_create", "tr_pt_destroy", "tr_pt_set_scene", "tr_pt_update_instances", "tr_pt_set_cameras",
     "tr_pt_set_distribution", "tr_pt_reset_accumulation", "tr_pt_render", "tr_pt_render_feature", "tr_pt_sync",
     "tr_pt_get_color_buffer", "tr_pt_read_color", "tr_pt_unshuffle", "tr_pt_set_peer_images", "tr_pt_set_stitch_blend", "tr_pt_get_stats",
     "tr_pt_set_gbuffer_layers", "tr_pt_get_gbuffer_layer", "tr_pt_read_gbuffer_layer",
@@ -52,6 +52,7 @@ def lib():
     l.tr_pt_destroy.argtypes = [vp]
     l.tr_pt_destroy.restype = None
     l.tr_pt_set_scene.argtypes = [vp, C.POINTER(abi.SceneDesc)]
+    l.tr_pt_update_instances.argtypes = [vp, vp, C.c_uint32]
     l.tr_pt_set_cameras.argtypes = [vp, vp, C.c_uint32]
     l.tr_pt_set_distribution.argtypes = [vp, C.POINTER(abi.Distribution)]
     l.tr_pt_reset_accumulation.argtypes = [vp, C.c_int]
@@ -128,6 +129,12 @@ class PathTracer:
     def set_scene(self, scene):
         d = scene.desc() if hasattr(scene, "desc") else scene
         self._check(self._l.tr_pt_set_scene(self._ctx, C.byref(d)), "tr_pt_set_scene")
+
+    def update_instances(self, instances):
+        """Per-frame scene update of an animated scene: `instances` = the new instance records
+        (abi.INSTANCE array, e.g. Scene.instance_table())."""
+        inst = np.ascontiguousarray(instances, dtype=abi.INSTANCE)
+        self._check(self._l.tr_pt_update_instances(self._ctx, inst.ctypes.data, inst.shape[0]), "tr_pt_update_instances")
 
     def set_cameras(self, pairs):
         pairs = np.ascontiguousarray(pairs, dtype=abi.CAMERA_PAIR)

@@ -92,6 +92,11 @@ class RtRenderer:
         self.views = len(cameras)
         self._apply_distribution()
 
+    def update_instances(self, instances):
+        """scene_stage::update for an animated scene (src/scene_stage.cc:1572-1675): new instance records ->
+        world-space vertices, tri lights and the acceleration structure, rebuilt on the device."""
+        self.tracer.update_instances(instances)
+
     def reset_accumulation(self, reset_sample_counter=True):
         """rt_renderer::reset_accumulation (src/rt_renderer.cc:66-81)."""
         self.tracer.reset_accumulation(reset_sample_counter)
