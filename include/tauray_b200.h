@@ -62,6 +62,12 @@ enum { TR_FEATURE_ALBEDO = 0, TR_FEATURE_WORLD_NORMAL = 1, TR_FEATURE_VIEW_NORMA
        TR_FEATURE_INSTANCE_ID = 9 };
 /* kernel organisation of the hot loop (ours) */
 enum { TR_KERNEL_WAVEFRONT = 0, TR_KERNEL_MEGAKERNEL = 1 };
+/* Which rgen program a render runs. TR_ESTIMATOR_DIRECT == direct_stage (src/direct_stage.cc:29-126 +
+ * shader/direct.rgen:50-132): one camera ray per pass, samples_per_pass next-event-estimation samples at
+ * the first hit, no MIS (direct_stage sets no MIS define, so nee_mis_pdf returns the light pdf), sphere
+ * lights hidden from the camera ray (mask 0xFF^0x02); max_ray_depth only bounds the Sobol dimension
+ * groups; mis_mode, hide_lights, russian roulette, clamping and regularisation do not apply. */
+enum { TR_ESTIMATOR_PATH_TRACER = 0, TR_ESTIMATOR_DIRECT = 1 };
 /* texture formats accepted in tr_texture */
 enum { TR_TEXTURE_RGBA8_UNORM = 0, TR_TEXTURE_RGBA32F = 1, TR_TEXTURE_RGBA16F = 2 };
 /* Layers of gbuffer_target the path tracer writes (TR_GBUFFER_ENTRIES, src/gbuffer.hh:18-51;
@@ -255,7 +261,8 @@ typedef struct tr_pt_options {
     int32_t tri_light_mode;             /* TR_TRI_LIGHT_SOLID_ANGLE (CLI default) */
     /* ours */
     int32_t kernel_mode;                /* TR_KERNEL_WAVEFRONT */
-    int32_t reserved[5];
+    int32_t estimator;                  /* TR_ESTIMATOR_PATH_TRACER; TR_ESTIMATOR_DIRECT == direct_stage */
+    int32_t reserved[4];
 } tr_pt_options;
 
 /* distribution_params, src/distribution_strategy.hh:20-27 */

@@ -947,6 +947,42 @@ struct orc_ctx
         reflection = V4(reflection_rgb, reflection_a);
     }
 
+    // shader/direct.rgen:50-100 (evaluate_direct_ray). One camera ray; SAMPLES_PER_PASS next-event samples at the
+    // first hit. `color` comes back as the SUM over the samples plus SAMPLES_PER_PASS times the directly seen
+    // light, like the shader's local before main() divides it.
+    void evaluate_direct_ray(local_sampler& lsampler, vec3 pos, vec3 view, vec3& color, vec4& diffuse, vec4& reflection,
+                             pt_vertex_data& first_hit_vertex, sampled_material& first_hit_material, counters& c) const
+    {
+        hit_payload payload;
+        payload.random_seed = pcg4d(lsampler.rs_seed).x;
+        color = V3(0);
+        diffuse = V4(0, 0, 0, 0);
+        reflection = V4(0, 0, 0, 0);
+        const uint32_t samples = (uint32_t)opt.samples_per_pass;
+        // traceRayEXT(..., 0xFF^0x02, ...): the sphere-light BLAS is masked out for the camera ray
+        trace_closest(pos, 0.0f, view, false, payload, c);
+        intersection_pdf nee_pdf;
+        vec3 light;
+        const bool terminal = !get_intersection_info(pos, view, payload, first_hit_vertex, nee_pdf, first_hit_material, light);
+        color += (light + first_hit_material.emission) * (float)samples;
+        if(terminal) return;
+        mat3 tbn = create_tangent_space(first_hit_vertex.mapped_normal);
+        vec3 shading_view = view_to_tangent_space(view, tbn);
+        vec3 diffuse_rgb = V3(0), reflection_rgb = V3(0);
+        float a = 0.0f;
+        for(uint32_t i = 0; i < samples; ++i)
+        {
+            bsdf_lobes lobes = {0, 0, 0, 0};
+            vec3 radiance = next_event_estimation(generate_ray_sample_uint(lsampler, i), tbn, shading_view,
+                                                  first_hit_material, first_hit_vertex, lobes, c);
+            color += radiance * modulate_bsdf(first_hit_material, lobes);
+            add_demodulated_color(lobes, radiance, diffuse_rgb, reflection_rgb);
+            a = 1.0f / length(first_hit_vertex.pos - pos);
+        }
+        diffuse = V4(diffuse_rgb, a);
+        reflection = V4(reflection_rgb, a);
+    }
+
     // shader/camera.glsl:25-59 (projection types 0 and 1)
     void get_camera_ray(const tr_camera_data& cam, vec2 pixel_coord, vec2 screen_size, vec2 dof_u, vec3& origin, vec3& dir) const
     {
@@ -1134,6 +1170,23 @@ struct orc_ctx
                     sampled_material first_hit_material{};
                     vec3 sum_color = V3(0);
                     vec4 sum_diffuse = V4(0, 0, 0, 0), sum_reflection = V4(0, 0, 0, 0);
+                    if(opt.estimator == TR_ESTIMATOR_DIRECT)
+                    {
+                        // shader/direct.rgen:102-131: the sampler is keyed by previous_samples alone
+                        local_sampler ls = init_local_sampler(
+                            uvec4{(uint32_t)px, (uint32_t)py, view, previous_samples}, sample_counter, rng_seed, z_curve_dims());
+                        vec3 origin, dir;
+                        get_world_camera_ray(ls, px, py, view, origin, dir);
+                        vec3 col_sum;
+                        vec4 diffuse, reflection;
+                        c.paths++;
+                        evaluate_direct_ray(ls, origin, dir, col_sum, diffuse, reflection, first_hit_vertex, first_hit_material, c);
+                        // main(): color /= SAMPLES_PER_PASS; diffuse /= SAMPLES_PER_PASS; -- reflection is NOT divided (kept)
+                        sum_color = col_sum;
+                        sum_diffuse = diffuse;
+                        sum_reflection = reflection;
+                    }
+                    else
                     for(uint32_t i = 0; i < spp_pass; ++i)
                     {
                         local_sampler ls = init_local_sampler(
@@ -1172,7 +1225,9 @@ struct orc_ctx
                         if(has_layer(TR_GBUFFER_DIFFUSE))
                             accumulate_rgba16f(&layers[TR_GBUFFER_DIFFUSE][texel * 8], sum_diffuse / (float)spp_pass, spp_pass, prev_samples);
                         if(has_layer(TR_GBUFFER_REFLECTION))
-                            accumulate_rgba16f(&layers[TR_GBUFFER_REFLECTION][texel * 8], sum_reflection / (float)spp_pass, spp_pass, prev_samples);
+                            accumulate_rgba16f(&layers[TR_GBUFFER_REFLECTION][texel * 8],
+                                               opt.estimator == TR_ESTIMATOR_DIRECT ? sum_reflection : sum_reflection / (float)spp_pass,
+                                               spp_pass, prev_samples);
                     }
                 }
             }
@@ -1206,6 +1261,7 @@ static int check_options(const tr_pt_options* o, std::string& why)
     if(o->samples_per_pass < 1 || o->samples_per_pixel < o->samples_per_pass) { why = "bad samples_per_pixel/samples_per_pass"; return TR_ERR_INVALID_ARGUMENT; }
     if(o->projection != TR_PROJECTION_PERSPECTIVE && o->projection != TR_PROJECTION_ORTHOGRAPHIC)
     { why = "only matrix cameras are supported"; return TR_ERR_UNSUPPORTED; }
+    if(o->estimator != TR_ESTIMATOR_PATH_TRACER && o->estimator != TR_ESTIMATOR_DIRECT) { why = "unknown estimator"; return TR_ERR_INVALID_ARGUMENT; }
     return TR_OK;
 }
 
@@ -1219,6 +1275,8 @@ int orc_create(orc_ctx** out, const tr_pt_options* opt, int threads)
     if(rc) return fail(nullptr, rc, why);
     orc_ctx* c = new orc_ctx();
     c->opt = *opt;
+    // direct_stage defines no MIS_* macro: nee_mis_pdf falls through to the light pdf (path_tracer.glsl:78-89)
+    if(c->opt.estimator == TR_ESTIMATOR_DIRECT) c->opt.mis_mode = TR_MIS_DISABLED;
     c->threads = threads > 0 ? threads : (int)std::max(1u, std::thread::hardware_concurrency());
     *out = c;
     return TR_OK;

@@ -24,6 +24,7 @@ PROJECTION_PERSPECTIVE, PROJECTION_ORTHOGRAPHIC = range(2)
 FEATURE_ALBEDO, FEATURE_WORLD_NORMAL, FEATURE_VIEW_NORMAL, FEATURE_WORLD_POS, FEATURE_VIEW_POS, FEATURE_DISTANCE = range(6)
 FEATURE_INSTANCE_ID = 9
 KERNEL_WAVEFRONT, KERNEL_MEGAKERNEL = range(2)
+ESTIMATOR_PATH_TRACER, ESTIMATOR_DIRECT = range(2)   # direct = direct_stage, shader/direct.rgen
 INSTRUMENT_VISITS, INSTRUMENT_TIMING = 1, 2
 TEXTURE_RGBA8_UNORM, TEXTURE_RGBA32F, TEXTURE_RGBA16F = range(3)
 ENVMAP_NONE, ENVMAP_LAT_LONG = -1, 0
@@ -116,7 +117,7 @@ class Options(C.Structure):
         ("sampling_weight_point_lights", C.c_float), ("sampling_weight_directional_lights", C.c_float),
         ("sampling_weight_envmap", C.c_float), ("sampling_weight_emissive_triangles", C.c_float),
         ("bounce_mode", C.c_int32), ("tri_light_mode", C.c_int32),
-        ("kernel_mode", C.c_int32), ("reserved", C.c_int32 * 5),
+        ("kernel_mode", C.c_int32), ("estimator", C.c_int32), ("reserved", C.c_int32 * 4),
     ]
 
 

@@ -143,6 +143,7 @@ int check_options(const tr_pt_options* o, std::string& why)
     if(o->film < 0 || o->film > 2 || o->mis_mode < 0 || o->mis_mode > 2 || o->bounce_mode < 0 || o->bounce_mode > 2 ||
        o->tri_light_mode < 0 || o->tri_light_mode > 2 || o->kernel_mode < 0 || o->kernel_mode > 1)
     { why = "enum option out of range"; return TR_ERR_INVALID_ARGUMENT; }
+    if(o->estimator != TR_ESTIMATOR_PATH_TRACER && o->estimator != TR_ESTIMATOR_DIRECT) { why = "unknown estimator"; return TR_ERR_INVALID_ARGUMENT; }
     return TR_OK;
 }
 
@@ -258,7 +259,7 @@ int prepare_targets(tr_pt_ctx* c)
     c->pass_batch = batch;
     const uint32_t slots = (uint32_t)(slots64 * batch);
     if(slots64 * batch >= (1ull << 31)) return fail(c, TR_ERR_UNSUPPORTED, "more than 2^31 launch slots in flight");
-    if(c->opt.kernel_mode == TR_KERNEL_WAVEFRONT && (c->wf.capacity < slots || !c->wf.counts))
+    if(c->opt.kernel_mode == TR_KERNEL_WAVEFRONT && c->opt.estimator == TR_ESTIMATOR_PATH_TRACER && (c->wf.capacity < slots || !c->wf.counts))
     {
         free_list(c->wf_allocs);
         tr_wavefront& w = c->wf;
@@ -350,6 +351,8 @@ int tr_pt_create(tr_pt_ctx** out, int cuda_device, const tr_pt_options* opt)
     c->device = cuda_device;
     c->sm_count = prop.multiProcessorCount;
     c->opt = *opt;
+    // direct_stage defines no MIS_* macro: nee_mis_pdf falls through to the light pdf (path_tracer.glsl:78-89)
+    if(c->opt.estimator == TR_ESTIMATOR_DIRECT) c->opt.mis_mode = TR_MIS_DISABLED;
     auto bail = [&](cudaError_t err, const char* what) { int r = fail_cuda(nullptr, err, what); tr_pt_destroy(c); return r; };
     if((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     if((e = cudaEventCreate(&c->ev_begin)) != cudaSuccess) return bail(e, "cudaEventCreate");
@@ -761,12 +764,14 @@ int tr_pt_render(tr_pt_ctx* c, void* cuda_stream)
     const uint32_t pass_count = (uint32_t)(c->opt.samples_per_pixel / c->opt.samples_per_pass); // path_tracer_stage.cc:37
     for(uint32_t pass = 0; pass < pass_count;)
     {
-        const bool wavefront = c->opt.kernel_mode == TR_KERNEL_WAVEFRONT;
+        const bool direct = c->opt.estimator == TR_ESTIMATOR_DIRECT;      // one kernel organisation: per-thread loop
+        const bool wavefront = !direct && c->opt.kernel_mode == TR_KERNEL_WAVEFRONT;
         const uint32_t batch = wavefront ? std::min(c->pass_batch, pass_count - pass) : 1u;
         P.frame.previous_samples = pass * (uint32_t)c->opt.samples_per_pass; // path_tracer_stage.cc:141
         P.last_pass = pass + batch == pass_count;
         cudaError_t e = wavefront ?
             tr_render_pass_wavefront(st, P, c->wf, c->sm_count, &launches, timer, batch) :
+            direct ? tr_render_pass_direct(st, P, c->sm_count, &launches, timer) :
             tr_render_pass_megakernel(st, P, c->sm_count, &launches, timer);
         if(e != cudaSuccess) return fail_cuda(c, e, "render pass launch");
         pass += batch;

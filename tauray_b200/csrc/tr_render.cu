@@ -647,6 +647,84 @@ __global__ void __launch_bounds__(WF_BLOCK) k_megakernel(const RenderParams P, u
     if((threadIdx.x & 31) == 0 && culled) atomicAdd(&P.counters->culled_shadow_rays, culled);
 }
 
+// ---- direct-light estimator: direct_stage (src/direct_stage.cc:29-126) + shader/direct.rgen:50-132 ----------------
+// One camera ray per pass (sphere lights masked out), then samples_per_pass next-event samples at the first hit.
+// The sampler is keyed by previous_samples alone (direct.rgen:106-113); MIS is off (tr_pt_create forces
+// mis_mode = DISABLED for this estimator, as direct_stage defines no MIS macro). main() divides colour and
+// diffuse (alpha included) by SAMPLES_PER_PASS but not reflection -- kept.
+template<bool STATS>
+__global__ void __launch_bounds__(WF_BLOCK) k_direct(const RenderParams P, uint32_t total_slots)
+{
+    const uint32_t stride = gridDim.x * blockDim.x;
+    TraceStats st; st.nodes = 0; st.tris = 0;
+    TraceStats sst; sst.nodes = 0; sst.tris = 0;
+    unsigned long long closest = 0, shadow = 0, paths = 0;
+    SobolTables tables;
+    tables.base = P.sobol_chunks;
+    tables.first_group = 0;
+    const uint32_t spp = (uint32_t)P.opt.samples_per_pass;
+    const bool first_layers = (P.gbuffer_mask & ~((1u << TR_GBUFFER_COLOR) | (1u << TR_GBUFFER_DIFFUSE) | (1u << TR_GBUFFER_REFLECTION))) != 0;
+    for(uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < total_slots; slot += stride)
+    {
+        uint32_t px, py, view, widx;
+        if(!map_slot(P.frame, slot, px, py, view, widx)) continue;
+        const uint32_t prev_samples = P.frame.samples_accumulated + P.frame.previous_samples;
+        PathState s;
+        uvec4 ss, rs;
+        path_begin(P, px, py, view, 0, s, ss, rs);
+        paths++;
+        Hit h;
+        closest_hit<STATS>(P, s.pos, 0.0f, s.view, false, s.random_seed, h, st);
+        closest++;
+        HitInfo hi;
+        get_intersection_info(P, h, s.pos, s.view, hi);
+        if(first_layers && prev_samples == 0) write_first_sample_layers(P, widx, view, hi);
+        vec3 color = (hi.light + hi.mat.emission) * (float)spp;
+        float a = 0.0f;
+        if(hi.surface)
+        {
+            const mat3 tbn = create_tangent_space(hi.mapped_normal);
+            const vec3 shading_view = view_to_tangent_space(s.view, tbn);
+            for(uint32_t i = 0; i < spp; ++i)
+            {
+                // next_event_estimation (path_tracer.glsl:302-344); the draw is made even when no light class is on
+                const uvec4 nee_rand = generate_ray_sample_uint(P, tables, ss, rs, i);
+                bsdf_lobes lobes = LOBES(0, 0, 0, 0);
+                vec3 radiance = V3(0);
+                if(nee_enabled(P))
+                {
+                    vec3 out_dir;
+                    float out_length = 0.0f;
+                    float light_pdf;
+                    vec3 contrib = sample_explicit_light(P, nee_rand, hi.pos, out_dir, out_length, light_pdf);
+                    const vec3 shading_light = mul(out_dir, tbn);
+                    const float bsdf_pdf = material_bsdf_pdf(P.opt.bounce_mode, shading_light, shading_view, hi.mat, lobes);
+                    correct_lobes_for_normal_map(out_dir, hi.hard_normal, lobes);
+                    if(contrib.x > 0.0001f || contrib.y > 0.0001f || contrib.z > 0.0001f)
+                    {
+                        contrib *= shadow_visibility<STATS>(P, hi.pos, P.opt.min_ray_dist, out_dir, out_length, sst);
+                        shadow++;
+                    }
+                    contrib /= nee_mis_pdf(P, light_pdf, bsdf_pdf);
+                    radiance = contrib;
+                }
+                color += radiance * modulate_bsdf(xyz(hi.mat.albedo), lobes);
+                add_demodulated(s, radiance, lobes.diffuse + lobes.transmission, lobes.dielectric_reflection + lobes.metallic_reflection);
+                a = 1.0f / length(hi.pos - s.pos);
+            }
+        }
+        const float alpha = P.opt.transparent_background ? hi.mat.albedo.w : 1.0f;
+        const float4 o = accumulate(P, color / (float)spp, alpha, widx);
+        if(P.gbuffer[TR_GBUFFER_DIFFUSE])
+            accumulate_rgba16f(reinterpret_cast<uint2*>(P.gbuffer[TR_GBUFFER_DIFFUSE]), widx, V4(s.diffuse, a) / (float)spp, spp, prev_samples);
+        if(P.gbuffer[TR_GBUFFER_REFLECTION])
+            accumulate_rgba16f(reinterpret_cast<uint2*>(P.gbuffer[TR_GBUFFER_REFLECTION]), widx, V4(s.reflection, a), spp, prev_samples);
+        store_to_peers(P, o, px, py, view);
+    }
+    flush_counters(P.counters, closest, shadow, paths, st.nodes, st.tris, 0);
+    flush_counters(P.counters, 0, 0, 0, sst.nodes, sst.tris, 1);
+}
+
 // ---- feature (AOV) tracer: shader/rt_feature.rgen:18-47, rt_feature.rahit, rt_feature.rchit ------
 __global__ void __launch_bounds__(WF_BLOCK) k_feature(const RenderParams P, int feature, float4 default_value, uint32_t total_slots)
 {
@@ -868,6 +946,20 @@ cudaError_t tr_render_pass_megakernel(cudaStream_t stream, const RenderParams& P
     if(timer) timer->mark(stream, TR_KCLASS_OTHER);
     if(P.stats) k_megakernel<true><<<grid, WF_BLOCK, 0, stream>>>(P, total);
     else k_megakernel<false><<<grid, WF_BLOCK, 0, stream>>>(P, total);
+    if(timer) timer->mark(stream, TR_KCLASS_END);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+cudaError_t tr_render_pass_direct(cudaStream_t stream, const RenderParams& P, int sm_count, uint64_t* launches,
+                                  tr_launch_timer* timer)
+{
+    const uint32_t total = P.frame.ray_count_x * P.frame.ray_count_y * P.frame.views;
+    if(total == 0) return cudaSuccess;
+    const int grid = grid_for(sm_count, 8, total);
+    if(timer) timer->mark(stream, TR_KCLASS_OTHER);
+    if(P.stats) k_direct<true><<<grid, WF_BLOCK, 0, stream>>>(P, total);
+    else k_direct<false><<<grid, WF_BLOCK, 0, stream>>>(P, total);
     if(timer) timer->mark(stream, TR_KCLASS_END);
     ++*launches;
     return cudaGetLastError();

@@ -155,6 +155,8 @@ public:
         light_sampling_weights sampling_weights;
         bounce_sampling_mode bounce_mode = bounce_sampling_mode::MATERIAL;
         tri_light_sampling_mode tri_light_mode = tri_light_sampling_mode::HYBRID;
+        // not a reference option (the reference has one stage class per rgen program): direct_stage sets it
+        int estimator = TR_ESTIMATOR_PATH_TRACER;
     };
 
     // `scene` plays scene_stage's role: the flattened tables (src/scene_stage.cc:1066-1116,1277-1354);
@@ -243,12 +245,56 @@ public:
         o.sampling_weight_emissive_triangles = opt.sampling_weights.emissive_triangles;
         o.bounce_mode = (int)opt.bounce_mode;
         o.tri_light_mode = (int)opt.tri_light_mode;
+        o.estimator = opt.estimator;
         return o;
     }
 
 private:
     tr_pt_ctx* ctx = nullptr;
     options opt;
+};
+
+// ---- src/direct_stage.hh: the direct-light renderer (shader/direct.rgen) -----------------------------
+// Same stage surface as path_tracer_stage; the options are direct_stage::options (src/direct_stage.hh:13-22):
+// film, film_radius, sampling_weights, bounce_mode, tri_light_mode on top of rt_camera_stage::options.
+class direct_stage: public path_tracer_stage
+{
+public:
+    struct options
+    {
+        int max_ray_depth = 8;
+        float min_ray_dist = 0.001f;
+        int rng_seed = 0;
+        sampler_type local_sampler = sampler_type::UNIFORM_RANDOM;
+        distribution_params distribution;
+        size_t active_viewport_count = 1;
+        int samples_per_pixel = 1;
+        int samples_per_pass = 1;
+        projection_type projection = PERSPECTIVE;
+        bool transparent_background = false;
+        film_filter film = film_filter::BLACKMAN_HARRIS;
+        float film_radius = 1.0f;
+        light_sampling_weights sampling_weights;
+        bounce_sampling_mode bounce_mode = bounce_sampling_mode::MATERIAL;
+        tri_light_sampling_mode tri_light_mode = tri_light_sampling_mode::HYBRID;
+    };
+    direct_stage(int cuda_device, const tr_pt_scene_desc& scene, const tr_camera_pair* cameras, uint32_t view_count,
+                 const options& opt)
+    : path_tracer_stage(cuda_device, scene, cameras, view_count, widen(opt)) {}
+
+    static path_tracer_stage::options widen(const options& d)
+    {
+        path_tracer_stage::options o;
+        o.max_ray_depth = d.max_ray_depth; o.min_ray_dist = d.min_ray_dist; o.rng_seed = d.rng_seed;
+        o.local_sampler = d.local_sampler; o.distribution = d.distribution;
+        o.active_viewport_count = d.active_viewport_count;
+        o.samples_per_pixel = d.samples_per_pixel; o.samples_per_pass = d.samples_per_pass;
+        o.projection = d.projection; o.transparent_background = d.transparent_background;
+        o.film = d.film; o.film_radius = d.film_radius; o.sampling_weights = d.sampling_weights;
+        o.bounce_mode = d.bounce_mode; o.tri_light_mode = d.tri_light_mode;
+        o.estimator = TR_ESTIMATOR_DIRECT;
+        return o;
+    }
 };
 
 // ---- src/load_balancer.{hh,cc} -------------------------------------------------------------------
