@@ -368,9 +368,12 @@ int tr_pt_get_color_buffer(tr_pt_ctx* ctx, void** device_ptr, size_t* bytes);
 /* == headless staging copy (src/headless.cc:125-171): D2H of the colour target. */
 int tr_pt_read_color(tr_pt_ctx* ctx, float* rgba32f_host, size_t bytes);
 
-/* == stitch_shuffled_strips.comp:21-63 / stitch_scanline.comp for ONE source strip: scatters
- * `strip` (count*views float4, device memory, e.g. one slice of an all-gather result) of the
- * device that rendered [index, index+count) into `full_image` (size.x*size.y*views float4).
+/* == stitch_shuffled_strips.comp:21-63 / stitch_scanline.comp:21-50 for ONE source device (the
+ * strategy is the context's distribution strategy). Shuffled strips: scatters `strip`
+ * (count*views float4, device memory, e.g. one slice of an all-gather result) of the device that
+ * rendered slots [index, index+count) into `full_image` (size.x*size.y*views float4). Scanline:
+ * `strip` holds the rows of device `index` of `count` devices (size.x * ceil((size.y-index)/count)
+ * float4 per view); row ly lands on image row ly*count+index.
  * blend_ratio < 1 mixes with the image's previous content, mix(old, new, blend_ratio)
  * (stitch_shuffled_strips.comp:50-57; stitch_stage::set_blend_ratio, src/stitch_stage.cc:112). */
 int tr_pt_unshuffle(tr_pt_ctx* ctx, const void* strip_device, uint32_t index, uint32_t count,

@@ -1679,6 +1679,23 @@ int orc_unshuffle(orc_ctx* ctx, const float* strip, uint32_t index, uint32_t cou
     if(!ctx || !strip || !full_image) return TR_ERR_INVALID_ARGUMENT;
     const uint32_t W = ctx->dist.size[0], H = ctx->dist.size[1];
     const uint32_t V = ctx->views();
+    if(ctx->dist.strategy == TR_DISTRIBUTION_SCANLINE)
+    {
+        // stitch_scanline.comp:21-50: row ly of device `index` of `count` -> row ly * count + index
+        if(count == 0 || index >= count) return fail(ctx, TR_ERR_INVALID_ARGUMENT, "scanline: index must be < count");
+        const uint32_t rows = H > index ? (H - index + count - 1) / count : 0;
+        for(uint32_t view = 0; view < V; ++view)
+            for(uint32_t ly = 0; ly < rows; ++ly)
+                for(uint32_t x = 0; x < W; ++x)
+                {
+                    float* dst = full_image + ((size_t)view * W * H + (size_t)(ly * count + index) * W + x) * 4;
+                    const float* src = strip + (((size_t)view * rows + ly) * W + x) * 4;
+                    vec4 o = V4(src[0], src[1], src[2], src[3]);
+                    if(blend_ratio < 1.0f) o = mix_(V4(dst[0], dst[1], dst[2], dst[3]), o, blend_ratio);
+                    dst[0] = o.x; dst[1] = o.y; dst[2] = o.z; dst[3] = o.w;
+                }
+        return TR_OK;
+    }
     for(uint32_t view = 0; view < V; ++view)
         for(uint32_t i = 0; i < count; ++i)
         {

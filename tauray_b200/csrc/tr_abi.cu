@@ -887,12 +887,16 @@ int tr_pt_unshuffle(tr_pt_ctx* c, const void* strip_device, uint32_t index, uint
 {
     if(!c || !strip_device || !full_image_device) return TR_ERR_INVALID_ARGUMENT;
     if(!c->has_dist || c->views == 0) return fail(c, TR_ERR_INVALID_ARGUMENT, "cameras / distribution not set");
-    if(c->dist.strategy != TR_DISTRIBUTION_SHUFFLED_STRIPS) return fail(c, TR_ERR_UNSUPPORTED, "unshuffle: shuffled strips only");
+    if(c->dist.strategy == TR_DISTRIBUTION_DUPLICATE) return fail(c, TR_ERR_UNSUPPORTED, "unshuffle: nothing to stitch under the duplicate distribution");
+    if(c->dist.strategy == TR_DISTRIBUTION_SCANLINE && (count == 0 || index >= count)) return fail(c, TR_ERR_INVALID_ARGUMENT, "scanline: index must be < count (device index / device count)");
     DeviceGuard guard(c->device);
     FrameParams f;
     fill_frame(c, f);
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
-    TRY_CUDA(c, tr_render_unshuffle(st, f, (const float4*)strip_device, index, count, (float4*)full_image_device, blend_ratio));
+    if(c->dist.strategy == TR_DISTRIBUTION_SCANLINE)
+        TRY_CUDA(c, tr_render_unscanline(st, f, (const float4*)strip_device, index, count, (float4*)full_image_device, blend_ratio));
+    else
+        TRY_CUDA(c, tr_render_unshuffle(st, f, (const float4*)strip_device, index, count, (float4*)full_image_device, blend_ratio));
     return TR_OK;
 }
 

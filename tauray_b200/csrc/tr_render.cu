@@ -987,6 +987,35 @@ cudaError_t tr_render_sample_test(cudaStream_t stream, const RenderParams& P, co
     return cudaGetLastError();
 }
 
+// stitch_scanline.comp:21-50 for one source device: row ly of device `index` of `count` is row ly * count + index.
+__global__ void k_unscanline(const FrameParams f, const float4* __restrict__ rows, uint32_t index, uint32_t count, uint32_t row_count,
+                             float4* __restrict__ full, float blend_ratio)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t view = blockIdx.y;
+    if(i >= row_count * f.size_x) return;
+    const uint32_t ly = i / f.size_x, x = i - ly * f.size_x;
+    float4 o = rows[(size_t)view * row_count * f.size_x + i];
+    float4* dst = full + (size_t)view * f.size_x * f.size_y + (size_t)(ly * count + index) * f.size_x + x;
+    if(blend_ratio < 1.0f)
+    {
+        const float4 q = *dst;
+        const vec4 m = mix_(V4(q.x, q.y, q.z, q.w), V4(o.x, o.y, o.z, o.w), blend_ratio);
+        o = make_float4(m.x, m.y, m.z, m.w);
+    }
+    *dst = o;
+}
+
+cudaError_t tr_render_unscanline(cudaStream_t stream, const FrameParams& f, const float4* rows, uint32_t index, uint32_t count, float4* full_image,
+                                 float blend_ratio)
+{
+    if(count == 0 || index >= count || f.views == 0 || f.size_y <= index) return cudaSuccess;
+    const uint32_t row_count = (f.size_y - index + count - 1) / count;
+    dim3 grid((row_count * f.size_x + 255) / 256, f.views);
+    k_unscanline<<<grid, 256, 0, stream>>>(f, rows, index, count, row_count, full_image, blend_ratio);
+    return cudaGetLastError();
+}
+
 cudaError_t tr_render_unshuffle(cudaStream_t stream, const FrameParams& f, const float4* strip, uint32_t index, uint32_t count, float4* full_image,
                                 float blend_ratio)
 {

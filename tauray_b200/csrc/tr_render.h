@@ -70,3 +70,5 @@ cudaError_t tr_render_sample_test(cudaStream_t stream, const trd::RenderParams& 
                                   int draw_index, uint32_t* out_dev);
 cudaError_t tr_render_unshuffle(cudaStream_t stream, const trd::FrameParams& f, const float4* strip, uint32_t index,
                                 uint32_t count, float4* full_image, float blend_ratio);
+cudaError_t tr_render_unscanline(cudaStream_t stream, const trd::FrameParams& f, const float4* strip, uint32_t index,
+                                uint32_t count, float4* full_image, float blend_ratio);

@@ -61,8 +61,8 @@ class RtRenderer:
             stitch = "none" if world == 1 else ("peer" if backend_is_cuda else "nccl")
         if stitch not in ("none", "peer", "nccl"):
             raise ValueError("stitch must be none|peer|nccl")
-        if world > 1 and strategy != abi.DISTRIBUTION_SHUFFLED_STRIPS:
-            raise NotImplementedError("multi-device stitching implements shuffled strips (the reference's default)")
+        if world > 1 and strategy == abi.DISTRIBUTION_DUPLICATE:
+            raise NotImplementedError("the duplicate distribution renders the whole image on every device: nothing to stitch")
         self.stitch = stitch
         # `primary`: the rank that plays the reference's display device -- it renders in place into its full
         # image and keeps accumulating across workload changes (src/rt_renderer.cc:165-175). None: no rank does
@@ -145,12 +145,15 @@ class RtRenderer:
         import torch
         dev = torch.device("cuda", self.device) if self.cuda else torch.device("cpu")
         W, H = self.size
-        self.max_count = max(d.count for d in self.dists)
+        # pixels per view in each device's own target: `count` strip slots, or this device's scanlines
+        self.pixels = [int(np.prod(dist_mod.get_ray_count(d))) for d in self.dists]
+        self.max_count = max(self.pixels)
         my = self.dists[self.rank]
+        my_pixels = self.pixels[self.rank]
         in_place = self.rank == self.primary          # the display device renders straight into the stitched image
         if self.cuda and not in_place:
             # strip target: caller-owned torch memory so NCCL can gather straight out of it
-            self._strip = torch.zeros((self.views, my.count, 4), dtype=torch.float32, device=dev)
+            self._strip = torch.zeros((self.views, my_pixels, 4), dtype=torch.float32, device=dev)
             self.tracer.set_color_buffer(self._strip.data_ptr(), self._strip.numel() * 4)
         if self.stitch == "nccl":
             self._send = torch.zeros((self.views, self.max_count, 4), dtype=torch.float32, device=dev)
@@ -211,16 +214,16 @@ class RtRenderer:
             td.all_reduce(self._flag, group=self.pg)
             return
         my = self.dists[self.rank]
+        my_pixels = self.pixels[self.rank]
         if not in_place:
             if self.cuda:
-                self._send[:, :my.count].copy_(self._strip)
+                self._send[:, :my_pixels].copy_(self._strip)
             else:
-                self._send[:, :my.count].copy_(torch.from_numpy(self.tracer.read_color()))
+                self._send[:, :my_pixels].copy_(torch.from_numpy(self.tracer.read_color()).reshape(self.views, my_pixels, 4))
         elif not self.cuda:
             # the primary's pixels, rendered in place in the tracer's own full-size target
             img = torch.from_numpy(self.tracer.read_color()).reshape(self.views, -1, 4)
-            j = dist_mod.permute_region_id(np.arange(my.index, my.index + my.count, dtype=np.uint64), self.size)
-            j = torch.from_numpy(j[j < self.size[0] * self.size[1]].astype(np.int64))
+            j = torch.from_numpy(self._pixel_ids(my))
             self._full.view(self.views, -1, 4)[:, j] = img[:, j]
         # concatenated-along-dim-0 form: accepted by both NCCL and gloo
         td.all_gather_into_tensor(self._gathered.view(self.world * self.views, self.max_count, 4), self._send, group=self.pg)
@@ -228,7 +231,8 @@ class RtRenderer:
             for r, d in enumerate(self.dists):
                 if r == self.primary:
                     continue                              # in place already, never blended (stitch_stage.cc:160)
-                src = self._gathered[r, :, :d.count].contiguous() if d.count != self.max_count else self._gathered[r]
+                n = self.pixels[r]
+                src = self._gathered[r, :, :n].contiguous() if n != self.max_count else self._gathered[r]
                 if self.cuda:
                     self.tracer.unshuffle(src.data_ptr(), d.index, d.count, self._full_ptr, stream, self._blend)
                 else:
@@ -237,10 +241,23 @@ class RtRenderer:
             # only the display device stitches in the reference; every rank gets the image here
             td.broadcast(self._full, src=self.primary, group=self.pg)
 
-    def _unshuffle_host(self, strip, index, count, blend=1.0):
-        """stitch_shuffled_strips.comp:21-63 on the host (gloo tests)."""
+    def _pixel_ids(self, d):
+        """Linear pixel index (y * W + x) of every pixel device distribution `d` renders, in target order."""
         W, H = self.size
-        j = dist_mod.permute_region_id(np.arange(index, index + count, dtype=np.uint64), self.size)
+        if self.strategy == abi.DISTRIBUTION_SCANLINE:
+            rows = np.arange(d.index, H, d.count, dtype=np.int64)
+            return (rows[:, None] * W + np.arange(W, dtype=np.int64)[None, :]).reshape(-1)
+        j = dist_mod.permute_region_id(np.arange(d.index, d.index + d.count, dtype=np.uint64), self.size)
+        return j[j < W * H].astype(np.int64)
+
+    def _unshuffle_host(self, strip, index, count, blend=1.0):
+        """stitch_shuffled_strips.comp:21-63 / stitch_scanline.comp:21-50 on the host (gloo tests)."""
+        W, H = self.size
+        if self.strategy == abi.DISTRIBUTION_SCANLINE:
+            rows = np.arange(index, H, count, dtype=np.int64)
+            j = (rows[:, None] * W + np.arange(W, dtype=np.int64)[None, :]).reshape(-1).astype(np.uint64)
+        else:
+            j = dist_mod.permute_region_id(np.arange(index, index + count, dtype=np.uint64), self.size)
         ok = j < W * H
         jj = j[ok].astype(np.int64)
         full = self._full.numpy().reshape(self.views, W * H, 4)

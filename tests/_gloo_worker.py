@@ -71,11 +71,14 @@ def main():
         rebalance(out_dir, 0 if sys.argv[2].endswith("primary0") else None)
         td.destroy_process_group()
         return
-    workloads = [float(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 and sys.argv[2] else None
+    scanline = len(sys.argv) > 2 and sys.argv[2].startswith("scanline")
+    primary = 0 if len(sys.argv) > 2 and sys.argv[2] == "scanline_primary0" else None
+    workloads = [float(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 and sys.argv[2] and not scanline else None
     rank, world = td.get_rank(), td.get_world_size()
     size = (96, 54)
     opt = abi.default_options(max_ray_depth=3, samples_per_pixel=2, local_sampler=abi.SAMPLER_SOBOL_OWEN)
-    ren = RtRenderer(opt, size, rank=rank, world=world, stitch="nccl", tracer_factory=OracleTracer, backend_is_cuda=False)
+    ren = RtRenderer(opt, size, rank=rank, world=world, stitch="nccl", tracer_factory=OracleTracer, backend_is_cuda=False,
+                     strategy=abi.DISTRIBUTION_SCANLINE if scanline else abi.DISTRIBUTION_SHUFFLED_STRIPS, primary=primary)
     cams = testscenes.cornell_cameras(size[0] / size[1])
     cams = np.concatenate([cams, cams])            # two views
     ren.set_scene(testscenes.cornell(), cams)

@@ -31,7 +31,7 @@ def single_device_image(size):
     return o.read_color()
 
 
-@pytest.mark.parametrize("world,workloads", [(2, ""), (3, "0.5,0.3,0.2")])
+@pytest.mark.parametrize("world,workloads", [(2, ""), (3, "0.5,0.3,0.2"), (2, "scanline"), (3, "scanline_primary0")])
 def test_multi_rank_stitch_equals_single_device(tmp_path, oracle_lib, world, workloads):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(free_port()),
