@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(WF_BLOCK, ANY ? TRACE_MIN_BLOCKS_SHADOW : TRAC
     RaySlab rs;
     rs = make_ray_slab(V3(0), V3(0));
     RayPre rp;
-    rp.kx = rp.ky = rp.kz = 0; rp.Sx = rp.Sy = rp.Sz = 0; rp.org = V3(0);
+    rp.kz = 0; rp.Sx = rp.Sy = rp.Sz = 0; rp.org = V3(0);
     Hit best;
     best.instance_id = -1; best.primitive_id = -1; best.u = best.v = best.t = 0; best.flags = 0;
     bool found = false;

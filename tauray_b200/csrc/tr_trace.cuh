@@ -14,9 +14,16 @@
 
 namespace trd {
 
+// Per-ray constants of the watertight ray-triangle test (Woop, Benthin, Wald 2013): kz = the dominant
+// direction axis, (kx, ky) = the two axes after it in cyclic order, S = the shear that maps the ray onto +z.
+// The paper (and the oracle) additionally swap kx and ky when dir[kz] < 0 to keep the winding; that swap
+// negates U, V, W, det and T exactly (every operation is sign-symmetric), so t = T / det and the barycentrics
+// V / det, W / det come out bit-identical without it. Leaving it out makes the vertex permutation a pure
+// rotation by kz: two selects per component on two per-ray predicates instead of three-way selects on three
+// independent indices.
 struct RayPre
 {
-    int kx, ky, kz;
+    int kz;
     float Sx, Sy, Sz;
     vec3 org;
 };
@@ -28,28 +35,37 @@ TRD RayPre precompute_ray(vec3 org, vec3 dir)
     RayPre r;
     float ax = fabsf(dir.x), ay = fabsf(dir.y), az = fabsf(dir.z);
     r.kz = (ax > ay) ? (ax > az ? 0 : 2) : (ay > az ? 1 : 2);
-    r.kx = r.kz + 1; if(r.kx == 3) r.kx = 0;
-    r.ky = r.kx + 1; if(r.ky == 3) r.ky = 0;
-    if(sel(dir, r.kz) < 0.0f) { int t = r.kx; r.kx = r.ky; r.ky = t; }
+    int kx = r.kz + 1; if(kx == 3) kx = 0;
+    int ky = kx + 1; if(ky == 3) ky = 0;
     float dz = sel(dir, r.kz);
-    r.Sx = sel(dir, r.kx) / dz;
-    r.Sy = sel(dir, r.ky) / dz;
+    r.Sx = sel(dir, kx) / dz;
+    r.Sy = sel(dir, ky) / dz;
     r.Sz = 1.0f / dz;
     r.org = org;
+    return r;
+}
+
+// (v[kx], v[ky], v[kz]) for kx = kz + 1, ky = kz + 2 (mod 3)
+TRD vec3 rotate_to_kz(vec3 v, bool kz0, bool kz1)
+{
+    vec3 r;
+    r.x = kz0 ? v.y : (kz1 ? v.z : v.x);
+    r.y = kz0 ? v.z : (kz1 ? v.x : v.y);
+    r.z = kz0 ? v.x : (kz1 ? v.y : v.z);
     return r;
 }
 
 TRD bool intersect_triangle(const RayPre& r, vec3 v0, vec3 v1, vec3 v2, float tmin, float tmax,
                             float& t_out, float& u_out, float& v_out)
 {
-    vec3 A = v0 - r.org, B = v1 - r.org, C = v2 - r.org;
-    float Akz = sel(A, r.kz), Bkz = sel(B, r.kz), Ckz = sel(C, r.kz);
-    float Ax = fma_(-r.Sx, Akz, sel(A, r.kx));
-    float Ay = fma_(-r.Sy, Akz, sel(A, r.ky));
-    float Bx = fma_(-r.Sx, Bkz, sel(B, r.kx));
-    float By = fma_(-r.Sy, Bkz, sel(B, r.ky));
-    float Cx = fma_(-r.Sx, Ckz, sel(C, r.kx));
-    float Cy = fma_(-r.Sy, Ckz, sel(C, r.ky));
+    const bool kz0 = r.kz == 0, kz1 = r.kz == 1;
+    const vec3 A = rotate_to_kz(v0 - r.org, kz0, kz1), B = rotate_to_kz(v1 - r.org, kz0, kz1), C = rotate_to_kz(v2 - r.org, kz0, kz1);
+    float Ax = fma_(-r.Sx, A.z, A.x);
+    float Ay = fma_(-r.Sy, A.z, A.y);
+    float Bx = fma_(-r.Sx, B.z, B.x);
+    float By = fma_(-r.Sy, B.z, B.y);
+    float Cx = fma_(-r.Sx, C.z, C.x);
+    float Cy = fma_(-r.Sy, C.z, C.y);
 
     // separately rounded products: exactly antisymmetric edge functions => watertight edges
     float U = __fsub_rn(__fmul_rn(Cx, By), __fmul_rn(Cy, Bx));
@@ -64,7 +80,7 @@ TRD bool intersect_triangle(const RayPre& r, vec3 v0, vec3 v1, vec3 v2, float tm
     if((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
     float det = U + V + W;
     if(det == 0.0f) return false;
-    float Az = r.Sz * Akz, Bz = r.Sz * Bkz, Cz = r.Sz * Ckz;
+    float Az = r.Sz * A.z, Bz = r.Sz * B.z, Cz = r.Sz * C.z;
     float T = fma_(W, Cz, fma_(V, Bz, U * Az));
     float rcp = 1.0f / det;
     float t = T * rcp;
