@@ -179,12 +179,19 @@ constexpr int SHORT_STACK = 8;
 constexpr int FETCH_THRESHOLD = 20;
 constexpr int MAX_FACTORS = 6;
 
+// Per-ray state that is touched only when a ray is fetched, hits a triangle or retires lives in shared memory
+// ([word][thread], conflict-free) instead of registers: the kernel runs at 64 registers / 8 blocks per SM, and what
+// the compiler spilled at that budget was reloaded from local memory on every node step.
+enum { COLD_ID = 0, COLD_SX, COLD_SY, COLD_SZ, COLD_KZ, COLD_INST, COLD_PRIM, COLD_U, COLD_V, COLD_FLAGS, COLD_WORDS,
+       COLD_NF = COLD_INST, COLD_OVERFLOW = COLD_PRIM };
+
 template<bool ANY, bool STATS>
 __global__ void __launch_bounds__(WF_BLOCK, ANY ? TRACE_MIN_BLOCKS_SHADOW : TRACE_MIN_BLOCKS_CLOSEST) k_wf_trace(const RenderParams P, const tr_wavefront wf, uint32_t bounce,
                                                         const uint32_t* __restrict__ queue, const uint32_t* __restrict__ count,
                                                         uint32_t* __restrict__ work_counter)
 {
     __shared__ uint2 s_stack[SHORT_STACK * WF_BLOCK];
+    __shared__ uint32_t s_cold[COLD_WORDS * WF_BLOCK];
     uint2 lstack[TR_BVH_STACK - SHORT_STACK];
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -196,28 +203,23 @@ __global__ void __launch_bounds__(WF_BLOCK, ANY ? TRACE_MIN_BLOCKS_SHADOW : TRAC
     const bool transparency = P.scene.any_non_opaque != 0;
 
     TraceStats st; st.nodes = 0; st.tris = 0;
-    unsigned long long rays = 0;
+    uint32_t rays = 0;
 
-    // per-lane ray + traversal state
+    // per-lane ray + traversal state held in registers
     uint2 G = make_uint2(0u, 0u), Gt = make_uint2(0u, 0u);
     int sp = 0;
     bool has_ray = false, exhausted = false, done = true;
-    uint32_t id = 0, seed = 0;
-    vec3 org = V3(0), dir = V3(0);
-    float tmin = 0.0f, tmax = 0.0f, best_t = 0.0f;
+    // closest: the culling bound = t of the best hit so far, +inf while there is none. shadow: the ray's tmax.
+    float tmin = 0.0f, best_t = 0.0f;
+    bool blocked = false;                 // shadow: an opaque blocker was found
     RaySlab rs;
     rs = make_ray_slab(V3(0), V3(0));
-    RayPre rp;
-    rp.kz = 0; rp.Sx = rp.Sy = rp.Sz = 0; rp.org = V3(0);
-    Hit best;
-    best.instance_id = -1; best.primitive_id = -1; best.u = best.v = best.t = 0; best.flags = 0;
-    bool found = false;
     // shadow rays through non-opaque geometry: (t, instance, primitive, 1 - alpha)
     float ft[MAX_FACTORS], ff[MAX_FACTORS];
     int fi[MAX_FACTORS], fp[MAX_FACTORS];
-    int nf = 0;
-    float overflow = 1.0f;
 
+#define COLD(w) s_cold[(w) * WF_BLOCK + tid]
+#define COLDF(w) reinterpret_cast<float*>(s_cold)[(w) * WF_BLOCK + tid]
 #define PUSH(v) do { if(sp < SHORT_STACK) s_stack[sp * WF_BLOCK + tid] = (v); else lstack[sp - SHORT_STACK] = (v); sp++; } while(0)
 #define POP(dst) do { sp--; dst = sp < SHORT_STACK ? s_stack[sp * WF_BLOCK + tid] : lstack[sp - SHORT_STACK]; } while(0)
 
@@ -227,13 +229,17 @@ __global__ void __launch_bounds__(WF_BLOCK, ANY ? TRACE_MIN_BLOCKS_SHADOW : TRAC
         if(has_ray && done)
         {
             bool retire = true;
+            const uint32_t id = COLD(COLD_ID);
             if(!ANY)
             {
+                const bool found = best_t < inf_();
                 // sphere lights + the in-t-order any-hit emulation (see closest_hit() in tr_path.cuh)
                 int light_id = -1;
                 float light_t = 0.0f;
-                if(include_lights)
+                if(include_lights && P.scene.point_light_count)
                 {
+                    const float4 d = wf.dir_seed[id];
+                    const vec3 org = V3(rs.ox, rs.oy, rs.oz), dir = V3(d.x, d.y, d.z);
                     for(uint32_t i = 0; i < P.scene.point_light_count; ++i)
                     {
                         const tr_point_light& pl = P.scene.point_lights[i];
@@ -244,25 +250,29 @@ __global__ void __launch_bounds__(WF_BLOCK, ANY ? TRACE_MIN_BLOCKS_SHADOW : TRAC
                         if(light_id < 0 || t < light_t) { light_id = (int)i; light_t = t; }
                     }
                 }
-                if(light_id >= 0 && (!found || light_t < best.t))
+                if(light_id >= 0 && (!found || light_t < best_t))
                     wf.hits[id] = make_int4(-1, light_id, __float_as_int(light_t), 0);
                 else if(!found)
                     wf.hits[id] = make_int4(-1, -1, 0, 0);
                 else
                 {
+                    const int b_inst = (int)COLD(COLD_INST), b_prim = (int)COLD(COLD_PRIM);
+                    const float b_u = COLDF(COLD_U), b_v = COLDF(COLD_V);
                     bool accept = true;
-                    if(transparency && !(best.flags & TR_TRI_FLAG_OPAQUE))
+                    if(transparency && !(COLD(COLD_FLAGS) & TR_TRI_FLAG_OPAQUE))
                     {
+                        // the any-hit shader's random number comes from the payload seed, which it advances
+                        uint32_t seed = __float_as_uint(wf.dir_seed[id].w);
                         float alpha_cutoff = (float)pcg(seed) * TR_INV_UINT32_MAX;
-                        if(hit_alpha(P.scene, best.instance_id, best.primitive_id, best.u, best.v) <= alpha_cutoff) accept = false;
+                        wf.dir_seed[id].w = __uint_as_float(seed);
+                        if(hit_alpha(P.scene, b_inst, b_prim, b_u, b_v) <= alpha_cutoff) accept = false;
                     }
-                    if(accept) wf.hits[id] = make_int4(best.instance_id, best.primitive_id, __float_as_int(best.u), __float_as_int(best.v));
+                    if(accept) wf.hits[id] = make_int4(b_inst, b_prim, __float_as_int(b_u), __float_as_int(b_v));
                     else
                     {
                         // ignored by the any-hit test: continue behind it
-                        tmin = best.t;
-                        best_t = tmax;
-                        found = false;
+                        tmin = best_t;
+                        best_t = inf_();
                         sp = 0;
                         G = make_uint2(0u, (0x01000000u << rs.octinv) | 1u);   // the root as a one-child group
                         Gt = make_uint2(0u, 0u);
@@ -270,12 +280,12 @@ __global__ void __launch_bounds__(WF_BLOCK, ANY ? TRACE_MIN_BLOCKS_SHADOW : TRAC
                         retire = false;
                     }
                 }
-                if(retire && transparency) wf.dir_seed[id].w = __uint_as_float(seed);
             }
             else
             {
-                float visibility = found ? 0.0f : 1.0f;   // found == an opaque blocker
-                if(!found && nf > 0)
+                float visibility = blocked ? 0.0f : 1.0f;
+                const int nf = transparency ? (int)COLD(COLD_NF) : 0;
+                if(!blocked && nf > 0)
                 {
                     for(int k = 0; k < nf; ++k)
                     {
@@ -289,7 +299,7 @@ __global__ void __launch_bounds__(WF_BLOCK, ANY ? TRACE_MIN_BLOCKS_SHADOW : TRAC
                         fi[m] = -2;
                         if(visibility == 0.0f) break;
                     }
-                    if(visibility != 0.0f) visibility *= overflow;
+                    if(visibility != 0.0f) visibility *= COLDF(COLD_OVERFLOW);
                 }
                 NeeJob job;
                 load_job(wf, id, (int)bounce, job);
@@ -319,29 +329,30 @@ __global__ void __launch_bounds__(WF_BLOCK, ANY ? TRACE_MIN_BLOCKS_SHADOW : TRAC
                     const uint32_t i = base + __popc(mask & ((1u << lane) - 1u));
                     if(i < n)
                     {
-                        id = queue[i];
+                        const uint32_t id = queue[i];
                         const float4 o = wf.pos_pdf[id];
-                        org = V3(o.x, o.y, o.z);
+                        const vec3 org = V3(o.x, o.y, o.z);
+                        vec3 dir;
                         if(ANY)
                         {
                             const float4 j0 = wf.nee[4 * (size_t)id];
                             dir = V3(j0.x, j0.y, j0.z);
-                            tmax = j0.w;
+                            best_t = j0.w;
                         }
                         else
                         {
                             const float4 d = wf.dir_seed[id];
                             dir = V3(d.x, d.y, d.z);
-                            seed = __float_as_uint(d.w);
-                            tmax = inf_();
+                            best_t = inf_();
                         }
                         tmin = ray_tmin;
-                        best_t = tmax;
-                        rp = precompute_ray(org, dir);
+                        const RayPre rp = precompute_ray(org, dir);
+                        COLD(COLD_ID) = id;
+                        COLDF(COLD_SX) = rp.Sx; COLDF(COLD_SY) = rp.Sy; COLDF(COLD_SZ) = rp.Sz; COLD(COLD_KZ) = (uint32_t)rp.kz;
+                        if(ANY && transparency) { COLD(COLD_NF) = 0u; COLDF(COLD_OVERFLOW) = 1.0f; }
                         rs = make_ray_slab(org, dir);
                         sp = 0;
-                        found = false;
-                        nf = 0; overflow = 1.0f;
+                        blocked = false;
                         has_ray = true;
                         done = false;
                         rays++;
@@ -388,30 +399,40 @@ __global__ void __launch_bounds__(WF_BLOCK, ANY ? TRACE_MIN_BLOCKS_SHADOW : TRAC
                 if(STATS) st.tris++;
                 const float4* tp = tris + 3 * (size_t)tri_index;
                 const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+                RayPre rp;
+                rp.kz = (int)COLD(COLD_KZ); rp.Sx = COLDF(COLD_SX); rp.Sy = COLDF(COLD_SY); rp.Sz = COLDF(COLD_SZ);
+                rp.org = V3(rs.ox, rs.oy, rs.oz);
                 float t, u, v;
-                if(!intersect_triangle(rp, f3(t0), f3(t1), f3(t2), tmin, tmax, t, u, v)) continue;
+                // closest: any t up to +inf qualifies here, the comparison with the best hit follows; shadow: t < tmax
+                if(!intersect_triangle(rp, f3(t0), f3(t1), f3(t2), tmin, ANY ? best_t : inf_(), t, u, v)) continue;
                 const int inst = __float_as_int(t0.w), prim = __float_as_int(t1.w);
                 const uint32_t flags = __float_as_uint(t2.w);
                 if(ANY)
                 {
                     if(flags & TR_TRI_FLAG_OPAQUE)
                     {
-                        found = true;          // terminate on the first opaque hit
+                        blocked = true;        // terminate on the first opaque hit
                         done = true;
                         Gt.y = 0u;
                         break;
                     }
                     const float f = 1.0f - hit_alpha(P.scene, inst, prim, u, v);
-                    if(nf < MAX_FACTORS) { ft[nf] = t; ff[nf] = f; fi[nf] = inst; fp[nf] = prim; nf++; }
-                    else overflow *= f;
+                    const int nf = (int)COLD(COLD_NF);
+                    if(nf < MAX_FACTORS) { ft[nf] = t; ff[nf] = f; fi[nf] = inst; fp[nf] = prim; COLD(COLD_NF) = (uint32_t)(nf + 1); }
+                    else COLDF(COLD_OVERFLOW) = COLDF(COLD_OVERFLOW) * f;
                     continue;
                 }
-                const bool better = !found || t < best.t ||
-                    (t == best.t && (inst < best.instance_id || (inst == best.instance_id && prim < best.primitive_id)));
+                // best_t is +inf while nothing was hit, so `t < best_t` covers the first hit; ties go to the lower ids
+                bool better = t < best_t;
+                if(t == best_t)
+                {
+                    const int b_inst = (int)COLD(COLD_INST), b_prim = (int)COLD(COLD_PRIM);
+                    better = inst < b_inst || (inst == b_inst && prim < b_prim);
+                }
                 if(better)
                 {
-                    found = true;
-                    best.instance_id = inst; best.primitive_id = prim; best.u = u; best.v = v; best.t = t; best.flags = flags;
+                    COLD(COLD_INST) = (uint32_t)inst; COLD(COLD_PRIM) = (uint32_t)prim;
+                    COLDF(COLD_U) = u; COLDF(COLD_V) = v; COLD(COLD_FLAGS) = flags;
                     best_t = t;
                 }
             }
@@ -429,6 +450,8 @@ __global__ void __launch_bounds__(WF_BLOCK, ANY ? TRACE_MIN_BLOCKS_SHADOW : TRAC
     }
 #undef PUSH
 #undef POP
+#undef COLD
+#undef COLDF
     flush_counters(P.counters, ANY ? 0 : rays, ANY ? rays : 0, 0, st.nodes, st.tris, ANY ? 1 : 0);
 }
 
