@@ -21,15 +21,14 @@
 namespace trd {
 
 constexpr int WF_BLOCK = 128;
-constexpr int TRACE_BLOCKS_PER_SM = 8;
 #ifndef TRACE_MIN_BLOCKS_CLOSEST
-#define TRACE_MIN_BLOCKS_CLOSEST 8
+#define TRACE_MIN_BLOCKS_CLOSEST 9
 #endif
 #ifndef SHADE_MIN_BLOCKS
 #define SHADE_MIN_BLOCKS 4
 #endif
 #ifndef TRACE_MIN_BLOCKS_SHADOW
-#define TRACE_MIN_BLOCKS_SHADOW 8
+#define TRACE_MIN_BLOCKS_SHADOW 9
 #endif
 
 // ---- SoA <-> registers ---------------------------------------------------------------------------
@@ -898,7 +897,8 @@ cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const RenderParams& P_
     RenderParams P = P_in;
     static const int k_fetch = env_int("TR_TUNE_FETCH", FETCH_THRESHOLD);
     static const int k_postpone = env_int("TR_TUNE_POSTPONE", 5);
-    static const int k_blocks = env_int("TR_TUNE_BLOCKS", TRACE_BLOCKS_PER_SM);
+    static const int k_blocks = env_int("TR_TUNE_BLOCKS", TRACE_MIN_BLOCKS_CLOSEST);
+    static const int k_blocks_shadow = env_int("TR_TUNE_BLOCKS_SHADOW", TRACE_MIN_BLOCKS_SHADOW);
     P.tune_fetch_threshold = k_fetch;
     P.tune_postpone_div = k_postpone;
 #define MARK(cls) do { if(timer) timer->mark(stream, cls); } while(0)
@@ -910,7 +910,8 @@ cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const RenderParams& P_
     const uint32_t total = base * batch;
     const int grid_full = grid_for(sm_count, 16, total);
     const int grid_finish = grid_for(sm_count, 16, base);
-    const int grid_persist = sm_count * k_blocks;
+    const int grid_persist = sm_count * k_blocks;            // persistent grids: resident blocks per SM = the launch bounds
+    const int grid_persist_shadow = sm_count * k_blocks_shadow;
     static const int k_shade_blocks = env_int("TR_TUNE_SHADE_BLOCKS", 4);
     const int grid_shade = sm_count * k_shade_blocks;   // 128 registers/thread: 4 resident blocks per SM
     // layers written only while prev_samples == 0 (pass 0 = the first `base` slots of a batch)
@@ -946,8 +947,8 @@ cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const RenderParams& P_
             if(b + 1 < D)
             {
                 MARK(TR_KCLASS_SHADOW);
-                if(P.stats) k_wf_trace<true, true><<<grid_persist, WF_BLOCK, 0, stream>>>(P, wf, b, wf.shadow_queue, shadow_counts + b, work_counters + 2 * b + 1);
-                else k_wf_trace<true, false><<<grid_persist, WF_BLOCK, 0, stream>>>(P, wf, b, wf.shadow_queue, shadow_counts + b, work_counters + 2 * b + 1);
+                if(P.stats) k_wf_trace<true, true><<<grid_persist_shadow, WF_BLOCK, 0, stream>>>(P, wf, b, wf.shadow_queue, shadow_counts + b, work_counters + 2 * b + 1);
+                else k_wf_trace<true, false><<<grid_persist_shadow, WF_BLOCK, 0, stream>>>(P, wf, b, wf.shadow_queue, shadow_counts + b, work_counters + 2 * b + 1);
                 ++*launches;
             }
         }
