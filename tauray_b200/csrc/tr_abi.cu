@@ -26,6 +26,7 @@ struct tr_pt_ctx
     cudaStream_t stream = nullptr;
     cudaStream_t last_stream = nullptr;   // stream of the last render (may be the caller's)
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    tr_overlap overlap{};                 // second stream for the shadow traversal (tr_render.h)
     tr_pt_options opt{};
     std::string error;
 
@@ -357,6 +358,9 @@ int tr_pt_create(tr_pt_ctx** out, int cuda_device, const tr_pt_options* opt)
     if((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     if((e = cudaEventCreate(&c->ev_begin)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if((e = cudaEventCreate(&c->ev_end)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if((e = cudaStreamCreateWithFlags(&c->overlap.aux, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    if((e = cudaEventCreateWithFlags(&c->overlap.shaded, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if((e = cudaEventCreateWithFlags(&c->overlap.shadowed, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if((e = cudaMalloc((void**)&c->counters, sizeof(Counters))) != cudaSuccess) return bail(e, "cudaMalloc(counters)");
     if((e = cudaMemset(c->counters, 0, sizeof(Counters))) != cudaSuccess) return bail(e, "cudaMemset(counters)");
     if((e = tr_render_init_constants()) != cudaSuccess) return bail(e, "upload of the Sobol table");
@@ -378,6 +382,9 @@ void tr_pt_destroy(tr_pt_ctx* c)
     if(c->counters) cudaFree(c->counters);
     if(c->ev_begin) cudaEventDestroy(c->ev_begin);
     if(c->ev_end) cudaEventDestroy(c->ev_end);
+    if(c->overlap.shaded) cudaEventDestroy(c->overlap.shaded);
+    if(c->overlap.shadowed) cudaEventDestroy(c->overlap.shadowed);
+    if(c->overlap.aux) cudaStreamDestroy(c->overlap.aux);
     if(c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -770,7 +777,7 @@ int tr_pt_render(tr_pt_ctx* c, void* cuda_stream)
         P.frame.previous_samples = pass * (uint32_t)c->opt.samples_per_pass; // path_tracer_stage.cc:141
         P.last_pass = pass + batch == pass_count;
         cudaError_t e = wavefront ?
-            tr_render_pass_wavefront(st, P, c->wf, c->sm_count, &launches, timer, batch) :
+            tr_render_pass_wavefront(st, P, c->wf, c->sm_count, &launches, timer, batch, &c->overlap) :
             direct ? tr_render_pass_direct(st, P, c->sm_count, &launches, timer) :
             tr_render_pass_megakernel(st, P, c->sm_count, &launches, timer);
         if(e != cudaSuccess) return fail_cuda(c, e, "render pass launch");

@@ -892,8 +892,11 @@ static int env_int(const char* name, int dflt)
 }
 
 cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const RenderParams& P_in, const tr_wavefront& wf, int sm_count, uint64_t* launches,
-                                     tr_launch_timer* timer, uint32_t batch)
+                                     tr_launch_timer* timer, uint32_t batch, const tr_overlap* overlap)
 {
+    // per-launch timing needs one stream; TR_TUNE_OVERLAP=0 switches the second stream off for A/B runs
+    static const int k_overlap = env_int("TR_TUNE_OVERLAP", 1);
+    const bool two_streams = overlap && overlap->aux && !timer && k_overlap;
     RenderParams P = P_in;
     static const int k_fetch = env_int("TR_TUNE_FETCH", FETCH_THRESHOLD);
     static const int k_postpone = env_int("TR_TUNE_POSTPONE", 5);
@@ -924,6 +927,7 @@ cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const RenderParams& P_
         uint32_t* active_counts = wf.counts;           // [D + 1]
         uint32_t* shadow_counts = wf.counts + D + 1;   // [D]
         uint32_t* work_counters = wf.counts + 2 * D + 1; // [2 D] dynamic-fetch cursors
+        bool shadow_pending = false;
         MARK(TR_KCLASS_OTHER);
         k_wf_generate<<<grid_full, WF_BLOCK, 0, stream>>>(P, wf, i, base, total, wf.queue[0], active_counts);
         ++*launches;
@@ -941,16 +945,43 @@ cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const RenderParams& P_
                 ++*launches;
             }
             MARK(TR_KCLASS_SHADE);
+            if(shadow_pending)
+            {
+                cudaError_t e2 = cudaStreamWaitEvent(stream, overlap->shadowed, 0);
+                if(e2 != cudaSuccess) return e2;
+                shadow_pending = false;
+            }
             k_wf_shade<<<grid_shade, WF_BLOCK, 0, stream>>>(P, wf, b, i, q_in, active_counts + b, q_out, active_counts + b + 1,
                                                               wf.shadow_queue, shadow_counts + b);
             *launches += 2;
             if(b + 1 < D)
             {
                 MARK(TR_KCLASS_SHADOW);
-                if(P.stats) k_wf_trace<true, true><<<grid_persist_shadow, WF_BLOCK, 0, stream>>>(P, wf, b, wf.shadow_queue, shadow_counts + b, work_counters + 2 * b + 1);
-                else k_wf_trace<true, false><<<grid_persist_shadow, WF_BLOCK, 0, stream>>>(P, wf, b, wf.shadow_queue, shadow_counts + b, work_counters + 2 * b + 1);
+                // shadow(b) only touches the NEE job and the path's accumulators; closest(b + 1) only the ray and the hit
+                // record: with a second stream they run side by side and shade(b + 1) waits for both
+                cudaStream_t ss = stream;
+                if(two_streams)
+                {
+                    cudaError_t e2 = cudaEventRecord(overlap->shaded, stream);
+                    if(e2 == cudaSuccess) e2 = cudaStreamWaitEvent(overlap->aux, overlap->shaded, 0);
+                    if(e2 != cudaSuccess) return e2;
+                    ss = overlap->aux;
+                }
+                if(P.stats) k_wf_trace<true, true><<<grid_persist_shadow, WF_BLOCK, 0, ss>>>(P, wf, b, wf.shadow_queue, shadow_counts + b, work_counters + 2 * b + 1);
+                else k_wf_trace<true, false><<<grid_persist_shadow, WF_BLOCK, 0, ss>>>(P, wf, b, wf.shadow_queue, shadow_counts + b, work_counters + 2 * b + 1);
                 ++*launches;
+                if(two_streams)
+                {
+                    cudaError_t e2 = cudaEventRecord(overlap->shadowed, overlap->aux);
+                    if(e2 != cudaSuccess) return e2;
+                    shadow_pending = true;
+                }
             }
+        }
+        if(shadow_pending)      // max_ray_depth == 1 never gets here with a pending shadow pass; kept for safety
+        {
+            cudaError_t e2 = cudaStreamWaitEvent(stream, overlap->shadowed, 0);
+            if(e2 != cudaSuccess) return e2;
         }
         MARK(TR_KCLASS_OTHER);
         k_wf_finish<<<grid_finish, WF_BLOCK, 0, stream>>>(P, wf, i, base, batch);

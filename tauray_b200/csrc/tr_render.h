@@ -55,11 +55,22 @@ struct tr_launch_timer
     void destroy() { for(int i = 0; i < created; ++i) cudaEventDestroy(events[i]); created = used = 0; }
 };
 
+// Second stream + events that let the shadow traversal of bounce b run beside the closest-hit traversal of bounce
+// b + 1 (both depend only on the shade pass of bounce b): the tail of one persistent grid, where SMs drain, is filled
+// by the blocks of the other. Optional (null = everything on the render stream).
+struct tr_overlap
+{
+    cudaStream_t aux = nullptr;
+    cudaEvent_t shaded = nullptr;       // recorded on the render stream after k_wf_shade(b)
+    cudaEvent_t shadowed = nullptr;     // recorded on aux after k_wf_trace<shadow>(b)
+};
+
 cudaError_t tr_render_init_constants();
 const uint4* tr_render_sobol_chunks();
 // One pass (= samples_per_pass samples of every slot) of path_tracer.rgen.
 cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const trd::RenderParams& P, const tr_wavefront& wf,
-                                     int sm_count, uint64_t* launches, tr_launch_timer* timer, uint32_t batch);
+                                     int sm_count, uint64_t* launches, tr_launch_timer* timer, uint32_t batch,
+                                     const tr_overlap* overlap = nullptr);
 cudaError_t tr_render_pass_megakernel(cudaStream_t stream, const trd::RenderParams& P, int sm_count, uint64_t* launches,
                                       tr_launch_timer* timer);
 cudaError_t tr_render_pass_direct(cudaStream_t stream, const trd::RenderParams& P, int sm_count, uint64_t* launches,
