@@ -65,7 +65,27 @@ int main(int argc, char** argv)
         if(const char* fake = std::getenv("TR_FAKE_DEVICES")) { devices.assign((size_t)std::atoi(fake), 0); }
 
         uvec2 size{(unsigned)std::atoi(argv[3]), (unsigned)std::atoi(argv[4])};
-        const bool rebalance = argc > 8 && std::string(argv[8]) == "rebalance";
+        const std::string mode = argc > 8 ? argv[8] : "";
+        if(mode == "direct")
+        {
+            // --renderer=direct: direct_stage (src/direct_stage.hh) on one device, 2 NEE samples per pass
+            direct_stage::options dopt;
+            dopt.max_ray_depth = opt.max_ray_depth; dopt.min_ray_dist = opt.min_ray_dist;
+            dopt.samples_per_pixel = opt.samples_per_pixel; dopt.samples_per_pass = 2;
+            dopt.local_sampler = opt.local_sampler;
+            dopt.film = film_filter::BOX; dopt.film_radius = 0.5f;
+            dopt.tri_light_mode = tri_light_sampling_mode::SOLID_ANGLE;
+            dopt.distribution = get_device_distribution_params(size, DISTRIBUTION_SHUFFLED_STRIPS, 0.0, 1.0, 0, 1, true);
+            direct_stage stage(devices[0], desc, cams.data(), nv, dopt);
+            stage.run();
+            stage.sync();
+            std::vector<float> img = stage.read_color();
+            std::ofstream o(argv[2], std::ios::binary);
+            o.write(reinterpret_cast<const char*>(img.data()), img.size() * sizeof(float));
+            std::printf("host_demo: direct, %zu floats\n", img.size());
+            return 0;
+        }
+        const bool rebalance = mode == "rebalance";
         opt.accumulate = rebalance;
         rt_renderer rr(devices, size, opt);
         rr.set_scene(desc, cams.data(), nv);
@@ -78,6 +98,18 @@ int main(int argc, char** argv)
             std::vector<double> w(rr.device_count(), rr.device_count() > 1 ? 0.7 / (double)(rr.device_count() - 1) : 1.0);
             if(rr.device_count() > 1) w[0] = 0.3;
             rr.set_device_workloads(w);
+            rr.render();
+        }
+        if(mode == "animate")
+        {
+            // scene_stage::update of an animated scene: instance 6 slides by (0.2, 0, 0.1); the previous transform
+            // feeds the screen-motion layer. Pure translation: model_normal is unchanged.
+            if(n < 7) throw std::runtime_error("animate: the scene needs at least 7 instances");
+            std::vector<tr_instance> moved = instances;
+            std::memcpy(moved[6].model_prev, moved[6].model, sizeof(moved[6].model));
+            moved[6].model[12] += 0.2f; moved[6].model[14] += 0.1f;
+            rr.update_instances(moved.data(), n);
+            rr.reset_accumulation();
             rr.render();
         }
         std::vector<float> img = rr.read_image();
