@@ -174,7 +174,10 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_generate(const RenderParams P, 
 //     shared-memory short stack ([entry][thread]), entries beyond SHORT_STACK spill to local memory;
 //   * node phase and triangle phase are separate loops; a lane with triangle hits waits for the warp's
 //     node phase only while other lanes still look for their first triangle group.
-constexpr int SHORT_STACK = 8;
+#ifndef TR_SHORT_STACK
+#define TR_SHORT_STACK 8
+#endif
+constexpr int SHORT_STACK = TR_SHORT_STACK;
 constexpr int FETCH_THRESHOLD = 20;
 constexpr int MAX_FACTORS = 6;
 
