@@ -368,6 +368,24 @@ int tr_pt_get_color_buffer(tr_pt_ctx* ctx, void** device_ptr, size_t* bytes);
 /* == headless staging copy (src/headless.cc:125-171): D2H of the colour target. */
 int tr_pt_read_color(tr_pt_ctx* ctx, float* rgba32f_host, size_t bytes);
 
+/* Accumulation checkpoint / resume. The reference has none for accumulation state (animation renders
+ * resume per frame with --skip-frames, src/options.hh:116-119); SURVEY.md section 8(f) lists the
+ * dump/reload of the fp32 accumulation buffer + counters as the natural addition for long
+ * accumulations (BASELINE configs[3]: 4096 spp). The state of a context is its colour target
+ * (tr_pt_read_color), rt_stage::frame_counter (-> sampling_data.sample_counter, src/rt_stage.cc:76-85)
+ * and rt_camera_stage::accumulated_samples (src/rt_camera_stage.cc:86,100).
+ * tr_pt_restore_accumulation writes the colour target (same size as tr_pt_read_color gives for the
+ * current cameras + distribution) and sets both counters: the next tr_pt_render continues the
+ * running mean exactly where the checkpointed context stopped (bit-identical to an uninterrupted
+ * run). The aux G-buffer light layers (diffuse / reflection) are not part of the checkpoint. */
+typedef struct tr_pt_accumulation_state {
+    uint32_t frame_counter;
+    uint32_t accumulated_samples;
+} tr_pt_accumulation_state;
+int tr_pt_get_accumulation_state(tr_pt_ctx* ctx, tr_pt_accumulation_state* out);
+int tr_pt_restore_accumulation(tr_pt_ctx* ctx, const float* rgba32f_host, size_t bytes,
+                               const tr_pt_accumulation_state* state);
+
 /* == stitch_shuffled_strips.comp:21-63 / stitch_scanline.comp:21-50 for ONE source device (the
  * strategy is the context's distribution strategy). Shuffled strips: scatters `strip`
  * (count*views float4, device memory, e.g. one slice of an all-gather result) of the device that

@@ -838,6 +838,31 @@ int tr_pt_read_color(tr_pt_ctx* c, float* out, size_t bytes)
     return TR_OK;
 }
 
+int tr_pt_get_accumulation_state(tr_pt_ctx* c, tr_pt_accumulation_state* out)
+{
+    if(!c || !out) return TR_ERR_INVALID_ARGUMENT;
+    out->frame_counter = c->frame_counter;
+    out->accumulated_samples = (uint32_t)c->accumulated_samples;
+    return TR_OK;
+}
+
+int tr_pt_restore_accumulation(tr_pt_ctx* c, const float* rgba32f_host, size_t bytes, const tr_pt_accumulation_state* state)
+{
+    if(!c || !rgba32f_host || !state) return fail(c, TR_ERR_INVALID_ARGUMENT, "null argument");
+    if(state->accumulated_samples > 0x7FFFFFFFu) return fail(c, TR_ERR_INVALID_ARGUMENT, "accumulated_samples out of range");
+    DeviceGuard guard(c->device);
+    int rc = prepare_targets(c);      // needs scene, cameras and distribution: they define the target
+    if(rc) return rc;
+    if(bytes != c->color_pixels * sizeof(float4))
+        return fail(c, TR_ERR_INVALID_ARGUMENT, "size mismatch: target has " + std::to_string(c->color_pixels * sizeof(float4)) + " bytes");
+    cudaStream_t st = c->last_stream ? c->last_stream : c->stream;
+    TRY_CUDA(c, cudaMemcpyAsync(c->color, rgba32f_host, bytes, cudaMemcpyHostToDevice, st));
+    TRY_CUDA(c, cudaStreamSynchronize(st));
+    c->frame_counter = state->frame_counter;
+    c->accumulated_samples = (int)state->accumulated_samples;
+    return TR_OK;
+}
+
 int tr_pt_set_gbuffer_layers(tr_pt_ctx* c, uint32_t layer_mask)
 {
     if(!c) return TR_ERR_INVALID_ARGUMENT;

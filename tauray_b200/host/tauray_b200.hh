@@ -212,6 +212,17 @@ public:
         check(tr_pt_read_color(ctx, out.data(), bytes), ctx, "tr_pt_read_color");
         return out;
     }
+    // accumulation checkpoint / resume (not in the reference)
+    tr_pt_accumulation_state accumulation_state()
+    {
+        tr_pt_accumulation_state st;
+        check(tr_pt_get_accumulation_state(ctx, &st), ctx, "tr_pt_get_accumulation_state");
+        return st;
+    }
+    void restore_accumulation(const std::vector<float>& color, const tr_pt_accumulation_state& st)
+    {
+        check(tr_pt_restore_accumulation(ctx, color.data(), color.size() * sizeof(float), &st), ctx, "tr_pt_restore_accumulation");
+    }
     tr_pt_stats get_stats() { tr_pt_stats s; check(tr_pt_get_stats(ctx, &s), ctx, "tr_pt_get_stats"); return s; }
     tr_pt_ctx* handle() { return ctx; }
     const options& get_options() const { return opt; }
