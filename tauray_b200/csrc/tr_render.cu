@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_generate(const RenderParams P, 
 #define TR_SHORT_STACK 8
 #endif
 constexpr int SHORT_STACK = TR_SHORT_STACK;
-constexpr int FETCH_THRESHOLD = 20;
+constexpr int FETCH_THRESHOLD = 24;
 constexpr int MAX_FACTORS = 6;
 
 // Per-ray state that is touched only when a ray is fetched, hits a triangle or retires lives in shared memory
@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(WF_BLOCK, ANY ? TRACE_MIN_BLOCKS_SHADOW : TRAC
         // ---- traverse ---------------------------------------------------------------------------
         // One node step per iteration for the lanes that have an open node group; lanes that popped a
         // (postponed) triangle group take it over. Triangle tests run right after, unless fewer than
-        // 1/5 of the lanes of this iteration have any -- then the group is pushed and traversal goes on.
+        // 1/4 of the lanes of this iteration have any -- then the group is pushed and traversal goes on.
         while(!done)
         {
             if(G.y & 0xFF000000u)
@@ -902,7 +902,7 @@ cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const RenderParams& P_
     const bool two_streams = overlap && overlap->aux && !timer && k_overlap;
     RenderParams P = P_in;
     static const int k_fetch = env_int("TR_TUNE_FETCH", FETCH_THRESHOLD);
-    static const int k_postpone = env_int("TR_TUNE_POSTPONE", 5);
+    static const int k_postpone = env_int("TR_TUNE_POSTPONE", 4);
     static const int k_blocks = env_int("TR_TUNE_BLOCKS", TRACE_MIN_BLOCKS_CLOSEST);
     static const int k_blocks_shadow = env_int("TR_TUNE_BLOCKS_SHADOW", TRACE_MIN_BLOCKS_SHADOW);
     P.tune_fetch_threshold = k_fetch;
