@@ -518,11 +518,13 @@ static int transform_and_build(tr_pt_ctx* c, const tr_instance* instances, uint3
     bin.instance_count = instance_count; bin.triangle_count = (uint32_t)g.triangle_total;
     tr_build_output bout;
     TRY_CUDA(c, tr_build_bvh(st, bin, &bout));
-    TRY_CUDA(c, cudaEventRecord(c->ev_end, st));
-    TRY_CUDA(c, cudaStreamSynchronize(st));   // also covers the host staging vectors above
+    // the new tree is owned from here on, whatever happens next
     if(g.bvh_nodes) cudaFree(g.bvh_nodes);
     if(g.bvh_tris) cudaFree(g.bvh_tris);
     g.bvh_nodes = bout.nodes; g.bvh_tris = bout.tris;
+    c->scene.bvh.nodes = nullptr; c->scene.bvh.tris = nullptr;
+    TRY_CUDA(c, cudaEventRecord(c->ev_end, st));
+    TRY_CUDA(c, cudaStreamSynchronize(st));   // also covers the host staging vectors above
     float build_ms = 0.0f;
     cudaEventElapsedTime(&build_ms, c->ev_begin, c->ev_end);
     if(bout.depth >= TR_BVH_STACK)
@@ -697,7 +699,9 @@ int tr_pt_update_instances(tr_pt_ctx* c, const tr_instance* instances, uint32_t 
     DeviceGuard guard(c->device);
     if(c->last_stream && c->last_stream != c->stream) TRY_CUDA(c, cudaStreamSynchronize(c->last_stream));
     TRY_CUDA(c, cudaStreamSynchronize(c->stream));
-    return transform_and_build(c, instances, instance_count);
+    const int rc = transform_and_build(c, instances, instance_count);
+    if(rc != TR_OK) c->has_scene = false;     // a half-updated scene must not be rendered: the next render fails loudly
+    return rc;
 }
 
 int tr_pt_set_cameras(tr_pt_ctx* c, const tr_camera_pair* pairs, uint32_t view_count)
