@@ -58,3 +58,33 @@ def test_load_balancer_matches_the_reference_update():
     w = lb.update([2.0, 1.0])     # device 1 is twice as fast
     assert w[1] > w[0] and abs(sum(w) - 1.0) < 1e-9
     assert abs(w[0] - (0.5 * 0.9 + (0.25 / 0.75) * 0.1)) < 1e-9
+
+
+def test_oracle_scanline_scatter_matches_numpy():
+    """orc_unshuffle under the scanline distribution (stitch_scanline.comp:21-50): row ly of device `index` of
+    `count` lands on image row ly * count + index; blend_ratio < 1 mixes with the previous content."""
+    from tauray_b200 import testscenes
+    from oracle.oracle_py import Oracle
+    size = (10, 7)
+    views = 2
+    o = Oracle(abi.default_options(max_ray_depth=1))
+    o.set_scene(testscenes.cornell(subdiv=1))
+    cams = testscenes.cornell_cameras(size[0] / size[1])
+    o.set_cameras(np.concatenate([cams] * views))
+    rng = np.random.RandomState(5)
+    full = rng.rand(views, size[1], size[0], 4).astype(np.float32)
+    want = full.copy()
+    for index in range(3):
+        o.set_distribution(D.make_distribution(size, abi.DISTRIBUTION_SCANLINE, index, 3, False))
+        rows = len(range(index, size[1], 3))
+        strip = rng.rand(views, rows, size[0], 4).astype(np.float32)
+        blend = 1.0 if index != 1 else 0.25
+        o.unshuffle(strip, index, 3, full, blend)
+        if blend == 1.0:
+            want[:, index::3] = strip
+        else:
+            a = np.float32(blend)
+            old = want[:, index::3]
+            t = (old * (np.float32(1.0) - a)).astype(np.float32)
+            want[:, index::3] = (strip.astype(np.float64) * np.float64(a) + t.astype(np.float64)).astype(np.float32)
+    assert full.tobytes() == want.tobytes()
