@@ -1,0 +1,34 @@
+#!/usr/bin/env python3
+"""Development aid: time ONE rank's share of the N-GPU bench workload on one GPU (no stitch), to study how the
+kernels behave on small per-rank queues. usage: strip_bench.py <world> [frames]"""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from tauray_b200 import abi, distribution, synthetic
+from tauray_b200.library import PathTracer
+import bench
+
+world = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+frames = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+size = (bench.WIDTH, bench.HEIGHT)
+opt = bench.bench_options(abi)
+scene = synthetic.atrium(bench.TRIANGLES)
+cams = synthetic.atrium_cameras(size[0] / size[1])
+dists = distribution.device_distributions(size, abi.DISTRIBUTION_SHUFFLED_STRIPS, [1.0 / world] * world)
+with PathTracer(opt) as pt:
+    pt.set_scene(scene); pt.set_cameras(cams); pt.set_distribution(dists[world // 2])
+    for timing in (0, abi.INSTRUMENT_TIMING):
+        pt.set_instrumentation(timing)
+        for _ in range(3):
+            pt.reset_accumulation(); pt.render()
+        pt.sync()
+        t0 = time.perf_counter()
+        for _ in range(frames):
+            pt.reset_accumulation(); pt.render()
+        pt.sync()
+        ms = 1e3 * (time.perf_counter() - t0) / frames
+        st = pt.stats()
+        if timing == 0:
+            print("world %d: %.3f ms/frame (ideal %.3f of the full frame's)" % (world, ms, 1.0 / world), end="  ")
+        else:
+            print("closest %.3f shadow %.3f shade %.3f other %.3f" % (st["closest_ms"], st["shadow_ms"], st["shade_ms"], st["other_ms"]))
