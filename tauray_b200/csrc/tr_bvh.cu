@@ -878,7 +878,7 @@ cudaError_t tr_build_bvh(cudaStream_t stream, const tr_build_input& in, tr_build
         CUDA_OK2(cudaMalloc((void**)&nodes_final, TR_BVH_NODE_VEC4 * sizeof(float4)));
         cudaError_t e0 = cudaMalloc((void**)&tris_empty, 3 * sizeof(float4));
         if(e0 != cudaSuccess) { cudaFree(nodes_final); return e0; }
-        k_wide_single<<<1, 1, 0, stream>>>(0, nullptr, nullptr, eps, tris_empty, nodes_final, tris_empty);
+        k_wide_single<<<1, 1, 0, stream>>>(0, nullptr, nullptr, eps, nullptr, nodes_final, tris_empty);
         e0 = cudaGetLastError();
         if(e0 == cudaSuccess) e0 = cudaStreamSynchronize(stream);
         if(e0 != cudaSuccess) { cudaFree(nodes_final); cudaFree(tris_empty); return e0; }
