@@ -86,6 +86,7 @@ int main(int argc, char** argv)
             return 0;
         }
         const bool rebalance = mode == "rebalance";
+        if(mode == "scanline") opt.strategy = DISTRIBUTION_SCANLINE;   // --distribution-strategy=scanline across the devices
         opt.accumulate = rebalance;
         rt_renderer rr(devices, size, opt);
         rr.set_scene(desc, cams.data(), nv);

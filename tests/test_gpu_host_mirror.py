@@ -135,6 +135,26 @@ def test_cpp_update_instances_matches_python(tmp_path, fake_devices):
 
 
 @pytest.mark.gpu
+def test_cpp_rt_renderer_scanline_across_three_stages(tmp_path):
+    """--distribution-strategy=scanline through the C++ mirror: three stages (TR_FAKE_DEVICES=3) render every third
+    row; the display stage renders in place, the others store their rows into its image over peer memory."""
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tauray_b200", "host")], check=True)
+    size = (96, 50)
+    scene = testscenes.cornell(alpha_card=False)
+    cams = testscenes.cornell_cameras(size[0] / size[1])
+    dump_scene(tmp_path / "scene.bin", scene, cams)
+    env = dict(os.environ, TR_FAKE_DEVICES="3")
+    r = subprocess.run([DEMO, str(tmp_path / "scene.bin"), str(tmp_path / "out.raw"), str(size[0]), str(size[1]), "2", "3", "1", "scanline"],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr
+    got = np.fromfile(tmp_path / "out.raw", dtype=np.float32).reshape(1, size[1], size[0], 4)
+    opt = abi.default_options(max_ray_depth=3, samples_per_pixel=2, local_sampler=abi.SAMPLER_SOBOL_OWEN)
+    with PathTracer(opt) as pt:
+        want = run(pt, scene, cams, full_dist(size))
+    assert bits_equal(got, want)
+
+
+@pytest.mark.gpu
 def test_cpp_errors_surface_as_runtime_error(tmp_path):
     r = subprocess.run([DEMO, str(tmp_path / "missing.bin"), str(tmp_path / "o.raw"), "8", "8", "1", "1", "1"],
                        capture_output=True, text=True)
