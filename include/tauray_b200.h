@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define TR_B200_ABI_VERSION 1
+#define TR_B200_ABI_VERSION 2
 
 typedef enum tr_status {
     TR_OK = 0,
@@ -377,10 +377,19 @@ int tr_pt_read_color(tr_pt_ctx* ctx, float* rgba32f_host, size_t bytes);
  * tr_pt_restore_accumulation writes the colour target (same size as tr_pt_read_color gives for the
  * current cameras + distribution) and sets both counters: the next tr_pt_render continues the
  * running mean exactly where the checkpointed context stopped (bit-identical to an uninterrupted
- * run). The aux G-buffer light layers (diffuse / reflection) are not part of the checkpoint. */
+ * run). The state also records what the counters only make sense with -- samples_per_pixel
+ * (sample_counter = frame_counter * samples_per_pixel), the target size and the enabled aux G-buffer
+ * layers -- and the restore fails with TR_ERR_INVALID_ARGUMENT when the context differs. With aux layers
+ * enabled they are part of the checkpoint (first-sample layers are never written again once
+ * accumulated_samples != 0): dump them with tr_pt_read_gbuffer_layer, and after
+ * tr_pt_restore_accumulation write every enabled layer back with tr_pt_write_gbuffer_layer;
+ * tr_pt_render fails with TR_ERR_INVALID_ARGUMENT while one is still missing. */
 typedef struct tr_pt_accumulation_state {
     uint32_t frame_counter;
     uint32_t accumulated_samples;
+    uint32_t samples_per_pixel;
+    uint32_t gbuffer_mask;
+    uint64_t color_pixels;              /* float4 texels of the colour target (all views) */
 } tr_pt_accumulation_state;
 int tr_pt_get_accumulation_state(tr_pt_ctx* ctx, tr_pt_accumulation_state* out);
 int tr_pt_restore_accumulation(tr_pt_ctx* ctx, const float* rgba32f_host, size_t bytes,
@@ -434,6 +443,8 @@ int tr_pt_set_color_buffer(tr_pt_ctx* ctx, void* device_ptr, size_t bytes);
 int tr_pt_set_gbuffer_layers(tr_pt_ctx* ctx, uint32_t layer_mask);
 int tr_pt_get_gbuffer_layer(tr_pt_ctx* ctx, int layer, void** device_ptr, size_t* bytes);
 int tr_pt_read_gbuffer_layer(tr_pt_ctx* ctx, int layer, void* host_dst, size_t bytes);
+/* The inverse of tr_pt_read_gbuffer_layer, for resuming from a checkpoint (see tr_pt_restore_accumulation). */
+int tr_pt_write_gbuffer_layer(tr_pt_ctx* ctx, int layer, const void* host_src, size_t bytes);
 
 int tr_pt_get_stats(tr_pt_ctx* ctx, tr_pt_stats* stats);
 int tr_pt_set_instrumentation(tr_pt_ctx* ctx, int flags);

@@ -11,7 +11,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # enums --------------------------------------------------------------------------------------
 SAMPLER_UNIFORM_RANDOM, SAMPLER_SOBOL_OWEN, SAMPLER_SOBOL_Z_ORDER_2D, SAMPLER_SOBOL_Z_ORDER_3D = range(4)
@@ -124,6 +124,12 @@ class Options(C.Structure):
 class Distribution(C.Structure):
     _fields_ = [("size", C.c_uint32 * 2), ("strategy", C.c_int32), ("index", C.c_uint32),
                 ("count", C.c_uint32), ("primary", C.c_int32)]
+
+
+class AccumulationState(C.Structure):
+    """tr_pt_accumulation_state"""
+    _fields_ = [("frame_counter", C.c_uint32), ("accumulated_samples", C.c_uint32), ("samples_per_pixel", C.c_uint32),
+                ("gbuffer_mask", C.c_uint32), ("color_pixels", C.c_uint64)]
 
 
 class Stats(C.Structure):

@@ -42,6 +42,7 @@ struct tr_pt_ctx
     float4* color = nullptr;        // the target in use (own_color or an external buffer)
     float4* own_color = nullptr;
     float stitch_blend = 1.0f;
+    uint32_t restore_pending_layers = 0;                    // aux layers a restored checkpoint still has to write back
     uint32_t gbuffer_mask = 0;                              // aux layers of gbuffer_target (tr_pt_set_gbuffer_layers)
     void* gbuffer[TR_GBUFFER_LAYER_COUNT] = {};
     size_t gbuffer_pixels = 0;
@@ -193,6 +194,14 @@ void fill_params(const tr_pt_ctx* c, RenderParams& P)
     for(int l = 1; l < TR_GBUFFER_LAYER_COUNT; ++l) P.gbuffer[l] = ((c->gbuffer_mask >> l) & 1u) ? c->gbuffer[l] : nullptr;
     P.gbuffer_mask = c->gbuffer_mask;
     P.prev_from_world = c->prev_from_world;
+}
+
+// Shared state (cameras, scene, wavefront buffers, counters) may still be in use by a render that runs on a
+// caller-provided stream: wait for it before mutating any of it or rendering on another stream.
+cudaError_t wait_last_stream(tr_pt_ctx* c, cudaStream_t next)
+{
+    if(c->last_stream && c->last_stream != next) return cudaStreamSynchronize(c->last_stream);
+    return cudaSuccess;
 }
 
 const size_t k_layer_texel_bytes[TR_GBUFFER_LAYER_COUNT] = {16, 8, 8, 8, 4, 4, 16, 16, 4};
@@ -527,7 +536,9 @@ static int transform_and_build(tr_pt_ctx* c, const tr_instance* instances, uint3
     TRY_CUDA(c, cudaStreamSynchronize(st));   // also covers the host staging vectors above
     float build_ms = 0.0f;
     cudaEventElapsedTime(&build_ms, c->ev_begin, c->ev_end);
-    if(bout.depth >= TR_BVH_STACK)
+    // The wavefront kernel's stack holds at most one sibling group per level plus the postponed triangle groups,
+    // and it postpones only while fewer than TR_BVH_POSTPONE_CAP entries are stacked (tr_render.cu).
+    if(bout.depth + TR_BVH_POSTPONE_CAP > TR_BVH_STACK)
     {
         free_scene(c);
         return fail(c, TR_ERR_UNSUPPORTED, "BVH depth " + std::to_string(bout.depth) + " exceeds the traversal stack");
@@ -555,6 +566,7 @@ int tr_pt_set_scene(tr_pt_ctx* c, const tr_pt_scene_desc* s)
     }
     if(s->instance_count && (!s->instances || !s->meshes)) return fail(c, TR_ERR_INVALID_ARGUMENT, "null instance tables");
     DeviceGuard guard(c->device);
+    TRY_CUDA(c, wait_last_stream(c, c->stream));
     TRY_CUDA(c, cudaStreamSynchronize(c->stream));
     free_scene(c);
     std::vector<void*>& A = c->scene_allocs;
@@ -708,6 +720,7 @@ int tr_pt_set_cameras(tr_pt_ctx* c, const tr_camera_pair* pairs, uint32_t view_c
 {
     if(!c || !pairs || view_count == 0) return fail(c, TR_ERR_INVALID_ARGUMENT, "null argument");
     DeviceGuard guard(c->device);
+    TRY_CUDA(c, wait_last_stream(c, c->stream));
     TRY_CUDA(c, cudaStreamSynchronize(c->stream));
     if(view_count != c->views || !c->cameras)
     {
@@ -739,6 +752,7 @@ int tr_pt_reset_accumulation(tr_pt_ctx* c, int reset_sample_counter)
 {
     if(!c) return TR_ERR_INVALID_ARGUMENT;
     c->accumulated_samples = 0;
+    c->restore_pending_layers = 0;
     if(reset_sample_counter) c->frame_counter = 0;
     return TR_OK;
 }
@@ -749,9 +763,12 @@ int tr_pt_render(tr_pt_ctx* c, void* cuda_stream)
     DeviceGuard guard(c->device);
     int rc = prepare_targets(c);
     if(rc) return rc;
+    if(c->restore_pending_layers & c->gbuffer_mask)
+        return fail(c, TR_ERR_INVALID_ARGUMENT, "restored checkpoint: write the aux G-buffer layers back (tr_pt_write_gbuffer_layer) before rendering");
     // A caller-provided stream is ordered after our own setup work.
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
     if(st != c->stream) TRY_CUDA(c, cudaStreamSynchronize(c->stream));
+    TRY_CUDA(c, wait_last_stream(c, st));
     RenderParams P;
     fill_params(c, P);
     // src/rt_stage.cc:76-85 (sampling UBO), src/rt_camera_stage.cc:74-101 (distribution UBO)
@@ -802,6 +819,7 @@ int tr_pt_render_feature(tr_pt_ctx* c, int feature, const float default_value[4]
     if(rc) return rc;
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
     if(st != c->stream) TRY_CUDA(c, cudaStreamSynchronize(c->stream));
+    TRY_CUDA(c, wait_last_stream(c, st));
     RenderParams P;
     fill_params(c, P);
     TRY_CUDA(c, tr_render_feature(st, P, feature, default_value));
@@ -847,6 +865,9 @@ int tr_pt_get_accumulation_state(tr_pt_ctx* c, tr_pt_accumulation_state* out)
     if(!c || !out) return TR_ERR_INVALID_ARGUMENT;
     out->frame_counter = c->frame_counter;
     out->accumulated_samples = (uint32_t)c->accumulated_samples;
+    out->samples_per_pixel = (uint32_t)c->opt.samples_per_pixel;
+    out->gbuffer_mask = c->gbuffer_mask;
+    out->color_pixels = c->color_pixels;
     return TR_OK;
 }
 
@@ -857,13 +878,19 @@ int tr_pt_restore_accumulation(tr_pt_ctx* c, const float* rgba32f_host, size_t b
     DeviceGuard guard(c->device);
     int rc = prepare_targets(c);      // needs scene, cameras and distribution: they define the target
     if(rc) return rc;
-    if(bytes != c->color_pixels * sizeof(float4))
+    if(bytes != c->color_pixels * sizeof(float4) || state->color_pixels != c->color_pixels)
         return fail(c, TR_ERR_INVALID_ARGUMENT, "size mismatch: target has " + std::to_string(c->color_pixels * sizeof(float4)) + " bytes");
+    if(state->samples_per_pixel != (uint32_t)c->opt.samples_per_pixel)
+        return fail(c, TR_ERR_INVALID_ARGUMENT, "the checkpoint was written with samples_per_pixel = " + std::to_string(state->samples_per_pixel));
+    if(state->gbuffer_mask != c->gbuffer_mask)
+        return fail(c, TR_ERR_INVALID_ARGUMENT, "the checkpoint's G-buffer layers differ from the context's");
     cudaStream_t st = c->last_stream ? c->last_stream : c->stream;
     TRY_CUDA(c, cudaMemcpyAsync(c->color, rgba32f_host, bytes, cudaMemcpyHostToDevice, st));
     TRY_CUDA(c, cudaStreamSynchronize(st));
     c->frame_counter = state->frame_counter;
     c->accumulated_samples = (int)state->accumulated_samples;
+    // first-sample layers are never written again once samples are accumulated: they have to come from the checkpoint
+    c->restore_pending_layers = state->accumulated_samples ? c->gbuffer_mask : 0u;
     return TR_OK;
 }
 
@@ -903,6 +930,22 @@ int tr_pt_read_gbuffer_layer(tr_pt_ctx* c, int layer, void* out, size_t bytes)
     cudaStream_t st = c->last_stream ? c->last_stream : c->stream;
     TRY_CUDA(c, cudaMemcpyAsync(out, c->gbuffer[layer], bytes, cudaMemcpyDeviceToHost, st));
     TRY_CUDA(c, cudaStreamSynchronize(st));
+    return TR_OK;
+}
+
+int tr_pt_write_gbuffer_layer(tr_pt_ctx* c, int layer, const void* src, size_t bytes)
+{
+    if(!c || !src || layer <= TR_GBUFFER_COLOR || layer >= TR_GBUFFER_LAYER_COUNT) return fail(c, TR_ERR_INVALID_ARGUMENT, "bad layer");
+    if(!((c->gbuffer_mask >> layer) & 1u)) return fail(c, TR_ERR_INVALID_ARGUMENT, "G-buffer layer not enabled");
+    DeviceGuard guard(c->device);
+    int rc = prepare_targets(c);
+    if(rc) return rc;
+    const size_t have = c->gbuffer_pixels * k_layer_texel_bytes[layer];
+    if(bytes != have) return fail(c, TR_ERR_INVALID_ARGUMENT, "size mismatch: layer has " + std::to_string(have) + " bytes");
+    cudaStream_t st = c->last_stream ? c->last_stream : c->stream;
+    TRY_CUDA(c, cudaMemcpyAsync(c->gbuffer[layer], src, bytes, cudaMemcpyHostToDevice, st));
+    TRY_CUDA(c, cudaStreamSynchronize(st));
+    c->restore_pending_layers &= ~(1u << layer);
     return TR_OK;
 }
 

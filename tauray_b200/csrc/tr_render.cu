@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(WF_BLOCK, ANY ? TRACE_MIN_BLOCKS_SHADOW : TRAC
             const int active = __popc(__activemask());
             while(Gt.y & 0xFFu)
             {
-                if(__popc(__activemask()) * P.tune_postpone_div < active)
+                if(__popc(__activemask()) * P.tune_postpone_div < active && sp < TR_BVH_POSTPONE_CAP)
                 {
                     PUSH(Gt);
                     Gt.y = 0u;

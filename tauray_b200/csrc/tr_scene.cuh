@@ -30,6 +30,8 @@ namespace trd {
 #define TR_BVH_NODE_VEC4 5
 #define TR_BVH_LEAF_TRIS 2
 #define TR_BVH_STACK 48
+// the wavefront kernel postpones a triangle group (one extra stack entry) only while fewer entries than this are stacked
+#define TR_BVH_POSTPONE_CAP 16
 #define TR_TRI_FLAG_OPAQUE 1u
 
 struct DeviceBvh

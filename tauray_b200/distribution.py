@@ -27,10 +27,13 @@ def get_region_size(image_size, b):
 
 
 def calculate_shuffled_strips_pixels_per_device(size, max_ratio):
-    """src/distribution_strategy.cc:79-83 (the reference passes the ratio as a float)."""
+    """src/distribution_strategy.cc:79-83. The reference's product is evaluated in binary32: `float * size_t`
+    and `float * int` both convert the integer to float, and each product rounds once."""
     b = calculate_shuffled_strips_b(size)
-    r = float(np.float32(max_ratio))
-    return int(math.ceil(r * get_region_size(size[0] * size[1], b) * (1 << b)))
+    r = np.float32(max_ratio)
+    prod = np.float32(r * np.float32(get_region_size(size[0] * size[1], b)))
+    prod = np.float32(prod * np.float32(1 << b))
+    return int(math.ceil(float(prod))) & 0xFFFFFFFF
 
 
 def make_distribution(size, strategy, index=0, count=1, primary=True):

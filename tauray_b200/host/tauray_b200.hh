@@ -223,6 +223,19 @@ public:
     {
         check(tr_pt_restore_accumulation(ctx, color.data(), color.size() * sizeof(float), &st), ctx, "tr_pt_restore_accumulation");
     }
+    // aux G-buffer layers are part of a checkpoint: dump with read_gbuffer_layer, write back after restore_accumulation
+    std::vector<unsigned char> read_gbuffer_layer(int layer)
+    {
+        void* p; size_t bytes;
+        check(tr_pt_get_gbuffer_layer(ctx, layer, &p, &bytes), ctx, "tr_pt_get_gbuffer_layer");
+        std::vector<unsigned char> out(bytes);
+        check(tr_pt_read_gbuffer_layer(ctx, layer, out.data(), bytes), ctx, "tr_pt_read_gbuffer_layer");
+        return out;
+    }
+    void write_gbuffer_layer(int layer, const std::vector<unsigned char>& texels)
+    {
+        check(tr_pt_write_gbuffer_layer(ctx, layer, texels.data(), texels.size()), ctx, "tr_pt_write_gbuffer_layer");
+    }
     tr_pt_stats get_stats() { tr_pt_stats s; check(tr_pt_get_stats(ctx, &s), ctx, "tr_pt_get_stats"); return s; }
     tr_pt_ctx* handle() { return ctx; }
     const options& get_options() const { return opt; }

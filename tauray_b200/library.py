@@ -23,7 +23,7 @@ EXPORTS = [
     "tr_pt_default_options", "tr_pt_create", "tr_pt_destroy", "tr_pt_set_scene", "tr_pt_update_instances", "tr_pt_set_cameras",
     "tr_pt_set_distribution", "tr_pt_reset_accumulation", "tr_pt_render", "tr_pt_render_feature", "tr_pt_sync",
     "tr_pt_get_color_buffer", "tr_pt_read_color", "tr_pt_get_accumulation_state", "tr_pt_restore_accumulation", "tr_pt_unshuffle", "tr_pt_set_peer_images", "tr_pt_set_stitch_blend", "tr_pt_get_stats",
-    "tr_pt_set_gbuffer_layers", "tr_pt_get_gbuffer_layer", "tr_pt_read_gbuffer_layer",
+    "tr_pt_set_gbuffer_layers", "tr_pt_get_gbuffer_layer", "tr_pt_read_gbuffer_layer", "tr_pt_write_gbuffer_layer",
     "tr_pt_set_instrumentation", "tr_pt_read_tri_lights", "tr_pt_read_alias_table", "tr_pt_trace_rays", "tr_pt_sample_test",
     "tr_pt_last_error", "tr_pt_abi_version", "tr_pt_alloc_full_image", "tr_pt_ipc_get_handle",
     "tr_pt_ipc_open_handle", "tr_pt_ipc_close_handle", "tr_pt_set_color_buffer", "tr_pt_read_full_image", "tr_pt_enable_peer_access",
@@ -60,8 +60,8 @@ def lib():
     l.tr_pt_render_feature.argtypes = [vp, C.c_int, C.POINTER(C.c_float), vp]
     l.tr_pt_sync.argtypes = [vp]
     l.tr_pt_get_color_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
-    l.tr_pt_get_accumulation_state.argtypes = [vp, C.POINTER(C.c_uint32 * 2)]
-    l.tr_pt_restore_accumulation.argtypes = [vp, vp, C.c_size_t, C.POINTER(C.c_uint32 * 2)]
+    l.tr_pt_get_accumulation_state.argtypes = [vp, C.POINTER(abi.AccumulationState)]
+    l.tr_pt_restore_accumulation.argtypes = [vp, vp, C.c_size_t, C.POINTER(abi.AccumulationState)]
     l.tr_pt_read_color.argtypes = [vp, vp, C.c_size_t]
     l.tr_pt_unshuffle.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, C.c_float, vp]
     l.tr_pt_set_stitch_blend.argtypes = [vp, C.c_float]
@@ -72,6 +72,7 @@ def lib():
     l.tr_pt_set_gbuffer_layers.argtypes = [vp, C.c_uint32]
     l.tr_pt_get_gbuffer_layer.argtypes = [vp, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     l.tr_pt_read_gbuffer_layer.argtypes = [vp, C.c_int, vp, C.c_size_t]
+    l.tr_pt_write_gbuffer_layer.argtypes = [vp, C.c_int, vp, C.c_size_t]
     l.tr_pt_read_alias_table.argtypes = [vp, vp, C.c_uint32]
     l.tr_pt_trace_rays.argtypes = [vp, vp, C.c_uint32, vp]
     l.tr_pt_sample_test.argtypes = [vp, vp, C.c_uint32, C.c_int, vp]
@@ -182,17 +183,29 @@ class PathTracer:
         self._check(self._l.tr_pt_read_color(self._ctx, host_ptr, nbytes), "tr_pt_read_color")
 
     def checkpoint(self):
-        """Accumulation checkpoint: the colour target + (frame_counter, accumulated_samples)."""
-        st = (C.c_uint32 * 2)()
+        """Accumulation checkpoint: the colour target, the enabled aux G-buffer layers and the counters."""
+        st = abi.AccumulationState()
         self._check(self._l.tr_pt_get_accumulation_state(self._ctx, C.byref(st)), "tr_pt_get_accumulation_state")
-        return {"color": self.read_color().copy(), "frame_counter": int(st[0]), "accumulated_samples": int(st[1])}
+        ck = {"color": self.read_color().copy()}
+        for name, _ in st._fields_:
+            ck[name] = int(getattr(st, name))
+        ck["layers"] = {l: self.read_gbuffer_layer(l).copy() for l in range(1, abi.GBUFFER_LAYER_COUNT) if (st.gbuffer_mask >> l) & 1}
+        return ck
 
     def restore(self, ck):
-        """Resume from PathTracer.checkpoint() (scene, cameras and distribution must already be set)."""
+        """Resume from PathTracer.checkpoint() (scene, cameras, distribution and layers must already be set)."""
         color = np.ascontiguousarray(ck["color"], dtype=np.float32)
-        st = (C.c_uint32 * 2)(int(ck["frame_counter"]), int(ck["accumulated_samples"]))
+        st = abi.AccumulationState(int(ck["frame_counter"]), int(ck["accumulated_samples"]),
+                                   int(ck.get("samples_per_pixel", self.options.samples_per_pixel)),
+                                   int(ck.get("gbuffer_mask", 0)), int(ck.get("color_pixels", color.size // 4)))
         self._check(self._l.tr_pt_restore_accumulation(self._ctx, color.ctypes.data, color.nbytes, C.byref(st)),
                     "tr_pt_restore_accumulation")
+        for l, texels in ck.get("layers", {}).items():
+            self.write_gbuffer_layer(l, texels)
+
+    def write_gbuffer_layer(self, layer, texels):
+        texels = np.ascontiguousarray(texels)
+        self._check(self._l.tr_pt_write_gbuffer_layer(self._ctx, int(layer), texels.ctypes.data, texels.nbytes), "tr_pt_write_gbuffer_layer")
 
     def color_buffer(self):
         """(device pointer, bytes) of the colour target."""

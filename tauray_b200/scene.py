@@ -255,6 +255,32 @@ def perspective_camera(transform, fov_deg, aspect, near=0.1, far=100.0, focus=(1
     return cam
 
 
+def orthographic_camera(transform, left, right, bottom, top, near=0.1, far=100.0):
+    """One tr_camera_data for an orthographic camera: camera::ortho + refresh (src/camera.cc:43-50,384-389:
+    glm::ortho, right-handed, depth 0..1), get_projection_info (src/camera.cc:348-356)."""
+    f32 = np.float32
+    proj = np.zeros((4, 4), dtype=np.float64)
+    proj[0, 0] = 2.0 / (right - left)
+    proj[1, 1] = 2.0 / (top - bottom)
+    proj[2, 2] = -1.0 / (far - near)
+    proj[0, 3] = -(right + left) / (right - left)
+    proj[1, 3] = -(top + bottom) / (top - bottom)
+    proj[2, 3] = -near / (far - near)
+    proj[3, 3] = 1.0
+    inv_view = np.asarray(transform, dtype=np.float64)
+    view = np.linalg.inv(inv_view)
+    cam = np.zeros((), dtype=abi.CAMERA_DATA)
+    cam["view"] = abi.mat_to_wire(view)
+    cam["view_inverse"] = abi.mat_to_wire(inv_view)
+    cam["view_proj"] = abi.mat_to_wire(proj @ view)
+    cam["proj_inverse"] = abi.mat_to_wire(np.linalg.inv(proj))
+    cam["origin"] = (inv_view @ np.array([0, 0, 0, 1.0])).astype(f32)
+    cam["dof_params"] = (1.0, 0.0, 0.0, 0.0)
+    cam["projection_info"] = (far - near, -far, right - left, top - bottom)
+    cam["pan"] = (0, 0, 0, 0)
+    return cam
+
+
 def camera_pairs(cameras):
     """tr_camera_pair[] with previous = current (a still frame)."""
     pairs = np.zeros(len(cameras), dtype=abi.CAMERA_PAIR)

@@ -206,3 +206,39 @@ def courtyard(subdiv=3, envmap=True, sun_in_sky=True, directional=False, emissiv
 def courtyard_cameras(aspect=1.0, fov_deg=55.0):
     cam = perspective_camera(look_at_transform((0.3, 0.6, 5.0), (0, -0.1, 0)), fov_deg, aspect, 0.1, 100.0)
     return camera_pairs([cam])
+
+
+def deep_chain(shells=44, emissive=True):
+    """A scene whose LBVH degenerates into a long chain: shells of small quads shrinking geometrically towards one
+    corner of a room (each shell is half the size of the previous one, so every Morton split peels one shell off).
+    Used to exercise deep traversal stacks (sibling groups + postponed triangle groups)."""
+    s = Scene()
+    w = 2.0
+    white = make_material(albedo=(0.8, 0.8, 0.8, 1))
+    room = merge([
+        quad((-w, -w, w), (w, -w, w), (w, -w, -w), (-w, -w, -w), 2),
+        quad((-w, w, -w), (w, w, -w), (w, w, w), (-w, w, w), 2),
+        quad((-w, -w, -w), (w, -w, -w), (w, w, -w), (-w, w, -w), 2),
+        quad((-w, -w, w), (-w, -w, -w), (-w, w, -w), (-w, w, w), 2),
+        quad((w, -w, -w), (w, -w, w), (w, w, w), (w, w, -w), 2),
+    ])
+    s.add_instance(*room, white)
+    corner = np.array([-w + 0.05, -w + 0.05, -w + 0.05])
+    parts = []
+    for k in range(shells):
+        r = 3.0 * 0.5 ** k
+        c = corner + r * np.array([1.0, 0.8, 0.6])
+        h = 0.22 * r
+        parts.append(quad(c + (-h, -h, 0), c + (h, -h, 0), c + (h, h, 0), c + (-h, h, 0), 1))
+        parts.append(quad(c + (0, -h, -h), c + (0, -h, h), c + (0, h, h), c + (0, h, -h), 1))
+        parts.append(quad(c + (-h, 0, h), c + (h, 0, h), c + (h, 0, -h), c + (-h, 0, -h), 1))
+    s.add_instance(*merge(parts), make_material(albedo=(0.9, 0.5, 0.2, 1), roughness=0.4))
+    if emissive:
+        em = make_material(albedo=(0, 0, 0, 1), emission=(10.0, 10.0, 9.0))
+        s.add_instance(*quad((-0.6, w - 0.01, -0.6), (0.6, w - 0.01, -0.6), (0.6, w - 0.01, 0.6), (-0.6, w - 0.01, 0.6), 1), em)
+    s.add_directional_light((1.0, 0.9, 0.7), (-0.4, -1.0, -0.3), angle_deg=1.0)
+    return s
+
+
+def deep_chain_cameras(aspect=1.0):
+    return camera_pairs([perspective_camera(look_at_transform((1.6, 1.2, 1.8), (-1.9, -1.9, -1.9)), 50.0, aspect, 0.01, 100.0)])

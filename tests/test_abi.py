@@ -29,7 +29,8 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "libtauray_b200.so does not export %s" % n
     assert set(names) == set(library.EXPORTS), (set(names) ^ set(library.EXPORTS))
-    assert lib.tr_pt_abi_version() == 1
+    from tauray_b200 import abi
+    assert lib.tr_pt_abi_version() == abi.ABI_VERSION == 2
 
 
 def test_every_entry_point_cites_the_reference():
@@ -42,7 +43,7 @@ def test_struct_layouts_match_the_c_compiler(tmp_path):
     src = tmp_path / "sizes.c"
     names = ["tr_vertex", "tr_material", "tr_instance", "tr_directional_light", "tr_point_light", "tr_tri_light",
              "tr_camera_data", "tr_camera_pair", "tr_alias_table_entry", "tr_mesh_ref", "tr_texture", "tr_pt_scene_desc",
-             "tr_pt_options", "tr_pt_distribution", "tr_pt_stats"]
+             "tr_pt_options", "tr_pt_distribution", "tr_pt_stats", "tr_pt_accumulation_state"]
     body = "".join('printf("%s %%zu\\n", sizeof(%s));' % (n, n) for n in names)
     body += 'printf("off_stats_render_ms %zu\\n", offsetof(tr_pt_stats, render_ms));'
     body += 'printf("off_opt_kernel_mode %zu\\n", offsetof(tr_pt_options, kernel_mode));'
@@ -58,6 +59,7 @@ def test_struct_layouts_match_the_c_compiler(tmp_path):
         "tr_camera_pair": abi.CAMERA_PAIR.itemsize, "tr_mesh_ref": C.sizeof(abi.MeshRef), "tr_texture": C.sizeof(abi.Texture),
         "tr_pt_scene_desc": C.sizeof(abi.SceneDesc), "tr_pt_options": C.sizeof(abi.Options),
         "tr_pt_distribution": C.sizeof(abi.Distribution), "tr_pt_stats": C.sizeof(abi.Stats),
+        "tr_pt_accumulation_state": C.sizeof(abi.AccumulationState),
         "off_stats_render_ms": abi.Stats.render_ms.offset, "off_opt_kernel_mode": abi.Options.kernel_mode.offset,
         "off_desc_envproj": abi.SceneDesc.environment_proj.offset,
     }

@@ -88,3 +88,40 @@ def test_oracle_scanline_scatter_matches_numpy():
             t = (old * (np.float32(1.0) - a)).astype(np.float32)
             want[:, index::3] = (strip.astype(np.float64) * np.float64(a) + t.astype(np.float64)).astype(np.float32)
     assert full.tobytes() == want.tobytes()
+
+
+def test_strip_boundaries_follow_the_reference_float32_arithmetic(tmp_path):
+    """calculate_shuffled_strips_pixels_per_device multiplies in binary32 (src/distribution_strategy.cc:79-83):
+    at interior split points that differs from a double product by one pixel (1280x720 over 3 devices: 307200,
+    not 307201). Checked against the C++ mirror of the same function, compiled here."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "strips.cc"
+    src.write_text("""
+#include "tauray_b200/host/tauray_b200.hh"
+#include <cstdio>
+int main()
+{
+    const unsigned sizes[][2] = {{1280, 720}, {640, 360}, {3840, 2160}, {1920, 1080}, {960, 540}};
+    for(auto& s: sizes)
+        for(unsigned world: {2u, 3u, 5u, 6u, 7u, 8u})
+            for(unsigned r = 0; r <= world; ++r)
+            {
+                tr_b200::uvec2 sz; sz.x = s[0]; sz.y = s[1];
+                double off = 0; for(unsigned k = 0; k < r; ++k) off += 1.0 / world;
+                printf("%u %u %u %u %u\\n", s[0], s[1], world, r, tr_b200::calculate_shuffled_strips_pixels_per_device(sz, (float)off));
+            }
+}
+""".replace("\\\\n", "\\n"))
+    exe = tmp_path / "strips"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-I", root, "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    rows = [tuple(int(x) for x in line.split()) for line in out.splitlines()]
+    assert len(rows) > 100
+    for w, h, world, r, want in rows:
+        off = 0.0
+        for _ in range(r):
+            off += 1.0 / world
+        assert D.calculate_shuffled_strips_pixels_per_device((w, h), off) == want, (w, h, world, r)
+    assert D.calculate_shuffled_strips_pixels_per_device((1280, 720), 1.0 / 3.0) == 307200

@@ -117,6 +117,44 @@ def test_scene_variants():
              modes=(abi.KERNEL_WAVEFRONT,))
 
 
+@pytest.mark.parametrize("shells", [20, 44])
+def test_deep_chain_scene_keeps_the_traversal_stack_in_bounds(shells):
+    """A degenerate (chain-like) tree: the wavefront kernel stacks one sibling group per level plus postponed
+    triangle groups. Either the scene is refused loudly (depth beyond the stack) or both kernel organisations give
+    the oracle's image bit for bit."""
+    scene = testscenes.deep_chain(shells=shells)
+    cams = testscenes.deep_chain_cameras(SIZE[0] / SIZE[1])
+    opt = abi.default_options(max_ray_depth=4, samples_per_pixel=2, local_sampler=abi.SAMPLER_SOBOL_OWEN)
+    with PathTracer(opt) as pt:
+        try:
+            pt.set_scene(scene)
+        except TaurayB200Error as e:
+            assert e.code == abi.ERR_UNSUPPORTED and "stack" in str(e)
+            return
+        depth = pt.stats()["bvh_depth"]
+    assert depth + 16 <= 48
+    both(opt, scene=scene, cams=cams)
+    if shells == 44:
+        assert depth >= 12, "the scene is meant to produce a deep tree (got depth %d)" % depth
+
+
+def test_orthographic_projection():
+    """shader/camera.glsl:25-59: orthographic rays start on the near plane with a constant direction."""
+    from tauray_b200.scene import orthographic_camera, look_at_transform, camera_pairs
+    cams = camera_pairs([orthographic_camera(look_at_transform((0.3, 0.2, 5.5), (0, -0.2, 0)), -2.2, 2.2, -1.65, 1.65, 0.1, 100.0)])
+    for kw in (dict(max_ray_depth=3, local_sampler=abi.SAMPLER_SOBOL_OWEN),
+               dict(max_ray_depth=2, film=abi.FILM_BLACKMAN_HARRIS, film_radius=1.0, samples_per_pixel=2),
+               dict(max_ray_depth=2, depth_of_field=1)):
+        opt = abi.default_options(projection=abi.PROJECTION_ORTHOGRAPHIC, **kw)
+        ref, outs = both(opt, cams=cams)
+        assert np.isfinite(ref).all() and ref[..., :3].max() > 0.05
+    # and it is a different image from the perspective one
+    persp, _ = both(abi.default_options(max_ray_depth=3, local_sampler=abi.SAMPLER_SOBOL_OWEN), modes=(abi.KERNEL_WAVEFRONT,))
+    opt = abi.default_options(projection=abi.PROJECTION_ORTHOGRAPHIC, max_ray_depth=3, local_sampler=abi.SAMPLER_SOBOL_OWEN)
+    ortho, _ = both(opt, cams=cams, modes=(abi.KERNEL_WAVEFRONT,))
+    assert not bits_equal(persp, ortho)
+
+
 def test_device_sampler_is_bit_exact():
     coords = np.random.RandomState(5).randint(0, 5000, size=(4096, 4)).astype(np.uint32)
     for sampler in (abi.SAMPLER_SOBOL_OWEN, abi.SAMPLER_UNIFORM_RANDOM, abi.SAMPLER_SOBOL_Z_ORDER_2D, abi.SAMPLER_SOBOL_Z_ORDER_3D):
