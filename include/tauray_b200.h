@@ -422,6 +422,39 @@ int tr_pt_set_stitch_blend(tr_pt_ctx* ctx, float blend_ratio);
  * peer's handle into this process (cudaIpcOpenMemHandle), tr_pt_ipc_close_handle unmaps it. */
 int tr_pt_alloc_full_image(tr_pt_ctx* ctx, void** device_ptr, size_t* bytes);
 int tr_pt_read_full_image(tr_pt_ctx* ctx, float* rgba32f_host, size_t bytes);
+/* The full image is an arena of two halves, each [colour | every aux layer enabled with tr_pt_set_gbuffer_layers
+ * when tr_pt_alloc_full_image ran]. The pointer tr_pt_alloc_full_image returns is the arena base = the colour of
+ * half 0, and its `bytes` the size of one colour image, as before. The reference stitches every transferred
+ * gbuffer_target entry (src/rt_renderer.cc:370-397, src/stitch_stage.cc:156-171): with peers set, tr_pt_render also
+ * stores this context's texels of the enabled aux layers into every peer arena (all arenas share one layout, so the
+ * layers, image size and view count must be the same on every rank).
+ * tr_pt_set_stitch_double_buffer(1): frames alternate between the halves (the parity of the number of tr_pt_render calls
+ * since tr_pt_set_peer_images, so all ranks must render the same frames): frame k+1 of a fast rank stores into the
+ * half nobody reads while a slower rank still copies frame k out, which a single image cannot guarantee with one
+ * barrier per frame (the reference uses per-frame-in-flight targets + timeline semaphores, src/stitch_stage.cc:128-196).
+ * Blending (tr_pt_set_stitch_blend) reads the previous content from the other half. tr_pt_read_full_image /
+ * _range / tr_pt_read_full_layer read the half the last tr_pt_render wrote. Default: off (half 0 only).
+ * tr_pt_set_render_in_full_image(1): the context's colour target and aux layers ARE its full image (the reference's
+ * display device renders in place into the stitched image and keeps accumulating across workload changes,
+ * src/rt_renderer.cc:165-175); needs a primary distribution. With double buffering the running means continue from
+ * the other half and layers written only by the first sample are carried over. */
+typedef struct tr_pt_full_image_info {
+    void* base;
+    uint64_t arena_bytes;
+    uint64_t half_bytes;
+    uint64_t layer_offset[TR_GBUFFER_LAYER_COUNT];   /* byte offset inside a half; ~0 = layer absent */
+    uint64_t pixels;                                 /* size.x * size.y * views */
+    uint32_t generation;                             /* increments whenever the arena is reallocated */
+    uint32_t current_half;                           /* the half the last tr_pt_render wrote */
+} tr_pt_full_image_info;
+int tr_pt_get_full_image_info(tr_pt_ctx* ctx, tr_pt_full_image_info* out);
+int tr_pt_set_stitch_double_buffer(tr_pt_ctx* ctx, int enable);
+int tr_pt_set_render_in_full_image(tr_pt_ctx* ctx, int enable);
+/* D2H of part of the stitched colour image (bytes [byte_offset, byte_offset + bytes) of the current half): lets every
+ * rank of a multi-GPU job copy its own share of the image into one shared pinned host buffer over its own PCIe link
+ * instead of all ranks (or one) copying everything (headless staging copy, src/headless.cc:125-171). */
+int tr_pt_read_full_image_range(tr_pt_ctx* ctx, void* host_dst, size_t byte_offset, size_t bytes);
+int tr_pt_read_full_layer(tr_pt_ctx* ctx, int layer, void* host_dst, size_t bytes);
 /* Single-process multi-GPU (the reference's own topology, src/context.cc:415): let this context's device
  * store into memory of `peer_cuda_device` (cudaDeviceEnablePeerAccess); then pass the peer context's
  * tr_pt_alloc_full_image pointer to tr_pt_set_peer_images directly, no IPC handle needed. */
@@ -439,7 +472,8 @@ int tr_pt_set_color_buffer(tr_pt_ctx* ctx, void* device_ptr, size_t bytes);
  * colour target's layout (views x layer pixels; full image on the primary device, strip otherwise).
  * They are written by tr_pt_render exactly as write_all_outputs does (shader/path_tracer.glsl:
  * 547-574): diffuse/reflection are running means in rgba16f, the others are written when no sample
- * has been accumulated yet. Default: none. Multi-GPU stitching covers the colour layer only. */
+ * has been accumulated yet. Default: none. With peer images set they are stitched across GPUs like the colour
+ * (see tr_pt_get_full_image_info). */
 int tr_pt_set_gbuffer_layers(tr_pt_ctx* ctx, uint32_t layer_mask);
 int tr_pt_get_gbuffer_layer(tr_pt_ctx* ctx, int layer, void** device_ptr, size_t* bytes);
 int tr_pt_read_gbuffer_layer(tr_pt_ctx* ctx, int layer, void* host_dst, size_t bytes);

@@ -132,6 +132,13 @@ class AccumulationState(C.Structure):
                 ("gbuffer_mask", C.c_uint32), ("color_pixels", C.c_uint64)]
 
 
+class FullImageInfo(C.Structure):
+    """tr_pt_full_image_info"""
+    _fields_ = [("base", C.c_void_p), ("arena_bytes", C.c_uint64), ("half_bytes", C.c_uint64),
+                ("layer_offset", C.c_uint64 * 9), ("pixels", C.c_uint64), ("generation", C.c_uint32),
+                ("current_half", C.c_uint32)]
+
+
 class Stats(C.Structure):
     _fields_ = [("closest_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("paths", C.c_uint64),
                 ("closest_node_visits", C.c_uint64), ("closest_triangle_tests", C.c_uint64),

@@ -67,8 +67,19 @@ struct tr_pt_ctx
     float4* external_color = nullptr;
     size_t external_bytes = 0;
     size_t color_pixels = 0;
-    float4* full_image = nullptr;   // library-owned stitched image (tr_pt_alloc_full_image)
+    // library-owned stitched image (tr_pt_alloc_full_image): an arena of two halves (ping-pong per frame when
+    // stitch_double_buffer is on), each [colour | enabled aux layers]
+    float4* full_image = nullptr;
     size_t full_image_pixels = 0;
+    size_t full_half_bytes = 0, full_arena_bytes = 0;
+    size_t full_layer_off[TR_GBUFFER_LAYER_COUNT] = {};
+    uint32_t full_mask = 0;
+    uint32_t full_generation = 0;
+    int stitch_double_buffer = 0;
+    uint32_t stitch_frame = 0;          // renders since the peers were set: its parity picks the half to write
+    uint32_t full_cur_half = 0;         // the half the last render wrote
+    int render_in_full = 0;             // the colour target (and aux layers) ARE the full image (display device)
+    bool wrote_first_sample_layers = false;
     tr_launch_timer* timer = nullptr;
     tr_wavefront wf{};
     std::vector<void*> wf_allocs;
@@ -82,6 +93,7 @@ struct tr_pt_ctx
     bool rendered = false;
     float4* peers[8] = {};
     int peer_count = 0;
+    int peer_self = -1;
 };
 
 static std::string g_create_error;
@@ -189,9 +201,14 @@ void fill_params(const tr_pt_ctx* c, RenderParams& P)
     P.stats = (c->instrumentation & TR_INSTRUMENT_VISITS) ? 1 : 0;
     for(int i = 0; i < c->peer_count; ++i) P.peers[i] = c->peers[i];
     P.peer_count = c->peer_count;
+    P.peer_self = c->peer_self;
     P.last_pass = 0;
     P.stitch_blend = c->stitch_blend;
+    P.color_prev = c->color;
     for(int l = 1; l < TR_GBUFFER_LAYER_COUNT; ++l) P.gbuffer[l] = ((c->gbuffer_mask >> l) & 1u) ? c->gbuffer[l] : nullptr;
+    for(int l = 1; l < TR_GBUFFER_LAYER_COUNT; ++l) P.gbuffer_prev[l] = P.gbuffer[l];
+    for(int l = 0; l < TR_GBUFFER_LAYER_COUNT; ++l) P.full_layer[l] = c->full_layer_off[l];
+    P.full_cur = P.full_prev = 0;
     P.gbuffer_mask = c->gbuffer_mask;
     P.prev_from_world = c->prev_from_world;
 }
@@ -224,7 +241,12 @@ int prepare_targets(tr_pt_ctx* c)
     FrameParams f;
     fill_frame(c, f);
     const size_t pixels = (size_t)f.layer_size * f.views;
-    if(c->external_color)
+    if(c->render_in_full && c->full_image)
+    {
+        c->color = reinterpret_cast<float4*>(reinterpret_cast<char*>(c->full_image) + c->full_cur_half * c->full_half_bytes);
+        c->color_pixels = pixels;
+    }
+    else if(c->external_color)
     {
         if(c->external_bytes != pixels * sizeof(float4))
             return fail(c, TR_ERR_INVALID_ARGUMENT, "external colour buffer has " + std::to_string(c->external_bytes) +
@@ -292,6 +314,60 @@ int prepare_targets(tr_pt_ctx* c)
         TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.shadow_queue, n));
         TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.counts, 4 * 64 + 2));
         w.capacity = slots;
+    }
+    return TR_OK;
+}
+
+// Layout of the full-image arena for the current image size, view count and aux layers.
+void full_image_layout(const tr_pt_ctx* c, size_t pixels, uint32_t mask, size_t off[TR_GBUFFER_LAYER_COUNT], size_t* half_bytes)
+{
+    size_t at = 0;
+    for(int l = 0; l < TR_GBUFFER_LAYER_COUNT; ++l)
+    {
+        off[l] = 0;
+        if(l != TR_GBUFFER_COLOR && !((mask >> l) & 1u)) continue;
+        off[l] = at;
+        at += (pixels * k_layer_texel_bytes[l] + 255) & ~(size_t)255;
+    }
+    *half_bytes = at;
+    (void)c;
+}
+
+// Picks the half of the full-image arena this frame writes and, for a context that renders in place into its full
+// image (the reference's display device), points the targets at it.
+int select_full_image_half(tr_pt_ctx* c, RenderParams& P)
+{
+    if(c->peer_count == 0 && !c->render_in_full) return TR_OK;
+    const uint32_t cur = c->stitch_double_buffer ? (c->stitch_frame & 1u) : 0u;
+    const uint32_t prev = c->stitch_double_buffer ? (cur ^ 1u) : 0u;
+    c->stitch_frame++;
+    c->full_cur_half = cur;
+    P.full_cur = cur * c->full_half_bytes;
+    P.full_prev = prev * c->full_half_bytes;
+    if(c->peer_count > 0 && c->gbuffer_mask && (!c->full_image || c->full_mask != c->gbuffer_mask))
+    {
+        // the peers' arenas are laid out like ours: without our own arena the layer offsets are unknown
+        if(c->full_image) return fail(c, TR_ERR_INVALID_ARGUMENT, "aux G-buffer layers changed: call tr_pt_alloc_full_image again (and re-exchange it) before rendering");
+        size_t half = 0;
+        full_image_layout(c, (size_t)c->dist.size[0] * c->dist.size[1] * c->views, c->gbuffer_mask, c->full_layer_off, &half);
+        for(int l = 0; l < TR_GBUFFER_LAYER_COUNT; ++l) P.full_layer[l] = c->full_layer_off[l];
+    }
+    if(c->render_in_full)
+    {
+        if(!c->full_image) return fail(c, TR_ERR_INVALID_ARGUMENT, "tr_pt_set_render_in_full_image needs tr_pt_alloc_full_image");
+        if(!c->dist.primary) return fail(c, TR_ERR_INVALID_ARGUMENT, "rendering in place into the full image needs a primary distribution");
+        if(c->full_image_pixels != c->color_pixels || c->full_mask != c->gbuffer_mask)
+            return fail(c, TR_ERR_INVALID_ARGUMENT, "the full image does not match the cameras / distribution / layers: call tr_pt_alloc_full_image again");
+        char* base = reinterpret_cast<char*>(c->full_image);
+        P.color = reinterpret_cast<float4*>(base + P.full_cur);
+        P.color_prev = reinterpret_cast<const float4*>(base + P.full_prev);
+        for(int l = 1; l < TR_GBUFFER_LAYER_COUNT; ++l)
+        {
+            if(!((c->gbuffer_mask >> l) & 1u)) continue;
+            P.gbuffer[l] = base + P.full_cur + c->full_layer_off[l];
+            P.gbuffer_prev[l] = base + P.full_prev + c->full_layer_off[l];
+        }
+        c->color = P.color;
     }
     return TR_OK;
 }
@@ -771,6 +847,8 @@ int tr_pt_render(tr_pt_ctx* c, void* cuda_stream)
     TRY_CUDA(c, wait_last_stream(c, st));
     RenderParams P;
     fill_params(c, P);
+    rc = select_full_image_half(c, P);
+    if(rc) return rc;
     // src/rt_stage.cc:76-85 (sampling UBO), src/rt_camera_stage.cc:74-101 (distribution UBO)
     P.frame.sample_counter = c->frame_counter * (uint32_t)c->opt.samples_per_pixel;
     P.frame.rng_seed = c->opt.rng_seed != 0 ? host_pcg((uint32_t)c->opt.rng_seed) : 0;
@@ -803,6 +881,24 @@ int tr_pt_render(tr_pt_ctx* c, void* cuda_stream)
             tr_render_pass_megakernel(st, P, c->sm_count, &launches, timer);
         if(e != cudaSuccess) return fail_cuda(c, e, "render pass launch");
         pass += batch;
+    }
+    // aux G-buffer layers across devices: this rank's texels -> every peer's arena (src/rt_renderer.cc:370-397)
+    if(c->peer_count > 0 && c->gbuffer_mask)
+    {
+        const bool first_sample_frame = P.frame.samples_accumulated == 0;
+        const void* src[TR_GBUFFER_LAYER_COUNT] = {};
+        int src_full[TR_GBUFFER_LAYER_COUNT] = {};
+        for(int l = 1; l < TR_GBUFFER_LAYER_COUNT; ++l)
+        {
+            if(!((c->gbuffer_mask >> l) & 1u)) continue;
+            const bool running_mean = l == TR_GBUFFER_DIFFUSE || l == TR_GBUFFER_REFLECTION;
+            // in-place targets: what this frame did not write is carried over from the half the previous frame wrote
+            src[l] = (c->render_in_full && !running_mean && !first_sample_frame) ? P.gbuffer_prev[l] : P.gbuffer[l];
+            src_full[l] = 0;
+        }
+        P.last_pass = 1;
+        TRY_CUDA(c, tr_render_stitch_aux_layers(st, P, src, src_full, c->sm_count));
+        launches++;
     }
     TRY_CUDA(c, cudaEventRecord(c->ev_end, st));
     c->last_stream = st;
@@ -915,6 +1011,8 @@ int tr_pt_get_gbuffer_layer(tr_pt_ctx* c, int layer, void** device_ptr, size_t* 
     int rc = prepare_targets(c);
     if(rc) return rc;
     if(device_ptr) *device_ptr = c->gbuffer[layer];
+    if(c->render_in_full && c->full_image && ((c->full_mask >> layer) & 1u) && device_ptr)   // in-place targets live in the arena
+        *device_ptr = reinterpret_cast<char*>(c->full_image) + c->full_cur_half * c->full_half_bytes + c->full_layer_off[layer];
     if(bytes) *bytes = c->gbuffer_pixels * k_layer_texel_bytes[layer];
     return TR_OK;
 }
@@ -924,6 +1022,7 @@ int tr_pt_read_gbuffer_layer(tr_pt_ctx* c, int layer, void* out, size_t bytes)
     if(!c || !out || layer < 0 || layer >= TR_GBUFFER_LAYER_COUNT) return TR_ERR_INVALID_ARGUMENT;
     if(layer == TR_GBUFFER_COLOR) return tr_pt_read_color(c, (float*)out, bytes);
     if(!((c->gbuffer_mask >> layer) & 1u) || !c->gbuffer[layer]) return fail(c, TR_ERR_INVALID_ARGUMENT, "G-buffer layer not enabled or nothing rendered yet");
+    if(c->render_in_full && c->full_image && ((c->full_mask >> layer) & 1u)) return tr_pt_read_full_layer(c, layer, out, bytes);
     DeviceGuard guard(c->device);
     const size_t have = c->gbuffer_pixels * k_layer_texel_bytes[layer];
     if(bytes != have) return fail(c, TR_ERR_INVALID_ARGUMENT, "size mismatch: layer has " + std::to_string(have) + " bytes");
@@ -949,16 +1048,39 @@ int tr_pt_write_gbuffer_layer(tr_pt_ctx* c, int layer, const void* src, size_t b
     return TR_OK;
 }
 
-int tr_pt_read_full_image(tr_pt_ctx* c, float* out, size_t bytes)
+// D2H of `bytes` bytes at `offset` of layer `layer` in the half of the full-image arena the last render wrote
+static int read_full(tr_pt_ctx* c, int layer, void* out, size_t offset, size_t bytes)
 {
-    if(!c || !out) return TR_ERR_INVALID_ARGUMENT;
+    if(!c || !out || layer < 0 || layer >= TR_GBUFFER_LAYER_COUNT) return TR_ERR_INVALID_ARGUMENT;
     DeviceGuard guard(c->device);
     if(!c->full_image) return fail(c, TR_ERR_INVALID_ARGUMENT, "tr_pt_alloc_full_image has not been called");
-    if(bytes != c->full_image_pixels * sizeof(float4)) return fail(c, TR_ERR_INVALID_ARGUMENT, "size mismatch");
+    if(layer != TR_GBUFFER_COLOR && !((c->full_mask >> layer) & 1u)) return fail(c, TR_ERR_INVALID_ARGUMENT, "the full image has no such layer");
+    const size_t have = c->full_image_pixels * k_layer_texel_bytes[layer];
+    if(offset > have || bytes > have - offset) return fail(c, TR_ERR_INVALID_ARGUMENT, "size mismatch: the layer has " + std::to_string(have) + " bytes");
+    if(bytes == 0) return TR_OK;
+    const char* src = reinterpret_cast<const char*>(c->full_image) + c->full_cur_half * c->full_half_bytes + c->full_layer_off[layer] + offset;
     cudaStream_t st = c->last_stream ? c->last_stream : c->stream;
-    TRY_CUDA(c, cudaMemcpyAsync(out, c->full_image, bytes, cudaMemcpyDeviceToHost, st));
+    TRY_CUDA(c, cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, st));
     TRY_CUDA(c, cudaStreamSynchronize(st));
     return TR_OK;
+}
+
+int tr_pt_read_full_image(tr_pt_ctx* c, float* out, size_t bytes)
+{
+    if(c && c->full_image && bytes != c->full_image_pixels * sizeof(float4)) return fail(c, TR_ERR_INVALID_ARGUMENT, "size mismatch");
+    return read_full(c, TR_GBUFFER_COLOR, out, 0, bytes);
+}
+
+int tr_pt_read_full_image_range(tr_pt_ctx* c, void* out, size_t byte_offset, size_t bytes)
+{
+    return read_full(c, TR_GBUFFER_COLOR, out, byte_offset, bytes);
+}
+
+int tr_pt_read_full_layer(tr_pt_ctx* c, int layer, void* out, size_t bytes)
+{
+    if(c && c->full_image && layer >= 0 && layer < TR_GBUFFER_LAYER_COUNT && bytes != c->full_image_pixels * k_layer_texel_bytes[layer])
+        return fail(c, TR_ERR_INVALID_ARGUMENT, "size mismatch");
+    return read_full(c, layer, out, 0, bytes);
 }
 
 int tr_pt_unshuffle(tr_pt_ctx* c, const void* strip_device, uint32_t index, uint32_t count, void* full_image_device, float blend_ratio,
@@ -982,8 +1104,14 @@ int tr_pt_unshuffle(tr_pt_ctx* c, const void* strip_device, uint32_t index, uint
 int tr_pt_set_peer_images(tr_pt_ctx* c, void* const* ptrs, int n)
 {
     if(!c || n < 0 || n > 8 || (n > 0 && !ptrs)) return fail(c, TR_ERR_INVALID_ARGUMENT, "0..8 peer images");
-    for(int i = 0; i < n; ++i) c->peers[i] = (float4*)ptrs[i];
+    c->peer_self = -1;
+    for(int i = 0; i < n; ++i)
+    {
+        c->peers[i] = (float4*)ptrs[i];
+        if(c->full_image && ptrs[i] == (void*)c->full_image) c->peer_self = i;
+    }
     c->peer_count = n;
+    c->stitch_frame = 0;
     return TR_OK;
 }
 
@@ -1061,16 +1189,60 @@ int tr_pt_alloc_full_image(tr_pt_ctx* c, void** device_ptr, size_t* bytes)
     if(!c->has_dist || c->views == 0) return fail(c, TR_ERR_INVALID_ARGUMENT, "cameras / distribution not set");
     DeviceGuard guard(c->device);
     const size_t pixels = (size_t)c->dist.size[0] * c->dist.size[1] * c->views;
-    if(!c->full_image || c->full_image_pixels != pixels)
+    if(!c->full_image || c->full_image_pixels != pixels || c->full_mask != c->gbuffer_mask)
     {
+        TRY_CUDA(c, wait_last_stream(c, c->stream));
+        TRY_CUDA(c, cudaStreamSynchronize(c->stream));
         if(c->full_image) cudaFree(c->full_image);
         c->full_image = nullptr;
-        TRY_CUDA(c, cudaMalloc((void**)&c->full_image, pixels * sizeof(float4)));
-        TRY_CUDA(c, cudaMemset(c->full_image, 0, pixels * sizeof(float4)));
+        c->full_image_pixels = 0;
+        size_t half = 0;
+        full_image_layout(c, pixels, c->gbuffer_mask, c->full_layer_off, &half);
+        TRY_CUDA(c, cudaMalloc((void**)&c->full_image, 2 * half));
+        TRY_CUDA(c, cudaMemset(c->full_image, 0, 2 * half));
         c->full_image_pixels = pixels;
+        c->full_half_bytes = half;
+        c->full_arena_bytes = 2 * half;
+        c->full_mask = c->gbuffer_mask;
+        c->full_generation++;
+        c->full_cur_half = 0;
+        c->stitch_frame = 0;
     }
     *device_ptr = c->full_image;
     if(bytes) *bytes = pixels * sizeof(float4);
+    return TR_OK;
+}
+
+int tr_pt_get_full_image_info(tr_pt_ctx* c, tr_pt_full_image_info* out)
+{
+    if(!c || !out) return TR_ERR_INVALID_ARGUMENT;
+    if(!c->full_image) return fail(c, TR_ERR_INVALID_ARGUMENT, "tr_pt_alloc_full_image has not been called");
+    memset(out, 0, sizeof(*out));
+    out->base = c->full_image;
+    out->arena_bytes = c->full_arena_bytes;
+    out->half_bytes = c->full_half_bytes;
+    for(int l = 0; l < TR_GBUFFER_LAYER_COUNT; ++l)
+        out->layer_offset[l] = (l == TR_GBUFFER_COLOR || ((c->full_mask >> l) & 1u)) ? c->full_layer_off[l] : ~0ull;
+    out->pixels = c->full_image_pixels;
+    out->generation = c->full_generation;
+    out->current_half = c->full_cur_half;
+    return TR_OK;
+}
+
+int tr_pt_set_stitch_double_buffer(tr_pt_ctx* c, int enable)
+{
+    if(!c) return TR_ERR_INVALID_ARGUMENT;
+    c->stitch_double_buffer = enable ? 1 : 0;
+    c->stitch_frame = 0;
+    return TR_OK;
+}
+
+int tr_pt_set_render_in_full_image(tr_pt_ctx* c, int enable)
+{
+    if(!c) return TR_ERR_INVALID_ARGUMENT;
+    if(enable && !c->full_image) return fail(c, TR_ERR_INVALID_ARGUMENT, "tr_pt_alloc_full_image has not been called");
+    c->render_in_full = enable ? 1 : 0;
+    if(!enable && c->color != c->own_color && c->color != c->external_color) { c->color = nullptr; c->color_pixels = 0; }
     return TR_OK;
 }
 

@@ -22,16 +22,25 @@ struct RenderParams
     FrameParams frame;
     const tr_camera_pair* cameras;
     float4* color;              // colour target of this device
+    const float4* color_prev;   // where the first pass of a frame reads the accumulated value (== color unless the target
+                                // is the double-buffered full image: then the other half of the ping-pong pair)
     Counters* counters;
     const uint4* sobol_chunks;  // g_sobol_chunks (global memory)
     int stats;                  // count node visits / triangle tests
     // fused stitch: full images of the peer GPUs (NVLink-mapped), written by the last pass
+    // Every peer pointer is the base of that rank's full-image arena: two halves (ping-pong per frame) of
+    // [colour | enabled aux layers]; full_cur / full_prev = byte offset of the half this frame writes / the previous
+    // frame wrote, full_layer[l] = byte offset of layer l inside a half (colour = 0).
     float4* peers[8];
     int peer_count;
+    int peer_self;              // index of this rank's own arena in peers[], -1 if it is not among them
     int last_pass;
     float stitch_blend;         // stitch_stage blend_ratio; 1 = plain store
+    size_t full_cur, full_prev;
+    size_t full_layer[TR_GBUFFER_LAYER_COUNT];
     // aux G-buffer layers (NULL when absent), texel formats of src/gbuffer.hh:18-51
     void* gbuffer[TR_GBUFFER_LAYER_COUNT];
+    const void* gbuffer_prev[TR_GBUFFER_LAYER_COUNT];   // see color_prev
     uint32_t gbuffer_mask;
     const float* prev_from_world;   // 16 floats per instance: model_prev * inverse(model), column-major
     // traversal tuning (defaults in tr_render.cu; TR_TUNE_* environment overrides for experiments)
@@ -982,11 +991,11 @@ TRD vec4 unpack_rgba16f(uint2 q)
     return V4(half_to_float_(q.x & 0xFFFFu), half_to_float_(q.x >> 16), half_to_float_(q.y & 0xFFFFu), half_to_float_(q.y >> 16));
 }
 // accumulate_gbuffer_diffuse / _reflection (gbuffer.glsl:68-78,118-128) on an rgba16f layer
-TRD void accumulate_rgba16f(uint2* __restrict__ layer, uint32_t index, vec4 v, uint32_t samples, uint32_t previous_samples)
+TRD void accumulate_rgba16f(uint2* layer, const uint2* layer_prev, uint32_t index, vec4 v, uint32_t samples, uint32_t previous_samples)
 {
     if(previous_samples != 0)
     {
-        const vec4 prev = unpack_rgba16f(layer[index]);
+        const vec4 prev = unpack_rgba16f(layer_prev[index]);
         const uint32_t tot = samples + previous_samples;
         v = mix_(v, prev, (float)previous_samples / (float)tot);
     }
@@ -1049,13 +1058,19 @@ TRD float4 accumulate(const RenderParams& P, vec3 color, float alpha, uint32_t w
     vec4 out = V4(color, alpha);
     if(prev_samples != 0)
     {
-        const float4 p = P.color[write_index];
+        // the first pass of a frame continues from what the previous frame left
+        const float4 p = (P.frame.previous_samples + pass_offset == 0 ? P.color_prev : P.color)[write_index];
         const uint32_t total = samples + prev_samples;
         out = mix_(out, V4(p.x, p.y, p.z, p.w), (float)prev_samples / (float)total);
     }
     const float4 o = make_float4(out.x, out.y, out.z, out.w);
     P.color[write_index] = o;
     return o;
+}
+
+template<typename T> TRD T* peer_texels(const RenderParams& P, int k, size_t half, int layer)
+{
+    return reinterpret_cast<T*>(reinterpret_cast<char*>(P.peers[k]) + half + P.full_layer[layer]);
 }
 
 // Fused stitch (replaces device_transfer + stitch_shuffled_strips.comp:21-63): the finished pixel
@@ -1066,16 +1081,20 @@ TRD void store_to_peers(const RenderParams& P, float4 o, uint32_t px, uint32_t p
     const size_t dst = (size_t)view * P.frame.size_x * P.frame.size_y + (size_t)py * P.frame.size_x + px;
     if(P.stitch_blend < 1.0f)
     {
-        // stitch_shuffled_strips.comp:50-57: every image holds the same previous content, so all stay identical
+        // stitch_shuffled_strips.comp:50-57: every image holds the same previous content, so all stay identical.
+        // The previous content is read from this rank's own image when it has one (no remote loads).
         for(int k = 0; k < P.peer_count; ++k)
         {
-            const float4 q = P.peers[k][dst];
+            const int from = P.peer_self >= 0 ? P.peer_self : k;
+            const float4 q = peer_texels<float4>(P, from, P.full_prev, TR_GBUFFER_COLOR)[dst];
             const vec4 m = mix_(V4(q.x, q.y, q.z, q.w), V4(o.x, o.y, o.z, o.w), P.stitch_blend);
-            P.peers[k][dst] = make_float4(m.x, m.y, m.z, m.w);
+            peer_texels<float4>(P, k, P.full_cur, TR_GBUFFER_COLOR)[dst] = make_float4(m.x, m.y, m.z, m.w);
         }
         return;
     }
-    for(int k = 0; k < P.peer_count; ++k) P.peers[k][dst] = o;
+    for(int k = 0; k < P.peer_count; ++k)
+        if(k != P.peer_self || peer_texels<float4>(P, k, P.full_cur, TR_GBUFFER_COLOR) != P.color)   // rendered in place already
+            peer_texels<float4>(P, k, P.full_cur, TR_GBUFFER_COLOR)[dst] = o;
 }
 
 } // namespace trd

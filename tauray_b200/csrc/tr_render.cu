@@ -529,6 +529,10 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_finish(const RenderParams P, co
     uint2* const diffuse_layer = reinterpret_cast<uint2*>(P.gbuffer[TR_GBUFFER_DIFFUSE]);
     uint2* const reflection_layer = reinterpret_cast<uint2*>(P.gbuffer[TR_GBUFFER_REFLECTION]);
     const bool light_layers = diffuse_layer || reflection_layer;
+    // the first pass of a frame continues from what the previous frame left (see RenderParams::color_prev)
+    const bool frame_start = P.frame.previous_samples == 0;
+    const uint2* const diffuse_prev = reinterpret_cast<const uint2*>(P.gbuffer_prev[TR_GBUFFER_DIFFUSE]);
+    const uint2* const reflection_prev = reinterpret_cast<const uint2*>(P.gbuffer_prev[TR_GBUFFER_REFLECTION]);
     for(uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < base_slots; slot += stride)
     {
         uint32_t px, py, view, widx;
@@ -579,8 +583,9 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_finish(const RenderParams P, co
             if(light_layers)
             {
                 const uint32_t prev_samples = P.frame.samples_accumulated + P.frame.previous_samples + pass * spp;
-                if(diffuse_layer) accumulate_rgba16f(diffuse_layer, widx, dif, spp, prev_samples);
-                if(reflection_layer) accumulate_rgba16f(reflection_layer, widx, ref, spp, prev_samples);
+                const bool from_prev = frame_start && pass == 0;
+                if(diffuse_layer) accumulate_rgba16f(diffuse_layer, from_prev ? diffuse_prev : diffuse_layer, widx, dif, spp, prev_samples);
+                if(reflection_layer) accumulate_rgba16f(reflection_layer, from_prev ? reflection_prev : reflection_layer, widx, ref, spp, prev_samples);
             }
         }
         if(spp > 1 && sample_in_pass + 1 < spp) continue;
@@ -606,6 +611,13 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_first_sample_layers(const Rende
         get_intersection_info(P, h, V3(o.x, o.y, o.z), V3(d.x, d.y, d.z), hi);
         write_first_sample_layers(P, widx, view, hi);
     }
+}
+
+// where a per-pass kernel reads the running mean of a light layer: the first pass of a frame continues from what the
+// previous frame left (RenderParams::gbuffer_prev), later passes from what this frame wrote
+TRD const uint2* light_layer_prev(const RenderParams& P, int layer)
+{
+    return reinterpret_cast<const uint2*>(P.frame.previous_samples == 0 ? P.gbuffer_prev[layer] : P.gbuffer[layer]);
 }
 
 // ---- megakernel ----------------------------------------------------------------------------------
@@ -669,9 +681,9 @@ __global__ void __launch_bounds__(WF_BLOCK) k_megakernel(const RenderParams P, u
         }
         const float4 o = accumulate(P, sum / (float)spp, alpha, widx);
         if(P.gbuffer[TR_GBUFFER_DIFFUSE])
-            accumulate_rgba16f(reinterpret_cast<uint2*>(P.gbuffer[TR_GBUFFER_DIFFUSE]), widx, sum_d / (float)spp, spp, prev_samples);
+            accumulate_rgba16f(reinterpret_cast<uint2*>(P.gbuffer[TR_GBUFFER_DIFFUSE]), light_layer_prev(P, TR_GBUFFER_DIFFUSE), widx, sum_d / (float)spp, spp, prev_samples);
         if(P.gbuffer[TR_GBUFFER_REFLECTION])
-            accumulate_rgba16f(reinterpret_cast<uint2*>(P.gbuffer[TR_GBUFFER_REFLECTION]), widx, sum_r / (float)spp, spp, prev_samples);
+            accumulate_rgba16f(reinterpret_cast<uint2*>(P.gbuffer[TR_GBUFFER_REFLECTION]), light_layer_prev(P, TR_GBUFFER_REFLECTION), widx, sum_r / (float)spp, spp, prev_samples);
         store_to_peers(P, o, px, py, view);
     }
     flush_counters(P.counters, closest, shadow, paths, st.nodes, st.tris, 0);
@@ -749,9 +761,9 @@ __global__ void __launch_bounds__(WF_BLOCK) k_direct(const RenderParams P, uint3
         const float alpha = P.opt.transparent_background ? hi.mat.albedo.w : 1.0f;
         const float4 o = accumulate(P, color / (float)spp, alpha, widx);
         if(P.gbuffer[TR_GBUFFER_DIFFUSE])
-            accumulate_rgba16f(reinterpret_cast<uint2*>(P.gbuffer[TR_GBUFFER_DIFFUSE]), widx, V4(s.diffuse, a) / (float)spp, spp, prev_samples);
+            accumulate_rgba16f(reinterpret_cast<uint2*>(P.gbuffer[TR_GBUFFER_DIFFUSE]), light_layer_prev(P, TR_GBUFFER_DIFFUSE), widx, V4(s.diffuse, a) / (float)spp, spp, prev_samples);
         if(P.gbuffer[TR_GBUFFER_REFLECTION])
-            accumulate_rgba16f(reinterpret_cast<uint2*>(P.gbuffer[TR_GBUFFER_REFLECTION]), widx, V4(s.reflection, a), spp, prev_samples);
+            accumulate_rgba16f(reinterpret_cast<uint2*>(P.gbuffer[TR_GBUFFER_REFLECTION]), light_layer_prev(P, TR_GBUFFER_REFLECTION), widx, V4(s.reflection, a), spp, prev_samples);
         store_to_peers(P, o, px, py, view);
     }
     flush_counters(P.counters, closest, shadow, paths, st.nodes, st.tris, 0);
@@ -800,6 +812,63 @@ __global__ void __launch_bounds__(WF_BLOCK) k_feature(const RenderParams P, int 
             break;
         }
         P.color[widx] = make_float4(data.x, data.y, data.z, data.w);
+    }
+}
+
+// ---- aux G-buffer layers across devices -----------------------------------------------------------
+// The reference transfers and stitches every gbuffer_target entry, not only the colour (src/rt_renderer.cc:370-397,
+// src/stitch_stage.cc:156-171). Here one kernel at the end of the frame copies this rank's texels of every enabled aux
+// layer to their un-shuffled position in every peer's full-image arena (NVLink stores). The running-mean layers
+// (diffuse / reflection) take the stitch blend like the colour; the layers only the first sample writes are copied as
+// they are. `src[l]` is where this rank's current texels of layer l live, `src_full[l]` says whether that is indexed by
+// full-image pixel (the primary's in-place targets and carried-over arena halves) or by the rank's own write index.
+struct AuxStitchSources
+{
+    const void* src[TR_GBUFFER_LAYER_COUNT];
+    int src_full[TR_GBUFFER_LAYER_COUNT];
+};
+
+template<typename T> TRD void copy_texel_to_peers(const RenderParams& P, int layer, const void* src, size_t src_index, size_t dst)
+{
+    const T v = reinterpret_cast<const T*>(src)[src_index];
+    for(int k = 0; k < P.peer_count; ++k)
+    {
+        T* out = peer_texels<T>(P, k, P.full_cur, layer);
+        if(static_cast<const void*>(out) == src) continue;    // rendered in place
+        out[dst] = v;
+    }
+}
+
+__global__ void __launch_bounds__(WF_BLOCK) k_stitch_aux_layers(const RenderParams P, const AuxStitchSources S, uint32_t base_slots)
+{
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for(uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < base_slots; slot += stride)
+    {
+        uint32_t px, py, view, widx;
+        if(!map_slot(P.frame, slot, px, py, view, widx)) continue;
+        const size_t dst = (size_t)view * P.frame.size_x * P.frame.size_y + (size_t)py * P.frame.size_x + px;
+        for(int l = TR_GBUFFER_DIFFUSE; l <= TR_GBUFFER_REFLECTION; ++l)
+        {
+            if(!S.src[l]) continue;
+            const size_t si = S.src_full[l] ? dst : (size_t)widx;
+            if(P.stitch_blend < 1.0f)
+            {
+                const vec4 v = unpack_rgba16f(reinterpret_cast<const uint2*>(S.src[l])[si]);
+                for(int k = 0; k < P.peer_count; ++k)
+                {
+                    const int from = P.peer_self >= 0 ? P.peer_self : k;
+                    const vec4 old = unpack_rgba16f(peer_texels<uint2>(P, from, P.full_prev, l)[dst]);
+                    peer_texels<uint2>(P, k, P.full_cur, l)[dst] = pack_rgba16f(mix_(old, v, P.stitch_blend));
+                }
+            }
+            else copy_texel_to_peers<uint2>(P, l, S.src[l], si, dst);
+        }
+        if(S.src[TR_GBUFFER_ALBEDO]) copy_texel_to_peers<uint2>(P, TR_GBUFFER_ALBEDO, S.src[TR_GBUFFER_ALBEDO], S.src_full[TR_GBUFFER_ALBEDO] ? dst : (size_t)widx, dst);
+        if(S.src[TR_GBUFFER_MATERIAL]) copy_texel_to_peers<uint32_t>(P, TR_GBUFFER_MATERIAL, S.src[TR_GBUFFER_MATERIAL], S.src_full[TR_GBUFFER_MATERIAL] ? dst : (size_t)widx, dst);
+        if(S.src[TR_GBUFFER_NORMAL]) copy_texel_to_peers<uint32_t>(P, TR_GBUFFER_NORMAL, S.src[TR_GBUFFER_NORMAL], S.src_full[TR_GBUFFER_NORMAL] ? dst : (size_t)widx, dst);
+        if(S.src[TR_GBUFFER_POS]) copy_texel_to_peers<float4>(P, TR_GBUFFER_POS, S.src[TR_GBUFFER_POS], S.src_full[TR_GBUFFER_POS] ? dst : (size_t)widx, dst);
+        if(S.src[TR_GBUFFER_SCREEN_MOTION]) copy_texel_to_peers<float4>(P, TR_GBUFFER_SCREEN_MOTION, S.src[TR_GBUFFER_SCREEN_MOTION], S.src_full[TR_GBUFFER_SCREEN_MOTION] ? dst : (size_t)widx, dst);
+        if(S.src[TR_GBUFFER_INSTANCE_ID]) copy_texel_to_peers<int32_t>(P, TR_GBUFFER_INSTANCE_ID, S.src[TR_GBUFFER_INSTANCE_ID], S.src_full[TR_GBUFFER_INSTANCE_ID] ? dst : (size_t)widx, dst);
     }
 }
 
@@ -1028,6 +1097,24 @@ cudaError_t tr_render_pass_direct(cudaStream_t stream, const RenderParams& P, in
     else k_direct<false><<<grid, WF_BLOCK, 0, stream>>>(P, total);
     if(timer) timer->mark(stream, TR_KCLASS_END);
     ++*launches;
+    return cudaGetLastError();
+}
+
+cudaError_t tr_render_stitch_aux_layers(cudaStream_t stream, const RenderParams& P, const void* const src[TR_GBUFFER_LAYER_COUNT],
+                                        const int src_full[TR_GBUFFER_LAYER_COUNT], int sm_count)
+{
+    const uint32_t base = P.frame.ray_count_x * P.frame.ray_count_y * P.frame.views;
+    if(base == 0 || P.peer_count == 0) return cudaSuccess;
+    AuxStitchSources S;
+    bool any = false;
+    for(int l = 0; l < TR_GBUFFER_LAYER_COUNT; ++l)
+    {
+        S.src[l] = l == TR_GBUFFER_COLOR ? nullptr : src[l];
+        S.src_full[l] = src_full[l];
+        any = any || S.src[l];
+    }
+    if(!any) return cudaSuccess;
+    k_stitch_aux_layers<<<grid_for(sm_count, 16, base), WF_BLOCK, 0, stream>>>(P, S, base);
     return cudaGetLastError();
 }
 

@@ -75,6 +75,9 @@ cudaError_t tr_render_pass_megakernel(cudaStream_t stream, const trd::RenderPara
                                       tr_launch_timer* timer);
 cudaError_t tr_render_pass_direct(cudaStream_t stream, const trd::RenderParams& P, int sm_count, uint64_t* launches,
                                       tr_launch_timer* timer);
+// Copies this rank's texels of the enabled aux G-buffer layers into every peer's full-image arena (end of a frame).
+cudaError_t tr_render_stitch_aux_layers(cudaStream_t stream, const trd::RenderParams& P, const void* const src[],
+                                        const int src_full[], int sm_count);
 cudaError_t tr_render_feature(cudaStream_t stream, const trd::RenderParams& P, int feature, const float default_value[4]);
 cudaError_t tr_render_trace_rays(cudaStream_t stream, const trd::RenderParams& P, const float* rays_dev, uint32_t n, void* hits_dev);
 cudaError_t tr_render_sample_test(cudaStream_t stream, const trd::RenderParams& P, const uint32_t* coords_dev, uint32_t n,

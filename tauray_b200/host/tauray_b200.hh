@@ -377,22 +377,26 @@ public:
             o.distribution = device_params(i);
             stages.emplace_back(new path_tracer_stage(devices[i], scene, cameras, view_count, o));
         }
-        if(devices.size() > 1)
-        {
-            // display device = device 0 (src/context.cc): it renders in place into the display image
-            // (primary distribution); every other stage stores its finished pixels straight into that image
-            // over NVLink (replaces device_transfer + stitch_stage)
-            void* full = nullptr; size_t bytes = 0;
-            check(tr_pt_alloc_full_image(stages[0]->handle(), &full, &bytes), stages[0]->handle(), "tr_pt_alloc_full_image");
-            check(tr_pt_set_color_buffer(stages[0]->handle(), full, bytes), stages[0]->handle(), "tr_pt_set_color_buffer");
-            for(size_t i = 1; i < devices.size(); ++i)
-            {
-                check(tr_pt_enable_peer_access(stages[i]->handle(), devices[0]), stages[i]->handle(), "tr_pt_enable_peer_access");
-                void* peers[1] = {full};
-                check(tr_pt_set_peer_images(stages[i]->handle(), peers, 1), stages[i]->handle(), "tr_pt_set_peer_images");
-            }
-        }
+        connect_display_image();
         accumulated_frames = 0;
+    }
+    // The other gbuffer_target entries (src/gbuffer.hh:18-51): rendered by every stage and gathered into the display
+    // device's image like the colour (src/rt_renderer.cc:370-397). `layer_mask`: bit (1 << TR_GBUFFER_x) per layer.
+    void set_gbuffer_layers(uint32_t layer_mask)
+    {
+        for(auto& s: stages) check(tr_pt_set_gbuffer_layers(s->handle(), layer_mask), s->handle(), "tr_pt_set_gbuffer_layers");
+        connect_display_image();
+    }
+    // one stitched aux layer on the display device, in the layer's texel format
+    std::vector<unsigned char> read_layer(int layer)
+    {
+        if(stages.size() == 1) return stages[0]->read_gbuffer_layer(layer);
+        tr_pt_full_image_info info;
+        check(tr_pt_get_full_image_info(stages[0]->handle(), &info), stages[0]->handle(), "tr_pt_get_full_image_info");
+        static const size_t texel_bytes[TR_GBUFFER_LAYER_COUNT] = {16, 8, 8, 8, 4, 4, 16, 16, 4};
+        std::vector<unsigned char> out((size_t)info.pixels * texel_bytes[layer]);
+        check(tr_pt_read_full_layer(stages[0]->handle(), layer, out.data(), out.size()), stages[0]->handle(), "tr_pt_read_full_layer");
+        return out;
     }
     // renderer::reset_accumulation (src/rt_renderer.cc:67-81)
     void reset_accumulation(bool reset_sample_counter = true)
@@ -451,6 +455,22 @@ public:
     size_t device_count() const { return devices.size(); }
 
 private:
+    void connect_display_image()
+    {
+        if(devices.size() <= 1) return;
+        // display device = device 0 (src/context.cc): it renders in place into the display image
+        // (primary distribution); every other stage stores its finished pixels (colour and aux layers) straight
+        // into that image over NVLink (replaces device_transfer + stitch_stage)
+        void* full = nullptr; size_t bytes = 0;
+        check(tr_pt_alloc_full_image(stages[0]->handle(), &full, &bytes), stages[0]->handle(), "tr_pt_alloc_full_image");
+        check(tr_pt_set_render_in_full_image(stages[0]->handle(), 1), stages[0]->handle(), "tr_pt_set_render_in_full_image");
+        for(size_t i = 1; i < devices.size(); ++i)
+        {
+            check(tr_pt_enable_peer_access(stages[i]->handle(), devices[0]), stages[i]->handle(), "tr_pt_enable_peer_access");
+            void* peers[1] = {full};
+            check(tr_pt_set_peer_images(stages[i]->handle(), peers, 1), stages[i]->handle(), "tr_pt_set_peer_images");
+        }
+    }
     distribution_params device_params(size_t i) const
     {
         if(devices.size() == 1)

@@ -27,6 +27,8 @@ EXPORTS = [
     "tr_pt_set_instrumentation", "tr_pt_read_tri_lights", "tr_pt_read_alias_table", "tr_pt_trace_rays", "tr_pt_sample_test",
     "tr_pt_last_error", "tr_pt_abi_version", "tr_pt_alloc_full_image", "tr_pt_ipc_get_handle",
     "tr_pt_ipc_open_handle", "tr_pt_ipc_close_handle", "tr_pt_set_color_buffer", "tr_pt_read_full_image", "tr_pt_enable_peer_access",
+    "tr_pt_get_full_image_info", "tr_pt_set_stitch_double_buffer", "tr_pt_set_render_in_full_image", "tr_pt_read_full_image_range",
+    "tr_pt_read_full_layer",
 ]
 
 
@@ -79,6 +81,11 @@ def lib():
     l.tr_pt_alloc_full_image.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     l.tr_pt_read_full_image.argtypes = [vp, vp, C.c_size_t]
     l.tr_pt_enable_peer_access.argtypes = [vp, C.c_int]
+    l.tr_pt_get_full_image_info.argtypes = [vp, C.POINTER(abi.FullImageInfo)]
+    l.tr_pt_set_stitch_double_buffer.argtypes = [vp, C.c_int]
+    l.tr_pt_set_render_in_full_image.argtypes = [vp, C.c_int]
+    l.tr_pt_read_full_image_range.argtypes = [vp, vp, C.c_size_t, C.c_size_t]
+    l.tr_pt_read_full_layer.argtypes = [vp, C.c_int, vp, C.c_size_t]
     l.tr_pt_ipc_get_handle.argtypes = [vp, C.c_char_p]
     l.tr_pt_ipc_open_handle.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
     l.tr_pt_ipc_close_handle.argtypes = [vp, vp]
@@ -234,6 +241,28 @@ class PathTracer:
 
     def read_full_image(self, out):
         self._check(self._l.tr_pt_read_full_image(self._ctx, out.ctypes.data, out.nbytes), "tr_pt_read_full_image")
+        return out
+
+    def full_image_info(self):
+        info = abi.FullImageInfo()
+        self._check(self._l.tr_pt_get_full_image_info(self._ctx, C.byref(info)), "tr_pt_get_full_image_info")
+        return info
+
+    def set_stitch_double_buffer(self, enable=True):
+        self._check(self._l.tr_pt_set_stitch_double_buffer(self._ctx, 1 if enable else 0), "tr_pt_set_stitch_double_buffer")
+
+    def set_render_in_full_image(self, enable=True):
+        self._check(self._l.tr_pt_set_render_in_full_image(self._ctx, 1 if enable else 0), "tr_pt_set_render_in_full_image")
+
+    def read_full_image_range(self, host_ptr, byte_offset, nbytes):
+        """D2H of bytes [byte_offset, byte_offset + nbytes) of the stitched colour image to host_ptr."""
+        self._check(self._l.tr_pt_read_full_image_range(self._ctx, host_ptr, byte_offset, nbytes), "tr_pt_read_full_image_range")
+
+    def read_full_layer(self, layer, size, views):
+        """Stitched aux layer as (views, H, W, channels) in the layer's own texel format."""
+        dt, ch = abi.GBUFFER_TEXEL[int(layer)]
+        out = np.zeros((views, size[1], size[0], ch), dtype=dt)
+        self._check(self._l.tr_pt_read_full_layer(self._ctx, int(layer), out.ctypes.data, out.nbytes), "tr_pt_read_full_layer")
         return out
 
     def ipc_get_handle(self):

@@ -8,7 +8,10 @@ samples, and the frame ends with the stitched rgba32f image resident on EVERY ra
   stitch="peer"  (default for world > 1): the tracer's last accumulation pass stores each finished
                  pixel straight into every rank's full image over NVLink peer memory (images
                  exchanged once as CUDA IPC handles) -- render, gather and un-shuffle in one kernel;
-                 the frame is closed by a device-side barrier (a 1-element NCCL all-reduce).
+                 the frame is closed by a device-side barrier (a 1-element NCCL all-reduce). The
+                 full images are double-buffered (frames alternate between two halves), so a fast
+                 rank's next frame never stores into the image a slower rank is still reading; the
+                 enabled aux G-buffer layers are stitched the same way.
   stitch="nccl"  the portable baseline: ncclAllGather of the strips + one un-shuffle kernel per
                  source rank (stitch_shuffled_strips.comp:21-63).
 
@@ -84,6 +87,25 @@ class RtRenderer:
         self._full_ptr = None
         self._peer_ptrs = []
         self._flag = None
+        self._full_key = None
+        self.layers = []
+
+    def set_gbuffer_layers(self, layers):
+        """The other gbuffer_target entries (diffuse, reflection, albedo, ...): rendered by every rank and, for the
+        peer stitch, gathered into every rank's full image like the colour (src/rt_renderer.cc:370-397). Collective."""
+        self.layers = [int(l) for l in layers]
+        self.tracer.set_gbuffer_layers(self.layers)
+        if self.world > 1 and self.views and self.dists is not None:
+            self._alloc_stitch_buffers()
+
+    def layer_image(self, layer):
+        """The stitched aux layer (views, H, W, channels) on the host."""
+        if self.world == 1 or self.stitch == "none":
+            W, H = self.size
+            return self.tracer.read_gbuffer_layer(layer).reshape(self.views, H, W, -1)
+        if self.stitch != "peer":
+            raise NotImplementedError("aux layers are stitched by the peer stitch only")
+        return self.tracer.read_full_layer(layer, self.size, self.views)
 
     # -- reference interface ---------------------------------------------------------------
     def set_scene(self, scene, cameras):
@@ -151,10 +173,12 @@ class RtRenderer:
         my = self.dists[self.rank]
         my_pixels = self.pixels[self.rank]
         in_place = self.rank == self.primary          # the display device renders straight into the stitched image
-        if self.cuda and not in_place:
+        if self.cuda and not in_place and self.stitch == "nccl":
             # strip target: caller-owned torch memory so NCCL can gather straight out of it
             self._strip = torch.zeros((self.views, my_pixels, 4), dtype=torch.float32, device=dev)
             self.tracer.set_color_buffer(self._strip.data_ptr(), self._strip.numel() * 4)
+        elif self.cuda and self.stitch == "peer":
+            self.tracer.set_color_buffer(None, 0)
         if self.stitch == "nccl":
             self._send = torch.zeros((self.views, self.max_count, 4), dtype=torch.float32, device=dev)
             self._gathered = torch.zeros((self.world, self.views, self.max_count, 4), dtype=torch.float32, device=dev)
@@ -166,9 +190,11 @@ class RtRenderer:
         elif self.stitch == "peer":
             import torch.distributed as td
             ptr, nbytes = self.tracer.alloc_full_image()
-            # same size => the library returns the same allocation on every rank: the (collective) handle
-            # exchange is needed only when the size changed
-            if nbytes != getattr(self, "_full_bytes", None):
+            info = self.tracer.full_image_info()
+            # same size and layers => the library keeps its allocation on every rank: the (collective) handle
+            # exchange is needed only when the arena was reallocated
+            if (ptr, info.generation) != self._full_key:
+                self._full_key = (ptr, info.generation)
                 self._full_ptr, self._full_bytes = ptr, nbytes
                 handles = [None] * self.world
                 td.all_gather_object(handles, self.tracer.ipc_get_handle(), group=self.pg)
@@ -184,9 +210,10 @@ class RtRenderer:
                         self._peer_ptrs.append(p)
                         ptrs.append(p)
                 self.tracer.set_peer_images(ptrs)
+                self.tracer.set_stitch_double_buffer(True)
                 self._flag = torch.zeros(1, dtype=torch.float32, device=dev)
-            if in_place:
-                self.tracer.set_color_buffer(ptr, nbytes)
+            # the display device renders in place into its (double-buffered) full image
+            self.tracer.set_render_in_full_image(in_place)
 
     # -- frame -----------------------------------------------------------------------------
     def render(self, stream=None):
@@ -283,6 +310,10 @@ class RtRenderer:
         return self.tracer.read_full_image(out)
 
     def full_image_ptr(self):
+        """Device pointer of the stitched colour image of the last frame."""
+        if self.stitch == "peer" and self.world > 1:
+            info = self.tracer.full_image_info()
+            return info.base + info.current_half * info.half_bytes
         return self._full_ptr
 
     def stats(self):

@@ -22,6 +22,13 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     td.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ok = run_checks(rank, world, local)
+    td.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+def run_checks(rank, world, local):
+    """All multi-GPU checks on an initialised NCCL process group (also behind `bench.py --gpus N --selftest`)."""
     size = (640, 360)
     opt = abi.default_options(max_ray_depth=4, samples_per_pixel=2, local_sampler=abi.SAMPLER_SOBOL_OWEN)
     scene = synthetic.atrium(60000)
@@ -52,6 +59,72 @@ def main():
         same = got.tobytes() == want.tobytes()
         print("rank %d stitch %s workloads %s: %s" % (rank, stitch, workloads, "identical" if same else "DIFFERENT"), flush=True)
         ok = ok and same
+        td.barrier()
+        ren.close()
+    # ---- consecutive frames with different cameras, no barrier between them, odd ranks slow to read back: a fast
+    # rank's frame k+1 must not tear the image a slow rank is still copying out (double-buffered full images)
+    cam_seq = []
+    for k in range(4):
+        ck = cams.copy()
+        ck["current"]["origin"][:, 0] += 0.35 * k
+        ck["current"]["view_inverse"][:, 3, 0] += 0.35 * k    # column-major wire layout: [column][row]
+        cam_seq.append(ck)
+    wants = []
+    with PathTracer(opt, device=local) as single:
+        single.set_scene(scene)
+        single.set_distribution(distribution.make_distribution(
+            size, abi.DISTRIBUTION_SHUFFLED_STRIPS, 0, distribution.calculate_shuffled_strips_pixels_per_device(size, 1.0), True))
+        for ck in cam_seq:
+            single.set_cameras(ck)
+            single.reset_accumulation()
+            single.render()
+            single.sync()
+            wants.append(single.read_color().copy())
+    assert wants[0].tobytes() != wants[1].tobytes()
+    ren = RtRenderer(opt, size, rank=rank, world=world, device=local, stitch="peer")
+    ren.set_scene(scene, cams)
+    same = True
+    for k, ck in enumerate(cam_seq):
+        ren.tracer.set_cameras(ck)
+        ren.reset_accumulation()
+        ren.render(stream.cuda_stream)
+        if rank % 2 == 1:
+            torch.cuda._sleep(400_000_000)          # ~0.2 s on the render stream before this rank reads frame k
+        got = ren.image()
+        same = same and got.tobytes() == wants[k].tobytes()
+    print("rank %d consecutive frames while a peer reads back: %s" % (rank, "identical" if same else "DIFFERENT"), flush=True)
+    ok = ok and same
+    torch.cuda.synchronize(local)
+    td.barrier()
+    ren.close()
+    # ---- aux G-buffer layers across devices (src/rt_renderer.cc:370-397): every rank's stitched layers == one device's
+    layers = [abi.GBUFFER_DIFFUSE, abi.GBUFFER_REFLECTION, abi.GBUFFER_ALBEDO, abi.GBUFFER_MATERIAL, abi.GBUFFER_NORMAL,
+              abi.GBUFFER_POS, abi.GBUFFER_SCREEN_MOTION, abi.GBUFFER_INSTANCE_ID]
+    with PathTracer(opt, device=local) as single:
+        single.set_scene(scene)
+        single.set_cameras(cams)
+        single.set_distribution(distribution.make_distribution(
+            size, abi.DISTRIBUTION_SHUFFLED_STRIPS, 0, distribution.calculate_shuffled_strips_pixels_per_device(size, 1.0), True))
+        single.set_gbuffer_layers(layers)
+        for _ in range(3):
+            single.render()
+        single.sync()
+        want_col = single.read_color().copy()
+        want_layers = {l: single.read_gbuffer_layer(l).copy() for l in layers}
+    for primary in (None, 0):
+        ren = RtRenderer(opt, size, rank=rank, world=world, device=local, stitch="peer", primary=primary, accumulate=True)
+        ren.set_scene(scene, cams)
+        ren.set_gbuffer_layers(layers)
+        for _ in range(3):                       # three accumulated frames: running means + carried-over first-sample layers
+            ren.render(stream.cuda_stream)
+        got_col = ren.image()
+        bad = [] if got_col.tobytes() == want_col.tobytes() else ["color"]
+        for l in layers:
+            if ren.layer_image(l).tobytes() != want_layers[l].tobytes():
+                bad.append(l)
+        print("rank %d aux layers primary %s: %s %s" % (rank, primary, "identical" if not bad else "DIFFERENT", bad), flush=True)
+        ok = ok and not bad
+        torch.cuda.synchronize(local)
         td.barrier()
         ren.close()
     # ---- workload change under accumulation (src/rt_renderer.cc:136-183, stitch_shuffled_strips.comp:50-57)
@@ -92,8 +165,7 @@ def main():
             ok = ok and same
             td.barrier()
             ren.close()
-    td.destroy_process_group()
-    sys.exit(0 if ok else 1)
+    return ok
 
 
 if __name__ == "__main__":

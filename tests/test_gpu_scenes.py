@@ -125,6 +125,87 @@ def test_config3_full_size_properties(atrium_scene):
         assert bits_equal(run(pt, atrium_scene, cams, full_dist(size)), full)
 
 
+def test_config3_full_size_vs_oracle(atrium_scene):
+    """BASELINE configs[2] at its full size -- 1920x1080, 4 spp, 4 bounces, 1.5 M triangles -- against the oracle, bit for
+    bit (8.3 M paths: a few seconds on the GPU box's host cores), ray counts included."""
+    size = (1920, 1080)
+    cams = synthetic.atrium_cameras(16 / 9)
+    opt = bench_opt()
+    o = Oracle(opt)
+    ref = run(o, atrium_scene, cams, full_dist(size))
+    so = o.stats()
+    with PathTracer(opt) as pt:
+        img = run(pt, atrium_scene, cams, full_dist(size))
+        sg = pt.stats()
+    assert assert_parity(img, ref, "atrium 1920x1080 4 spp")
+    assert (sg["closest_rays"], sg["shadow_rays"] + sg["culled_shadow_rays"], sg["paths"]) == (so["closest_rays"], so["shadow_rays"], so["paths"])
+
+
+def test_config4_long_accumulation_vs_oracle(atrium_scene):
+    """BASELINE configs[3]: 4096 spp accumulated as 1024 frames of 4 spp. Against the oracle at 48x27 (5.3 M paths), frame
+    by frame running mean, sample counter running."""
+    size = (48, 27)
+    cams = synthetic.atrium_cameras(16 / 9)
+    opt = bench_opt()
+    frames = 1024
+    ref = run(Oracle(opt), atrium_scene, cams, full_dist(size), frames=frames)
+    with PathTracer(opt) as pt:
+        img = run(pt, atrium_scene, cams, full_dist(size), frames=frames)
+        ck = pt.checkpoint()
+    assert ck["accumulated_samples"] == 4096 and ck["frame_counter"] == frames
+    assert assert_parity(img, ref, "atrium 48x27 4096 spp")
+
+
+def test_config4_full_size_accumulation_resumes_bit_exactly(atrium_scene):
+    """configs[3] at 1920x1080: 64 accumulated frames (256 spp) straight through == 40 frames, checkpoint, a fresh context,
+    restore, 24 more frames; and the running mean converges (frame-to-frame change shrinks)."""
+    size = (1920, 1080)
+    cams = synthetic.atrium_cameras(16 / 9)
+    opt = bench_opt()
+    dist = full_dist(size)
+    with PathTracer(opt) as pt:
+        pt.set_scene(atrium_scene); pt.set_cameras(cams); pt.set_distribution(dist)
+        for _ in range(8):
+            pt.render()
+        pt.sync()
+        at8 = pt.read_color().copy()
+        for _ in range(32):
+            pt.render()
+        pt.sync()
+        ck = pt.checkpoint()
+        at40 = ck["color"]
+        for _ in range(24):
+            pt.render()
+        pt.sync()
+        want = pt.read_color().copy()
+    with PathTracer(opt) as pt:
+        pt.set_scene(atrium_scene); pt.set_cameras(cams); pt.set_distribution(dist)
+        pt.restore(ck)
+        for _ in range(24):
+            pt.render()
+        pt.sync()
+        got = pt.read_color()
+    assert bits_equal(got, want)
+    d1 = np.abs(at40[..., :3] - at8[..., :3]).mean()
+    d2 = np.abs(want[..., :3] - at40[..., :3]).mean()
+    assert d2 < d1 and np.isfinite(want).all()
+
+
+def test_config5_full_size_vs_oracle(atrium_scene):
+    """BASELINE configs[4] at its full size: 5x9 camera grid = 45 views of 960x540, 2 spp, 4 bounces (46.7 M paths: the pass
+    batch is bounded by the 16 Mi-slot budget, the view index enters the sampler key). Bit for bit against the oracle."""
+    size = (960, 540)
+    cams = synthetic.atrium_camera_grid(16 / 9)
+    assert len(cams) == 45
+    opt = bench_opt(samples_per_pixel=2)
+    ref = run(Oracle(opt), atrium_scene, cams, full_dist(size))
+    with PathTracer(opt) as pt:
+        img = run(pt, atrium_scene, cams, full_dist(size))
+    assert img.shape == (45, 540, 960, 4)
+    assert assert_parity(img, ref, "light field 45 x 960x540")
+    assert not bits_equal(img[0], img[44])
+
+
 def test_fused_peer_stitch_on_one_gpu(atrium_scene):
     """tr_pt_set_peer_images: two contexts (two 'ranks') store their strips straight into one full image."""
     size = (640, 360)
