@@ -135,7 +135,9 @@ def test_deep_chain_scene_keeps_the_traversal_stack_in_bounds(shells):
     assert depth + 16 <= 48
     both(opt, scene=scene, cams=cams)
     if shells == 44:
-        assert depth >= 12, "the scene is meant to produce a deep tree (got depth %d)" % depth
+        # 8-wide nodes flatten the chain by ~3 binary levels per node; beyond the Morton grid's resolution the shells
+        # share a cell and split evenly. Deep enough to push sibling + postponed groups past the 8-entry shared stack.
+        assert depth >= 9, "the scene is meant to produce a deep tree (got depth %d)" % depth
 
 
 def test_orthographic_projection():
