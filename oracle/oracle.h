@@ -39,6 +39,11 @@ int orc_unshuffle(orc_ctx* ctx, const float* strip, uint32_t index, uint32_t cou
 /* elementary functions of "TR math", for unit tests: op 0 sin,1 cos,2 atan2(a,b),3 pow(a,b),4 log2,5 exp2,
  * 6 asin, 7 acos */
 int orc_math(int op, const float* a, const float* b, float* out, uint32_t n);
+/* Single-ray closest hit (thread-safe, no alpha test): user = the orc_ctx. The ray caster of the reference-shader
+ * harness (oracle/ref_glsl/ref_api.h: ref_trace_fn). */
+int orc_trace_one(void* user, const float* ray8, void* hit_out);
+/* The restatement's version of function `fn` of the table in oracle/ref_glsl/ref_unit_fn.cc over n packed records. */
+int orc_function(orc_ctx* ctx, int fn, const uint32_t* in, uint32_t* out, uint32_t n);
 const char* orc_last_error(orc_ctx* ctx);
 
 #ifdef __cplusplus

@@ -51,6 +51,8 @@ def lib():
         l.orc_sample_test.argtypes = [vp, vp, C.c_uint32, C.c_int, vp]
         l.orc_unshuffle.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, C.c_float]
         l.orc_math.argtypes = [C.c_int, vp, vp, vp, C.c_uint32]
+        l.orc_function.argtypes = [vp, C.c_int, vp, vp, C.c_uint32]
+        l.orc_trace_one.argtypes = [vp, vp, vp]
         l.orc_last_error.argtypes = [vp]
         l.orc_last_error.restype = C.c_char_p
         _lib = l
@@ -164,6 +166,13 @@ class Oracle:
         coords = np.ascontiguousarray(coords, dtype=np.uint32).reshape(-1, 4)
         out = np.zeros_like(coords)
         self._check(self._l.orc_sample_test(self._ctx, coords.ctypes.data, coords.shape[0], draw_index, out.ctypes.data), "orc_sample_test")
+        return out
+
+    def function(self, fn, records, words_out):
+        """The restatement's version of function `fn` of oracle/ref_glsl/ref_unit_fn.cc's table over packed records."""
+        rec = np.ascontiguousarray(records, dtype=np.uint32)
+        out = np.zeros((rec.shape[0], words_out), dtype=np.uint32)
+        self._check(self._l.orc_function(self._ctx, int(fn), rec.ctypes.data, out.ctypes.data, rec.shape[0]), "orc_function")
         return out
 
     def unshuffle(self, strip, index, count, full_image, blend_ratio=1.0):

@@ -29,8 +29,15 @@ template<typename T, int M, int... I> struct swz
     T d[M];
     static constexpr int K = sizeof...(I);
     using V = vec_t<T, K>;
-    operator V() const { return V(d[I]...); }
-    V get() const { return V(d[I]...); }
+    // GLSL's implicit conversions: int -> uint, int / uint -> float (4.1.10); everything else needs a constructor
+    template<typename U> static constexpr bool implicit_to = (std::is_same<T, int>::value && std::is_same<U, uint32_t>::value) ||
+        (std::is_integral<T>::value && !std::is_same<T, bool>::value && std::is_same<U, float>::value);
+    static constexpr bool is_prefix() { const int idx[K] = {I...}; for(int k = 0; k < K; ++k) if(idx[k] != k) return false; return true; }
+    operator V() const { return get(); }
+    // a swizzle naming the leading components in order is an l-value with V's own layout: usable as an inout argument
+    template<typename Dummy = void, typename = std::enable_if_t<is_prefix(), Dummy>> operator V&() { return *reinterpret_cast<V*>(d); }
+    template<typename U, typename = std::enable_if_t<!std::is_same<U, T>::value>> explicit(!implicit_to<U>) operator vec_t<U, K>() const { return vec_t<U, K>(get()); }
+    V get() const { V v; const int idx[K] = {I...}; for(int k = 0; k < K; ++k) v.d[k] = d[idx[k]]; return v; }
     swz& set(const V& v) { const int idx[K] = {I...}; for(int k = 0; k < K; ++k) d[idx[k]] = v.d[k]; return *this; }
     swz& operator=(const V& v) { return set(v); }
     swz& operator=(const swz& o) { return set(o.get()); }
@@ -45,6 +52,27 @@ template<typename T, int M, int... I> struct swz
     swz& operator/=(T s) { return set(get() / s); }
 };
 
+// GLSL constructors take any mix of scalars and vectors and flatten them, converting every component.
+template<typename T, int N, typename A, typename = std::enable_if_t<std::is_arithmetic<A>::value>>
+inline void glsl_append(T (&d)[N], int& k, A a) { if(k < N) d[k] = T(a); ++k; }
+template<typename T, int N, typename U, int M>
+inline void glsl_append(T (&d)[N], int& k, const vec_t<U, M>& v) { for(int i = 0; i < M; ++i) { if(k < N) d[k] = T(v.d[i]); ++k; } }
+template<typename T, int N, typename U, int M, int... I>
+inline void glsl_append(T (&d)[N], int& k, const swz<U, M, I...>& s) { glsl_append(d, k, s.get()); }
+#define GLSL_CTORS(N) \
+    vec_t() { for(int i = 0; i < N; ++i) d[i] = T(0); } \
+    explicit vec_t(T s) { for(int i = 0; i < N; ++i) d[i] = s; } \
+    vec_t(const vec_t& o) { for(int i = 0; i < N; ++i) d[i] = o.d[i]; } \
+    template<typename U, int M, typename = std::enable_if_t<(M >= N) && !(M == N && std::is_same<U, T>::value)>> \
+    explicit(!(M == N && ((std::is_same<U, int>::value && std::is_same<T, uint32_t>::value) || \
+                          (std::is_integral<U>::value && !std::is_same<U, bool>::value && std::is_same<T, float>::value)))) \
+    vec_t(const vec_t<U, M>& o) { for(int i = 0; i < N; ++i) d[i] = T(o.d[i]); } \
+    template<typename A0, typename A1, typename... Rest> vec_t(const A0& a0, const A1& a1, const Rest&... rest) \
+    { int k = 0; glsl_append(d, k, a0); glsl_append(d, k, a1); (glsl_append(d, k, rest), ...); } \
+    vec_t& operator=(const vec_t& o) { for(int i = 0; i < N; ++i) d[i] = o.d[i]; return *this; } \
+    T& operator[](int i) { return d[i]; } \
+    const T& operator[](int i) const { return d[i]; }
+
 #define GLSL_SWZ2(M, a, b, A, B) swz<T, M, A, B> a##b;
 #define GLSL_SWZ3(M, a, b, c, A, B, C) swz<T, M, A, B, C> a##b##c;
 #define GLSL_SWZ4(M, a, b, c, e, A, B, C, E) swz<T, M, A, B, C, E> a##b##c##e;
@@ -55,19 +83,10 @@ template<typename T> struct vec_t<T, 2>
         T d[2];
         struct { T x, y; };
         struct { T r, g; };
+        GLSL_SWZ2(2, r, g, 0, 1) GLSL_SWZ2(2, g, r, 1, 0)
         GLSL_SWZ2(2, x, x, 0, 0) GLSL_SWZ2(2, x, y, 0, 1) GLSL_SWZ2(2, y, x, 1, 0) GLSL_SWZ2(2, y, y, 1, 1)
     };
-    vec_t() : d{T(0), T(0)} {}
-    explicit vec_t(T s) : d{s, s} {}
-    template<typename A, typename B, typename = std::enable_if_t<std::is_arithmetic<A>::value && std::is_arithmetic<B>::value>>
-    vec_t(A a, B b) : d{T(a), T(b)} {}
-    vec_t(const vec_t& o) : d{o.d[0], o.d[1]} {}
-    template<typename U> explicit vec_t(const vec_t<U, 2>& o) : d{T(o.d[0]), T(o.d[1])} {}
-    template<typename U> explicit vec_t(const vec_t<U, 3>& o) : d{T(o.d[0]), T(o.d[1])} {}
-    template<typename U> explicit vec_t(const vec_t<U, 4>& o) : d{T(o.d[0]), T(o.d[1])} {}
-    vec_t& operator=(const vec_t& o) { d[0] = o.d[0]; d[1] = o.d[1]; return *this; }
-    T& operator[](int i) { return d[i]; }
-    const T& operator[](int i) const { return d[i]; }
+    GLSL_CTORS(2)
 };
 
 template<typename T> struct vec_t<T, 3>
@@ -80,20 +99,9 @@ template<typename T> struct vec_t<T, 3>
         GLSL_SWZ2(3, y, z, 1, 2) GLSL_SWZ2(3, z, y, 2, 1)
         GLSL_SWZ3(3, x, y, z, 0, 1, 2) GLSL_SWZ3(3, y, z, x, 1, 2, 0) GLSL_SWZ3(3, z, x, y, 2, 0, 1)
         GLSL_SWZ3(3, x, z, y, 0, 2, 1) GLSL_SWZ3(3, y, x, z, 1, 0, 2) GLSL_SWZ3(3, z, y, x, 2, 1, 0)
-        GLSL_SWZ3(3, r, g, b, 0, 1, 2)
+        GLSL_SWZ3(3, r, g, b, 0, 1, 2) GLSL_SWZ2(3, r, g, 0, 1) GLSL_SWZ2(3, b, g, 2, 1)
     };
-    vec_t() : d{T(0), T(0), T(0)} {}
-    explicit vec_t(T s) : d{s, s, s} {}
-    template<typename A, typename B, typename C, typename = std::enable_if_t<std::is_arithmetic<A>::value && std::is_arithmetic<B>::value && std::is_arithmetic<C>::value>>
-    vec_t(A a, B b, C c) : d{T(a), T(b), T(c)} {}
-    template<typename C, typename = std::enable_if_t<std::is_arithmetic<C>::value>> vec_t(const vec_t<T, 2>& a, C c) : d{a.d[0], a.d[1], T(c)} {}
-    template<typename A, typename = std::enable_if_t<std::is_arithmetic<A>::value>> vec_t(A a, const vec_t<T, 2>& b) : d{T(a), b.d[0], b.d[1]} {}
-    vec_t(const vec_t& o) : d{o.d[0], o.d[1], o.d[2]} {}
-    template<typename U> explicit vec_t(const vec_t<U, 3>& o) : d{T(o.d[0]), T(o.d[1]), T(o.d[2])} {}
-    template<typename U> explicit vec_t(const vec_t<U, 4>& o) : d{T(o.d[0]), T(o.d[1]), T(o.d[2])} {}
-    vec_t& operator=(const vec_t& o) { d[0] = o.d[0]; d[1] = o.d[1]; d[2] = o.d[2]; return *this; }
-    T& operator[](int i) { return d[i]; }
-    const T& operator[](int i) const { return d[i]; }
+    GLSL_CTORS(3)
 };
 
 template<typename T> struct vec_t<T, 4>
@@ -107,21 +115,9 @@ template<typename T> struct vec_t<T, 4>
         GLSL_SWZ3(4, y, z, x, 1, 2, 0) GLSL_SWZ3(4, z, x, y, 2, 0, 1)
         GLSL_SWZ4(4, x, y, z, w, 0, 1, 2, 3) GLSL_SWZ4(4, y, z, x, y, 1, 2, 0, 1) GLSL_SWZ4(4, w, x, y, z, 3, 0, 1, 2)
         GLSL_SWZ4(4, y, z, w, x, 1, 2, 3, 0) GLSL_SWZ4(4, z, w, x, y, 2, 3, 0, 1)
+        GLSL_SWZ4(4, r, g, b, a, 0, 1, 2, 3) GLSL_SWZ2(4, r, g, 0, 1) GLSL_SWZ2(4, b, g, 2, 1)
     };
-    vec_t() : d{T(0), T(0), T(0), T(0)} {}
-    explicit vec_t(T s) : d{s, s, s, s} {}
-    template<typename A, typename B, typename C, typename D,
-             typename = std::enable_if_t<std::is_arithmetic<A>::value && std::is_arithmetic<B>::value && std::is_arithmetic<C>::value && std::is_arithmetic<D>::value>>
-    vec_t(A a, B b, C c, D e) : d{T(a), T(b), T(c), T(e)} {}
-    template<typename D, typename = std::enable_if_t<std::is_arithmetic<D>::value>> vec_t(const vec_t<T, 3>& a, D e) : d{a.d[0], a.d[1], a.d[2], T(e)} {}
-    template<typename C, typename D, typename = std::enable_if_t<std::is_arithmetic<C>::value && std::is_arithmetic<D>::value>>
-    vec_t(const vec_t<T, 2>& a, C c, D e) : d{a.d[0], a.d[1], T(c), T(e)} {}
-    vec_t(const vec_t<T, 2>& a, const vec_t<T, 2>& b) : d{a.d[0], a.d[1], b.d[0], b.d[1]} {}
-    vec_t(const vec_t& o) : d{o.d[0], o.d[1], o.d[2], o.d[3]} {}
-    template<typename U> explicit vec_t(const vec_t<U, 4>& o) : d{T(o.d[0]), T(o.d[1]), T(o.d[2]), T(o.d[3])} {}
-    vec_t& operator=(const vec_t& o) { d[0] = o.d[0]; d[1] = o.d[1]; d[2] = o.d[2]; d[3] = o.d[3]; return *this; }
-    T& operator[](int i) { return d[i]; }
-    const T& operator[](int i) const { return d[i]; }
+    GLSL_CTORS(4)
 };
 
 using vec2 = vec_t<float, 2>; using vec3 = vec_t<float, 3>; using vec4 = vec_t<float, 4>;
@@ -146,6 +142,23 @@ GLSL_ARITH(ivec2, int, 2) GLSL_ARITH(ivec3, int, 3) GLSL_ARITH(ivec4, int, 4)
 GLSL_ARITH(uvec2, uint, 2) GLSL_ARITH(uvec3, uint, 3) GLSL_ARITH(uvec4, uint, 4)
 GLSL_INTOPS(ivec2, int, 2) GLSL_INTOPS(ivec3, int, 3) GLSL_INTOPS(ivec4, int, 4)
 GLSL_INTOPS(uvec2, uint, 2) GLSL_INTOPS(uvec3, uint, 3) GLSL_INTOPS(uvec4, uint, 4)
+
+// swizzle (op) swizzle of the same component type: the natural vector type (keeps overload resolution unambiguous)
+#define GLSL_SWZ_OP(op) \
+    template<typename T, int M1, int... I, int M2, int... J> \
+    inline auto operator op(const swz<T, M1, I...>& a, const swz<T, M2, J...>& b) { return a.get() op b.get(); } \
+    template<typename T, int M1, int... I> \
+    inline auto operator op(const swz<T, M1, I...>& a, const vec_t<T, (int)sizeof...(I)>& b) { return a.get() op b; } \
+    template<typename T, int M1, int... I> \
+    inline auto operator op(const vec_t<T, (int)sizeof...(I)>& a, const swz<T, M1, I...>& b) { return a op b.get(); }
+GLSL_SWZ_OP(+) GLSL_SWZ_OP(-) GLSL_SWZ_OP(*) GLSL_SWZ_OP(/) GLSL_SWZ_OP(%) GLSL_SWZ_OP(&) GLSL_SWZ_OP(|) GLSL_SWZ_OP(^) GLSL_SWZ_OP(<<) GLSL_SWZ_OP(>>)
+
+#define GLSL_MIXED(FV, IV, N, op) \
+    inline FV operator op(const FV& a, const IV& b) { GLSL_FOR(FV, N, a.d[i] op float(b.d[i])) } \
+    inline FV operator op(const IV& a, const FV& b) { GLSL_FOR(FV, N, float(a.d[i]) op b.d[i]) }
+#define GLSL_MIXED_ALL(FV, IV, N) GLSL_MIXED(FV, IV, N, +) GLSL_MIXED(FV, IV, N, -) GLSL_MIXED(FV, IV, N, *) GLSL_MIXED(FV, IV, N, /)
+GLSL_MIXED_ALL(vec2, ivec2, 2) GLSL_MIXED_ALL(vec3, ivec3, 3) GLSL_MIXED_ALL(vec4, ivec4, 4)
+GLSL_MIXED_ALL(vec2, uvec2, 2) GLSL_MIXED_ALL(vec3, uvec3, 3) GLSL_MIXED_ALL(vec4, uvec4, 4)
 
 // ---- scalar built-ins ----------------------------------------------------------------------------
 template<typename A, typename B> using common_t = std::common_type_t<A, B>;
@@ -250,6 +263,10 @@ GLSL_MAP1(ivec2, ivec2, 2, abs) GLSL_MAP1(ivec3, ivec3, 3, abs) GLSL_MAP1(ivec4,
 GLSL_MAP1(ivec2, ivec2, 2, sign) GLSL_MAP1(ivec3, ivec3, 3, sign) GLSL_MAP1(ivec4, ivec4, 4, sign)
 GLSL_MAP1(uvec2, uvec2, 2, bitfieldReverse) GLSL_MAP1(uvec3, uvec3, 3, bitfieldReverse) GLSL_MAP1(uvec4, uvec4, 4, bitfieldReverse)
 
+#define GLSL_EQ(V, N) \
+    inline bool operator==(const V& a, const V& b) { for(int i = 0; i < N; ++i) if(!(a.d[i] == b.d[i])) return false; return true; } \
+    inline bool operator!=(const V& a, const V& b) { return !(a == b); }
+GLSL_EQ(vec2, 2) GLSL_EQ(vec3, 3) GLSL_EQ(vec4, 4) GLSL_EQ(ivec2, 2) GLSL_EQ(ivec3, 3) GLSL_EQ(ivec4, 4) GLSL_EQ(uvec2, 2) GLSL_EQ(uvec3, 3) GLSL_EQ(uvec4, 4)
 inline bool all(const bvec2& b) { return b.d[0] && b.d[1]; }
 inline bool all(const bvec3& b) { return b.d[0] && b.d[1] && b.d[2]; }
 inline bool all(const bvec4& b) { return b.d[0] && b.d[1] && b.d[2] && b.d[3]; }
@@ -259,12 +276,14 @@ inline bool any(const bvec4& b) { return b.d[0] || b.d[1] || b.d[2] || b.d[3]; }
 inline vec3 cross(const vec3& a, const vec3& b) { return vec3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y); }
 
 // ---- matrices (column-major, m[c] = column c) ---------------------------------------------------------
+struct mat4;
 struct mat3
 {
     vec3 c[3];
     mat3() {}
     mat3(const vec3& a, const vec3& b, const vec3& e) { c[0] = a; c[1] = b; c[2] = e; }
     explicit mat3(float s) { c[0] = vec3(s, 0, 0); c[1] = vec3(0, s, 0); c[2] = vec3(0, 0, s); }
+    explicit inline mat3(const mat4& m);
     vec3& operator[](int i) { return c[i]; }
     const vec3& operator[](int i) const { return c[i]; }
 };
@@ -277,6 +296,8 @@ struct mat4
     vec4& operator[](int i) { return c[i]; }
     const vec4& operator[](int i) const { return c[i]; }
 };
+inline mat3::mat3(const mat4& m) { for(int i = 0; i < 3; ++i) c[i] = vec3(m.c[i].x, m.c[i].y, m.c[i].z); }
+inline float determinant(const mat3& m) { return dot(m.c[0], cross(m.c[1], m.c[2])); }
 inline vec3 operator*(const mat3& m, const vec3& v) { return m.c[0] * v.x + m.c[1] * v.y + m.c[2] * v.z; }
 inline vec3 operator*(const vec3& v, const mat3& m) { return vec3(dot(v, m.c[0]), dot(v, m.c[1]), dot(v, m.c[2])); }
 inline vec4 operator*(const mat4& m, const vec4& v) { return m.c[0] * v.x + m.c[1] * v.y + m.c[2] * v.z + m.c[3] * v.w; }
