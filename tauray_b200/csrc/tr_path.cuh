@@ -46,6 +46,9 @@ struct RenderParams
     // traversal tuning (defaults in tr_render.cu; TR_TUNE_* environment overrides for experiments)
     int tune_fetch_threshold;
     int tune_postpone_div;
+    int tune_tma;               // bit 0: Sobol tables of the shade kernel via TMA, bit 1: top-of-tree nodes in shared memory
+    int tune_coop_groups;       // k_wf_trace_coop: posted triangle groups per warp that start a triangle phase
+    int tune_coop_wait;         // ... or this many lanes out of nodes and waiting for their triangles
 };
 
 // Path state carried from bounce to bounce (evaluate_ray's locals).

@@ -15,6 +15,7 @@
 // registers); it exists as the A/B baseline for the wavefront numbers.
 #include "tr_path.cuh"
 #include "tr_render.h"
+#include "tr_tma.cuh"
 #include <cstdlib>
 #include <vector>
 
@@ -187,18 +188,32 @@ constexpr int MAX_FACTORS = 6;
 enum { COLD_ID = 0, COLD_SX, COLD_SY, COLD_SZ, COLD_KZ, COLD_INST, COLD_PRIM, COLD_U, COLD_V, COLD_FLAGS, COLD_WORDS,
        COLD_NF = COLD_INST, COLD_OVERFLOW = COLD_PRIM };
 
-template<bool ANY, bool STATS>
+// TOPSM: the first TOP_NODES nodes of the breadth-first node array (root, its children, their children) are staged in
+// shared memory with one TMA bulk copy per block and read from there (TR_TUNE_TMA bit 1; measured).
+constexpr int TOP_NODES = 73;
+template<bool ANY, bool STATS, bool TOPSM = false>
 __global__ void __launch_bounds__(WF_BLOCK, ANY ? TRACE_MIN_BLOCKS_SHADOW : TRACE_MIN_BLOCKS_CLOSEST) k_wf_trace(const RenderParams P, const tr_wavefront wf, uint32_t bounce,
                                                         const uint32_t* __restrict__ queue, const uint32_t* __restrict__ count,
                                                         uint32_t* __restrict__ work_counter)
 {
     __shared__ uint2 s_stack[SHORT_STACK * WF_BLOCK];
     __shared__ uint32_t s_cold[COLD_WORDS * WF_BLOCK];
+    __shared__ __align__(128) float4 s_top[TOPSM ? TOP_NODES * TR_BVH_NODE_VEC4 : 1];
+    __shared__ uint64_t s_top_mbar;
     uint2 lstack[TR_BVH_STACK - SHORT_STACK];
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const uint32_t n = *count;
     const float4* __restrict__ nodes = P.scene.bvh.nodes;
+    uint32_t top_count = 0;
+    if(TOPSM)
+    {
+        top_count = P.scene.bvh.node_count < (uint32_t)TOP_NODES ? P.scene.bvh.node_count : (uint32_t)TOP_NODES;
+        if(tid == 0) mbar_init(&s_top_mbar, 1);
+        __syncthreads();
+        if(tid == 0) tma_load_bulk(s_top, nodes, top_count * TR_BVH_NODE_VEC4 * (uint32_t)sizeof(float4), &s_top_mbar);
+        mbar_wait(&s_top_mbar, 0);
+    }
     const float4* __restrict__ tris = P.scene.bvh.tris;
     const bool include_lights = !ANY && !(P.opt.hide_lights && bounce == 0);
     const float ray_tmin = ANY ? P.opt.min_ray_dist : (bounce == 0 ? 0.0f : P.opt.min_ray_dist);
@@ -388,7 +403,8 @@ __global__ void __launch_bounds__(WF_BLOCK, ANY ? TRACE_MIN_BLOCKS_SHADOW : TRAC
                 const uint32_t child = child_of_bit(G, bit, rs.octinv);
                 if(G.y & 0xFF000000u) PUSH(G);
                 if(STATS) st.nodes++;
-                intersect_node8(nodes, child, rs, tmin, best_t, G, Gt);
+                if(TOPSM) intersect_node8_at(child < top_count ? s_top + TR_BVH_NODE_VEC4 * child : nodes + TR_BVH_NODE_VEC4 * (size_t)child, rs, tmin, best_t, G, Gt);
+                else intersect_node8(nodes, child, rs, tmin, best_t, G, Gt);
             }
             else
             {
@@ -465,23 +481,382 @@ __global__ void __launch_bounds__(WF_BLOCK, ANY ? TRACE_MIN_BLOCKS_SHADOW : TRAC
     flush_counters(P.counters, ANY ? 0 : rays, ANY ? rays : 0, 0, st.nodes, st.tris, ANY ? 1 : 0);
 }
 
+// ---- persistent traversal with a warp-cooperative triangle phase --------------------------------------
+// Same rays, same node steps, same predicate and tie-break as k_wf_trace -- the result is identical -- but triangle
+// tests no longer run at the few lanes that happen to have a leaf hit in the current node step (measured: 7-8 of 32
+// lanes, 36 % of the kernel's warp instructions). A lane only POSTS the triangle group of a node step (8 bytes, up to
+// POST_CAP per lane in shared memory). When the warp has posted `tune_coop_groups` groups, or `tune_coop_wait` lanes
+// have run out of nodes and wait for their triangles, or no lane has node work left, the whole warp runs a triangle
+// phase: the posted groups are expanded into (ray lane, triangle) pairs in a per-warp queue and tested 32 at a time by
+// ALL lanes -- lane L tests pair L with the source lane's ray (origin / tmin by shuffle, shear constants from shared
+// memory). Closest hit: the pairs of one ray are reduced with shared-memory atomicMin on the bits of t (positive floats
+// order like integers), then on the instance id and the primitive id among the ties, so the (t, instance, primitive)
+// minimum wins exactly like in the sequential loop. Shadow rays (opaque scenes only): any hit sets the ray's blocked flag.
+constexpr int POST_CAP = 4;
+enum { COOP_COLD_T = COLD_WORDS, COOP_COLD_WORDS };
+
+template<bool ANY, bool STATS>
+__global__ void __launch_bounds__(WF_BLOCK, ANY ? TRACE_MIN_BLOCKS_SHADOW : TRACE_MIN_BLOCKS_CLOSEST) k_wf_trace_coop(const RenderParams P, const tr_wavefront wf, uint32_t bounce,
+                                                        const uint32_t* __restrict__ queue, const uint32_t* __restrict__ count,
+                                                        uint32_t* __restrict__ work_counter)
+{
+    __shared__ uint2 s_stack[SHORT_STACK * WF_BLOCK];
+    __shared__ uint32_t s_cold[COOP_COLD_WORDS * WF_BLOCK];
+    __shared__ uint2 s_post[POST_CAP * WF_BLOCK];
+    __shared__ uint32_t s_pairs[(WF_BLOCK / 32) * 64];
+    uint2 lstack[TR_BVH_STACK - SHORT_STACK];
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int wbase = tid & ~31;
+    uint32_t* const pairs = s_pairs + (tid >> 5) * 64;
+    const uint32_t lanes_below = (1u << lane) - 1u;
+    const uint32_t n = *count;
+    const float4* __restrict__ nodes = P.scene.bvh.nodes;
+    const float4* __restrict__ tris = P.scene.bvh.tris;
+    const bool include_lights = !ANY && !(P.opt.hide_lights && bounce == 0);
+    const float ray_tmin = ANY ? P.opt.min_ray_dist : (bounce == 0 ? 0.0f : P.opt.min_ray_dist);
+    const bool transparency = P.scene.any_non_opaque != 0;
+
+    TraceStats st; st.nodes = 0; st.tris = 0;
+    uint32_t rays = 0;
+    uint2 G = make_uint2(0u, 0u);
+    int sp = 0, npost = 0;
+    bool has_ray = false, exhausted = false, done = true;
+    float tmin = 0.0f, best_t = 0.0f;
+    bool blocked = false;
+    RaySlab rs;
+    rs = make_ray_slab(V3(0), V3(0));
+    int wposted = 0;                       // warp-uniform: groups posted since the last triangle phase
+
+#define COLD(w) s_cold[(w) * WF_BLOCK + tid]
+#define COLDF(w) reinterpret_cast<float*>(s_cold)[(w) * WF_BLOCK + tid]
+#define COLD_OF(w, l) s_cold[(w) * WF_BLOCK + wbase + (l)]
+    uint32_t stack_base = (uint32_t)__cvta_generic_to_shared(&s_stack[tid]);
+    if(ANY) asm volatile("mov.u32 %0, %0;" : "+r"(stack_base));
+#define PUSH(v) do { if(sp < SHORT_STACK) { const uint2 v_ = (v); asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(stack_base + (uint32_t)sp * (uint32_t)(WF_BLOCK * sizeof(uint2))), "r"(v_.x), "r"(v_.y) : "memory"); } \
+                     else lstack[sp - SHORT_STACK] = (v); sp++; } while(0)
+#define POP(dst) do { sp--; if(sp < SHORT_STACK) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(dst.x), "=r"(dst.y) : "r"(stack_base + (uint32_t)sp * (uint32_t)(WF_BLOCK * sizeof(uint2))) : "memory"); \
+                      else dst = lstack[sp - SHORT_STACK]; } while(0)
+
+    // One batch of `m` (<= 32) queued pairs, executed by all 32 lanes.
+    auto test_batch = [&](int m)
+    {
+        __syncwarp();
+        const bool valid = lane < m;
+        const uint32_t e = valid ? pairs[lane] : 0u;
+        const int src = (int)(e >> 27);
+        const uint32_t tri_index = e & 0x07FFFFFFu;
+        RayPre rp;
+        rp.org = V3(__shfl_sync(0xFFFFFFFFu, rs.ox, src), __shfl_sync(0xFFFFFFFFu, rs.oy, src), __shfl_sync(0xFFFFFFFFu, rs.oz, src));
+        const float tmin_s = __shfl_sync(0xFFFFFFFFu, tmin, src);
+        const float tmax_s = ANY ? __shfl_sync(0xFFFFFFFFu, best_t, src) : inf_();
+        rp.kz = (int)COLD_OF(COLD_KZ, src);
+        rp.Sx = __uint_as_float(COLD_OF(COLD_SX, src)); rp.Sy = __uint_as_float(COLD_OF(COLD_SY, src)); rp.Sz = __uint_as_float(COLD_OF(COLD_SZ, src));
+        bool hit = false;
+        float t = 0.0f, u = 0.0f, v = 0.0f;
+        int inst = 0, prim = 0;
+        uint32_t flags = 0u;
+        if(valid && !(ANY && COLD_OF(COLD_FLAGS, src)))
+        {
+            if(STATS) st.tris++;
+            const float4* tp = tris + 3 * (size_t)tri_index;
+            const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+            hit = intersect_triangle(rp, f3(t0), f3(t1), f3(t2), tmin_s, tmax_s, t, u, v);
+            inst = __float_as_int(t0.w); prim = __float_as_int(t1.w); flags = __float_as_uint(t2.w);
+        }
+        if(ANY)
+        {
+            if(hit) COLD_OF(COLD_FLAGS, src) = 1u;              // opaque scenes only: every hit blocks
+            __syncwarp();
+            return;
+        }
+        // (t, instance, primitive) minimum per ray, the old best included
+        const uint32_t old_t = __float_as_uint(best_t);
+        const uint32_t key = __float_as_uint(t);
+        if(hit) atomicMin(&COLD_OF(COOP_COLD_T, src), key);
+        __syncwarp();
+        if(COLD(COOP_COLD_T) != old_t) { COLD(COLD_INST) = 0x7FFFFFFFu; COLD(COLD_PRIM) = 0x7FFFFFFFu; }
+        __syncwarp();
+        const bool cand = hit && key == COLD_OF(COOP_COLD_T, src);
+        const uint32_t inst_before = COLD(COLD_INST);
+        if(cand) atomicMin(&COLD_OF(COLD_INST, src), (uint32_t)inst);
+        __syncwarp();
+        if(COLD(COLD_INST) != inst_before) COLD(COLD_PRIM) = 0x7FFFFFFFu;
+        __syncwarp();
+        const bool cand2 = cand && (uint32_t)inst == COLD_OF(COLD_INST, src);
+        if(cand2) atomicMin(&COLD_OF(COLD_PRIM, src), (uint32_t)prim);
+        __syncwarp();
+        if(cand2 && (uint32_t)prim == COLD_OF(COLD_PRIM, src))
+        {
+            COLD_OF(COLD_U, src) = __float_as_uint(u); COLD_OF(COLD_V, src) = __float_as_uint(v); COLD_OF(COLD_FLAGS, src) = flags;
+        }
+        __syncwarp();
+        best_t = __uint_as_float(COLD(COOP_COLD_T));
+    };
+
+    // The warp-wide triangle phase: expand every posted group into pairs, test them 32 at a time.
+    auto triangle_phase = [&]()
+    {
+        if(!ANY) COLD(COOP_COLD_T) = __float_as_uint(best_t);
+        int qcount = 0;
+        uint2 Gp = make_uint2(0u, 0u);
+        for(;;)
+        {
+            if(!(Gp.y & 0xFFu) && npost > 0) { npost--; Gp = s_post[npost * WF_BLOCK + tid]; }
+            const bool has = (Gp.y & 0xFFu) != 0u;
+            const uint32_t mask = __ballot_sync(0xFFFFFFFFu, has);
+            if(mask == 0u) break;
+            if(has)
+            {
+                const uint32_t tri_index = pop_triangle(Gp, rs.octinv);
+                pairs[qcount + __popc(mask & lanes_below)] = ((uint32_t)lane << 27) | tri_index;
+            }
+            qcount += __popc(mask);
+            if(qcount >= 32)
+            {
+                test_batch(32);
+                const uint32_t keep = (lane < qcount - 32) ? pairs[32 + lane] : 0u;
+                __syncwarp();
+                if(lane < qcount - 32) pairs[lane] = keep;
+                qcount -= 32;
+            }
+        }
+        if(qcount) test_batch(qcount);
+        if(ANY && has_ray && COLD(COLD_FLAGS)) { blocked = true; done = true; sp = 0; G = make_uint2(0u, 0u); }
+    };
+
+    for(;;)
+    {
+        // ---- retire finished rays (no posted triangles left) -----------------------------------------
+        if(has_ray && done && npost == 0)
+        {
+            bool retire = true;
+            const uint32_t id = COLD(COLD_ID);
+            if(!ANY)
+            {
+                const bool found = best_t < inf_();
+                int light_id = -1;
+                float light_t = 0.0f;
+                if(include_lights && P.scene.point_light_count)
+                {
+                    const float4 d = wf.dir_seed[id];
+                    const vec3 org = V3(rs.ox, rs.oy, rs.oz), dir = V3(d.x, d.y, d.z);
+                    for(uint32_t i = 0; i < P.scene.point_light_count; ++i)
+                    {
+                        const tr_point_light& pl = P.scene.point_lights[i];
+                        if(pl.radius == 0.0f) continue;
+                        float t = sphere_intersection(ld3(pl.pos), pl.radius, org, dir);
+                        if(!(t > 0)) continue;
+                        if(!(t >= tmin)) continue;
+                        if(light_id < 0 || t < light_t) { light_id = (int)i; light_t = t; }
+                    }
+                }
+                if(light_id >= 0 && (!found || light_t < best_t))
+                    wf.hits[id] = make_int4(-1, light_id, __float_as_int(light_t), 0);
+                else if(!found)
+                    wf.hits[id] = make_int4(-1, -1, 0, 0);
+                else
+                {
+                    const int b_inst = (int)COLD(COLD_INST), b_prim = (int)COLD(COLD_PRIM);
+                    const float b_u = COLDF(COLD_U), b_v = COLDF(COLD_V);
+                    bool accept = true;
+                    if(transparency && !(COLD(COLD_FLAGS) & TR_TRI_FLAG_OPAQUE))
+                    {
+                        uint32_t seed = __float_as_uint(wf.dir_seed[id].w);
+                        float alpha_cutoff = (float)pcg(seed) * TR_INV_UINT32_MAX;
+                        wf.dir_seed[id].w = __uint_as_float(seed);
+                        if(hit_alpha(P.scene, b_inst, b_prim, b_u, b_v) <= alpha_cutoff) accept = false;
+                    }
+                    if(accept) wf.hits[id] = make_int4(b_inst, b_prim, __float_as_int(b_u), __float_as_int(b_v));
+                    else
+                    {
+                        tmin = best_t;
+                        best_t = inf_();
+                        sp = 0;
+                        G = make_uint2(0u, (0x01000000u << rs.octinv) | 1u);
+                        done = false;
+                        retire = false;
+                    }
+                }
+            }
+            else
+            {
+                const float visibility = blocked ? 0.0f : 1.0f;
+                NeeJob job;
+                load_job(wf, id, (int)bounce, job);
+                PathState s;
+                const float4 e = wf.diffuse[id], f = wf.reflection[id];
+                s.diffuse = V3(e.x, e.y, e.z);
+                s.reflection = V3(f.x, f.y, f.z);
+                nee_finish(P, job, visibility, s);
+                wf.diffuse[id] = make_float4(s.diffuse.x, s.diffuse.y, s.diffuse.z, e.w);
+                wf.reflection[id] = make_float4(s.reflection.x, s.reflection.y, s.reflection.z, 0.0f);
+            }
+            if(retire) has_ray = false;
+        }
+
+        // ---- refill idle lanes: one atomicAdd per warp ----------------------------------------
+        {
+            const bool want = !has_ray && !exhausted;
+            const uint32_t mask = __ballot_sync(0xFFFFFFFFu, want);
+            if(mask)
+            {
+                const int leader = __ffs(mask) - 1;
+                uint32_t base = 0;
+                if(lane == leader) base = atomicAdd(work_counter, (uint32_t)__popc(mask));
+                base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                if(want)
+                {
+                    const uint32_t i = base + __popc(mask & lanes_below);
+                    if(i < n)
+                    {
+                        const uint32_t id = queue[i];
+                        const float4 o = wf.pos_pdf[id];
+                        const vec3 org = V3(o.x, o.y, o.z);
+                        vec3 dir;
+                        if(ANY)
+                        {
+                            const float4 j0 = wf.nee[4 * (size_t)id];
+                            dir = V3(j0.x, j0.y, j0.z);
+                            best_t = j0.w;
+                        }
+                        else
+                        {
+                            const float4 d = wf.dir_seed[id];
+                            dir = V3(d.x, d.y, d.z);
+                            best_t = inf_();
+                        }
+                        tmin = ray_tmin;
+                        const RayPre rp = precompute_ray(org, dir);
+                        COLD(COLD_ID) = id;
+                        COLDF(COLD_SX) = rp.Sx; COLDF(COLD_SY) = rp.Sy; COLDF(COLD_SZ) = rp.Sz; COLD(COLD_KZ) = (uint32_t)rp.kz;
+                        COLD(COLD_FLAGS) = 0u;
+                        if(!ANY) { COLD(COLD_INST) = 0x7FFFFFFFu; COLD(COLD_PRIM) = 0x7FFFFFFFu; }
+                        rs = make_ray_slab(org, dir);
+                        sp = 0;
+                        blocked = false;
+                        has_ray = true;
+                        done = false;
+                        rays++;
+                        G = make_uint2(0u, (0x01000000u << rs.octinv) | 1u);
+                    }
+                    else exhausted = true;
+                }
+            }
+            if(__ballot_sync(0xFFFFFFFFu, has_ray) == 0) break;
+        }
+
+        // ---- traverse: warp-uniform loop, one node step per lane and iteration ------------------------------
+        for(;;)
+        {
+            bool posted = false;
+            if(has_ray && !done)
+            {
+                uint2 Gt = make_uint2(0u, 0u);
+                if(G.y & 0xFF000000u)
+                {
+                    const uint32_t bit = 31u - (uint32_t)__clz((int)G.y);
+                    G.y &= ~(1u << bit);
+                    const uint32_t child = child_of_bit(G, bit, rs.octinv);
+                    if(G.y & 0xFF000000u) PUSH(G);
+                    if(STATS) st.nodes++;
+                    intersect_node8(nodes, child, rs, tmin, best_t, G, Gt);
+                }
+                if(Gt.y & 0xFFu)
+                {
+                    if(npost < POST_CAP) { s_post[npost * WF_BLOCK + tid] = Gt; npost++; posted = true; }
+                    else
+                    {
+                        // the lane's post list is full: test this group right here (rare)
+                        while(Gt.y & 0xFFu)
+                        {
+                            const uint32_t tri_index = pop_triangle(Gt, rs.octinv);
+                            if(STATS) st.tris++;
+                            const float4* tp = tris + 3 * (size_t)tri_index;
+                            const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+                            RayPre rp;
+                            rp.kz = (int)COLD(COLD_KZ); rp.Sx = COLDF(COLD_SX); rp.Sy = COLDF(COLD_SY); rp.Sz = COLDF(COLD_SZ);
+                            rp.org = V3(rs.ox, rs.oy, rs.oz);
+                            float t, u, v;
+                            if(!intersect_triangle(rp, f3(t0), f3(t1), f3(t2), tmin, ANY ? best_t : inf_(), t, u, v)) continue;
+                            if(ANY) { COLD(COLD_FLAGS) = 1u; blocked = true; done = true; sp = 0; G = make_uint2(0u, 0u); break; }
+                            const int inst = __float_as_int(t0.w), prim = __float_as_int(t1.w);
+                            bool better = t < best_t;
+                            if(t == best_t)
+                            {
+                                const int b_inst = (int)COLD(COLD_INST), b_prim = (int)COLD(COLD_PRIM);
+                                better = inst < b_inst || (inst == b_inst && prim < b_prim);
+                            }
+                            if(better)
+                            {
+                                COLD(COLD_INST) = (uint32_t)inst; COLD(COLD_PRIM) = (uint32_t)prim;
+                                COLDF(COLD_U) = u; COLDF(COLD_V) = v; COLD(COLD_FLAGS) = __float_as_uint(t2.w);
+                                best_t = t;
+                            }
+                        }
+                    }
+                }
+                if(!done && (G.y & 0xFF000000u) == 0u)
+                {
+                    if(sp == 0) done = true;
+                    else POP(G);
+                }
+            }
+            wposted += __popc(__ballot_sync(0xFFFFFFFFu, posted));
+            const uint32_t working = __ballot_sync(0xFFFFFFFFu, has_ray && !done);
+            const uint32_t waiting = __ballot_sync(0xFFFFFFFFu, has_ray && done && npost > 0);
+            if(wposted > 0 && (wposted >= P.tune_coop_groups || __popc(waiting) >= P.tune_coop_wait || working == 0u))
+            {
+                triangle_phase();
+                wposted = 0;
+            }
+            // too few lanes left busy: go retire and refill
+            if(__popc(__ballot_sync(0xFFFFFFFFu, has_ray && !(done && npost == 0))) < P.tune_fetch_threshold) break;
+        }
+    }
+#undef PUSH
+#undef POP
+#undef COLD
+#undef COLDF
+#undef COLD_OF
+    flush_counters(P.counters, ANY ? 0 : rays, ANY ? rays : 0, 0, st.nodes, st.tris, ANY ? 1 : 0);
+}
+
 __global__ void __launch_bounds__(WF_BLOCK, SHADE_MIN_BLOCKS) k_wf_shade(const RenderParams P, const tr_wavefront wf, uint32_t bounce, uint32_t sample_in_pass,
                                                         const uint32_t* __restrict__ queue, const uint32_t* __restrict__ count,
                                                         uint32_t* __restrict__ next_queue, uint32_t* __restrict__ next_count,
                                                         uint32_t* __restrict__ shadow_queue, uint32_t* __restrict__ shadow_count)
 {
     // Sobol byte-chunk tables of this bounce's two dimension groups (2b: NEE, 2b+1: BSDF) in shared memory
-    __shared__ uint4 s_chunks[2 * 1024];
+    __shared__ __align__(128) uint4 s_chunks[2 * 1024];
+    __shared__ uint64_t s_mbar;
     SobolTables tables;
     tables.base = P.sobol_chunks;
     tables.first_group = 0;
-    if(P.opt.local_sampler != TR_SAMPLER_UNIFORM_RANDOM && 2 * bounce + 1 < P.frame.max_sobol_bounces)
+    const bool stage_tables = P.opt.local_sampler != TR_SAMPLER_UNIFORM_RANDOM && 2 * bounce + 1 < P.frame.max_sobol_bounces;
+    if(P.tune_tma & 1)
     {
-        for(int k = threadIdx.x; k < 2 * 1024; k += blockDim.x) s_chunks[k] = P.sobol_chunks[(size_t)2 * bounce * 1024 + k];
-        tables.base = s_chunks;
-        tables.first_group = 2 * bounce;
+        // one 32 KB bulk copy through the TMA unit instead of 2048 LDG.128 + STS.128 spread over the block
+        if(threadIdx.x == 0) mbar_init(&s_mbar, 1);
+        __syncthreads();
+        if(stage_tables)
+        {
+            if(threadIdx.x == 0) tma_load_bulk(s_chunks, P.sobol_chunks + (size_t)2 * bounce * 1024, 2 * 1024 * sizeof(uint4), &s_mbar);
+            mbar_wait(&s_mbar, 0);
+            tables.base = s_chunks;
+            tables.first_group = 2 * bounce;
+        }
     }
-    __syncthreads();
+    else
+    {
+        if(stage_tables)
+        {
+            for(int k = threadIdx.x; k < 2 * 1024; k += blockDim.x) s_chunks[k] = P.sobol_chunks[(size_t)2 * bounce * 1024 + k];
+            tables.base = s_chunks;
+            tables.first_group = 2 * bounce;
+        }
+        __syncthreads();
+    }
     const uint32_t n = *count;
     const uint32_t rounded = (n + 31u) & ~31u;
     const uint32_t stride = gridDim.x * blockDim.x;
@@ -984,6 +1359,20 @@ cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const RenderParams& P_
     static const int k_blocks_shadow = env_int("TR_TUNE_BLOCKS_SHADOW", TRACE_MIN_BLOCKS_SHADOW);
     P.tune_fetch_threshold = k_fetch;
     P.tune_postpone_div = k_postpone;
+    // warp-cooperative triangle phase (k_wf_trace_coop): TR_TUNE_COOP bit 0 = closest-hit kernel, bit 1 = shadow kernel.
+    // The pair queue packs the triangle index into 27 bits; the shadow variant needs an all-opaque scene.
+    // TMA staging (tr_tma.cuh): bit 0 = the shade kernel's Sobol chunk tables, bit 1 = the top of the node array in the
+    // traversal kernels
+    static const int k_tma = env_int("TR_TUNE_TMA", 1);
+    P.tune_tma = k_tma;
+    static const int k_coop = env_int("TR_TUNE_COOP", 0);
+    static const int k_coop_groups = env_int("TR_TUNE_COOP_GROUPS", 24);
+    static const int k_coop_wait = env_int("TR_TUNE_COOP_WAIT", 6);
+    P.tune_coop_groups = k_coop_groups;
+    P.tune_coop_wait = k_coop_wait;
+    const bool coop_ok = P.scene.bvh.tri_count < (1u << 27);
+    const bool coop_closest = coop_ok && (k_coop & 1);
+    const bool coop_shadow = coop_ok && (k_coop & 2) && !P.scene.any_non_opaque;
 #define MARK(cls) do { if(timer) timer->mark(stream, cls); } while(0)
     const uint32_t base = P.frame.ray_count_x * P.frame.ray_count_y * P.frame.views;
     if(base == 0) return cudaSuccess;
@@ -1016,7 +1405,13 @@ cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const RenderParams& P_
             uint32_t* q_in = wf.queue[b & 1];
             uint32_t* q_out = wf.queue[(b + 1) & 1];
             MARK(TR_KCLASS_CLOSEST);
-            if(P.stats) k_wf_trace<false, true><<<grid_persist, WF_BLOCK, 0, stream>>>(P, wf, b, q_in, active_counts + b, work_counters + 2 * b);
+            if(coop_closest)
+            {
+                if(P.stats) k_wf_trace_coop<false, true><<<grid_persist, WF_BLOCK, 0, stream>>>(P, wf, b, q_in, active_counts + b, work_counters + 2 * b);
+                else k_wf_trace_coop<false, false><<<grid_persist, WF_BLOCK, 0, stream>>>(P, wf, b, q_in, active_counts + b, work_counters + 2 * b);
+            }
+            else if(P.stats) k_wf_trace<false, true><<<grid_persist, WF_BLOCK, 0, stream>>>(P, wf, b, q_in, active_counts + b, work_counters + 2 * b);
+            else if(P.tune_tma & 2) k_wf_trace<false, false, true><<<grid_persist, WF_BLOCK, 0, stream>>>(P, wf, b, q_in, active_counts + b, work_counters + 2 * b);
             else k_wf_trace<false, false><<<grid_persist, WF_BLOCK, 0, stream>>>(P, wf, b, q_in, active_counts + b, work_counters + 2 * b);
             if(b == 0 && first_sample_layers && i + 1 == spp)
             {
@@ -1047,7 +1442,13 @@ cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const RenderParams& P_
                     if(e2 != cudaSuccess) return e2;
                     ss = overlap->aux;
                 }
-                if(P.stats) k_wf_trace<true, true><<<grid_persist_shadow, WF_BLOCK, 0, ss>>>(P, wf, b, wf.shadow_queue, shadow_counts + b, work_counters + 2 * b + 1);
+                if(coop_shadow)
+                {
+                    if(P.stats) k_wf_trace_coop<true, true><<<grid_persist_shadow, WF_BLOCK, 0, ss>>>(P, wf, b, wf.shadow_queue, shadow_counts + b, work_counters + 2 * b + 1);
+                    else k_wf_trace_coop<true, false><<<grid_persist_shadow, WF_BLOCK, 0, ss>>>(P, wf, b, wf.shadow_queue, shadow_counts + b, work_counters + 2 * b + 1);
+                }
+                else if(P.stats) k_wf_trace<true, true><<<grid_persist_shadow, WF_BLOCK, 0, ss>>>(P, wf, b, wf.shadow_queue, shadow_counts + b, work_counters + 2 * b + 1);
+                else if(P.tune_tma & 2) k_wf_trace<true, false, true><<<grid_persist_shadow, WF_BLOCK, 0, ss>>>(P, wf, b, wf.shadow_queue, shadow_counts + b, work_counters + 2 * b + 1);
                 else k_wf_trace<true, false><<<grid_persist_shadow, WF_BLOCK, 0, ss>>>(P, wf, b, wf.shadow_queue, shadow_counts + b, work_counters + 2 * b + 1);
                 ++*launches;
                 if(two_streams)

@@ -163,15 +163,25 @@ TRD void fma2_bcast(float& d0, float& d1, float a0, float a1, float b, float c)
 // octant, so taking the highest set bit first visits children roughly front to back without sorting.
 // The node stores its inner-child mask already permuted into that order for octants 0..3; octant o >= 4
 // is the bit reversal of octant o ^ 7. Empty slots carry an inverted box and can never be hit.
+TRD void intersect_node8_regs(const float4 n0, const float4 n1, const float4 n2, const float4 n3, const float4 n4, const RaySlab& r,
+                              float tmin, float tmax, uint2& G, uint2& Gt);
+
 TRD void intersect_node8(const float4* __restrict__ nodes, uint32_t node_index, const RaySlab& r,
                          float tmin, float tmax, uint2& G, uint2& Gt)
 {
     const float4* n = nodes + TR_BVH_NODE_VEC4 * (size_t)node_index;
-    const float4 n0 = __ldg(n + 0);
-    const float4 n1 = __ldg(n + 1);
-    const float4 n2 = __ldg(n + 2);
-    const float4 n3 = __ldg(n + 3);
-    const float4 n4 = __ldg(n + 4);
+    intersect_node8_regs(__ldg(n + 0), __ldg(n + 1), __ldg(n + 2), __ldg(n + 3), __ldg(n + 4), r, tmin, tmax, G, Gt);
+}
+
+// The same from a generic pointer: the node may live in shared memory (top of the tree staged by TMA) or in global memory.
+TRD void intersect_node8_at(const float4* n, const RaySlab& r, float tmin, float tmax, uint2& G, uint2& Gt)
+{
+    intersect_node8_regs(n[0], n[1], n[2], n[3], n[4], r, tmin, tmax, G, Gt);
+}
+
+TRD void intersect_node8_regs(const float4 n0, const float4 n1, const float4 n2, const float4 n3, const float4 n4, const RaySlab& r,
+                              float tmin, float tmax, uint2& G, uint2& Gt)
+{
     const uint32_t e = __float_as_uint(n0.w);
     // 128 * 2^e: the exponent byte already includes the factor (tr_bvh.cu writes e + 7)
     const float sx = __uint_as_float((e & 0xFFu) << 23);
