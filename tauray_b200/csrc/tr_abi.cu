@@ -765,6 +765,7 @@ int tr_pt_set_scene(tr_pt_ctx* c, const tr_pt_scene_desc* s)
     memcpy(ds.environment_factor, s->environment_factor, 16);
     ds.environment_proj = s->environment_proj;
     ds.any_non_opaque = any_non_opaque ? 1u : 0u;
+    ds.has_textures = s->texture_count ? 1u : 0u;
     ds.envmap = env_tex;
     ds.alias_table = d_alias;
     c->has_scene = true;

@@ -345,21 +345,21 @@ TRD sampled_material sample_material(const RenderParams& P, const DeviceInstance
     const tr_material& mat = inst.mat;
     sampled_material res;
     res.albedo = V4(mat.albedo_factor[0], mat.albedo_factor[1], mat.albedo_factor[2], mat.albedo_factor[3]);
-    if(mat.albedo_tex_id >= 0)
+    if(P.scene.has_textures && mat.albedo_tex_id >= 0)
     {
         vec4 tex_col = sample_texture(P.scene, mat.albedo_tex_id, v.uv);
         vec3 lin = inverse_srgb_correction(xyz(tex_col));
         res.albedo = res.albedo * V4(lin, tex_col.w);
     }
     vec2 mr = V2(mat.metallic_roughness_factor[0], mat.metallic_roughness_factor[1]);
-    if(mat.metallic_roughness_tex_id >= 0)
+    if(P.scene.has_textures && mat.metallic_roughness_tex_id >= 0)
     {
         vec4 t = sample_texture(P.scene, mat.metallic_roughness_tex_id, v.uv);
         mr = mr * V2(t.z, t.y);
     }
     res.metallic = mr.x;
     res.roughness = mr.y * mr.y;
-    if(mat.normal_tex_id >= 0)
+    if(P.scene.has_textures && mat.normal_tex_id >= 0)
     {
         mat3 tbn;
         tbn.c0 = v.tangent; tbn.c1 = v.bitangent; tbn.c2 = v.smooth_normal;
@@ -369,7 +369,7 @@ TRD sampled_material sample_material(const RenderParams& P, const DeviceInstance
         if(any_nan(v.mapped_normal)) v.mapped_normal = v.smooth_normal;
     }
     res.emission = V3(mat.emission_factor[0], mat.emission_factor[1], mat.emission_factor[2]);
-    if(mat.emission_tex_id >= 0)
+    if(P.scene.has_textures && mat.emission_tex_id >= 0)
         res.emission = res.emission * xyz(sample_texture(P.scene, mat.emission_tex_id, v.uv));
     res.transmittance = mat.transmittance;
     if(v.back_facing && res.transmittance > 0.0001f)

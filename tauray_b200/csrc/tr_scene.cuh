@@ -79,6 +79,7 @@ struct DeviceScene
     float environment_factor[4];
     int32_t environment_proj;
     uint32_t any_non_opaque;
+    uint32_t has_textures;                         // texture_count > 0: otherwise every material texture id is -1
     DeviceTexture envmap;                          // lat-long texels (environment_proj >= 0)
     const tr_alias_table_entry* alias_table;       // envmap.width * envmap.height entries
 };
