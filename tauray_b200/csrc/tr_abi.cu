@@ -562,7 +562,7 @@ static void build_alias_table(std::vector<float>& imp, uint32_t width, uint32_t 
 // model_prev * inverse(model), extract_tri_lights.comp and the BVH (the reference's per-frame
 // scene_stage::record_as_build / record_tri_light_extraction + instance-buffer refresh,
 // src/scene_stage.cc:1572-1675). Used by tr_pt_set_scene and tr_pt_update_instances.
-static int transform_and_build(tr_pt_ctx* c, const tr_instance* instances, uint32_t instance_count)
+static int transform_and_build(tr_pt_ctx* c, const tr_instance* instances, uint32_t instance_count, bool quality_build)
 {
     tr_pt_ctx::Geometry& g = c->geom;
     cudaStream_t st = c->stream;
@@ -601,6 +601,7 @@ static int transform_and_build(tr_pt_ctx* c, const tr_instance* instances, uint3
     tr_build_input bin;
     bin.vertices = g.v_world; bin.indices = g.indices; bin.instances = g.binst.data();
     bin.instance_count = instance_count; bin.triangle_count = (uint32_t)g.triangle_total;
+    bin.quality = quality_build ? 1u : 0u;
     tr_build_output bout;
     TRY_CUDA(c, tr_build_bvh(st, bin, &bout));
     // the new tree is owned from here on, whatever happens next
@@ -754,7 +755,8 @@ int tr_pt_set_scene(tr_pt_ctx* c, const tr_pt_scene_desc* s)
 
     // ---- transforms, tri lights, BVH
     {
-        const int rc = transform_and_build(c, s->instances, s->instance_count);
+        // static upload: the quality (binned SAH) build, like the reference's fast-trace static BLAS
+        const int rc = transform_and_build(c, s->instances, s->instance_count, true);
         if(rc != TR_OK) return rc;
     }
     DeviceScene& ds = c->scene;
@@ -788,7 +790,8 @@ int tr_pt_update_instances(tr_pt_ctx* c, const tr_instance* instances, uint32_t 
     DeviceGuard guard(c->device);
     if(c->last_stream && c->last_stream != c->stream) TRY_CUDA(c, cudaStreamSynchronize(c->last_stream));
     TRY_CUDA(c, cudaStreamSynchronize(c->stream));
-    const int rc = transform_and_build(c, instances, instance_count);
+    // per-frame update: the fast radix-tree rebuild
+    const int rc = transform_and_build(c, instances, instance_count, false);
     if(rc != TR_OK) c->has_scene = false;     // a half-updated scene must not be rendered: the next render fails loudly
     return rc;
 }

@@ -20,6 +20,7 @@ struct tr_build_input
     const tr_build_instance* instances;   // host
     uint32_t instance_count;
     uint32_t triangle_count;
+    uint32_t quality;                     // 1: binned-SAH hierarchy (static scenes), 0: radix tree (per-frame rebuilds)
 };
 
 struct tr_build_output

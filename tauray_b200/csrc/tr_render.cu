@@ -191,7 +191,7 @@ enum { COLD_ID = 0, COLD_SX, COLD_SY, COLD_SZ, COLD_KZ, COLD_INST, COLD_PRIM, CO
 // TOPSM: the first TOP_NODES nodes of the breadth-first node array (root, its children, their children) are staged in
 // shared memory with one TMA bulk copy per block and read from there (TR_TUNE_TMA bit 1; measured).
 constexpr int TOP_NODES = 73;
-template<bool ANY, bool STATS, bool TOPSM = false>
+template<bool ANY, bool STATS, bool TOPSM = false, bool NEAR = false>
 __global__ void __launch_bounds__(WF_BLOCK, ANY ? TRACE_MIN_BLOCKS_SHADOW : TRACE_MIN_BLOCKS_CLOSEST) k_wf_trace(const RenderParams P, const tr_wavefront wf, uint32_t bounce,
                                                         const uint32_t* __restrict__ queue, const uint32_t* __restrict__ count,
                                                         uint32_t* __restrict__ work_counter)
@@ -224,6 +224,7 @@ __global__ void __launch_bounds__(WF_BLOCK, ANY ? TRACE_MIN_BLOCKS_SHADOW : TRAC
 
     // per-lane ray + traversal state held in registers
     uint2 G = make_uint2(0u, 0u), Gt = make_uint2(0u, 0u);
+    uint32_t near_bit = 0u;               // NEAR: hit bit of the nearest inner child of the group just produced
     int sp = 0;
     bool has_ray = false, exhausted = false, done = true;
     // closest: the culling bound = t of the best hit so far, +inf while there is none. shadow: the ray's tmax.
@@ -301,6 +302,7 @@ __global__ void __launch_bounds__(WF_BLOCK, ANY ? TRACE_MIN_BLOCKS_SHADOW : TRAC
                         sp = 0;
                         G = make_uint2(0u, (0x01000000u << rs.octinv) | 1u);   // the root as a one-child group
                         Gt = make_uint2(0u, 0u);
+                        near_bit = 0u;
                         done = false;
                         retire = false;
                     }
@@ -383,6 +385,7 @@ __global__ void __launch_bounds__(WF_BLOCK, ANY ? TRACE_MIN_BLOCKS_SHADOW : TRAC
                         rays++;
                         G = make_uint2(0u, (0x01000000u << rs.octinv) | 1u);   // the root as a one-child group
                         Gt = make_uint2(0u, 0u);
+                        near_bit = 0u;
                     }
                     else exhausted = true;
                 }
@@ -398,12 +401,14 @@ __global__ void __launch_bounds__(WF_BLOCK, ANY ? TRACE_MIN_BLOCKS_SHADOW : TRAC
         {
             if(G.y & 0xFF000000u)
             {
-                const uint32_t bit = 31u - (uint32_t)__clz((int)G.y);
+                uint32_t bit = 31u - (uint32_t)__clz((int)G.y);
+                if(NEAR && near_bit) bit = near_bit;
                 G.y &= ~(1u << bit);
                 const uint32_t child = child_of_bit(G, bit, rs.octinv);
                 if(G.y & 0xFF000000u) PUSH(G);
                 if(STATS) st.nodes++;
                 if(TOPSM) intersect_node8_at(child < top_count ? s_top + TR_BVH_NODE_VEC4 * child : nodes + TR_BVH_NODE_VEC4 * (size_t)child, rs, tmin, best_t, G, Gt);
+                else if(NEAR) intersect_node8_nearest(nodes, child, rs, tmin, best_t, G, Gt, near_bit);
                 else intersect_node8(nodes, child, rs, tmin, best_t, G, Gt);
             }
             else
@@ -468,6 +473,7 @@ __global__ void __launch_bounds__(WF_BLOCK, ANY ? TRACE_MIN_BLOCKS_SHADOW : TRAC
             {
                 if(sp == 0) { done = true; break; }
                 POP(G);
+                if(NEAR) near_bit = 0u;
             }
 
             // too few lanes left busy: go refill
@@ -1384,6 +1390,8 @@ cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const RenderParams& P_
     // traversal kernels
     static const int k_tma = env_int("TR_TUNE_TMA", 1);
     P.tune_tma = k_tma;
+    // closest-hit kernel: descend into the inner child with the smallest entry distance first (TR_TUNE_NEAREST)
+    static const int k_nearest = env_int("TR_TUNE_NEAREST", 0);
     static const int k_coop = env_int("TR_TUNE_COOP", 0);
     static const int k_coop_groups = env_int("TR_TUNE_COOP_GROUPS", 24);
     static const int k_coop_wait = env_int("TR_TUNE_COOP_WAIT", 6);
@@ -1440,6 +1448,7 @@ cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const RenderParams& P_
             }
             else if(P.stats) k_wf_trace<false, true><<<grid_persist, WF_BLOCK, 0, stream>>>(P, wf, b, q_in, active_counts + b, work_counters + 2 * b);
             else if(P.tune_tma & 2) k_wf_trace<false, false, true><<<grid_persist, WF_BLOCK, 0, stream>>>(P, wf, b, q_in, active_counts + b, work_counters + 2 * b);
+            else if(k_nearest) k_wf_trace<false, false, false, true><<<grid_persist, WF_BLOCK, 0, stream>>>(P, wf, b, q_in, active_counts + b, work_counters + 2 * b);
             else k_wf_trace<false, false><<<grid_persist, WF_BLOCK, 0, stream>>>(P, wf, b, q_in, active_counts + b, work_counters + 2 * b);
             if(b == 0 && first_sample_layers && i + 1 == spp)
             {

@@ -179,8 +179,12 @@ TRD void intersect_node8_at(const float4* n, const RaySlab& r, float tmin, float
     intersect_node8_regs(n[0], n[1], n[2], n[3], n[4], r, tmin, tmax, G, Gt);
 }
 
-TRD void intersect_node8_regs(const float4 n0, const float4 n1, const float4 n2, const float4 n3, const float4 n4, const RaySlab& r,
-                              float tmin, float tmax, uint2& G, uint2& Gt)
+// NEAREST: also reports, in `near_bit`, the hit bit (24..31 in G.y) of the INNER child with the smallest entry distance
+// (0 = none): the closest-hit kernel descends into it first and leaves the rest of the group in octant order. The key
+// packs the entry distance (a non-negative float orders like its bits) with the test index in the low 3 bits.
+template<bool NEAREST>
+TRD void intersect_node8_core(const float4 n0, const float4 n1, const float4 n2, const float4 n3, const float4 n4, const RaySlab& r,
+                              float tmin, float tmax, uint2& G, uint2& Gt, uint32_t& near_bit)
 {
     const uint32_t e = __float_as_uint(n0.w);
     // 128 * 2^e: the exponent byte already includes the factor (tr_bvh.cu writes e + 7)
@@ -191,6 +195,7 @@ TRD void intersect_node8_regs(const float4 n0, const float4 n1, const float4 n2,
     const float bx = (n0.x - r.ox) * r.idx - ax, by = (n0.y - r.oy) * r.idy - ay, bz = (n0.z - r.oz) * r.idz - az;
     const uint32_t sel0 = r.sel0, sel1 = sel0 ^ 0x100u, sel2 = sel0 ^ 0x200u, sel3 = sel0 ^ 0x300u;
     uint32_t acc[2] = {0u, 0u};
+    uint32_t near_key[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
 #pragma unroll
     for(int half = 0; half < 2; ++half)
     {
@@ -209,6 +214,7 @@ TRD void intersect_node8_regs(const float4 n0, const float4 n1, const float4 n2,
             const float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));                                   \
             const float cmax = fminf(fminf(tfx, tfy), fminf(tfz, tmax));                                   \
             if(cmin <= cmax) acc[half] |= 1u << K;                                                         \
+            if(NEAREST) near_key[half] = min(near_key[half], cmin <= cmax ? ((__float_as_uint(cmin) & ~3u) | (uint32_t)K) : 0xFFFFFFFFu); \
         }
         TR_CHILD(0, sel0) TR_CHILD(1, sel1) TR_CHILD(2, sel2) TR_CHILD(3, sel3)
 #undef TR_CHILD
@@ -220,8 +226,30 @@ TRD void intersect_node8_regs(const float4 n0, const float4 n1, const float4 n2,
     if(hi_octant) imask_oct = __brev(imask_oct) >> 24;
     G.x = __float_as_uint(n1.x);
     G.y = ((hits & imask_oct) << 24) | (perm_word & 0xFFu);
+    if(NEAREST)
+    {
+        // nearest hit of each half -> its position in `hits`; leaf slots are not descended into, so only an inner child counts
+        const uint32_t p0 = (near_key[0] & 3u) + hi_octant, p1 = (near_key[1] & 3u) + (4u - hi_octant);
+        const bool v0 = near_key[0] != 0xFFFFFFFFu && ((imask_oct >> p0) & 1u), v1 = near_key[1] != 0xFFFFFFFFu && ((imask_oct >> p1) & 1u);
+        const bool first0 = v0 && (!v1 || (near_key[0] & ~3u) <= (near_key[1] & ~3u));
+        near_bit = first0 ? 24u + p0 : (v1 ? 24u + p1 : 0u);
+    }
     Gt.x = __float_as_uint(n1.y);
     Gt.y = (hits & ~imask_oct) | (__float_as_uint(n1.w) << 8);
+}
+
+TRD void intersect_node8_regs(const float4 n0, const float4 n1, const float4 n2, const float4 n3, const float4 n4, const RaySlab& r,
+                              float tmin, float tmax, uint2& G, uint2& Gt)
+{
+    uint32_t unused;
+    intersect_node8_core<false>(n0, n1, n2, n3, n4, r, tmin, tmax, G, Gt, unused);
+}
+
+TRD void intersect_node8_nearest(const float4* __restrict__ nodes, uint32_t node_index, const RaySlab& r,
+                                 float tmin, float tmax, uint2& G, uint2& Gt, uint32_t& near_bit)
+{
+    const float4* n = nodes + TR_BVH_NODE_VEC4 * (size_t)node_index;
+    intersect_node8_core<true>(__ldg(n + 0), __ldg(n + 1), __ldg(n + 2), __ldg(n + 3), __ldg(n + 4), r, tmin, tmax, G, Gt, near_bit);
 }
 
 // Takes the next triangle out of a triangle group: the leaf slot with the highest octant-order hit
