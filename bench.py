@@ -363,6 +363,9 @@ def main():
     torch.cuda.synchronize(local_rank)
     image = ren.image()
     image_sha = sha256_of(image)
+    st_img = ren.stats()
+    img_closest = sum_over_ranks(float(st_img["closest_rays"]))
+    img_shadow_incl_culled = sum_over_ranks(float(st_img["shadow_rays"] + st_img["culled_shadow_rays"]))
     stitch_check = None
     if td is not None:
         shas = [None] * world
@@ -563,7 +566,7 @@ def main():
                   "max_rel": float(rel.max()) if rel.size else 0.0, "tolerance_rel": 1e-5,
                   "pixels": int(got.shape[0] * got.shape[1] * got.shape[2]), "nan_pattern_equal": bool((np.isnan(got) == np.isnan(want)).all()),
                   "ray_counts_equal": bool(views_used != VIEWS or (so["closest_rays"], so["shadow_rays"]) ==
-                                           (int(closest_all), int(rays_all / args.steps - closest_all + culled_all)))}
+                                           (int(img_closest), int(img_shadow_incl_culled)))}
         ora.close()
 
     # animated-scene update (tr_pt_update_instances: world-space vertices, tri lights and the fast radix-tree rebuild), last
