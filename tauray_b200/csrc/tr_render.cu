@@ -910,7 +910,18 @@ __global__ void __launch_bounds__(WF_BLOCK, SHADE_MIN_BLOCKS) k_wf_shade(const R
                 else if(job.needs_shadow_ray) { store_job(wf, id, job); shadow = true; }
                 else nee_finish(P, job, 1.0f, s);
             }
-            store_state(wf, id, s);
+            // only what somebody reads again: the ray and the attenuation if the path goes on or a shadow ray starts from this
+            // hit, the primary lobes once (they are set at bounce 0), the two accumulators always
+            if(alive || shadow)
+            {
+                store_ray(wf, id, s);
+                wf.atten_reg[id] = make_float4(s.attenuation.x, s.attenuation.y, s.attenuation.z, s.regularization);
+            }
+            if(bounce == 0)
+                wf.lobes[id] = make_float4(s.primary_lobes.transmission, s.primary_lobes.diffuse,
+                                           s.primary_lobes.dielectric_reflection, s.primary_lobes.metallic_reflection);
+            wf.diffuse[id] = make_float4(s.diffuse.x, s.diffuse.y, s.diffuse.z, s.aux_alpha);
+            wf.reflection[id] = make_float4(s.reflection.x, s.reflection.y, s.reflection.z, 0.0f);
             if(bounce == 0) store_first_hit(wf, id, s);
             if(P.opt.local_sampler != TR_SAMPLER_SOBOL_OWEN) wf.rs_seed[id] = make_uint4(rs.x, rs.y, rs.z, rs.w);
         }
