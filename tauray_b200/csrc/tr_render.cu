@@ -150,8 +150,8 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_generate(const RenderParams P, 
                 PathState s;
                 uvec4 ss, rs;
                 path_begin(P, px, py, view, sample_in_pass + pass * (uint32_t)P.opt.samples_per_pass, s, ss, rs);
-                store_state(wf, slot, s);
-                store_first_hit(wf, slot, s);
+                // only the ray: the rest of a fresh path's state is constant and k_wf_shade sets it itself at bounce 0
+                store_ray(wf, slot, s);
                 // one 16-byte sampler record per slot: the PCG stream state (uniform-random sampler) or the
                 // constant Sobol-Owen seed (sobol-owen sampler) / Sobol index (sobol-z samplers)
                 if(P.opt.local_sampler != TR_SAMPLER_UNIFORM_RANDOM) wf.rs_seed[slot] = make_uint4(ss.x, ss.y, ss.z, ss.w);
@@ -894,7 +894,18 @@ __global__ void __launch_bounds__(WF_BLOCK, SHADE_MIN_BLOCKS) k_wf_shade(const R
         {
             id = queue[i];
             PathState s;
-            load_state(wf, id, s);
+            if(bounce == 0)
+            {
+                // a fresh path (path_begin): k_wf_generate stores only the ray
+                const float4 a = wf.pos_pdf[id], b = wf.dir_seed[id];
+                s.pos = V3(a.x, a.y, a.z); s.bsdf_pdf = a.w;
+                s.view = V3(b.x, b.y, b.z); s.random_seed = __float_as_uint(b.w);
+                s.attenuation = V3(1); s.regularization = 1.0f;
+                s.primary_lobes = LOBES(0, 0, 0, 1);
+                s.diffuse = V3(0); s.reflection = V3(0); s.aux_alpha = 0.0f;
+                s.fh_emission = V3(0); s.fh_albedo = V4(0, 0, 0, 0); s.fh_metallic = 1.0f;
+            }
+            else load_state(wf, id, s);
             const int4 hr = wf.hits[id];
             Hit h;
             h.instance_id = hr.x; h.primitive_id = hr.y; h.u = __int_as_float(hr.z); h.v = __int_as_float(hr.w); h.t = h.u; h.flags = 0;
