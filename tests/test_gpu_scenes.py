@@ -269,3 +269,20 @@ def test_edge_cases():
         ref = run(Oracle(opt), s, cams, dist)
         with PathTracer(opt) as pt:
             assert assert_parity(run(pt, s, cams, dist), ref, "tiny scene %d" % len(verts))
+
+
+def test_cuda_frames_against_the_reference_pipeline_images():
+    """The CUDA path against frames rendered by the reference's OWN shader code (oracle/_ref: path_tracer.rgen and its
+    hit shaders compiled for the CPU; committed by tools/make_ref_fixtures.py as tests/golden/ref_glsl_images.npz): the
+    chain reference text -> oracle -> CUDA closed on the GPU box. Criterion as in tests/test_ref_glsl.py (a path tracer
+    is chaotic: >= 98.5 % of the pixels within 1e-4 relative, image means within 1e-3)."""
+    import test_ref_glsl as T
+    from ref_compare import compare_images
+    fx = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_glsl_images.npz"))
+    for name in sorted(T.IMAGE_CASES):
+        variant, scene, cams, size, opt = T.image_case(name)
+        with PathTracer(opt) as pt:
+            img = run(pt, scene, cams, distribution.make_distribution(size, abi.DISTRIBUTION_DUPLICATE), frames=2)
+        close, mean_rel = compare_images(fx[name], img, name)
+        min_close, max_mean = T.IMAGE_LIMITS.get(name, T.DEFAULT_LIMITS)
+        assert close >= min_close and mean_rel <= max_mean, (name, close, mean_rel)
