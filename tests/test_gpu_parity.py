@@ -224,10 +224,16 @@ def test_errors_are_reported_not_swallowed():
 
 
 @pytest.mark.parametrize("env", [{"TR_TUNE_BUILDER": "ploc"}, {"TR_TUNE_LEAF": "1"}, {"TR_TUNE_LEAF": "3", "TR_TUNE_BUILDER": "ploc"},
-                                 {"TR_TUNE_FETCH": "32", "TR_TUNE_POSTPONE": "2"}])
+                                 {"TR_TUNE_FETCH": "32", "TR_TUNE_POSTPONE": "2"},
+                                 {"TR_TUNE_BUILDER": "lbvh", "TR_TUNE_BOTTOM": "0"}, {"TR_TUNE_BUILDER": "sah", "TR_TUNE_SAH_AXES": "0"},
+                                 {"TR_TUNE_BUILDER": "sah", "TR_TUNE_SAH_AXES": "2", "TR_TUNE_BOTTOM": "16"},
+                                 {"TR_TUNE_COOP": "3"}, {"TR_TUNE_COOP": "3", "TR_TUNE_COOP_GROUPS": "4", "TR_TUNE_COOP_WAIT": "1"},
+                                 {"TR_TUNE_NEAREST": "1"}, {"TR_TUNE_TMA": "3"}, {"TR_TUNE_TMA": "0", "TR_TUNE_SHADE_SPEC": "0"}])
 def test_image_does_not_depend_on_the_tree_or_the_schedule(env):
-    """The predicate, not the acceleration structure, defines the image: the optional PLOC hierarchy, other leaf sizes
-    and other traversal schedules (refill / postponement thresholds) must all give the oracle's image bit for bit."""
+    """The predicate, not the acceleration structure, defines the image: every hierarchy builder (radix tree, binned SAH
+    with any axis rule, PLOC), other leaf sizes, bottom-node cuts and traversal schedules, and the measured-and-rejected
+    kernel variants that stay in the tree behind TR_TUNE_* (warp-cooperative triangle phase, nearest-first descent, TMA
+    staging of the top of the tree, the unspecialised shade kernel) must all give the oracle's image bit for bit."""
     import os
     import subprocess
     import sys
