@@ -226,7 +226,13 @@ class RtRenderer:
             self.tracer.write_color(self._full.numpy())      # CPU stand-in for "the target is the stitched image"
         self.tracer.render(stream)
         if self.world > 1 and self.stitch != "none":
-            self._stitch(stream, in_place)
+            if self.cuda and stream is not None:
+                # the torch / NCCL work of the stitch goes on the stream the frame was rendered on
+                import torch
+                with torch.cuda.stream(torch.cuda.ExternalStream(stream, device=torch.device("cuda", self.device))):
+                    self._stitch(stream, in_place)
+            else:
+                self._stitch(stream, in_place)
             # "Reset temporary blending from stitching" (src/rt_renderer.cc:126-127)
             if self._blend != 1.0:
                 self._set_blend(1.0)
