@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -56,6 +57,7 @@ struct tr_pt_ctx
         float* matrices = nullptr;           // 32 floats per instance: model, model_normal
         DeviceInstance* d_instances = nullptr;
         tr_tri_light* d_tri_lights = nullptr;
+        float4* shade_tris = nullptr;        // scene allocation: 6 float4 per triangle
         float4* bvh_nodes = nullptr;         // owned here, replaced by every rebuild
         float4* bvh_tris = nullptr;
         std::vector<tr_build_instance> binst;
@@ -578,6 +580,7 @@ static int transform_and_build(tr_pt_ctx* c, const tr_instance* instances, uint3
         d.mat = instances[i].mat;
         d.light_base_id = instances[i].light_base_id;
         d.shadow_terminator_mul = instances[i].shadow_terminator_mul;
+        d.triangle_base = g.binst[i].triangle_base;
     }
     if(instance_count)
     {
@@ -588,6 +591,11 @@ static int transform_and_build(tr_pt_ctx* c, const tr_instance* instances, uint3
     for(uint32_t i = 0; i < instance_count; ++i)
         TRY_CUDA(c, tr_build_pre_transform(st, g.v_raw + g.binst[i].vertex_base, g.v_world + g.binst[i].vertex_base, g.vertex_counts[i],
                                            g.matrices + 32 * (size_t)i, g.matrices + 32 * (size_t)i + 16));
+    // ---- per-triangle shading records
+    if(g.shade_tris)
+        for(uint32_t i = 0; i < instance_count; ++i)
+            TRY_CUDA(c, tr_build_shade_tris(st, g.v_world + g.binst[i].vertex_base, g.indices + g.binst[i].index_base, g.binst[i].triangle_count,
+                                            g.shade_tris + 6 * (size_t)g.binst[i].triangle_base));
     // ---- extract_tri_lights.comp
     if(g.tri_light_count) TRY_CUDA(c, cudaMemsetAsync(g.d_tri_lights, 0, sizeof(tr_tri_light) * g.tri_light_count, st));
     for(uint32_t i = 0; i < instance_count; ++i)
@@ -697,6 +705,10 @@ int tr_pt_set_scene(tr_pt_ctx* c, const tr_pt_scene_desc* s)
     TRY_CUDA(c, dev_alloc(A, &g.d_instances, s->instance_count));
     TRY_CUDA(c, dev_alloc(A, &c->prev_from_world, (size_t)s->instance_count * 16));
     TRY_CUDA(c, dev_alloc(A, &g.d_tri_lights, tri_light_count));
+    {
+        static const bool use_shade_tris = !(getenv("TR_TUNE_SHADE_TRIS") && atoi(getenv("TR_TUNE_SHADE_TRIS")) == 0);
+        if(use_shade_tris) TRY_CUDA(c, dev_alloc(A, &g.shade_tris, 6 * (size_t)ttotal));
+    }
     for(uint32_t i = 0; i < s->instance_count; ++i)
     {
         const tr_mesh_ref& m = s->meshes[i];
@@ -760,7 +772,7 @@ int tr_pt_set_scene(tr_pt_ctx* c, const tr_pt_scene_desc* s)
         if(rc != TR_OK) return rc;
     }
     DeviceScene& ds = c->scene;
-    ds.instances = g.d_instances; ds.vertices = g.v_world; ds.indices = g.indices;
+    ds.instances = g.d_instances; ds.vertices = g.v_world; ds.indices = g.indices; ds.shade_tris = g.shade_tris;
     ds.point_lights = d_pl; ds.directional_lights = d_dl; ds.tri_lights = g.d_tri_lights; ds.textures = d_tex;
     ds.instance_count = s->instance_count; ds.point_light_count = s->point_light_count;
     ds.directional_light_count = s->directional_light_count; ds.tri_light_count = (uint32_t)tri_light_count;

@@ -34,6 +34,8 @@ struct tr_build_output
 
 cudaError_t tr_build_pre_transform(cudaStream_t stream, const tr_vertex* in, tr_vertex* out, uint32_t count,
                                    const float* model_dev, const float* model_normal_dev);
+// 96-byte shading record per triangle (pos, normal, uv of its three world-space vertices), see DeviceScene::shade_tris
+cudaError_t tr_build_shade_tris(cudaStream_t stream, const tr_vertex* verts, const uint32_t* indices, uint32_t triangle_count, float4* out);
 cudaError_t tr_build_extract_tri_lights(cudaStream_t stream, const tr_vertex* verts, const uint32_t* indices,
                                         uint32_t triangle_count, uint32_t instance_id, int32_t light_base_id,
                                         const float emission[3], int32_t emission_tex_id, tr_tri_light* out);

@@ -77,6 +77,22 @@ __global__ void k_extract_tri_lights(const tr_vertex* __restrict__ verts, const 
 }
 
 // ---------------------------------------------------------------------------------------------
+// 2b. per-triangle shading records (DeviceScene::shade_tris)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_shade_tris(const tr_vertex* __restrict__ verts, const uint32_t* __restrict__ indices, uint32_t triangle_count,
+                             float4* __restrict__ out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= triangle_count) return;
+    for(int k = 0; k < 3; ++k)
+    {
+        const float4* v = reinterpret_cast<const float4*>(verts + indices[3 * (size_t)i + k]);
+        out[6 * (size_t)i + 2 * k] = v[0];
+        out[6 * (size_t)i + 2 * k + 1] = v[1];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // 3. gather triangles + scene bounds
 // ---------------------------------------------------------------------------------------------
 // Order-preserving float <-> uint mapping for atomicMin/Max.
@@ -1116,6 +1132,13 @@ cudaError_t tr_build_pre_transform(cudaStream_t stream, const tr_vertex* in, tr_
 {
     if(count == 0) return cudaSuccess;
     k_pre_transform<<<div_up(count, 256), 256, 0, stream>>>(in, out, count, model_dev, model_normal_dev);
+    return cudaGetLastError();
+}
+
+cudaError_t tr_build_shade_tris(cudaStream_t stream, const tr_vertex* verts, const uint32_t* indices, uint32_t triangle_count, float4* out)
+{
+    if(triangle_count == 0) return cudaSuccess;
+    k_shade_tris<<<div_up(triangle_count, 256), 256, 0, stream>>>(verts, indices, triangle_count, out);
     return cudaGetLastError();
 }
 

@@ -260,6 +260,14 @@ struct TriVerts
 
 TRD void fetch_triangle(const DeviceScene& s, const DeviceInstance& inst, int primitive_id, bool want_tangent, TriVerts& tv)
 {
+    if(s.shade_tris && !want_tangent)
+    {
+        const float4* r = s.shade_tris + 6 * ((size_t)inst.triangle_base + (size_t)primitive_id);
+        tv.a0 = __ldg(r); tv.a1 = __ldg(r + 1);
+        tv.b0 = __ldg(r + 2); tv.b1 = __ldg(r + 3);
+        tv.c0 = __ldg(r + 4); tv.c1 = __ldg(r + 5);
+        return;
+    }
     const uint32_t* idx = s.indices + inst.index_base + 3 * (size_t)primitive_id;
     const uint32_t i0 = __ldg(idx), i1 = __ldg(idx + 1), i2 = __ldg(idx + 2);
     const float4* v0 = reinterpret_cast<const float4*>(s.vertices + inst.vertex_base + i0);

@@ -53,7 +53,8 @@ struct DeviceInstance
     uint32_t index_base;
     uint32_t opaque;
     float shadow_terminator_mul;
-    uint32_t pad[3];
+    uint32_t triangle_base;   // first record of the instance in DeviceScene::shade_tris
+    uint32_t pad[2];
 };                            // 112 B
 
 struct DeviceTexture
@@ -68,6 +69,10 @@ struct DeviceScene
     const DeviceInstance* instances;
     const tr_vertex* vertices;      // world space (pre_transform.comp)
     const uint32_t* indices;
+    // Per-triangle shading records, 6 float4 = 96 B: for each of the three vertices (pos.xyz, normal.x) (normal.yz, uv.xy)
+    // -- the first 32 bytes of the world-space tr_vertex, gathered through the index buffer once per scene (update), so
+    // that shading a hit is ONE contiguous 96-byte fetch instead of indices -> three scattered vertices.
+    const float4* shade_tris;
     const tr_point_light* point_lights;
     const tr_directional_light* directional_lights;
     const tr_tri_light* tri_lights;
