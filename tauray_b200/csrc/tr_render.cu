@@ -22,6 +22,9 @@
 namespace trd {
 
 constexpr int WF_BLOCK = 128;
+#ifndef TRACE_BLOCK
+#define TRACE_BLOCK 128          // threads per block of the persistent traversal kernel (64: measured)
+#endif
 #ifndef TRACE_MIN_BLOCKS_CLOSEST
 #define TRACE_MIN_BLOCKS_CLOSEST 9
 #endif
@@ -192,12 +195,12 @@ enum { COLD_ID = 0, COLD_SX, COLD_SY, COLD_SZ, COLD_KZ, COLD_INST, COLD_PRIM, CO
 // shared memory with one TMA bulk copy per block and read from there (TR_TUNE_TMA bit 1; measured).
 constexpr int TOP_NODES = 73;
 template<bool ANY, bool STATS, bool TOPSM = false, bool NEAR = false>
-__global__ void __launch_bounds__(WF_BLOCK, ANY ? TRACE_MIN_BLOCKS_SHADOW : TRACE_MIN_BLOCKS_CLOSEST) k_wf_trace(const RenderParams P, const tr_wavefront wf, uint32_t bounce,
+__global__ void __launch_bounds__(TRACE_BLOCK, ANY ? TRACE_MIN_BLOCKS_SHADOW : TRACE_MIN_BLOCKS_CLOSEST) k_wf_trace(const RenderParams P, const tr_wavefront wf, uint32_t bounce,
                                                         const uint32_t* __restrict__ queue, const uint32_t* __restrict__ count,
                                                         uint32_t* __restrict__ work_counter)
 {
-    __shared__ uint2 s_stack[SHORT_STACK * WF_BLOCK];
-    __shared__ uint32_t s_cold[COLD_WORDS * WF_BLOCK];
+    __shared__ uint2 s_stack[SHORT_STACK * TRACE_BLOCK];
+    __shared__ uint32_t s_cold[COLD_WORDS * TRACE_BLOCK];
     __shared__ __align__(128) float4 s_top[TOPSM ? TOP_NODES * TR_BVH_NODE_VEC4 : 1];
     __shared__ uint64_t s_top_mbar;
     uint2 lstack[TR_BVH_STACK - SHORT_STACK];
@@ -236,17 +239,17 @@ __global__ void __launch_bounds__(WF_BLOCK, ANY ? TRACE_MIN_BLOCKS_SHADOW : TRAC
     float ft[MAX_FACTORS], ff[MAX_FACTORS];
     int fi[MAX_FACTORS], fp[MAX_FACTORS];
 
-#define COLD(w) s_cold[(w) * WF_BLOCK + tid]
-#define COLDF(w) reinterpret_cast<float*>(s_cold)[(w) * WF_BLOCK + tid]
+#define COLD(w) s_cold[(w) * TRACE_BLOCK + tid]
+#define COLDF(w) reinterpret_cast<float*>(s_cold)[(w) * TRACE_BLOCK + tid]
     // The thread's column of the shared-memory stack as a 32-bit shared address, accessed with explicit ld/st.shared:
     // the generic-pointer form cost an address rebuild from two special-register reads (S2R) plus spills on every push
     // and pop. In the shadow kernel the value is made opaque so that it stays in a register (measured: shadow 5.67 ->
     // 5.44 ms); the closest-hit kernel is better off letting the compiler rematerialise it (11.50 -> 11.26 ms).
     uint32_t stack_base = (uint32_t)__cvta_generic_to_shared(&s_stack[tid]);
     if(ANY) asm volatile("mov.u32 %0, %0;" : "+r"(stack_base));
-#define PUSH(v) do { if(sp < SHORT_STACK) { const uint2 v_ = (v); asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(stack_base + (uint32_t)sp * (uint32_t)(WF_BLOCK * sizeof(uint2))), "r"(v_.x), "r"(v_.y) : "memory"); } \
+#define PUSH(v) do { if(sp < SHORT_STACK) { const uint2 v_ = (v); asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(stack_base + (uint32_t)sp * (uint32_t)(TRACE_BLOCK * sizeof(uint2))), "r"(v_.x), "r"(v_.y) : "memory"); } \
                      else lstack[sp - SHORT_STACK] = (v); sp++; } while(0)
-#define POP(dst) do { sp--; if(sp < SHORT_STACK) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(dst.x), "=r"(dst.y) : "r"(stack_base + (uint32_t)sp * (uint32_t)(WF_BLOCK * sizeof(uint2))) : "memory"); \
+#define POP(dst) do { sp--; if(sp < SHORT_STACK) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(dst.x), "=r"(dst.y) : "r"(stack_base + (uint32_t)sp * (uint32_t)(TRACE_BLOCK * sizeof(uint2))) : "memory"); \
                       else dst = lstack[sp - SHORT_STACK]; } while(0)
 
     for(;;)
@@ -1468,10 +1471,10 @@ cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const RenderParams& P_
                 if(P.stats) k_wf_trace_coop<false, true><<<grid_persist, WF_BLOCK, 0, stream>>>(P, wf, b, q_in, active_counts + b, work_counters + 2 * b);
                 else k_wf_trace_coop<false, false><<<grid_persist, WF_BLOCK, 0, stream>>>(P, wf, b, q_in, active_counts + b, work_counters + 2 * b);
             }
-            else if(P.stats) k_wf_trace<false, true><<<grid_persist, WF_BLOCK, 0, stream>>>(P, wf, b, q_in, active_counts + b, work_counters + 2 * b);
-            else if(P.tune_tma & 2) k_wf_trace<false, false, true><<<grid_persist, WF_BLOCK, 0, stream>>>(P, wf, b, q_in, active_counts + b, work_counters + 2 * b);
-            else if(k_nearest) k_wf_trace<false, false, false, true><<<grid_persist, WF_BLOCK, 0, stream>>>(P, wf, b, q_in, active_counts + b, work_counters + 2 * b);
-            else k_wf_trace<false, false><<<grid_persist, WF_BLOCK, 0, stream>>>(P, wf, b, q_in, active_counts + b, work_counters + 2 * b);
+            else if(P.stats) k_wf_trace<false, true><<<grid_persist, TRACE_BLOCK, 0, stream>>>(P, wf, b, q_in, active_counts + b, work_counters + 2 * b);
+            else if(P.tune_tma & 2) k_wf_trace<false, false, true><<<grid_persist, TRACE_BLOCK, 0, stream>>>(P, wf, b, q_in, active_counts + b, work_counters + 2 * b);
+            else if(k_nearest) k_wf_trace<false, false, false, true><<<grid_persist, TRACE_BLOCK, 0, stream>>>(P, wf, b, q_in, active_counts + b, work_counters + 2 * b);
+            else k_wf_trace<false, false><<<grid_persist, TRACE_BLOCK, 0, stream>>>(P, wf, b, q_in, active_counts + b, work_counters + 2 * b);
             if(b == 0 && first_sample_layers && i + 1 == spp)
             {
                 MARK(TR_KCLASS_OTHER);
@@ -1508,9 +1511,9 @@ cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const RenderParams& P_
                     if(P.stats) k_wf_trace_coop<true, true><<<grid_persist_shadow, WF_BLOCK, 0, ss>>>(P, wf, b, wf.shadow_queue, shadow_counts + b, work_counters + 2 * b + 1);
                     else k_wf_trace_coop<true, false><<<grid_persist_shadow, WF_BLOCK, 0, ss>>>(P, wf, b, wf.shadow_queue, shadow_counts + b, work_counters + 2 * b + 1);
                 }
-                else if(P.stats) k_wf_trace<true, true><<<grid_persist_shadow, WF_BLOCK, 0, ss>>>(P, wf, b, wf.shadow_queue, shadow_counts + b, work_counters + 2 * b + 1);
-                else if(P.tune_tma & 2) k_wf_trace<true, false, true><<<grid_persist_shadow, WF_BLOCK, 0, ss>>>(P, wf, b, wf.shadow_queue, shadow_counts + b, work_counters + 2 * b + 1);
-                else k_wf_trace<true, false><<<grid_persist_shadow, WF_BLOCK, 0, ss>>>(P, wf, b, wf.shadow_queue, shadow_counts + b, work_counters + 2 * b + 1);
+                else if(P.stats) k_wf_trace<true, true><<<grid_persist_shadow, TRACE_BLOCK, 0, ss>>>(P, wf, b, wf.shadow_queue, shadow_counts + b, work_counters + 2 * b + 1);
+                else if(P.tune_tma & 2) k_wf_trace<true, false, true><<<grid_persist_shadow, TRACE_BLOCK, 0, ss>>>(P, wf, b, wf.shadow_queue, shadow_counts + b, work_counters + 2 * b + 1);
+                else k_wf_trace<true, false><<<grid_persist_shadow, TRACE_BLOCK, 0, ss>>>(P, wf, b, wf.shadow_queue, shadow_counts + b, work_counters + 2 * b + 1);
                 ++*launches;
                 if(two_streams)
                 {

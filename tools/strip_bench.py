@@ -10,8 +10,9 @@ import bench
 
 world = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 frames = int(sys.argv[2]) if len(sys.argv) > 2 else 10
-size = (bench.WIDTH, bench.HEIGHT)
-opt = bench.bench_options(abi)
+_, W, H, SPP, _, _ = bench.CONFIGS["c3"]
+size = (W, H)
+opt = bench.bench_options(abi, SPP)
 scene = synthetic.atrium(bench.TRIANGLES)
 cams = synthetic.atrium_cameras(size[0] / size[1])
 dists = distribution.device_distributions(size, abi.DISTRIBUTION_SHUFFLED_STRIPS, [1.0 / world] * world)
