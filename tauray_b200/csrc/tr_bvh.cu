@@ -1296,9 +1296,9 @@ cudaError_t tr_build_bvh(cudaStream_t stream, const tr_build_input& in, tr_build
         while(task_count > 0)
         {
             CUDA_OK2(cudaMemsetAsync(next_count, 0, sizeof(int), stream));
-            // beyond 64 levels only median splits: bounds the depth of pathological inputs
+            // beyond 48 levels only median splits: bounds the depth of pathological inputs (<= 48 + log2(n) binary levels)
             k_sah_level<<<task_count, SAH_BLOCK, 0, stream>>>(tasks_a, task_count, boxes, perm_a, perm_b, perm_final, children, counts, inner_boxes,
-                                                             tasks_b, next_count, node_counter, level >= 64 ? 1 : 0, sah_axis_mode, level, sah_axis_penalty);
+                                                             tasks_b, next_count, node_counter, level >= 48 ? 1 : 0, sah_axis_mode, level, sah_axis_penalty);
             CUDA_OK2(cudaMemcpyAsync(&task_count, next_count, sizeof(int), cudaMemcpyDeviceToHost, stream));
             CUDA_OK2(cudaStreamSynchronize(stream));
             std::swap(tasks_a, tasks_b);
