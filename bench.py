@@ -415,8 +415,26 @@ def main():
     else:
         img_host = torch.empty((VIEWS, HEIGHT, WIDTH, 4), dtype=torch.float32).pin_memory()
 
+    # N = 1, frames that start from a clean accumulation: two frames in flight like the reference's headless loop
+    # (MAX_FRAMES_IN_FLIGHT = 2) -- the frame renders into one of two device targets (tr_pt_set_color_buffer) and its
+    # staging copy (tr_pt_read_color_async, on a copy stream, into one of two pinned host images) runs beside the next
+    # frame. Every step's camera upload and image read-back are inside the timed region; the host images are checked.
+    pipelined = world == 1 and reset_each_step
+    if pipelined:
+        targets = [torch.empty((VIEWS, HEIGHT, WIDTH, 4), dtype=torch.float32, device="cuda") for _ in range(2)]
+        hosts = [torch.empty((VIEWS, HEIGHT, WIDTH, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
+        copy_stream = torch.cuda.Stream(device=local_rank)
+        e2e_count = [0]
+
     def e2e_step():
         ren.tracer.set_cameras(cam_np)                      # H2D (pinned)
+        if pipelined:
+            b = e2e_count[0] & 1
+            e2e_count[0] += 1
+            ren.tracer.set_color_buffer(targets[b].data_ptr(), targets[b].numel() * 4)
+            frame()
+            ren.tracer.read_color_async(hosts[b].data_ptr(), hosts[b].numel() * 4, copy_stream.cuda_stream)   # D2H (pinned), no host sync
+            return
         frame()
         if world == 1:
             ren.tracer.read_color_into(img_np.ctypes.data, img_np.nbytes)   # D2H (pinned) + sync
@@ -431,12 +449,16 @@ def main():
     t0 = time.perf_counter()
     for _ in range(args.steps):
         e2e_step()
-    barrier()
+    barrier()                                               # synchronises the device: the last staging copy included
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = rays_all / e2e_s / 1e6
     h2d = cam_host.numel() * world
     d2h = img_bytes
     e2e_image_ok = None
+    if pipelined:
+        # both host images hold a finished frame of the checked camera, rendered from a clean accumulation
+        e2e_image_ok = all(sha256_of(h.numpy()) == image_sha for h in hosts)
+        ren.tracer.set_color_buffer(None, 0)
     if shared is not None:
         # one more frame from a clean accumulation so that the shared host image must equal the checked one
         ren.reset_accumulation()
@@ -614,7 +636,8 @@ def main():
             "stitch_compare": stitch_compare,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_s / args.steps * 1e3,
-                    "readback": "one pinned host image" if world == 1 else
+                    "readback": ("two frames in flight: two device targets, staging copies on a copy stream into two pinned host images (tr_pt_read_color_async)"
+                                 if pipelined else "one pinned host image") if world == 1 else
                                 ("every rank copies its 1/N byte range into one shared pinned host image%s" % ("" if pinned else " (NOT pinned: cudaHostRegister failed)")
                                  if ren.stitch == "peer" else "rank 0 copies the stitched image"),
                     "host_image_equal": e2e_image_ok},

@@ -368,6 +368,13 @@ int tr_pt_get_color_buffer(tr_pt_ctx* ctx, void** device_ptr, size_t* bytes);
 /* == headless staging copy (src/headless.cc:125-171): D2H of the colour target. */
 int tr_pt_read_color(tr_pt_ctx* ctx, float* rgba32f_host, size_t bytes);
 
+/* The same without blocking the host, for frames in flight (the reference keeps MAX_FRAMES_IN_FLIGHT = 2 staging
+ * copies going, src/headless.cc:125-171 + src/context.hh): the copy is enqueued on `copy_stream` (a cudaStream_t of the
+ * caller, not the render stream), ordered after the frame rendered last; `rgba32f_host` (pinned memory) is valid once
+ * `copy_stream` has reached that point. A later tr_pt_render that writes the SAME colour target waits for the copy on
+ * the device; one that renders into another target (tr_pt_set_color_buffer with a second buffer) runs beside it. */
+int tr_pt_read_color_async(tr_pt_ctx* ctx, float* rgba32f_host, size_t bytes, void* copy_stream);
+
 /* Accumulation checkpoint / resume. The reference has none for accumulation state (animation renders
  * resume per frame with --skip-frames, src/options.hh:116-119); SURVEY.md section 8(f) lists the
  * dump/reload of the fp32 accumulation buffer + counters as the natural addition for long

@@ -27,6 +27,10 @@ struct tr_pt_ctx
     cudaStream_t stream = nullptr;
     cudaStream_t last_stream = nullptr;   // stream of the last render (may be the caller's)
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    // tr_pt_read_color_async: copies still reading a colour target (a render into the same target waits for them)
+    struct PendingCopy { const void* src = nullptr; cudaEvent_t done = nullptr; };
+    PendingCopy pending_copies[4];
+    int pending_next = 0;
     tr_overlap overlap{};                 // second stream for the shadow traversal (tr_render.h)
     tr_pt_options opt{};
     std::string error;
@@ -467,6 +471,7 @@ void tr_pt_destroy(tr_pt_ctx* c)
     if(c->full_image) cudaFree(c->full_image);
     if(c->timer) { c->timer->destroy(); delete c->timer; }
     if(c->counters) cudaFree(c->counters);
+    for(auto& pc : c->pending_copies) if(pc.done) cudaEventDestroy(pc.done);
     if(c->ev_begin) cudaEventDestroy(c->ev_begin);
     if(c->ev_end) cudaEventDestroy(c->ev_end);
     if(c->overlap.shaded) cudaEventDestroy(c->overlap.shaded);
@@ -861,6 +866,9 @@ int tr_pt_render(tr_pt_ctx* c, void* cuda_stream)
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
     if(st != c->stream) TRY_CUDA(c, cudaStreamSynchronize(c->stream));
     TRY_CUDA(c, wait_last_stream(c, st));
+    // asynchronous read-backs (tr_pt_read_color_async) of the target this frame writes finish first, on the device
+    for(auto& pc : c->pending_copies)
+        if(pc.src && pc.src == c->color) { TRY_CUDA(c, cudaStreamWaitEvent(st, pc.done, 0)); pc.src = nullptr; }
     RenderParams P;
     fill_params(c, P);
     rc = select_full_image_half(c, P);
@@ -969,6 +977,25 @@ int tr_pt_read_color(tr_pt_ctx* c, float* out, size_t bytes)
     cudaStream_t st = c->last_stream ? c->last_stream : c->stream;
     TRY_CUDA(c, cudaMemcpyAsync(out, c->color, bytes, cudaMemcpyDeviceToHost, st));
     TRY_CUDA(c, cudaStreamSynchronize(st));
+    return TR_OK;
+}
+
+int tr_pt_read_color_async(tr_pt_ctx* c, float* out, size_t bytes, void* copy_stream)
+{
+    if(!c || !out || !copy_stream) return TR_ERR_INVALID_ARGUMENT;
+    DeviceGuard guard(c->device);
+    if(!c->color || !c->rendered) return fail(c, TR_ERR_INVALID_ARGUMENT, "nothing rendered yet");
+    if(bytes != c->color_pixels * sizeof(float4))
+        return fail(c, TR_ERR_INVALID_ARGUMENT, "size mismatch: target has " + std::to_string(c->color_pixels * sizeof(float4)) + " bytes");
+    cudaStream_t cs = (cudaStream_t)copy_stream;
+    tr_pt_ctx::PendingCopy& pc = c->pending_copies[c->pending_next];
+    c->pending_next = (c->pending_next + 1) % 4;
+    if(!pc.done) TRY_CUDA(c, cudaEventCreateWithFlags(&pc.done, cudaEventDisableTiming));
+    else if(pc.src) TRY_CUDA(c, cudaEventSynchronize(pc.done));      // a slot is reused only after its copy has finished
+    TRY_CUDA(c, cudaStreamWaitEvent(cs, c->ev_end, 0));              // after the frame rendered last
+    TRY_CUDA(c, cudaMemcpyAsync(out, c->color, bytes, cudaMemcpyDeviceToHost, cs));
+    TRY_CUDA(c, cudaEventRecord(pc.done, cs));
+    pc.src = c->color;
     return TR_OK;
 }
 

@@ -49,6 +49,12 @@ struct RenderParams
     int tune_tma;               // bit 0: Sobol tables of the shade kernel via TMA, bit 1: top-of-tree nodes in shared memory
     int tune_coop_groups;       // k_wf_trace_coop: posted triangle groups per warp that start a triangle phase
     int tune_coop_wait;         // ... or this many lanes out of nodes and waiting for their triangles
+    int tune_shade_prefetch;    // k_wf_shade: prefetch the next path's records (0 off, 1 L2, 2 L1)
+    int tune_split_stage;       // k_wf_trace<..., SPLIT>: run the split stage
+    int tune_split_steps;       // ... and split a ray early once it has taken this many node steps (<= 255)
+    unsigned long long tune_probe_bin_ns;
+    int probe_slot;             // TR_DEBUG_DRAIN: index of this launch in the frame's timeline
+    unsigned long long* probe;  // TR_DEBUG_DRAIN: per launch {first warp start, first / last warp that found the queue empty, last exit} (ns)
 };
 
 // Path state carried from bounce to bounce (evaluate_ray's locals).

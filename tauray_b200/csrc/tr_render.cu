@@ -16,6 +16,7 @@
 #include "tr_path.cuh"
 #include "tr_render.h"
 #include "tr_tma.cuh"
+#include <cstdio>
 #include <cstdlib>
 #include <vector>
 
@@ -130,6 +131,21 @@ TRD void flush_counters(Counters* c, unsigned long long closest, unsigned long l
     }
 }
 
+// TR_DEBUG_DRAIN (development aid): every wavefront kernel notes when its first thread started and its last one left
+TRD unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+constexpr int PROBE_TIMELINE = 136 * 2 * 16;     // offset of the per-launch {start, end} pairs behind the per-bounce drain records
+constexpr int PROBE_LAUNCHES = 128;
+TRD void probe_begin(const RenderParams& P) { if(P.probe && (threadIdx.x & 31) == 0) atomicMin(P.probe + PROBE_TIMELINE + 2 * P.probe_slot, globaltimer_ns()); }
+TRD void probe_end(const RenderParams& P) { if(P.probe && (threadIdx.x & 31) == 0) atomicMax(P.probe + PROBE_TIMELINE + 2 * P.probe_slot + 1, globaltimer_ns()); }
+
+TRD void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+TRD void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
+
 // ---- wavefront kernels ---------------------------------------------------------------------------
 // `batch` passes of one sample each are traced together (slot = pass * base_slots + base slot): the samples
 // of different passes are independent, only their accumulation order matters, and k_wf_finish keeps it.
@@ -138,6 +154,7 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_generate(const RenderParams P, 
                                                            uint32_t* __restrict__ queue, uint32_t* __restrict__ count)
 {
     unsigned long long paths = 0;
+    probe_begin(P);
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t rounded = (total_slots + 31u) & ~31u;
     for(uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < rounded; slot += stride)
@@ -165,6 +182,7 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_generate(const RenderParams P, 
         warp_push(queue, count, valid, slot);
     }
     flush_counters(P.counters, 0, 0, paths, 0, 0, 0);
+    probe_end(P);
 }
 
 // ---- persistent-threads traversal kernel ---------------------------------------------------------
@@ -188,16 +206,35 @@ constexpr int MAX_FACTORS = 6;
 // Per-ray state that is touched only when a ray is fetched, hits a triangle or retires lives in shared memory
 // ([word][thread], conflict-free) instead of registers: the kernel runs at 64 registers / 8 blocks per SM, and what
 // the compiler spilled at that budget was reloaded from local memory on every node step.
-enum { COLD_ID = 0, COLD_SX, COLD_SY, COLD_SZ, COLD_KZ, COLD_INST, COLD_PRIM, COLD_U, COLD_V, COLD_FLAGS, COLD_WORDS,
+enum { COLD_ID = 0, COLD_SX, COLD_SY, COLD_SZ, COLD_KZ, COLD_INST, COLD_PRIM, COLD_U, COLD_V, COLD_FLAGS, COLD_SPLIT, COLD_WORDS,
        COLD_NF = COLD_INST, COLD_OVERFLOW = COLD_PRIM };
 
 // TOPSM: the first TOP_NODES nodes of the breadth-first node array (root, its children, their children) are staged in
 // shared memory with one TMA bulk copy per block and read from there (TR_TUNE_TMA bit 1; measured).
 constexpr int TOP_NODES = 73;
-template<bool ANY, bool STATS, bool TOPSM = false, bool NEAR = false>
+//
+// SPLIT (tail splitting): once the queue is empty a launch ends with a few lanes finishing rays of several hundred node
+// steps while the rest of the GPU idles -- a constant ~0.17 ms per launch that is 3-6 % of a full-frame launch and a third
+// of a 1/8-frame one. Idle lanes of the warp then take over subtrees from the busy ones: a lane
+// with stacked node groups gives its BOTTOM stack entry (the largest pending subtree) to an idle lane together with the
+// ray (shuffles + the shared-memory column); the helper traverses it like any ray, helpers donate in turn, and a
+// finished helper hands its best hit back to the ray's own lane, which retires the ray when no helper is left. Closest
+// hit: the (t, instance, primitive) minimum is order independent, so the result is the sequential one bit for bit; every
+// round the lanes of a ray share the best hit so far (the culling bound). Shadow rays (opaque scenes): any helper's
+// blocker blocks the ray and ends the others. COLD_SPLIT = the ray's own lane | helpers outstanding << 8.
+//
+// FUSED: ONE launch traces the closest-hit rays of bounce `bounce` and the shadow rays of bounce `bounce - 1` -- both
+// depend only on the shade pass before them. Two persistent grids cannot share the machine (the first one fills it, the
+// second one only gets the SMs the first one drains from), so on two streams the pair still paid most of both drain
+// phases; here the work list is [closest queue | shadow queue], every lane fetches from it, and the lanes that the long
+// closest-hit rays leave idle are filled with shadow rays: one drain phase per bounce. The ray kind is per lane (bit 2 of
+// the COLD_KZ word); node steps are the same code for both kinds. Opaque scenes only (no any-hit factor lists); ANY is
+// ignored.
+template<bool ANY, bool STATS, bool TOPSM = false, bool NEAR = false, bool SPLIT = false, bool FUSED = false>
 __global__ void __launch_bounds__(TRACE_BLOCK, ANY ? TRACE_MIN_BLOCKS_SHADOW : TRACE_MIN_BLOCKS_CLOSEST) k_wf_trace(const RenderParams P, const tr_wavefront wf, uint32_t bounce,
                                                         const uint32_t* __restrict__ queue, const uint32_t* __restrict__ count,
-                                                        uint32_t* __restrict__ work_counter)
+                                                        uint32_t* __restrict__ work_counter,
+                                                        const uint32_t* __restrict__ queue2 = nullptr, const uint32_t* __restrict__ count2 = nullptr)
 {
     __shared__ uint2 s_stack[SHORT_STACK * TRACE_BLOCK];
     __shared__ uint32_t s_cold[COLD_WORDS * TRACE_BLOCK];
@@ -206,8 +243,15 @@ __global__ void __launch_bounds__(TRACE_BLOCK, ANY ? TRACE_MIN_BLOCKS_SHADOW : T
     uint2 lstack[TR_BVH_STACK - SHORT_STACK];
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-    const uint32_t n = *count;
+    const uint32_t n_first = *count;                              // FUSED: closest-hit rays first (the long ones), then the shadow rays
+    const uint32_t n = FUSED ? n_first + *count2 : n_first;
     const float4* __restrict__ nodes = P.scene.bvh.nodes;
+    // TR_DEBUG_DRAIN (development aid): when does the first warp start, when do the first and the last warp find the
+    // queue empty, when does the last warp leave
+    unsigned long long* const probe = SPLIT && P.probe ? P.probe + 136 * (2 * bounce + (ANY ? 1 : 0)) : nullptr;
+    bool probe_seen = false;
+    if(SPLIT && probe && lane == 0) atomicMin(probe + 0, globaltimer_ns());
+    if(SPLIT) probe_begin(P);
     uint32_t top_count = 0;
     if(TOPSM)
     {
@@ -218,12 +262,17 @@ __global__ void __launch_bounds__(TRACE_BLOCK, ANY ? TRACE_MIN_BLOCKS_SHADOW : T
         mbar_wait(&s_top_mbar, 0);
     }
     const float4* __restrict__ tris = P.scene.bvh.tris;
-    const bool include_lights = !ANY && !(P.opt.hide_lights && bounce == 0);
+    const bool include_lights = (FUSED || !ANY) && !(P.opt.hide_lights && bounce == 0);
     const float ray_tmin = ANY ? P.opt.min_ray_dist : (bounce == 0 ? 0.0f : P.opt.min_ray_dist);
-    const bool transparency = P.scene.any_non_opaque != 0;
+    const bool transparency = !FUSED && P.scene.any_non_opaque != 0;
+    // the kind of the lane's ray: a template constant, or (FUSED) bit 2 of the COLD_KZ word
+#define KIND_ANY() (FUSED ? (COLD(COLD_KZ) >> 2) != 0u : ANY)
 
     TraceStats st; st.nodes = 0; st.tris = 0;
+    // rays fetched by this thread: closest-hit rays in bits 0..11, shadow rays (FUSED) in bits 12..23; SPLIT: bits 24..31 =
+    // node steps of the current ray (wraps at 256)
     uint32_t rays = 0;
+    int warp_helpers = 0;                 // SPLIT: helper lanes at work in this warp (warp-uniform)
 
     // per-lane ray + traversal state held in registers
     uint2 G = make_uint2(0u, 0u), Gt = make_uint2(0u, 0u);
@@ -241,12 +290,13 @@ __global__ void __launch_bounds__(TRACE_BLOCK, ANY ? TRACE_MIN_BLOCKS_SHADOW : T
 
 #define COLD(w) s_cold[(w) * TRACE_BLOCK + tid]
 #define COLDF(w) reinterpret_cast<float*>(s_cold)[(w) * TRACE_BLOCK + tid]
+#define COLD_AT(w, l) s_cold[(w) * TRACE_BLOCK + (tid & ~31) + (l)]
     // The thread's column of the shared-memory stack as a 32-bit shared address, accessed with explicit ld/st.shared:
     // the generic-pointer form cost an address rebuild from two special-register reads (S2R) plus spills on every push
     // and pop. In the shadow kernel the value is made opaque so that it stays in a register (measured: shadow 5.67 ->
     // 5.44 ms); the closest-hit kernel is better off letting the compiler rematerialise it (11.50 -> 11.26 ms).
     uint32_t stack_base = (uint32_t)__cvta_generic_to_shared(&s_stack[tid]);
-    if(ANY) asm volatile("mov.u32 %0, %0;" : "+r"(stack_base));
+    if(ANY && !FUSED) asm volatile("mov.u32 %0, %0;" : "+r"(stack_base));
 #define PUSH(v) do { if(sp < SHORT_STACK) { const uint2 v_ = (v); asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(stack_base + (uint32_t)sp * (uint32_t)(TRACE_BLOCK * sizeof(uint2))), "r"(v_.x), "r"(v_.y) : "memory"); } \
                      else lstack[sp - SHORT_STACK] = (v); sp++; } while(0)
 #define POP(dst) do { sp--; if(sp < SHORT_STACK) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(dst.x), "=r"(dst.y) : "r"(stack_base + (uint32_t)sp * (uint32_t)(TRACE_BLOCK * sizeof(uint2))) : "memory"); \
@@ -255,11 +305,12 @@ __global__ void __launch_bounds__(TRACE_BLOCK, ANY ? TRACE_MIN_BLOCKS_SHADOW : T
     for(;;)
     {
         // ---- retire finished rays --------------------------------------------------------------
-        if(has_ray && done)
+        // (SPLIT: only on the ray's own lane, and only when no helper lane is still out)
+        if(has_ray && done && (!SPLIT || COLD(COLD_SPLIT) == (uint32_t)lane))
         {
             bool retire = true;
             const uint32_t id = COLD(COLD_ID);
-            if(!ANY)
+            if(!KIND_ANY())
             {
                 const bool found = best_t < inf_();
                 // sphere lights + the in-t-order any-hit emulation (see closest_hit() in tr_path.cuh)
@@ -332,7 +383,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, ANY ? TRACE_MIN_BLOCKS_SHADOW : T
                     if(visibility != 0.0f) visibility *= COLDF(COLD_OVERFLOW);
                 }
                 NeeJob job;
-                load_job(wf, id, (int)bounce, job);
+                load_job(wf, id, (int)(FUSED ? bounce - 1u : bounce), job);
                 PathState s;
                 const float4 e = wf.diffuse[id], f = wf.reflection[id];
                 s.diffuse = V3(e.x, e.y, e.z);
@@ -342,6 +393,165 @@ __global__ void __launch_bounds__(TRACE_BLOCK, ANY ? TRACE_MIN_BLOCKS_SHADOW : T
                 wf.reflection[id] = make_float4(s.reflection.x, s.reflection.y, s.reflection.z, 0.0f);
             }
             if(retire) has_ray = false;
+        }
+
+        // ---- split: idle lanes take over subtrees of rays still in flight (see SPLIT above) ---------
+        // Runs in the tail (the queue is empty: `exhausted`), and before that for rays that have already taken
+        // `tune_split_steps` node steps -- the few rays of several hundred steps that would otherwise end every launch.
+        if(SPLIT && probe && !probe_seen && __ballot_sync(0xFFFFFFFFu, exhausted))
+        {
+            probe_seen = true;
+            if(lane == 0)
+            {
+                const unsigned long long t = globaltimer_ns();
+                atomicMin(probe + 1, t); atomicMax(probe + 2, t);
+                const unsigned long long bin = (t - *(volatile unsigned long long*)probe) / P.tune_probe_bin_ns;
+                atomicAdd(probe + 72 + (bin < 63ull ? bin : 63ull), 1ull);
+            }
+        }
+        if(SPLIT && P.tune_split_stage && (FUSED || !ANY || !transparency))
+        {
+            const uint32_t FULL = 0xFFFFFFFFu;
+            const bool can_give = has_ray && !done && sp > 0;
+            const uint32_t tail = __ballot_sync(FULL, exhausted);
+            const uint32_t longs = __ballot_sync(FULL, can_give && (rays >> 24) >= (uint32_t)P.tune_split_steps);
+            if(tail | longs | warp_helpers)
+            {
+                // The stage is rare and the kernel has no register to spare: the hot per-lane state is parked in local
+                // memory by hand for its duration (the compiler otherwise spills inside the traversal loop instead).
+                volatile uint32_t park[14];
+                park[0] = G.x; park[1] = G.y; park[2] = Gt.x; park[3] = Gt.y;
+                park[4] = __float_as_uint(rs.idx); park[5] = __float_as_uint(rs.idy); park[6] = __float_as_uint(rs.idz);
+                park[7] = __float_as_uint(rs.ox); park[8] = __float_as_uint(rs.oy); park[9] = __float_as_uint(rs.oz);
+                park[10] = rs.octinv; park[11] = rs.sel0; park[12] = __float_as_uint(tmin); park[13] = __float_as_uint(best_t);
+                const uint32_t below = (1u << lane) - 1u;
+                __syncwarp();
+                // (1) a finished helper hands its result to the ray's own lane and becomes idle
+                uint32_t fin = warp_helpers ? __ballot_sync(FULL, has_ray && done && (COLD(COLD_SPLIT) & 0xFFu) != (uint32_t)lane) : 0u;
+                while(fin)
+                {
+                    const int h = __ffs(fin) - 1;
+                    fin &= fin - 1u;
+                    warp_helpers--;
+                    const int o = (int)(COLD_AT(COLD_SPLIT, h) & 0xFFu);
+                    if(FUSED ? (COLD_AT(COLD_KZ, h) >> 2) != 0u : ANY)
+                    {
+                        const bool hb = __shfl_sync(FULL, blocked ? 1 : 0, h) != 0;
+                        if(lane == o && hb) { blocked = true; done = true; }
+                    }
+                    else
+                    {
+                        const float ht = __uint_as_float(__shfl_sync(FULL, park[13], h));
+                        if(lane == o && ht < inf_())
+                        {
+                            const int h_inst = (int)COLD_AT(COLD_INST, h), h_prim = (int)COLD_AT(COLD_PRIM, h);
+                            const float own_t = __uint_as_float(park[13]);
+                            bool better = ht < own_t;
+                            if(ht == own_t)
+                            {
+                                const int b_inst = (int)COLD(COLD_INST), b_prim = (int)COLD(COLD_PRIM);
+                                better = h_inst < b_inst || (h_inst == b_inst && h_prim < b_prim);
+                            }
+                            if(better)
+                            {
+                                COLD(COLD_INST) = (uint32_t)h_inst; COLD(COLD_PRIM) = (uint32_t)h_prim;
+                                COLD(COLD_U) = COLD_AT(COLD_U, h); COLD(COLD_V) = COLD_AT(COLD_V, h); COLD(COLD_FLAGS) = COLD_AT(COLD_FLAGS, h);
+                                park[13] = __float_as_uint(ht);
+                            }
+                        }
+                    }
+                    if(lane == o) COLD(COLD_SPLIT) -= 0x100u;
+                    if(lane == h) has_ray = false;
+                    __syncwarp();
+                }
+                // (2) the lanes working on one ray share what they found so far
+                if(warp_helpers)
+                {
+                    const int own = has_ray ? (int)(COLD(COLD_SPLIT) & 0xFFu) : -1;
+                    if(FUSED || ANY)
+                    {
+                        const bool ob = __shfl_sync(FULL, blocked ? 1 : 0, own < 0 ? lane : own) != 0;
+                        if(has_ray && own != lane && ob) done = true;          // the (shadow) ray is blocked: its helpers stop
+                    }
+                    if(FUSED || !ANY)
+                    {
+                        uint32_t todo = __ballot_sync(FULL, has_ray && COLD(COLD_SPLIT) >= 0x100u && !KIND_ANY());    // closest-hit rays with helpers out
+                        while(todo)
+                        {
+                            const int o = __ffs(todo) - 1;
+                            todo &= todo - 1u;
+                            const bool member = own == o;
+                            const uint32_t key = member ? park[13] : 0xFFFFFFFFu;     // t > 0 or +inf: ordered like its bits
+                            const uint32_t m = __reduce_min_sync(FULL, key);
+                            if(m >= 0x7F800000u) continue;
+                            const int src = __ffs(__ballot_sync(FULL, member && key == m)) - 1;
+                            if(member && key > m)
+                            {
+                                COLD(COLD_INST) = COLD_AT(COLD_INST, src); COLD(COLD_PRIM) = COLD_AT(COLD_PRIM, src);
+                                COLD(COLD_U) = COLD_AT(COLD_U, src); COLD(COLD_V) = COLD_AT(COLD_V, src); COLD(COLD_FLAGS) = COLD_AT(COLD_FLAGS, src);
+                                park[13] = m;
+                            }
+                            __syncwarp();
+                        }
+                    }
+                }
+                // (3) the k-th idle lane takes the bottom stack entry (the largest pending subtree) of the k-th giving lane.
+                // The ray travels through the taker's own, idle, column of the shared-memory stack.
+                const uint32_t idle = __ballot_sync(FULL, !has_ray);
+                const uint32_t givers = tail ? __ballot_sync(FULL, has_ray && !done && sp > 0) : longs;
+                const int pairs = min(__popc(idle), __popc(givers));
+                if(pairs > 0)
+                {
+                    const bool gives = ((givers >> lane) & 1u) && __popc(givers & below) < pairs;
+                    const bool takes = !has_ray && __popc(idle & below) < pairs;
+                    if(gives)
+                    {
+                        uint2* const box = s_stack + (tid & ~31) + __fns(idle, 0u, __popc(givers & below) + 1);
+                        box[0 * TRACE_BLOCK] = s_stack[tid];
+                        for(int k = 1; k <= 5; ++k) box[k * TRACE_BLOCK] = make_uint2(park[2 + 2 * k], park[3 + 2 * k]);
+                        box[6 * TRACE_BLOCK] = make_uint2((uint32_t)lane, 0u);
+                        for(int k = 1; k < sp; ++k)
+                        {
+                            const uint2 v = k < SHORT_STACK ? s_stack[k * TRACE_BLOCK + tid] : lstack[k - SHORT_STACK];
+                            if(k - 1 < SHORT_STACK) s_stack[(k - 1) * TRACE_BLOCK + tid] = v;
+                            else lstack[k - 1 - SHORT_STACK] = v;
+                        }
+                        sp--;
+                        rays = (rays & 0x00FFFFFFu) | (((uint32_t)P.tune_split_steps >> 1) << 24);    // gives again after half the threshold
+                    }
+                    __syncwarp();
+                    if(takes)
+                    {
+                        const uint2* const box = s_stack + tid;
+                        uint2 v = box[0 * TRACE_BLOCK];
+                        park[0] = v.x; park[1] = v.y; park[2] = 0u; park[3] = 0u;
+                        for(int k = 1; k <= 5; ++k) { v = box[k * TRACE_BLOCK]; park[2 + 2 * k] = v.x; park[3 + 2 * k] = v.y; }
+                        const int src = (int)box[6 * TRACE_BLOCK].x;
+                        for(int w = COLD_ID; w <= COLD_FLAGS; ++w) COLD(w) = COLD_AT(w, src);
+                        COLD(COLD_SPLIT) = COLD_AT(COLD_SPLIT, src) & 0xFFu;       // helper of the giver's ray
+                        near_bit = 0u;
+                        sp = 0;
+                        blocked = false;
+                        done = false;
+                        has_ray = true;
+                        rays &= 0x00FFFFFFu;
+                    }
+                    __syncwarp();
+                    uint32_t took = __ballot_sync(FULL, takes);
+                    warp_helpers += __popc(took);
+                    while(took)
+                    {
+                        const int h = __ffs(took) - 1;
+                        took &= took - 1u;
+                        if(lane == (int)(COLD_AT(COLD_SPLIT, h) & 0xFFu)) COLD(COLD_SPLIT) += 0x100u;
+                    }
+                    __syncwarp();
+                }
+                G = make_uint2(park[0], park[1]); Gt = make_uint2(park[2], park[3]);
+                rs.idx = __uint_as_float(park[4]); rs.idy = __uint_as_float(park[5]); rs.idz = __uint_as_float(park[6]);
+                rs.ox = __uint_as_float(park[7]); rs.oy = __uint_as_float(park[8]); rs.oz = __uint_as_float(park[9]);
+                rs.octinv = park[10]; rs.sel0 = park[11]; tmin = __uint_as_float(park[12]); best_t = __uint_as_float(park[13]);
+            }
         }
 
         // ---- refill idle lanes: one atomicAdd per warp ----------------------------------------
@@ -359,11 +569,12 @@ __global__ void __launch_bounds__(TRACE_BLOCK, ANY ? TRACE_MIN_BLOCKS_SHADOW : T
                     const uint32_t i = base + __popc(mask & ((1u << lane) - 1u));
                     if(i < n)
                     {
-                        const uint32_t id = queue[i];
+                        const bool any = FUSED ? i >= n_first : ANY;
+                        const uint32_t id = (FUSED && any) ? queue2[i - n_first] : queue[i];
                         const float4 o = wf.pos_pdf[id];
                         const vec3 org = V3(o.x, o.y, o.z);
                         vec3 dir;
-                        if(ANY)
+                        if(any)
                         {
                             const float4 j0 = wf.nee[4 * (size_t)id];
                             dir = V3(j0.x, j0.y, j0.z);
@@ -378,14 +589,15 @@ __global__ void __launch_bounds__(TRACE_BLOCK, ANY ? TRACE_MIN_BLOCKS_SHADOW : T
                         tmin = ray_tmin;
                         const RayPre rp = precompute_ray(org, dir);
                         COLD(COLD_ID) = id;
-                        COLDF(COLD_SX) = rp.Sx; COLDF(COLD_SY) = rp.Sy; COLDF(COLD_SZ) = rp.Sz; COLD(COLD_KZ) = (uint32_t)rp.kz;
+                        COLDF(COLD_SX) = rp.Sx; COLDF(COLD_SY) = rp.Sy; COLDF(COLD_SZ) = rp.Sz; COLD(COLD_KZ) = (uint32_t)rp.kz | (FUSED && any ? 4u : 0u);
                         if(ANY && transparency) { COLD(COLD_NF) = 0u; COLDF(COLD_OVERFLOW) = 1.0f; }
+                        if(SPLIT) COLD(COLD_SPLIT) = (uint32_t)lane;
                         rs = make_ray_slab(org, dir);
                         sp = 0;
                         blocked = false;
                         has_ray = true;
                         done = false;
-                        rays++;
+                        rays = (rays & 0x00FFFFFFu) + ((FUSED && any) ? 0x1000u : 1u);
                         G = make_uint2(0u, (0x01000000u << rs.octinv) | 1u);   // the root as a one-child group
                         Gt = make_uint2(0u, 0u);
                         near_bit = 0u;
@@ -410,6 +622,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, ANY ? TRACE_MIN_BLOCKS_SHADOW : T
                 const uint32_t child = child_of_bit(G, bit, rs.octinv);
                 if(G.y & 0xFF000000u) PUSH(G);
                 if(STATS) st.nodes++;
+                if(SPLIT) rays += 1u << 24;
                 if(TOPSM) intersect_node8_at(child < top_count ? s_top + TR_BVH_NODE_VEC4 * child : nodes + TR_BVH_NODE_VEC4 * (size_t)child, rs, tmin, best_t, G, Gt);
                 else if(NEAR) intersect_node8_nearest(nodes, child, rs, tmin, best_t, G, Gt, near_bit);
                 else intersect_node8(nodes, child, rs, tmin, best_t, G, Gt);
@@ -434,16 +647,18 @@ __global__ void __launch_bounds__(TRACE_BLOCK, ANY ? TRACE_MIN_BLOCKS_SHADOW : T
                 const float4* tp = tris + 3 * (size_t)tri_index;
                 const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
                 RayPre rp;
-                rp.kz = (int)COLD(COLD_KZ); rp.Sx = COLDF(COLD_SX); rp.Sy = COLDF(COLD_SY); rp.Sz = COLDF(COLD_SZ);
+                const uint32_t kz_word = COLD(COLD_KZ);
+                const bool any = FUSED ? (kz_word >> 2) != 0u : ANY;
+                rp.kz = (int)(FUSED ? kz_word & 3u : kz_word); rp.Sx = COLDF(COLD_SX); rp.Sy = COLDF(COLD_SY); rp.Sz = COLDF(COLD_SZ);
                 rp.org = V3(rs.ox, rs.oy, rs.oz);
                 float t, u, v;
                 // closest: any t up to +inf qualifies here, the comparison with the best hit follows; shadow: t < tmax
-                if(!intersect_triangle(rp, f3(t0), f3(t1), f3(t2), tmin, ANY ? best_t : inf_(), t, u, v)) continue;
+                if(!intersect_triangle(rp, f3(t0), f3(t1), f3(t2), tmin, any ? best_t : inf_(), t, u, v)) continue;
                 const int inst = __float_as_int(t0.w), prim = __float_as_int(t1.w);
                 const uint32_t flags = __float_as_uint(t2.w);
-                if(ANY)
+                if(any)
                 {
-                    if(flags & TR_TRI_FLAG_OPAQUE)
+                    if(FUSED || (flags & TR_TRI_FLAG_OPAQUE))
                     {
                         blocked = true;        // terminate on the first opaque hit
                         done = true;
@@ -487,7 +702,19 @@ __global__ void __launch_bounds__(TRACE_BLOCK, ANY ? TRACE_MIN_BLOCKS_SHADOW : T
 #undef POP
 #undef COLD
 #undef COLDF
-    flush_counters(P.counters, ANY ? 0 : rays, ANY ? rays : 0, 0, st.nodes, st.tris, ANY ? 1 : 0);
+#undef COLD_AT
+#undef KIND_ANY
+    rays &= 0x00FFFFFFu;
+    if(FUSED) flush_counters(P.counters, rays & 0xFFFu, rays >> 12, 0, st.nodes, st.tris, 0);
+    else flush_counters(P.counters, ANY ? 0 : rays, ANY ? rays : 0, 0, st.nodes, st.tris, ANY ? 1 : 0);
+    if(SPLIT && probe && lane == 0)
+    {
+        const unsigned long long t = globaltimer_ns();
+        atomicMax(probe + 3, t);
+        const unsigned long long bin = (t - *(volatile unsigned long long*)probe) / P.tune_probe_bin_ns;
+        atomicAdd(probe + 8 + (bin < 63ull ? bin : 63ull), 1ull);
+    }
+    if(SPLIT) probe_end(P);
 }
 
 // ---- persistent traversal with a warp-cooperative triangle phase --------------------------------------
@@ -844,6 +1071,7 @@ __global__ void __launch_bounds__(WF_BLOCK, SHADE_MIN_BLOCKS) k_wf_shade(const R
 {
     // Sobol byte-chunk tables of this bounce's two dimension groups (2b: NEE, 2b+1: BSDF) in shared memory
     RenderParams P = P_in;
+    probe_begin(P);
     if(SPEC)
     {
         P.opt.local_sampler = TR_SAMPLER_SOBOL_OWEN; P.opt.film = TR_FILM_POINT; P.opt.mis_mode = TR_MIS_POWER_HEURISTIC;
@@ -889,10 +1117,33 @@ __global__ void __launch_bounds__(WF_BLOCK, SHADE_MIN_BLOCKS) k_wf_shade(const R
     const uint32_t rounded = (n + 31u) & ~31u;
     const uint32_t stride = gridDim.x * blockDim.x;
     unsigned long long culled = 0;
-    for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += stride)
+    // The kernel is latency bound (4 warps per scheduler at 125 registers, a third of the stall samples on the state loads
+    // below): the records of the path this thread shades NEXT are prefetched one iteration ahead (its id was loaded two
+    // iterations ahead). tune_shade_prefetch: 0 off, 1 into L2, 2 into L1.
+    const uint32_t first = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t id_next = first + stride < n ? queue[first + stride] : 0u;
+    for(uint32_t i = first; i < rounded; i += stride)
     {
         bool alive = false, shadow = false;
         uint32_t id = 0;
+        if(P.tune_shade_prefetch)
+        {
+            const uint32_t id_pf = id_next;
+            if(i + 2u * stride < n) id_next = queue[i + 2u * stride];
+            if(i + stride < n)
+            {
+                if(P.tune_shade_prefetch == 1)
+                {
+                    prefetch_l2(wf.hits + id_pf); prefetch_l2(wf.pos_pdf + id_pf); prefetch_l2(wf.dir_seed + id_pf); prefetch_l2(wf.rs_seed + id_pf);
+                    if(bounce != 0) { prefetch_l2(wf.atten_reg + id_pf); prefetch_l2(wf.lobes + id_pf); prefetch_l2(wf.diffuse + id_pf); prefetch_l2(wf.reflection + id_pf); }
+                }
+                else
+                {
+                    prefetch_l1(wf.hits + id_pf); prefetch_l1(wf.pos_pdf + id_pf); prefetch_l1(wf.dir_seed + id_pf); prefetch_l1(wf.rs_seed + id_pf);
+                    if(bounce != 0) { prefetch_l1(wf.atten_reg + id_pf); prefetch_l1(wf.lobes + id_pf); prefetch_l1(wf.diffuse + id_pf); prefetch_l1(wf.reflection + id_pf); }
+                }
+            }
+        }
         if(i < n)
         {
             id = queue[i];
@@ -944,11 +1195,13 @@ __global__ void __launch_bounds__(WF_BLOCK, SHADE_MIN_BLOCKS) k_wf_shade(const R
     }
     for(int off = 16; off > 0; off >>= 1) culled += __shfl_xor_sync(0xFFFFFFFFu, culled, off);
     if((threadIdx.x & 31) == 0 && culled) atomicAdd(&P.counters->culled_shadow_rays, culled);
+    probe_end(P);
 }
 
 __global__ void __launch_bounds__(WF_BLOCK) k_wf_finish(const RenderParams P, const tr_wavefront wf, uint32_t sample_in_pass,
                                                          uint32_t base_slots, uint32_t batch)
 {
+    probe_begin(P);
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t spp = (uint32_t)P.opt.samples_per_pass;
     uint2* const diffuse_layer = reinterpret_cast<uint2*>(P.gbuffer[TR_GBUFFER_DIFFUSE]);
@@ -1016,6 +1269,7 @@ __global__ void __launch_bounds__(WF_BLOCK) k_wf_finish(const RenderParams P, co
         if(spp > 1 && sample_in_pass + 1 < spp) continue;
         store_to_peers(P, o, px, py, view);
     }
+    probe_end(P);
 }
 
 // The G-buffer layers only the first sample writes (write_all_outputs, path_tracer.glsl:547-563): recomputed
@@ -1415,14 +1669,48 @@ cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const RenderParams& P_
     // traversal kernels
     static const int k_tma = env_int("TR_TUNE_TMA", 1);
     P.tune_tma = k_tma;
+    static const int k_nearest_early = env_int("TR_TUNE_NEAREST", 0) || env_int("TR_TUNE_COOP", 0);
     // closest-hit kernel: descend into the inner child with the smallest entry distance first (TR_TUNE_NEAREST)
     static const int k_nearest = env_int("TR_TUNE_NEAREST", 0);
+    // tail splitting (k_wf_trace<..., SPLIT>): bit 0 = closest-hit kernel, bit 1 = shadow kernel
+    static const int k_split = env_int("TR_TUNE_SPLIT", 0);
+    // fused traversal (k_wf_trace<..., FUSED>): closest-hit rays of bounce b + 1 and shadow rays of bounce b in one launch;
+    // bit 1: with the tail-splitting stage compiled in
+    static const int k_fuse = env_int("TR_TUNE_FUSE", 0);
+    const bool fused = k_fuse && !timer && !P.stats && !P.scene.any_non_opaque && !(P.tune_tma & 2) && !k_nearest_early;
+    // TR_TUNE_SPLIT_STAGE=0 keeps the SPLIT kernels but never runs their tail stage (A/B of the stage itself)
+    static const int k_split_stage = env_int("TR_TUNE_SPLIT_STAGE", 1);
+    P.tune_split_stage = k_split_stage;
+    static const int k_split_steps = env_int("TR_TUNE_SPLIT_STEPS", 96);
+    P.tune_split_steps = k_split_steps < 2 ? 2 : (k_split_steps > 255 ? 255 : k_split_steps);
+    // TR_DEBUG_DRAIN=1 (development aid): per-launch start / queue-empty / exit times of the traversal kernels on stderr
+    static const int k_probe = env_int("TR_DEBUG_DRAIN", 0);
+    static unsigned long long* probe_dev = nullptr;
+    static unsigned long long probe_init[136 * 2 * 16 + 2 * 128];
+    static const char* probe_names[128];
+    int probe_launch = 0;
+    static const int k_probe_bin = env_int("TR_DEBUG_DRAIN_BIN_US", 16);
+    P.tune_probe_bin_ns = (unsigned long long)k_probe_bin * 1000ull;
+    P.probe = nullptr;
+    if(k_probe && (uint32_t)P.opt.max_ray_depth <= 16u)
+    {
+        if(!probe_dev && cudaMalloc(&probe_dev, sizeof(probe_init)) != cudaSuccess) probe_dev = nullptr;
+        if(probe_dev)
+        {
+            for(int k = 0; k < 2 * 16; ++k) { for(int j = 0; j < 136; ++j) probe_init[136 * k + j] = 0ull; probe_init[136 * k] = probe_init[136 * k + 1] = ~0ull; }
+            for(int k = 0; k < 128; ++k) { probe_init[136 * 2 * 16 + 2 * k] = ~0ull; probe_init[136 * 2 * 16 + 2 * k + 1] = 0ull; }
+            cudaMemcpyAsync(probe_dev, probe_init, sizeof(probe_init), cudaMemcpyHostToDevice, stream);
+            P.probe = probe_dev;
+        }
+    }
     static const int k_coop = env_int("TR_TUNE_COOP", 0);
     static const int k_coop_groups = env_int("TR_TUNE_COOP_GROUPS", 24);
     static const int k_coop_wait = env_int("TR_TUNE_COOP_WAIT", 6);
     P.tune_coop_groups = k_coop_groups;
     P.tune_coop_wait = k_coop_wait;
     static const int k_shade_spec = env_int("TR_TUNE_SHADE_SPEC", 1);
+    static const int k_shade_prefetch = env_int("TR_TUNE_SHADE_PREFETCH", 1);
+    P.tune_shade_prefetch = k_shade_prefetch;
     const tr_pt_options& o = P.opt;
     const bool shade_spec = k_shade_spec && (P.tune_tma & 1) &&
         o.local_sampler == TR_SAMPLER_SOBOL_OWEN && o.film == TR_FILM_POINT && o.mis_mode == TR_MIS_POWER_HEURISTIC &&
@@ -1435,6 +1723,7 @@ cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const RenderParams& P_
     const bool coop_closest = coop_ok && (k_coop & 1);
     const bool coop_shadow = coop_ok && (k_coop & 2) && !P.scene.any_non_opaque;
 #define MARK(cls) do { if(timer) timer->mark(stream, cls); } while(0)
+#define SLOT(name) do { if(P.probe && probe_launch < 127) { probe_names[probe_launch] = name; P.probe_slot = probe_launch++; } } while(0)
     const uint32_t base = P.frame.ray_count_x * P.frame.ray_count_y * P.frame.views;
     if(base == 0) return cudaSuccess;
     const uint32_t D = (uint32_t)P.opt.max_ray_depth;
@@ -1459,6 +1748,7 @@ cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const RenderParams& P_
         uint32_t* work_counters = wf.counts + 2 * D + 1; // [2 D] dynamic-fetch cursors
         bool shadow_pending = false;
         MARK(TR_KCLASS_OTHER);
+        SLOT("generate");
         k_wf_generate<<<grid_full, WF_BLOCK, 0, stream>>>(P, wf, i, base, total, wf.queue[0], active_counts);
         ++*launches;
         for(uint32_t b = 0; b < D; ++b)
@@ -1466,7 +1756,16 @@ cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const RenderParams& P_
             uint32_t* q_in = wf.queue[b & 1];
             uint32_t* q_out = wf.queue[(b + 1) & 1];
             MARK(TR_KCLASS_CLOSEST);
-            if(coop_closest)
+            SLOT(fused && b > 0 ? "fused" : "closest");
+            if(fused && b > 0)
+            {
+                // closest(b) + shadow(b - 1): one work list, one drain phase
+                if(k_fuse & 2) k_wf_trace<false, false, false, false, true, true><<<grid_persist, TRACE_BLOCK, 0, stream>>>(P, wf, b, q_in, active_counts + b, work_counters + 2 * b,
+                                                                                                                         wf.shadow_queue, shadow_counts + b - 1);
+                else k_wf_trace<false, false, false, false, false, true><<<grid_persist, TRACE_BLOCK, 0, stream>>>(P, wf, b, q_in, active_counts + b, work_counters + 2 * b,
+                                                                                                               wf.shadow_queue, shadow_counts + b - 1);
+            }
+            else if(coop_closest)
             {
                 if(P.stats) k_wf_trace_coop<false, true><<<grid_persist, WF_BLOCK, 0, stream>>>(P, wf, b, q_in, active_counts + b, work_counters + 2 * b);
                 else k_wf_trace_coop<false, false><<<grid_persist, WF_BLOCK, 0, stream>>>(P, wf, b, q_in, active_counts + b, work_counters + 2 * b);
@@ -1474,6 +1773,7 @@ cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const RenderParams& P_
             else if(P.stats) k_wf_trace<false, true><<<grid_persist, TRACE_BLOCK, 0, stream>>>(P, wf, b, q_in, active_counts + b, work_counters + 2 * b);
             else if(P.tune_tma & 2) k_wf_trace<false, false, true><<<grid_persist, TRACE_BLOCK, 0, stream>>>(P, wf, b, q_in, active_counts + b, work_counters + 2 * b);
             else if(k_nearest) k_wf_trace<false, false, false, true><<<grid_persist, TRACE_BLOCK, 0, stream>>>(P, wf, b, q_in, active_counts + b, work_counters + 2 * b);
+            else if(k_split & 1) k_wf_trace<false, false, false, false, true><<<grid_persist, TRACE_BLOCK, 0, stream>>>(P, wf, b, q_in, active_counts + b, work_counters + 2 * b);
             else k_wf_trace<false, false><<<grid_persist, TRACE_BLOCK, 0, stream>>>(P, wf, b, q_in, active_counts + b, work_counters + 2 * b);
             if(b == 0 && first_sample_layers && i + 1 == spp)
             {
@@ -1488,14 +1788,16 @@ cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const RenderParams& P_
                 if(e2 != cudaSuccess) return e2;
                 shadow_pending = false;
             }
+            SLOT("shade");
             if(shade_spec) k_wf_shade<1><<<grid_shade, WF_BLOCK, 0, stream>>>(P, wf, b, i, q_in, active_counts + b, q_out, active_counts + b + 1,
                                                                              wf.shadow_queue, shadow_counts + b);
             else k_wf_shade<0><<<grid_shade, WF_BLOCK, 0, stream>>>(P, wf, b, i, q_in, active_counts + b, q_out, active_counts + b + 1,
                                                                    wf.shadow_queue, shadow_counts + b);
             *launches += 2;
-            if(b + 1 < D)
+            if(b + 1 < D && !fused)
             {
                 MARK(TR_KCLASS_SHADOW);
+                SLOT("shadow");
                 // shadow(b) only touches the NEE job and the path's accumulators; closest(b + 1) only the ray and the hit
                 // record: with a second stream they run side by side and shade(b + 1) waits for both
                 cudaStream_t ss = stream;
@@ -1513,6 +1815,7 @@ cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const RenderParams& P_
                 }
                 else if(P.stats) k_wf_trace<true, true><<<grid_persist_shadow, TRACE_BLOCK, 0, ss>>>(P, wf, b, wf.shadow_queue, shadow_counts + b, work_counters + 2 * b + 1);
                 else if(P.tune_tma & 2) k_wf_trace<true, false, true><<<grid_persist_shadow, TRACE_BLOCK, 0, ss>>>(P, wf, b, wf.shadow_queue, shadow_counts + b, work_counters + 2 * b + 1);
+                else if(k_split & 2) k_wf_trace<true, false, false, false, true><<<grid_persist_shadow, TRACE_BLOCK, 0, ss>>>(P, wf, b, wf.shadow_queue, shadow_counts + b, work_counters + 2 * b + 1);
                 else k_wf_trace<true, false><<<grid_persist_shadow, TRACE_BLOCK, 0, ss>>>(P, wf, b, wf.shadow_queue, shadow_counts + b, work_counters + 2 * b + 1);
                 ++*launches;
                 if(two_streams)
@@ -1529,11 +1832,37 @@ cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const RenderParams& P_
             if(e2 != cudaSuccess) return e2;
         }
         MARK(TR_KCLASS_OTHER);
+        SLOT("finish");
         k_wf_finish<<<grid_finish, WF_BLOCK, 0, stream>>>(P, wf, i, base, batch);
         ++*launches;
     }
     MARK(TR_KCLASS_END);
 #undef MARK
+    if(P.probe)
+    {
+        static unsigned long long got[136 * 2 * 16 + 2 * 128];
+        cudaStreamSynchronize(stream);
+        if(overlap && overlap->aux) cudaStreamSynchronize(overlap->aux);
+        cudaMemcpy(got, P.probe, sizeof(got), cudaMemcpyDeviceToHost);
+        for(uint32_t b = 0; b < D; ++b)
+            for(int kind = 0; kind < 2; ++kind)
+            {
+                const unsigned long long* g = got + 136 * (2 * b + kind);
+                if(g[3] == 0ull) continue;
+                fprintf(stderr, "drain: bounce %u %s  run %.1f us  first-empty at %.1f  last-empty at %.1f  (tail %.1f us)\n", b, kind ? "shadow " : "closest",
+                        (g[3] - g[0]) * 1e-3, (g[1] - g[0]) * 1e-3, (g[2] - g[0]) * 1e-3, (g[3] - g[1]) * 1e-3);
+                fprintf(stderr, "   warps leaving per %d us:", k_probe_bin);
+                for(int j = 0; j < 64; ++j) if(g[8 + j]) fprintf(stderr, " [%d]%llu", j * k_probe_bin, g[8 + j]);
+                fprintf(stderr, "\n");
+            }
+        const unsigned long long* tl = got + 136 * 2 * 16;
+        unsigned long long t0 = ~0ull;
+        for(int k = 0; k < probe_launch; ++k) if(tl[2 * k] < t0) t0 = tl[2 * k];
+        for(int k = 0; k < probe_launch; ++k)
+            if(tl[2 * k + 1]) fprintf(stderr, "timeline: %-9s start %8.1f  end %8.1f  (%7.1f us)\n", probe_names[k], (tl[2 * k] - t0) * 1e-3, (tl[2 * k + 1] - t0) * 1e-3,
+                                      (tl[2 * k + 1] - tl[2 * k]) * 1e-3);
+    }
+#undef SLOT
     return cudaGetLastError();
 }
 

@@ -182,6 +182,9 @@ TRD void intersect_node8_at(const float4* n, const RaySlab& r, float tmin, float
 // NEAREST: also reports, in `near_bit`, the hit bit (24..31 in G.y) of the INNER child with the smallest entry distance
 // (0 = none): the closest-hit kernel descends into it first and leaves the rest of the group in octant order. The key
 // packs the entry distance (a non-negative float orders like its bits) with the test index in the low 3 bits.
+#ifndef TR_SIGNBITS
+#define TR_SIGNBITS 0
+#endif
 template<bool NEAREST>
 TRD void intersect_node8_core(const float4 n0, const float4 n1, const float4 n2, const float4 n3, const float4 n4, const RaySlab& r,
                               float tmin, float tmax, uint2& G, uint2& Gt, uint32_t& near_bit)
@@ -213,10 +216,15 @@ TRD void intersect_node8_core(const float4 n0, const float4 n1, const float4 n2,
             fma2_bcast(tnz, tfz, qbyte_to_float(nz, SEL), qbyte_to_float(fz, SEL), az, bz);      \
             const float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));                                   \
             const float cmax = fminf(fminf(tfx, tfy), fminf(tfz, tmax));                                   \
-            if(cmin <= cmax) acc[half] |= 1u << K;                                                         \
+            if(TR_SIGNBITS && !NEAREST) acc[half] = __funnelshift_l(__float_as_uint(__fsub_rn(cmax, cmin)), acc[half], 1); \
+            else if(cmin <= cmax) acc[half] |= 1u << K;                                                    \
             if(NEAREST) near_key[half] = min(near_key[half], cmin <= cmax ? ((__float_as_uint(cmin) & ~3u) | (uint32_t)K) : 0xFFFFFFFFu); \
         }
-        TR_CHILD(0, sel0) TR_CHILD(1, sel1) TR_CHILD(2, sel2) TR_CHILD(3, sel3)
+        // TR_SIGNBITS: the hit bit is the (inverted) sign of cmax - cmin, shifted into the mask by a funnel shift -- one
+        // FADD (FMA pipe) + one SHF instead of FSETP + SEL/IADD on the ALU pipe, which is the pipe that bounds the kernel.
+        // A node that holds an acceptable hit has cmin < t <= cmax, so the difference is > 0 and cannot round below +0.
+        if(TR_SIGNBITS && !NEAREST) { TR_CHILD(3, sel3) TR_CHILD(2, sel2) TR_CHILD(1, sel1) TR_CHILD(0, sel0) acc[half] = ~acc[half] & 0xFu; }
+        else { TR_CHILD(0, sel0) TR_CHILD(1, sel1) TR_CHILD(2, sel2) TR_CHILD(3, sel3) }
 #undef TR_CHILD
     }
     const uint32_t hi_octant = r.octinv & 4u;

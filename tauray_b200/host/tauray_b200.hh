@@ -212,6 +212,11 @@ public:
         check(tr_pt_read_color(ctx, out.data(), bytes), ctx, "tr_pt_read_color");
         return out;
     }
+    // frames in flight: the staging copy of the frame rendered last, on the caller's copy stream (pinned host memory)
+    void read_color_async(float* pinned_host, size_t bytes, void* copy_stream)
+    {
+        check(tr_pt_read_color_async(ctx, pinned_host, bytes, copy_stream), ctx, "tr_pt_read_color_async");
+    }
     // accumulation checkpoint / resume (not in the reference)
     tr_pt_accumulation_state accumulation_state()
     {

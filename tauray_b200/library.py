@@ -28,7 +28,7 @@ EXPORTS = [
     "tr_pt_last_error", "tr_pt_abi_version", "tr_pt_alloc_full_image", "tr_pt_ipc_get_handle",
     "tr_pt_ipc_open_handle", "tr_pt_ipc_close_handle", "tr_pt_set_color_buffer", "tr_pt_read_full_image", "tr_pt_enable_peer_access",
     "tr_pt_get_full_image_info", "tr_pt_set_stitch_double_buffer", "tr_pt_set_render_in_full_image", "tr_pt_read_full_image_range",
-    "tr_pt_read_full_layer",
+    "tr_pt_read_full_layer", "tr_pt_read_color_async",
 ]
 
 
@@ -65,6 +65,7 @@ def lib():
     l.tr_pt_get_accumulation_state.argtypes = [vp, C.POINTER(abi.AccumulationState)]
     l.tr_pt_restore_accumulation.argtypes = [vp, vp, C.c_size_t, C.POINTER(abi.AccumulationState)]
     l.tr_pt_read_color.argtypes = [vp, vp, C.c_size_t]
+    l.tr_pt_read_color_async.argtypes = [vp, vp, C.c_size_t, vp]
     l.tr_pt_unshuffle.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, C.c_float, vp]
     l.tr_pt_set_stitch_blend.argtypes = [vp, C.c_float]
     l.tr_pt_set_peer_images.argtypes = [vp, C.POINTER(vp), C.c_int]
@@ -188,6 +189,10 @@ class PathTracer:
 
     def read_color_into(self, host_ptr, nbytes):
         self._check(self._l.tr_pt_read_color(self._ctx, host_ptr, nbytes), "tr_pt_read_color")
+
+    def read_color_async(self, host_ptr, nbytes, copy_stream):
+        """D2H of the colour target on `copy_stream` without blocking the host (frames in flight)."""
+        self._check(self._l.tr_pt_read_color_async(self._ctx, host_ptr, nbytes, copy_stream), "tr_pt_read_color_async")
 
     def checkpoint(self):
         """Accumulation checkpoint: the colour target, the enabled aux G-buffer layers and the counters."""
