@@ -199,8 +199,10 @@ class SharedHostImage:
     """One pinned host buffer shared by all ranks of the node (a /dev/shm file, cudaHostRegister'ed in every process):
     every rank copies its own byte range of the stitched image into it over its own PCIe link."""
 
-    def __init__(self, np, torch, td, rank, world, nbytes):
+    def __init__(self, np, torch, td, rank, world, image_bytes, images=1):
         self.np, self.torch = np, torch
+        self.image_bytes = image_bytes
+        nbytes = image_bytes * images          # `images` host images back to back (frames in flight)
         name = [None]
         if rank == 0:
             name[0] = "/dev/shm/tauray_b200_%d_%d" % (os.getpid(), int(time.time() * 1e3) & 0xFFFFFF)
@@ -218,9 +220,9 @@ class SharedHostImage:
             self.registered = int(rc) == 0
         except Exception:
             self.registered = False
-        per = (nbytes // world + 15) & ~15
-        self.offset = min(rank * per, nbytes)
-        self.count = min(per, nbytes - self.offset) if rank + 1 < world else nbytes - self.offset
+        per = (image_bytes // world + 15) & ~15
+        self.offset = min(rank * per, image_bytes)
+        self.count = min(per, image_bytes - self.offset) if rank + 1 < world else image_bytes - self.offset
 
     def close(self):
         try:
@@ -411,7 +413,7 @@ def main():
         img_host = torch.empty((VIEWS, HEIGHT, WIDTH, 4), dtype=torch.float32).pin_memory()
         img_np = img_host.numpy()
     elif ren.stitch == "peer":
-        shared = SharedHostImage(np, torch, td, rank, world, img_bytes)
+        shared = SharedHostImage(np, torch, td, rank, world, img_bytes, images=2)
     else:
         img_host = torch.empty((VIEWS, HEIGHT, WIDTH, 4), dtype=torch.float32).pin_memory()
 
@@ -420,11 +422,11 @@ def main():
     # staging copy (tr_pt_read_color_async, on a copy stream, into one of two pinned host images) runs beside the next
     # frame. Every step's camera upload and image read-back are inside the timed region; the host images are checked.
     pipelined = world == 1 and reset_each_step
+    e2e_count = [0]
     if pipelined:
         targets = [torch.empty((VIEWS, HEIGHT, WIDTH, 4), dtype=torch.float32, device="cuda") for _ in range(2)]
         hosts = [torch.empty((VIEWS, HEIGHT, WIDTH, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
         copy_stream = torch.cuda.Stream(device=local_rank)
-        e2e_count = [0]
 
     def e2e_step():
         ren.tracer.set_cameras(cam_np)                      # H2D (pinned)
@@ -439,7 +441,10 @@ def main():
         if world == 1:
             ren.tracer.read_color_into(img_np.ctypes.data, img_np.nbytes)   # D2H (pinned) + sync
         elif shared is not None:
-            ren.tracer.read_full_image_range(shared.ptr + shared.offset, shared.offset, shared.count)   # my 1/N of the image
+            # my 1/N of the stitched image into one of the two shared host images, on a copy stream beside the next frame
+            b = e2e_count[0] & 1
+            e2e_count[0] += 1
+            ren.read_back_async(shared.ptr + b * img_bytes + shared.offset, shared.offset, shared.count, sptr)
         elif rank == 0:
             img_host.copy_(ren._full, non_blocking=False)
 
@@ -463,10 +468,12 @@ def main():
         # one more frame from a clean accumulation so that the shared host image must equal the checked one
         ren.reset_accumulation()
         ren.render(sptr)
-        ren.tracer.read_full_image_range(shared.ptr + shared.offset, shared.offset, shared.count)
+        ren.read_back_async(shared.ptr + shared.offset, shared.offset, shared.count, sptr)
         barrier()
         if rank == 0:
-            e2e_image_ok = sha256_of(shared.buf) == image_sha
+            e2e_image_ok = sha256_of(shared.buf[:img_bytes]) == image_sha
+            if reset_each_step:      # the other host image holds a frame of the timed loop: the same picture
+                e2e_image_ok = e2e_image_ok and sha256_of(shared.buf[img_bytes:]) == image_sha
         pinned = shared.registered
         shared.close()
     else:
@@ -638,7 +645,7 @@ def main():
                     "ms_per_step": e2e_s / args.steps * 1e3,
                     "readback": ("two frames in flight: two device targets, staging copies on a copy stream into two pinned host images (tr_pt_read_color_async)"
                                  if pipelined else "one pinned host image") if world == 1 else
-                                ("every rank copies its 1/N byte range into one shared pinned host image%s" % ("" if pinned else " (NOT pinned: cudaHostRegister failed)")
+                                ("two frames in flight: every rank copies its 1/N byte range of the double-buffered stitched image into one of two shared pinned host images on a copy stream%s" % ("" if pinned else " (NOT pinned: cudaHostRegister failed)")
                                  if ren.stitch == "peer" else "rank 0 copies the stitched image"),
                     "host_image_equal": e2e_image_ok},
             "gpu_launches": int(launches),

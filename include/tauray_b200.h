@@ -461,6 +461,12 @@ int tr_pt_set_render_in_full_image(tr_pt_ctx* ctx, int enable);
  * rank of a multi-GPU job copy its own share of the image into one shared pinned host buffer over its own PCIe link
  * instead of all ranks (or one) copying everything (headless staging copy, src/headless.cc:125-171). */
 int tr_pt_read_full_image_range(tr_pt_ctx* ctx, void* host_dst, size_t byte_offset, size_t bytes);
+/* The same without blocking the host (frames in flight): enqueued on `copy_stream`, which the caller has already ordered
+ * after the frame's barrier (the fused stitch is complete only once EVERY rank has finished the frame). The copy reads
+ * the half the last tr_pt_render wrote; with tr_pt_set_stitch_double_buffer the next frame writes the other half, and
+ * the caller lets its copy finish before it passes the NEXT frame's barrier, so no rank can store into a half that is
+ * still being read (tauray_b200/renderer.py: read_back_async). `host_dst` must be pinned. */
+int tr_pt_read_full_image_range_async(tr_pt_ctx* ctx, void* host_dst, size_t byte_offset, size_t bytes, void* copy_stream);
 int tr_pt_read_full_layer(tr_pt_ctx* ctx, int layer, void* host_dst, size_t bytes);
 /* Single-process multi-GPU (the reference's own topology, src/context.cc:415): let this context's device
  * store into memory of `peer_cuda_device` (cudaDeviceEnablePeerAccess); then pass the peer context's

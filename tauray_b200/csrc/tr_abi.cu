@@ -1092,7 +1092,7 @@ int tr_pt_write_gbuffer_layer(tr_pt_ctx* c, int layer, const void* src, size_t b
 }
 
 // D2H of `bytes` bytes at `offset` of layer `layer` in the half of the full-image arena the last render wrote
-static int read_full(tr_pt_ctx* c, int layer, void* out, size_t offset, size_t bytes)
+static int read_full(tr_pt_ctx* c, int layer, void* out, size_t offset, size_t bytes, cudaStream_t async_stream = nullptr)
 {
     if(!c || !out || layer < 0 || layer >= TR_GBUFFER_LAYER_COUNT) return TR_ERR_INVALID_ARGUMENT;
     DeviceGuard guard(c->device);
@@ -1102,10 +1102,21 @@ static int read_full(tr_pt_ctx* c, int layer, void* out, size_t offset, size_t b
     if(offset > have || bytes > have - offset) return fail(c, TR_ERR_INVALID_ARGUMENT, "size mismatch: the layer has " + std::to_string(have) + " bytes");
     if(bytes == 0) return TR_OK;
     const char* src = reinterpret_cast<const char*>(c->full_image) + c->full_cur_half * c->full_half_bytes + c->full_layer_off[layer] + offset;
+    if(async_stream)
+    {
+        TRY_CUDA(c, cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, async_stream));
+        return TR_OK;
+    }
     cudaStream_t st = c->last_stream ? c->last_stream : c->stream;
     TRY_CUDA(c, cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, st));
     TRY_CUDA(c, cudaStreamSynchronize(st));
     return TR_OK;
+}
+
+int tr_pt_read_full_image_range_async(tr_pt_ctx* c, void* out, size_t byte_offset, size_t bytes, void* copy_stream)
+{
+    if(!copy_stream) return TR_ERR_INVALID_ARGUMENT;
+    return read_full(c, TR_GBUFFER_COLOR, out, byte_offset, bytes, (cudaStream_t)copy_stream);
 }
 
 int tr_pt_read_full_image(tr_pt_ctx* c, float* out, size_t bytes)

@@ -28,7 +28,7 @@ EXPORTS = [
     "tr_pt_last_error", "tr_pt_abi_version", "tr_pt_alloc_full_image", "tr_pt_ipc_get_handle",
     "tr_pt_ipc_open_handle", "tr_pt_ipc_close_handle", "tr_pt_set_color_buffer", "tr_pt_read_full_image", "tr_pt_enable_peer_access",
     "tr_pt_get_full_image_info", "tr_pt_set_stitch_double_buffer", "tr_pt_set_render_in_full_image", "tr_pt_read_full_image_range",
-    "tr_pt_read_full_layer", "tr_pt_read_color_async",
+    "tr_pt_read_full_layer", "tr_pt_read_color_async", "tr_pt_read_full_image_range_async",
 ]
 
 
@@ -86,6 +86,7 @@ def lib():
     l.tr_pt_set_stitch_double_buffer.argtypes = [vp, C.c_int]
     l.tr_pt_set_render_in_full_image.argtypes = [vp, C.c_int]
     l.tr_pt_read_full_image_range.argtypes = [vp, vp, C.c_size_t, C.c_size_t]
+    l.tr_pt_read_full_image_range_async.argtypes = [vp, vp, C.c_size_t, C.c_size_t, vp]
     l.tr_pt_read_full_layer.argtypes = [vp, C.c_int, vp, C.c_size_t]
     l.tr_pt_ipc_get_handle.argtypes = [vp, C.c_char_p]
     l.tr_pt_ipc_open_handle.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
@@ -262,6 +263,11 @@ class PathTracer:
     def read_full_image_range(self, host_ptr, byte_offset, nbytes):
         """D2H of bytes [byte_offset, byte_offset + nbytes) of the stitched colour image to host_ptr."""
         self._check(self._l.tr_pt_read_full_image_range(self._ctx, host_ptr, byte_offset, nbytes), "tr_pt_read_full_image_range")
+
+    def read_full_image_range_async(self, host_ptr, byte_offset, nbytes, copy_stream):
+        """The same on `copy_stream` without blocking the host; the caller orders the stream after the frame's barrier."""
+        self._check(self._l.tr_pt_read_full_image_range_async(self._ctx, host_ptr, byte_offset, nbytes, copy_stream),
+                    "tr_pt_read_full_image_range_async")
 
     def read_full_layer(self, layer, size, views):
         """Stitched aux layer as (views, H, W, channels) in the layer's own texel format."""

@@ -87,6 +87,8 @@ class RtRenderer:
         self._full_ptr = None
         self._peer_ptrs = []
         self._flag = None
+        self._copy_stream = None          # read_back_async
+        self._copy_done = None
         self._full_key = None
         self.layers = []
 
@@ -242,6 +244,11 @@ class RtRenderer:
         import torch
         import torch.distributed as td
         if self.stitch == "peer":
+            # an asynchronous read-back of the previous frame (read_back_async) must have left its half of the image
+            # before this rank reports the frame done: past this barrier the peers start storing into that half again
+            if self._copy_done is not None:
+                torch.cuda.current_stream(self.device).wait_event(self._copy_done)
+                self._copy_done = None
             # all peers' stores into my image are complete once every rank's kernels finished:
             # a 1-element all-reduce on the same stream is the frame barrier.
             td.all_reduce(self._flag, group=self.pg)
@@ -314,6 +321,27 @@ class RtRenderer:
             return self._full.cpu().numpy()
         out = np.empty((self.views, H, W, 4), dtype=np.float32)
         return self.tracer.read_full_image(out)
+
+    def read_back_async(self, host_ptr, byte_offset, nbytes, stream=None):
+        """Frames in flight (the reference keeps MAX_FRAMES_IN_FLIGHT staging copies going, src/headless.cc:125-171): copy
+        bytes [byte_offset, byte_offset + nbytes) of the stitched colour image of the frame rendered last into pinned host
+        memory on a copy stream, beside the next frame. The copy starts after the frame's barrier; the next frame writes the
+        other half of the double-buffered image, and this rank passes the NEXT barrier only when the copy has finished.
+        `stream` = the stream the frame was rendered on (default: torch's current stream). Returns the torch event that
+        marks the host bytes valid."""
+        import torch
+        assert self.cuda and self.world > 1 and self.stitch == "peer"
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        rs = torch.cuda.current_stream(self.device) if stream is None else \
+            torch.cuda.ExternalStream(stream, device=torch.device("cuda", self.device))
+        frame_done = torch.cuda.Event()
+        frame_done.record(rs)
+        self._copy_stream.wait_event(frame_done)
+        self.tracer.read_full_image_range_async(host_ptr, byte_offset, nbytes, self._copy_stream.cuda_stream)
+        self._copy_done = torch.cuda.Event()
+        self._copy_done.record(self._copy_stream)
+        return self._copy_done
 
     def full_image_ptr(self):
         """Device pointer of the stitched colour image of the last frame."""

@@ -96,6 +96,22 @@ def run_checks(rank, world, local):
     ok = ok and same
     torch.cuda.synchronize(local)
     td.barrier()
+    # ---- frames in flight: every rank reads the WHOLE stitched image of frame k back asynchronously (copy stream, pinned
+    # host memory, read_back_async) while frame k + 1 renders and the peers store into the other half; odd ranks' copies
+    # start late. Each host image must be the single-device frame.
+    hosts = [torch.zeros(wants[0].shape, dtype=torch.float32).pin_memory() for _ in cam_seq]
+    for k, ck in enumerate(cam_seq):
+        ren.tracer.set_cameras(ck)
+        ren.reset_accumulation()
+        ren.render(stream.cuda_stream)
+        if rank % 2 == 1:
+            torch.cuda._sleep(100_000_000)
+        ren.read_back_async(hosts[k].data_ptr(), 0, hosts[k].numel() * 4, stream.cuda_stream)
+    torch.cuda.synchronize(local)
+    same = all(hosts[k].numpy().tobytes() == wants[k].tobytes() for k in range(len(cam_seq)))
+    print("rank %d asynchronous read-back with two frames in flight: %s" % (rank, "identical" if same else "DIFFERENT"), flush=True)
+    ok = ok and same
+    td.barrier()
     ren.close()
     # ---- aux G-buffer layers across devices (src/rt_renderer.cc:370-397): every rank's stitched layers == one device's
     layers = [abi.GBUFFER_DIFFUSE, abi.GBUFFER_REFLECTION, abi.GBUFFER_ALBEDO, abi.GBUFFER_MATERIAL, abi.GBUFFER_NORMAL,
