@@ -601,6 +601,28 @@ def main():
     # animated-scene update (tr_pt_update_instances: world-space vertices, tri lights and the fast radix-tree rebuild), last
     # so that every timed frame above ran on the static scene's quality build; same records, timed once after a warm-up
     inst_table = scene.instance_table()
+    # first the refit (tr_pt_set_update_mode: the quality tree keeps its topology, boxes recomputed bottom-up) ...
+    ren.tracer.set_update_mode(abi.UPDATE_REFIT)
+    ren.update_instances(inst_table)
+    torch.cuda.synchronize(local_rank)
+    t0 = time.perf_counter()
+    ren.update_instances(inst_table)
+    torch.cuda.synchronize(local_rank)
+    t_refit = time.perf_counter() - t0
+    refit_stats = ren.stats()
+
+    def frames_ms(k=3):
+        frame(); barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(k):
+            frame()
+        ev1.record(stream)
+        barrier()
+        return max_over_ranks(ev0.elapsed_time(ev1)) / k
+    ms_on_refitted = frames_ms()
+    # ... then the rebuild
+    ren.tracer.set_update_mode(abi.UPDATE_REBUILD)
     ren.update_instances(inst_table)
     torch.cuda.synchronize(local_rank)
     t0 = time.perf_counter()
@@ -608,6 +630,7 @@ def main():
     torch.cuda.synchronize(local_rank)
     t_update = time.perf_counter() - t0
     update_stats = ren.stats()
+    ms_on_rebuilt = frames_ms()
 
     failed = None
     if stitch_check and (not stitch_check["all_ranks_equal"] or stitch_check.get("equal_single_rank") is False):
@@ -634,6 +657,8 @@ def main():
                        "bvh_builder": "binned SAH, on device (static scene); radix tree for per-frame updates",
                        "bvh_build_ms": build_stats["bvh_build_ms"], "bvh_nodes": build_stats["bvh_node_count"], "bvh_depth": build_stats["bvh_depth"],
                        "bvh_update_rebuild_ms": update_stats["bvh_build_ms"],
+                       "bvh_update_refit_ms": refit_stats["bvh_build_ms"], "scene_update_refit_ms": 1e3 * t_refit,
+                       "ms_per_frame_after_refit": ms_on_refitted, "ms_per_frame_after_rebuild": ms_on_rebuilt,
                        "scene_upload_s": t_scene, "scene_update_ms": 1e3 * t_update, "scene_generate_s": t_gen, "wall_s_timed": wall},
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,

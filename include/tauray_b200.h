@@ -337,6 +337,17 @@ int tr_pt_set_scene(tr_pt_ctx* ctx, const tr_pt_scene_desc* scene);
  * reference (the application calls reset_accumulation). */
 int tr_pt_update_instances(tr_pt_ctx* ctx, const tr_instance* instances, uint32_t instance_count);
 
+/* How tr_pt_update_instances brings the acceleration structure up to date:
+ * TR_UPDATE_REBUILD (default) -- a new radix tree every frame (above);
+ * TR_UPDATE_REFIT -- the tree tr_pt_set_scene built (the quality build) keeps its topology, slot assignment and
+ *   triangle order; the leaf triangles are re-fetched and the quantised child boxes recomputed bottom-up. This is what
+ *   the reference asks of the driver for animated geometry (bottom-level `eUpdate` builds of fast-build+update BLASes,
+ *   src/acceleration_structure.cc:187-262; top level :376-443): cheaper than a build and as good as the original tree
+ *   while the motion is moderate. The image never depends on the tree, so both modes render identical pictures. */
+#define TR_UPDATE_REBUILD 0
+#define TR_UPDATE_REFIT 1
+int tr_pt_set_update_mode(tr_pt_ctx* ctx, int mode);
+
 /* == camera UBO upload (src/scene_stage.cc:1145-1174); `pairs` = view_count tr_camera_pair. */
 int tr_pt_set_cameras(tr_pt_ctx* ctx, const tr_camera_pair* pairs, uint32_t view_count);
 

@@ -26,6 +26,7 @@ FEATURE_INSTANCE_ID = 9
 KERNEL_WAVEFRONT, KERNEL_MEGAKERNEL = range(2)
 ESTIMATOR_PATH_TRACER, ESTIMATOR_DIRECT = range(2)   # direct = direct_stage, shader/direct.rgen
 INSTRUMENT_VISITS, INSTRUMENT_TIMING = 1, 2
+UPDATE_REBUILD, UPDATE_REFIT = 0, 1          # tr_pt_set_update_mode
 TEXTURE_RGBA8_UNORM, TEXTURE_RGBA32F, TEXTURE_RGBA16F = range(3)
 ENVMAP_NONE, ENVMAP_LAT_LONG = -1, 0
 (GBUFFER_COLOR, GBUFFER_DIFFUSE, GBUFFER_REFLECTION, GBUFFER_ALBEDO, GBUFFER_MATERIAL, GBUFFER_NORMAL, GBUFFER_POS,

@@ -64,6 +64,10 @@ struct tr_pt_ctx
         float4* shade_tris = nullptr;        // scene allocation: 6 float4 per triangle
         float4* bvh_nodes = nullptr;         // owned here, replaced by every rebuild
         float4* bvh_tris = nullptr;
+        std::vector<uint32_t> level_offsets; // breadth-first levels of the node array (refit runs them bottom-up)
+        tr_build_instance* d_binst = nullptr;   // refit: binst on the device, allocated on first use
+        float* refit_scratch = nullptr;      // refit: 6 floats per node + 1 word
+        uint32_t refit_scratch_nodes = 0;
         std::vector<tr_build_instance> binst;
         std::vector<DeviceInstance> dinst;
         std::vector<uint32_t> vertex_counts;
@@ -97,6 +101,7 @@ struct tr_pt_ctx
     uint32_t pass_batch = 1;
     tr_pt_stats stats{};
     bool rendered = false;
+    int update_mode = TR_UPDATE_REBUILD;     // tr_pt_set_update_mode
     float4* peers[8] = {};
     int peer_count = 0;
     int peer_self = -1;
@@ -383,6 +388,9 @@ void free_scene(tr_pt_ctx* c)
     free_list(c->scene_allocs);
     if(c->geom.bvh_nodes) cudaFree(c->geom.bvh_nodes);
     if(c->geom.bvh_tris) cudaFree(c->geom.bvh_tris);
+    if(c->geom.d_binst) cudaFree(c->geom.d_binst);
+    if(c->geom.refit_scratch) cudaFree(c->geom.refit_scratch);
+    c->geom.d_binst = nullptr; c->geom.refit_scratch = nullptr; c->geom.refit_scratch_nodes = 0; c->geom.level_offsets.clear();
     c->geom = tr_pt_ctx::Geometry();
     c->prev_from_world = nullptr;
     memset(&c->scene, 0, sizeof(c->scene));
@@ -569,7 +577,7 @@ static void build_alias_table(std::vector<float>& imp, uint32_t width, uint32_t 
 // model_prev * inverse(model), extract_tri_lights.comp and the BVH (the reference's per-frame
 // scene_stage::record_as_build / record_tri_light_extraction + instance-buffer refresh,
 // src/scene_stage.cc:1572-1675). Used by tr_pt_set_scene and tr_pt_update_instances.
-static int transform_and_build(tr_pt_ctx* c, const tr_instance* instances, uint32_t instance_count, bool quality_build)
+static int transform_and_build(tr_pt_ctx* c, const tr_instance* instances, uint32_t instance_count, bool quality_build, bool refit = false)
 {
     tr_pt_ctx::Geometry& g = c->geom;
     cudaStream_t st = c->stream;
@@ -615,8 +623,33 @@ static int transform_and_build(tr_pt_ctx* c, const tr_instance* instances, uint3
     bin.vertices = g.v_world; bin.indices = g.indices; bin.instances = g.binst.data();
     bin.instance_count = instance_count; bin.triangle_count = (uint32_t)g.triangle_total;
     bin.quality = quality_build ? 1u : 0u;
+    if(refit && g.bvh_nodes && g.bvh_tris && !g.level_offsets.empty())
+    {
+        // the tree keeps its topology: re-fetch the leaf triangles, recompute the child boxes bottom-up (tr_bvh.cu)
+        const uint32_t node_count = c->scene.bvh.node_count;
+        if(!g.d_binst && instance_count)
+        {
+            TRY_CUDA(c, cudaMalloc((void**)&g.d_binst, sizeof(tr_build_instance) * instance_count));
+            TRY_CUDA(c, cudaMemcpyAsync(g.d_binst, g.binst.data(), sizeof(tr_build_instance) * instance_count, cudaMemcpyHostToDevice, st));
+        }
+        if(g.refit_scratch_nodes < node_count)
+        {
+            if(g.refit_scratch) cudaFree(g.refit_scratch);
+            g.refit_scratch = nullptr; g.refit_scratch_nodes = 0;
+            TRY_CUDA(c, cudaMalloc((void**)&g.refit_scratch, (6 * (size_t)node_count + 1) * sizeof(float)));
+            g.refit_scratch_nodes = node_count;
+        }
+        TRY_CUDA(c, tr_build_refit_bvh(st, bin, g.d_binst, g.bvh_nodes, g.bvh_tris, node_count, g.level_offsets, g.refit_scratch));
+        TRY_CUDA(c, cudaEventRecord(c->ev_end, st));
+        TRY_CUDA(c, cudaStreamSynchronize(st));
+        float refit_ms = 0.0f;
+        cudaEventElapsedTime(&refit_ms, c->ev_begin, c->ev_end);
+        c->stats.bvh_build_ms = refit_ms;
+        return TR_OK;
+    }
     tr_build_output bout;
     TRY_CUDA(c, tr_build_bvh(st, bin, &bout));
+    g.level_offsets = bout.level_offsets;
     // the new tree is owned from here on, whatever happens next
     if(g.bvh_nodes) cudaFree(g.bvh_nodes);
     if(g.bvh_tris) cudaFree(g.bvh_tris);
@@ -807,10 +840,18 @@ int tr_pt_update_instances(tr_pt_ctx* c, const tr_instance* instances, uint32_t 
     DeviceGuard guard(c->device);
     if(c->last_stream && c->last_stream != c->stream) TRY_CUDA(c, cudaStreamSynchronize(c->last_stream));
     TRY_CUDA(c, cudaStreamSynchronize(c->stream));
-    // per-frame update: the fast radix-tree rebuild
-    const int rc = transform_and_build(c, instances, instance_count, false);
+    // per-frame update: the fast radix-tree rebuild, or a refit of the tree the scene has (tr_pt_set_update_mode)
+    const int rc = transform_and_build(c, instances, instance_count, false, c->update_mode == TR_UPDATE_REFIT);
     if(rc != TR_OK) c->has_scene = false;     // a half-updated scene must not be rendered: the next render fails loudly
     return rc;
+}
+
+int tr_pt_set_update_mode(tr_pt_ctx* c, int mode)
+{
+    if(!c) return TR_ERR_INVALID_ARGUMENT;
+    if(mode != TR_UPDATE_REBUILD && mode != TR_UPDATE_REFIT) return fail(c, TR_ERR_INVALID_ARGUMENT, "unknown update mode");
+    c->update_mode = mode;
+    return TR_OK;
 }
 
 int tr_pt_set_cameras(tr_pt_ctx* c, const tr_camera_pair* pairs, uint32_t view_count)

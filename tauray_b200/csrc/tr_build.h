@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <vector>
 #include "../../include/tauray_b200.h"
 
 struct tr_build_instance
@@ -30,6 +31,7 @@ struct tr_build_output
     uint32_t node_count;
     uint32_t depth;           // number of breadth-first levels
     float eps;                // box inflation
+    std::vector<uint32_t> level_offsets;   // depth + 1 entries: nodes [level_offsets[l], level_offsets[l + 1]) form level l
 };
 
 cudaError_t tr_build_pre_transform(cudaStream_t stream, const tr_vertex* in, tr_vertex* out, uint32_t count,
@@ -43,3 +45,10 @@ cudaError_t tr_build_extract_tri_lights(cudaStream_t stream, const tr_vertex* ve
 cudaError_t tr_build_envmap_importance(cudaStream_t stream, const void* texels, uint32_t format, uint32_t width, uint32_t height,
                                        float* importance_dev);
 cudaError_t tr_build_bvh(cudaStream_t stream, const tr_build_input& in, tr_build_output* out);
+// Refit of an existing wide tree to moved vertices (the BLAS / TLAS `update` of src/acceleration_structure.cc:187-262,
+// :376-443): the topology, the slot assignment and the triangle order stay, the leaf triangles are re-fetched and the
+// quantised child boxes recomputed level by level from the bottom. `instances_dev` = in.instances on the device,
+// `scratch` = 6 floats per node + 1 word.
+cudaError_t tr_build_refit_bvh(cudaStream_t stream, const tr_build_input& in, const tr_build_instance* instances_dev,
+                               float4* nodes, float4* tris, uint32_t node_count, const std::vector<uint32_t>& level_offsets,
+                               float* scratch);

@@ -1055,6 +1055,96 @@ __global__ void k_reorder_tris(const float4* __restrict__ tris, const uint32_t* 
     out[3 * (size_t)i + 2] = tris[3 * (size_t)t + 2];
 }
 
+// ---------------------------------------------------------------------------------------------
+// 9. refit of the wide tree to moved vertices (src/acceleration_structure.cc:187-262 `eUpdate`)
+// ---------------------------------------------------------------------------------------------
+// The leaf records keep their order and their (instance, primitive) words; only the positions are re-fetched.
+__global__ void k_refit_leaf_tris(const tr_vertex* __restrict__ verts, const uint32_t* __restrict__ indices,
+                                  const tr_build_instance* __restrict__ inst, uint32_t n, float4* __restrict__ tris,
+                                  uint32_t* __restrict__ maxabs_bits)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    float m = 0.0f;
+    if(i < n)
+    {
+        float4* o = tris + 3 * (size_t)i;
+        const int instance = __float_as_int(o[0].w), prim = __float_as_int(o[1].w);
+        const tr_build_instance I = inst[instance];
+        const uint32_t* idx = indices + I.index_base + 3 * (size_t)prim;
+        for(int k = 0; k < 3; ++k)
+        {
+            const tr_vertex& v = verts[I.vertex_base + idx[k]];
+            o[k] = make_float4(v.pos[0], v.pos[1], v.pos[2], o[k].w);
+            m = fmaxf(m, fmaxf(fabsf(v.pos[0]), fmaxf(fabsf(v.pos[1]), fabsf(v.pos[2]))));
+        }
+    }
+    for(int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, off));
+    if((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(maxabs_bits, __float_as_uint(m));   // non-negative floats order like their bits
+}
+
+// One thread per wide node of one level (the levels below are done): exact bounds of every occupied slot -- an inner
+// child's from `node_bounds`, a leaf slot's from its one or two triangles --, then the same inflation, quantisation and
+// masks as at build time (write_wide_node) with the slot assignment, child base and triangle base the node already has.
+__global__ void k_refit_level(float4* __restrict__ nodes, const float4* __restrict__ tris, float* __restrict__ node_bounds,
+                              uint32_t begin, uint32_t end, const uint32_t* __restrict__ maxabs_bits)
+{
+    const uint32_t node = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if(node >= end) return;
+    const float eps = __uint_as_float(*maxabs_bits) * (1.0f / 65536.0f);
+    float4* out = nodes + TR_BVH_NODE_VEC4 * (size_t)node;
+    const float4 n1 = out[1];
+    const uint32_t child_base = __float_as_uint(n1.x), tri_base = __float_as_uint(n1.y);
+    const uint32_t imask = __float_as_uint(n1.z) & 0xFFu;            // octant 0 = slot order
+    const uint32_t leaf8 = __float_as_uint(n1.w) & 0xFFu, two8 = (__float_as_uint(n1.w) >> 8) & 0xFFu;
+    float clo[8][3], chi[8][3];
+    int slot_child[8];
+    uint32_t count_of_slot[8];
+    float elo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, ehi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    int n = 0;
+    for(int s = 0; s < 8; ++s)
+    {
+        slot_child[s] = -1;
+        count_of_slot[s] = 0u;
+        const uint32_t below = (1u << s) - 1u;
+        float lo[3], hi[3];
+        if((imask >> s) & 1u)
+        {
+            const float* b = node_bounds + 6 * (size_t)(child_base + __popc(imask & below));
+            for(int a = 0; a < 3; ++a) { lo[a] = b[a]; hi[a] = b[3 + a]; }
+        }
+        else if((leaf8 >> s) & 1u)
+        {
+            const uint32_t first = tri_base + __popc(leaf8 & below) + __popc(two8 & below);
+            const uint32_t cnt = 1u + ((two8 >> s) & 1u);
+            for(int a = 0; a < 3; ++a) { lo[a] = FLT_MAX; hi[a] = -FLT_MAX; }
+            for(uint32_t t = 0; t < 3u * cnt; ++t)
+            {
+                const float4 v = tris[3 * (size_t)first + t];
+                lo[0] = fminf(lo[0], v.x); lo[1] = fminf(lo[1], v.y); lo[2] = fminf(lo[2], v.z);
+                hi[0] = fmaxf(hi[0], v.x); hi[1] = fmaxf(hi[1], v.y); hi[2] = fmaxf(hi[2], v.z);
+            }
+            count_of_slot[s] = cnt;
+        }
+        else continue;
+        slot_child[s] = s;
+        n++;
+        for(int a = 0; a < 3; ++a)
+        {
+            clo[s][a] = lo[a] - eps; chi[s][a] = hi[a] + eps;
+            elo[a] = fminf(elo[a], lo[a]); ehi[a] = fmaxf(ehi[a], hi[a]);
+        }
+    }
+    float* nb = node_bounds + 6 * (size_t)node;
+    if(n == 0)
+    {
+        for(int a = 0; a < 3; ++a) { nb[a] = 0.0f; nb[3 + a] = 0.0f; }
+        return;                                                    // the empty scene's only node stays as it is
+    }
+    float nlo[3], nhi[3];
+    for(int a = 0; a < 3; ++a) { nlo[a] = elo[a] - eps; nhi[a] = ehi[a] + eps; nb[a] = elo[a]; nb[3 + a] = ehi[a]; }
+    write_wide_node(out, nlo, nhi, n, clo, chi, slot_child, count_of_slot, imask, child_base, tri_base);
+}
+
 __global__ void k_init_bounds(uint32_t* bounds)
 {
     if(threadIdx.x < 3) bounds[threadIdx.x] = 0xFFFFFFFFu;
@@ -1189,7 +1279,7 @@ cudaError_t tr_build_envmap_importance(cudaStream_t stream, const void* texels, 
 cudaError_t tr_build_bvh(cudaStream_t stream, const tr_build_input& in, tr_build_output* out)
 {
     const uint32_t n = in.triangle_count;
-    out->nodes = nullptr; out->tris = nullptr; out->node_count = 0; out->depth = 0;
+    out->nodes = nullptr; out->tris = nullptr; out->node_count = 0; out->depth = 0; out->level_offsets.clear();
     ScopedFree tmp;
     PhaseTimer timer(stream);
     {
@@ -1250,6 +1340,7 @@ cudaError_t tr_build_bvh(cudaStream_t stream, const tr_build_input& in, tr_build
         if(e0 == cudaSuccess) e0 = cudaStreamSynchronize(stream);
         if(e0 != cudaSuccess) { cudaFree(nodes_final); cudaFree(tris_empty); return e0; }
         out->nodes = nodes_final; out->tris = tris_empty; out->node_count = 1; out->depth = 1;
+        out->level_offsets = {0u, 1u};
         return cudaSuccess;
     }
 
@@ -1398,6 +1489,7 @@ cudaError_t tr_build_bvh(cudaStream_t stream, const tr_build_input& in, tr_build
     {
         k_wide_single<<<1, 1, 0, stream>>>((int)n, leaf_boxes, inner_boxes, eps, tris_sorted, nodes, tris_final);
         node_count = 1; depth = 1;
+        out->level_offsets = {0u, 1u};
     }
     else
     {
@@ -1409,6 +1501,7 @@ cudaError_t tr_build_bvh(cudaStream_t stream, const tr_build_input& in, tr_build
         CUDA_OK3(cudaMemsetAsync(tri_counter, 0, sizeof(uint32_t), stream));
         int frontier_size = 1;
         int out_base = 0;
+        out->level_offsets.assign(1, 0u);
         while(frontier_size > 0)
         {
             CUDA_OK3(cudaMemsetAsync(next_count, 0, sizeof(int), stream));
@@ -1420,6 +1513,7 @@ cudaError_t tr_build_bvh(cudaStream_t stream, const tr_build_input& in, tr_build
             CUDA_OK3(cudaMemcpyAsync(&next_size, next_count, sizeof(int), cudaMemcpyDeviceToHost, stream));
             CUDA_OK3(cudaStreamSynchronize(stream));
             out_base = next_out_base;
+            out->level_offsets.push_back((uint32_t)out_base);
             frontier_size = next_size;
             std::swap(frontier_a, frontier_b);
             depth++;
@@ -1441,4 +1535,22 @@ cudaError_t tr_build_bvh(cudaStream_t stream, const tr_build_input& in, tr_build
     out->node_count = node_count;
     out->depth = depth;
     return cudaSuccess;
+}
+
+cudaError_t tr_build_refit_bvh(cudaStream_t stream, const tr_build_input& in, const tr_build_instance* instances_dev,
+                               float4* nodes, float4* tris, uint32_t node_count, const std::vector<uint32_t>& level_offsets,
+                               float* scratch)
+{
+    if(level_offsets.size() < 2 || level_offsets.back() != node_count) return cudaErrorInvalidValue;
+    uint32_t* maxabs_bits = reinterpret_cast<uint32_t*>(scratch + 6 * (size_t)node_count);
+    cudaError_t e = cudaMemsetAsync(maxabs_bits, 0, sizeof(uint32_t), stream);
+    if(e != cudaSuccess) return e;
+    const uint32_t n = in.triangle_count;
+    if(n) k_refit_leaf_tris<<<div_up(n, 256), 256, 0, stream>>>(in.vertices, in.indices, instances_dev, n, tris, maxabs_bits);
+    for(size_t l = level_offsets.size() - 1; l-- > 0;)
+    {
+        const uint32_t begin = level_offsets[l], end = level_offsets[l + 1];
+        if(end > begin) k_refit_level<<<div_up(end - begin, 128), 128, 0, stream>>>(nodes, tris, scratch, begin, end, maxabs_bits);
+    }
+    return cudaGetLastError();
 }

@@ -204,6 +204,8 @@ public:
     {
         check(tr_pt_update_instances(ctx, instances, instance_count), ctx, "tr_pt_update_instances");
     }
+    // TR_UPDATE_REBUILD (default) or TR_UPDATE_REFIT: how update_instances brings the acceleration structure up to date
+    void set_update_mode(int mode) { check(tr_pt_set_update_mode(ctx, mode), ctx, "tr_pt_set_update_mode"); }
     std::vector<float> read_color()
     {
         void* p; size_t bytes;

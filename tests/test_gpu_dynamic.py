@@ -100,3 +100,63 @@ def test_update_instances_rejects_a_different_layout():
         with pytest.raises(TaurayB200Error):
             pt.update_instances(table)
         pt.update_instances(scene.instance_table())              # unchanged records are fine
+
+
+# ---- TR_UPDATE_REFIT: the scene's tree keeps its topology, only the boxes follow the motion ---------------------------
+@pytest.mark.parametrize("mode", [abi.KERNEL_WAVEFRONT, abi.KERNEL_MEGAKERNEL])
+def test_refit_updates_equal_a_fresh_scene(mode):
+    opt = abi.default_options(max_ray_depth=3, samples_per_pixel=2, local_sampler=abi.SAMPLER_SOBOL_OWEN)
+    opt.kernel_mode = mode
+    cams = testscenes.cornell_cameras(SIZE[0] / SIZE[1])
+    dist = full_dist(SIZE)
+    scene = testscenes.cornell()
+    with PathTracer(opt) as pt:
+        pt.set_scene(scene)
+        pt.set_update_mode(abi.UPDATE_REFIT)
+        nodes_before = pt.stats()["bvh_node_count"]
+        first = _render(pt, cams, dist)
+        for step in (1, 2, 3):
+            _moved(scene, step)
+            pt.update_instances(scene.instance_table())
+            assert pt.stats()["bvh_node_count"] == nodes_before          # same tree
+            pt.reset_accumulation(False)
+            got = _render(pt, cams, dist)
+            lights = pt.tri_lights()
+            with PathTracer(opt) as fresh:
+                fresh.set_scene(scene)
+                for _ in range(step):
+                    fresh.set_cameras(cams); fresh.set_distribution(dist); fresh.render()
+                fresh.reset_accumulation(False)
+                want = _render(fresh, cams, dist)
+                assert fresh.tri_lights().tobytes() == lights.tobytes()
+            assert bits_equal(got, want), "step %d: the refitted tree renders another image than a fresh scene" % step
+            assert not bits_equal(got, first)
+        with pytest.raises(TaurayB200Error):
+            pt.set_update_mode(7)
+
+
+def test_an_identity_refit_reproduces_the_built_tree():
+    """Refitting to the unchanged instance records must give back the boxes the build wrote: the same image AND the same
+    number of node visits and triangle tests (a looser box would still render the right image). The visit counts of the
+    persistent kernel depend a little on which rays share a warp (postponed triangle groups), hence the 0.1 % allowance."""
+    from tauray_b200 import synthetic
+    opt = abi.default_options(max_ray_depth=3, samples_per_pixel=1, local_sampler=abi.SAMPLER_SOBOL_OWEN)
+    size = (160, 90)
+    scene = synthetic.atrium(20000)
+    cams = synthetic.atrium_cameras(size[0] / size[1])
+    dist = full_dist(size)
+    with PathTracer(opt) as pt:
+        pt.set_scene(scene)
+        pt.set_instrumentation(abi.INSTRUMENT_VISITS)
+        want = _render(pt, cams, dist)
+        st0 = pt.stats()
+        pt.set_update_mode(abi.UPDATE_REFIT)
+        pt.update_instances(scene.instance_table())
+        pt.reset_accumulation(True)
+        got = _render(pt, cams, dist)
+        st1 = pt.stats()
+    assert bits_equal(got, want)
+    for k in ("closest_rays", "shadow_rays"):
+        assert st0[k] == st1[k] and st0[k] > 0, k
+    for k in ("closest_node_visits", "closest_triangle_tests", "shadow_node_visits", "shadow_triangle_tests"):
+        assert st0[k] > 0 and abs(st0[k] - st1[k]) <= 1e-3 * st0[k], (k, st0[k], st1[k])
