@@ -852,7 +852,7 @@ __global__ void k_wide_level(int leaf_tris, const int* __restrict__ frontier, in
                              const float* __restrict__ leaf_boxes, const float* __restrict__ inner_boxes, float eps,
                              const float4* __restrict__ tris_sorted, float4* __restrict__ nodes, float4* __restrict__ tris_out,
                              int* __restrict__ next_frontier, int* __restrict__ next_count, int next_out_base,
-                             uint32_t* __restrict__ tri_counter, int bottom_tris)
+                             uint32_t* __restrict__ tri_counter, int bottom_tris, int keep_closed)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if(i >= frontier_size) return;
@@ -934,7 +934,7 @@ __global__ void k_wide_level(int leaf_tris, const int* __restrict__ frontier, in
             for(int k = 0; k < n; ++k)
             {
                 const int c = cand[k];
-                if(c < 0 || range_size(ranges, c) <= leaf_tris) continue;
+                if(c < 0 || range_size(ranges, c) <= keep_closed) continue;
                 const float* b = inner_boxes + 6 * (size_t)c;
                 const float dx = b[3] - b[0], dy = b[4] - b[1], dz = b[5] - b[2];
                 const float area = dx * dy + dy * dz + dz * dx;
@@ -1479,6 +1479,13 @@ cudaError_t tr_build_bvh(cudaStream_t stream, const tr_build_input& in, tr_build
     // measured on the atrium (ms/frame, triangle tests per closest ray): off 20.54 / 5.50, 8: 20.31 / 5.07, 12: 20.27 / 4.98,
     // 16: 20.30 / 5.07 -- node steps stay at 17.5, the gain is the tighter leaf boxes of the optimal cut
     static const int bottom_tris = getenv("TR_TUNE_BOTTOM") ? atoi(getenv("TR_TUNE_BOTTOM")) : 12;
+    // the greedy opening leaves subtrees of at most this many triangles closed (they become ONE bottom node at the next level
+    // instead of being cut into several tiny ones); TR_TUNE_KEEP_CLOSED, 0 = open everything above the leaf size. Measured on
+    // the atrium (TR_DEBUG_BVH_STATS: 201 k of the 261 k nodes are bottom nodes, 52 k of them with only 2-3 leaf slots): keeping
+    // them closed costs more than it saves -- 0: 20.10 ms / 17.49 node steps per closest ray, 4: 20.30 / 17.98, 8: 20.34 / 18.11,
+    // 12: 20.43 / 18.04 -- the parent's node step culls eight small tight boxes better than one visit of a fuller node
+    static const int keep_closed_env = getenv("TR_TUNE_KEEP_CLOSED") ? atoi(getenv("TR_TUNE_KEEP_CLOSED")) : 0;
+    const int keep_closed = std::max(leaf_tris, std::min(keep_closed_env, bottom_tris));
     uint32_t node_count = 0, depth = 0;
     // tris_sorted holds the Morton order; the wide emission re-packs triangles per node into tris_final
     float4* tris_final = nullptr;
@@ -1508,7 +1515,7 @@ cudaError_t tr_build_bvh(cudaStream_t stream, const tr_build_input& in, tr_build
             const int next_out_base = out_base + frontier_size;
             k_wide_level<<<div_up((uint32_t)frontier_size, 128), 128, 0, stream>>>(
                 leaf_tris, frontier_a, frontier_size, out_base, children, counts, leaf_boxes, inner_boxes, eps, tris_sorted, nodes,
-                tris_final, frontier_b, next_count, next_out_base, tri_counter, bottom_tris);
+                tris_final, frontier_b, next_count, next_out_base, tri_counter, bottom_tris, keep_closed);
             int next_size = 0;
             CUDA_OK3(cudaMemcpyAsync(&next_size, next_count, sizeof(int), cudaMemcpyDeviceToHost, stream));
             CUDA_OK3(cudaStreamSynchronize(stream));
@@ -1528,6 +1535,30 @@ cudaError_t tr_build_bvh(cudaStream_t stream, const tr_build_input& in, tr_build
     if(ef == cudaSuccess) ef = cudaStreamSynchronize(stream);
     if(ef != cudaSuccess) { cudaFree(nodes_final); return fail2(ef); }
     timer.mark("end");
+    if(getenv("TR_DEBUG_BVH_STATS"))
+    {
+        // development aid: how full are the wide nodes, level by level
+        std::vector<float4> h((size_t)node_count * TR_BVH_NODE_VEC4);
+        cudaMemcpy(h.data(), nodes_final, h.size() * sizeof(float4), cudaMemcpyDeviceToHost);
+        const std::vector<uint32_t>& lo = out->level_offsets;
+        for(size_t l = 0; l + 1 < lo.size(); ++l)
+        {
+            unsigned long long inner = 0, leaf = 0, two = 0, hist[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, bottom = 0;
+            for(uint32_t k = lo[l]; k < lo[l + 1]; ++k)
+            {
+                uint32_t wz, ww;
+                memcpy(&wz, &h[(size_t)k * TR_BVH_NODE_VEC4 + 1].z, 4); memcpy(&ww, &h[(size_t)k * TR_BVH_NODE_VEC4 + 1].w, 4);
+                const int ni = __builtin_popcount(wz & 0xFFu), nl = __builtin_popcount(ww & 0xFFu), nt = __builtin_popcount((ww >> 8) & 0xFFu);
+                inner += ni; leaf += nl; two += nt; hist[ni + nl]++;
+                if(ni == 0) bottom++;
+            }
+            const double cnt = (double)(lo[l + 1] - lo[l]);
+            fprintf(stderr, "bvh level %2zu: %8u nodes (%7llu without inner children)  inner/node %.2f  leaf slots/node %.2f  tris/node %.2f  children histogram", l,
+                    lo[l + 1] - lo[l], bottom, inner / cnt, leaf / cnt, (leaf + two) / cnt);
+            for(int c = 1; c <= 8; ++c) fprintf(stderr, " %d:%llu", c, hist[c]);
+            fprintf(stderr, "\n");
+        }
+    }
     nodes = nodes_final;
     tris_sorted = tris_final;
     out->nodes = nodes;

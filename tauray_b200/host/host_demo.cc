@@ -101,8 +101,9 @@ int main(int argc, char** argv)
             rr.set_device_workloads(w);
             rr.render();
         }
-        if(mode == "animate")
+        if(mode == "animate" || mode == "refit")
         {
+            if(mode == "refit") rr.set_update_mode(TR_UPDATE_REFIT);
             // scene_stage::update of an animated scene: instance 6 slides by (0.2, 0, 0.1); the previous transform
             // feeds the screen-motion layer. Pure translation: model_normal is unchanged.
             if(n < 7) throw std::runtime_error("animate: the scene needs at least 7 instances");

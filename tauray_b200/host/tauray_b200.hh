@@ -372,6 +372,11 @@ public:
     {
         for(auto& s: stages) s->update_instances(instances, instance_count);
     }
+    // acceleration-structure update of animated scenes: TR_UPDATE_REFIT (the reference's eUpdate builds) or TR_UPDATE_REBUILD
+    void set_update_mode(int mode)
+    {
+        for(auto& s: stages) s->set_update_mode(mode);
+    }
 
     // renderer::set_scene (src/rt_renderer.cc:60-65): builds one stage per device
     void set_scene(const tr_pt_scene_desc& scene, const tr_camera_pair* cameras, uint32_t view_count)

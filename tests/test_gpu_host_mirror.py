@@ -105,16 +105,17 @@ def test_cpp_direct_stage_matches_python(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("fake_devices", [1, 2])
-def test_cpp_update_instances_matches_python(tmp_path, fake_devices):
-    """rt_renderer::update_instances (scene_stage::update of an animated scene) through the C++ mirror."""
+@pytest.mark.parametrize("fake_devices,demo_mode", [(1, "animate"), (2, "animate"), (1, "refit")])
+def test_cpp_update_instances_matches_python(tmp_path, fake_devices, demo_mode):
+    """rt_renderer::update_instances (scene_stage::update of an animated scene) through the C++ mirror; `refit` =
+    rt_renderer::set_update_mode(TR_UPDATE_REFIT), which must render the same picture."""
     subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tauray_b200", "host")], check=True)
     size = (96, 64)
     scene = testscenes.cornell(alpha_card=False)
     cams = testscenes.cornell_cameras(size[0] / size[1])
     dump_scene(tmp_path / "scene.bin", scene, cams)
     env = dict(os.environ, TR_FAKE_DEVICES=str(fake_devices))
-    r = subprocess.run([DEMO, str(tmp_path / "scene.bin"), str(tmp_path / "out.raw"), str(size[0]), str(size[1]), "2", "3", "1", "animate"],
+    r = subprocess.run([DEMO, str(tmp_path / "scene.bin"), str(tmp_path / "out.raw"), str(size[0]), str(size[1]), "2", "3", "1", demo_mode],
                        capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stderr
     got = np.fromfile(tmp_path / "out.raw", dtype=np.float32).reshape(1, size[1], size[0], 4)
