@@ -417,36 +417,45 @@ def main():
     else:
         img_host = torch.empty((VIEWS, HEIGHT, WIDTH, 4), dtype=torch.float32).pin_memory()
 
-    # N = 1, frames that start from a clean accumulation: two frames in flight like the reference's headless loop
-    # (MAX_FRAMES_IN_FLIGHT = 2) -- the frame renders into one of two device targets (tr_pt_set_color_buffer) and its
-    # staging copy (tr_pt_read_color_async, on a copy stream, into one of two pinned host images) runs beside the next
-    # frame. Every step's camera upload and image read-back are inside the timed region; the host images are checked.
+    # Two frames in flight, like the reference's headless loop (MAX_FRAMES_IN_FLIGHT = 2, src/headless.cc:125-171): the
+    # camera table goes up in stream order (tr_pt_set_cameras_async), the frame renders, and its staging copy runs on a
+    # copy stream into one of two pinned host images beside the next frame; before a host image is reused the host waits
+    # for the copy that filled it two frames ago (that is the throttle, and where a consumer would read the picture).
+    # N = 1: two device targets (tr_pt_set_color_buffer) + tr_pt_read_color_async; N > 1: every rank copies its 1/N byte
+    # range of the double-buffered stitched image (RtRenderer.read_back_async). Every step's camera upload and image
+    # read-back are inside the timed region; the host images are checked afterwards.
     pipelined = world == 1 and reset_each_step
+    in_flight = pipelined or shared is not None
     e2e_count = [0]
+    copied = [None, None]
     if pipelined:
         targets = [torch.empty((VIEWS, HEIGHT, WIDTH, 4), dtype=torch.float32, device="cuda") for _ in range(2)]
         hosts = [torch.empty((VIEWS, HEIGHT, WIDTH, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
         copy_stream = torch.cuda.Stream(device=local_rank)
 
     def e2e_step():
-        ren.tracer.set_cameras(cam_np)                      # H2D (pinned)
+        if not in_flight:
+            ren.tracer.set_cameras(cam_np)                  # H2D (pinned), blocking
+            frame()
+            if world == 1:
+                ren.tracer.read_color_into(img_np.ctypes.data, img_np.nbytes)   # D2H (pinned) + sync
+            elif rank == 0:
+                img_host.copy_(ren._full, non_blocking=False)
+            return
+        b = e2e_count[0] & 1
+        e2e_count[0] += 1
+        if copied[b] is not None:
+            copied[b].synchronize()                         # host image b is free again (frame k - 2 has been delivered)
+        ren.tracer.set_cameras_async(cam_np, sptr)          # H2D (pinned), in stream order
         if pipelined:
-            b = e2e_count[0] & 1
-            e2e_count[0] += 1
             ren.tracer.set_color_buffer(targets[b].data_ptr(), targets[b].numel() * 4)
             frame()
-            ren.tracer.read_color_async(hosts[b].data_ptr(), hosts[b].numel() * 4, copy_stream.cuda_stream)   # D2H (pinned), no host sync
-            return
-        frame()
-        if world == 1:
-            ren.tracer.read_color_into(img_np.ctypes.data, img_np.nbytes)   # D2H (pinned) + sync
-        elif shared is not None:
-            # my 1/N of the stitched image into one of the two shared host images, on a copy stream beside the next frame
-            b = e2e_count[0] & 1
-            e2e_count[0] += 1
-            ren.read_back_async(shared.ptr + b * img_bytes + shared.offset, shared.offset, shared.count, sptr)
-        elif rank == 0:
-            img_host.copy_(ren._full, non_blocking=False)
+            ren.tracer.read_color_async(hosts[b].data_ptr(), hosts[b].numel() * 4, copy_stream.cuda_stream)   # D2H (pinned)
+            copied[b] = torch.cuda.Event()
+            copied[b].record(copy_stream)
+        else:
+            frame()
+            copied[b] = ren.read_back_async(shared.ptr + b * img_bytes + shared.offset, shared.offset, shared.count, sptr)
 
     for _ in range(2):
         e2e_step()

@@ -350,6 +350,11 @@ int tr_pt_set_update_mode(tr_pt_ctx* ctx, int mode);
 
 /* == camera UBO upload (src/scene_stage.cc:1145-1174); `pairs` = view_count tr_camera_pair. */
 int tr_pt_set_cameras(tr_pt_ctx* ctx, const tr_camera_pair* pairs, uint32_t view_count);
+/* The same in stream order, for frames in flight: the table is copied on `cuda_stream` -- the stream the following
+ * tr_pt_render calls use -- so it lands after the frames already enqueued there and before the next one, and the host
+ * does not wait for the frame in flight. `pairs` must be pinned host memory and stay untouched until the copy has run.
+ * A different `view_count` than the current one re-allocates the table and blocks like tr_pt_set_cameras. */
+int tr_pt_set_cameras_async(tr_pt_ctx* ctx, const tr_camera_pair* pairs, uint32_t view_count, void* cuda_stream);
 
 /* == rt_camera_stage::reset_distribution_params (src/rt_camera_stage.cc:141-145) */
 int tr_pt_set_distribution(tr_pt_ctx* ctx, const tr_pt_distribution* dist);

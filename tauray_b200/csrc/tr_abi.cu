@@ -872,6 +872,18 @@ int tr_pt_set_cameras(tr_pt_ctx* c, const tr_camera_pair* pairs, uint32_t view_c
     return TR_OK;
 }
 
+int tr_pt_set_cameras_async(tr_pt_ctx* c, const tr_camera_pair* pairs, uint32_t view_count, void* cuda_stream)
+{
+    if(!c || !pairs || view_count == 0) return fail(c, TR_ERR_INVALID_ARGUMENT, "null argument");
+    if(!cuda_stream || view_count != c->views || !c->cameras) return tr_pt_set_cameras(c, pairs, view_count);
+    DeviceGuard guard(c->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    // frames rendered on another stream read the table too: they finish first (normally there are none)
+    TRY_CUDA(c, wait_last_stream(c, st));
+    TRY_CUDA(c, cudaMemcpyAsync(c->cameras, pairs, sizeof(tr_camera_pair) * view_count, cudaMemcpyHostToDevice, st));
+    return TR_OK;
+}
+
 int tr_pt_set_distribution(tr_pt_ctx* c, const tr_pt_distribution* d)
 {
     if(!c || !d) return fail(c, TR_ERR_INVALID_ARGUMENT, "null argument");

@@ -28,7 +28,7 @@ EXPORTS = [
     "tr_pt_last_error", "tr_pt_abi_version", "tr_pt_alloc_full_image", "tr_pt_ipc_get_handle",
     "tr_pt_ipc_open_handle", "tr_pt_ipc_close_handle", "tr_pt_set_color_buffer", "tr_pt_read_full_image", "tr_pt_enable_peer_access",
     "tr_pt_get_full_image_info", "tr_pt_set_stitch_double_buffer", "tr_pt_set_render_in_full_image", "tr_pt_read_full_image_range",
-    "tr_pt_read_full_layer", "tr_pt_read_color_async", "tr_pt_read_full_image_range_async", "tr_pt_set_update_mode",
+    "tr_pt_read_full_layer", "tr_pt_read_color_async", "tr_pt_read_full_image_range_async", "tr_pt_set_update_mode", "tr_pt_set_cameras_async",
 ]
 
 
@@ -66,6 +66,7 @@ def lib():
     l.tr_pt_restore_accumulation.argtypes = [vp, vp, C.c_size_t, C.POINTER(abi.AccumulationState)]
     l.tr_pt_read_color.argtypes = [vp, vp, C.c_size_t]
     l.tr_pt_set_update_mode.argtypes = [vp, C.c_int]
+    l.tr_pt_set_cameras_async.argtypes = [vp, vp, C.c_uint32, vp]
     l.tr_pt_read_color_async.argtypes = [vp, vp, C.c_size_t, vp]
     l.tr_pt_unshuffle.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, C.c_float, vp]
     l.tr_pt_set_stitch_blend.argtypes = [vp, C.c_float]
@@ -148,6 +149,13 @@ class PathTracer:
         (abi.INSTANCE array, e.g. Scene.instance_table())."""
         inst = np.ascontiguousarray(instances, dtype=abi.INSTANCE)
         self._check(self._l.tr_pt_update_instances(self._ctx, inst.ctypes.data, inst.shape[0]), "tr_pt_update_instances")
+
+    def set_cameras_async(self, pinned_pairs, stream):
+        """The camera table in stream order (frames in flight): `pinned_pairs` = abi.CAMERA_PAIR array in pinned host
+        memory that stays untouched until the copy has run on `stream`, the stream the next renders use."""
+        assert pinned_pairs.dtype == abi.CAMERA_PAIR and pinned_pairs.flags["C_CONTIGUOUS"]
+        self._views = pinned_pairs.shape[0]
+        self._check(self._l.tr_pt_set_cameras_async(self._ctx, pinned_pairs.ctypes.data, pinned_pairs.shape[0], stream), "tr_pt_set_cameras_async")
 
     def set_update_mode(self, mode):
         """abi.UPDATE_REBUILD (a new radix tree per update) or abi.UPDATE_REFIT (the scene's tree keeps its topology)."""

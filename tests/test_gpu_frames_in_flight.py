@@ -49,8 +49,14 @@ def test_async_staging_copies_equal_the_blocking_read():
         pt.set_distribution(full_dist(SIZE))
         with pytest.raises(TaurayB200Error):
             pt.read_color_async(hosts[0].data_ptr(), hosts[0].numel() * 4, copy_stream.cuda_stream)   # nothing rendered yet
+        # the camera tables go up in stream order too (tr_pt_set_cameras_async): one pinned table per frame, untouched
+        # until its copy has run; the host never waits inside this loop
+        pinned = []
         for k in range(frames):
-            pt.set_cameras(_cams(k))
+            t = torch.from_numpy(np.frombuffer(_cams(k).tobytes(), dtype=np.uint8).copy()).pin_memory()
+            pinned.append(t)
+        for k in range(frames):
+            pt.set_cameras_async(pinned[k].numpy().view(abi.CAMERA_PAIR), render_stream.cuda_stream)
             pt.set_color_buffer(targets[k & 1].data_ptr(), targets[k & 1].numel() * 4)
             pt.reset_accumulation()
             pt.render(render_stream.cuda_stream)
