@@ -248,6 +248,8 @@ def main():
     ap.add_argument("--stitch", default=None, choices=[None, "peer", "nccl"])
     ap.add_argument("--kernel", default="wavefront", choices=["wavefront", "megakernel"])
     ap.add_argument("--triangles", type=int, default=TRIANGLES)
+    ap.add_argument("--frames-in-flight", type=int, default=2, choices=[1, 2],
+                    help="2: tr_pt_render_begin(k + 1) is issued before tr_pt_render_end(k) (two frames' traversal work queued); 1: frame by frame")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the oracle leg (cpu_baseline + parity)")
     ap.add_argument("--no-checks", action="store_true", help="N > 1: skip the single-rank image check and the NCCL-stitch comparison")
     ap.add_argument("--selftest", action="store_true", help="N > 1: run the whole multi-GPU test worker (tests/_nccl_worker.py) and exit")
@@ -330,10 +332,34 @@ def main():
             r.reset_accumulation()
         r.render(sptr)
 
+    # two frames in flight on the device: begin(k + 1) before end(k) (tr_pt_render_begin / tr_pt_render_end)
+    fif = args.frames_in_flight == 2 and args.kernel == "wavefront"
+
+    def frame_begin(r=ren):
+        if reset_each_step:
+            r.reset_accumulation()
+        r.render_begin(sptr)
+
+    def frame_end(r=ren):
+        r.render_end(sptr)
+
     # ---- value: device-resident, CUDA events on the launching stream around exactly K frames ----
     ren.tracer.set_instrumentation(0)
-    for _ in range(args.warmup):
-        frame()
+
+    def frames(k, r=ren):
+        """EXACTLY k frames, begun and ended inside the call: with frames in flight the pipeline starts empty and is
+        drained (begin(0); { begin(i + 1); end(i) }), so the fill and the drain are part of what is timed."""
+        if not fif:
+            for _ in range(k):
+                frame(r)
+            return
+        frame_begin(r)
+        for i in range(k):
+            if i + 1 < k:
+                frame_begin(r)
+            frame_end(r)
+
+    frames(args.warmup)
     barrier()
     clocks = ClockSampler(local_rank)
     if rank == 0:
@@ -341,8 +367,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     wall0 = time.perf_counter()
     e0.record(stream)
-    for _ in range(args.steps):
-        frame()
+    frames(args.steps)
     e1.record(stream)
     barrier()
     wall = time.perf_counter() - wall0
@@ -442,27 +467,49 @@ def main():
             elif rank == 0:
                 img_host.copy_(ren._full, non_blocking=False)
             return
-        b = e2e_count[0] & 1
+        k = e2e_count[0]
         e2e_count[0] += 1
+        b = k & 1
         if copied[b] is not None:
             copied[b].synchronize()                         # host image b is free again (frame k - 2 has been delivered)
-        ren.tracer.set_cameras_async(cam_np, sptr)          # H2D (pinned), in stream order
-        if pipelined:
-            ren.tracer.set_color_buffer(targets[b].data_ptr(), targets[b].numel() * 4)
+        if fif_e2e:
+            if k + 1 < e2e_total[0]:
+                e2e_issue(k + 1)                            # the NEXT frame's camera upload + traversal work ...
+            frame_end()                                     # ... then this frame's accumulation / stitch
+        else:
+            ren.tracer.set_cameras_async(cam_np, sptr)      # H2D (pinned), in stream order
+            if pipelined:
+                ren.tracer.set_color_buffer(targets[b].data_ptr(), targets[b].numel() * 4)
             frame()
+        if pipelined:
             ren.tracer.read_color_async(hosts[b].data_ptr(), hosts[b].numel() * 4, copy_stream.cuda_stream)   # D2H (pinned)
             copied[b] = torch.cuda.Event()
             copied[b].record(copy_stream)
         else:
-            frame()
             copied[b] = ren.read_back_async(shared.ptr + b * img_bytes + shared.offset, shared.offset, shared.count, sptr)
 
-    for _ in range(2):
-        e2e_step()
+    fif_e2e = fif and in_flight
+
+    def e2e_issue(k):
+        ren.tracer.set_cameras_async(cam_np, sptr)          # H2D (pinned), in stream order
+        if pipelined:
+            ren.tracer.set_color_buffer(targets[k & 1].data_ptr(), targets[k & 1].numel() * 4)
+        frame_begin()
+
+    e2e_total = [0]
+
+    def e2e_run(k):
+        """EXACTLY k end-to-end steps; with frames in flight on the device the pipeline starts empty and ends drained."""
+        e2e_count[0] = 0
+        e2e_total[0] = k
+        if fif_e2e:
+            e2e_issue(0)
+        for _ in range(k):
+            e2e_step()
+    e2e_run(2)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
+    e2e_run(args.steps)
     barrier()                                               # synchronises the device: the last staging copy included
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = rays_all / e2e_s / 1e6
@@ -493,13 +540,12 @@ def main():
     if td is not None and not args.no_checks and ren.stitch == "peer":
         ren2 = RtRenderer(opt, size, rank=rank, world=world, device=local_rank, stitch="nccl")
         ren2.set_scene(scene, cams)
-        for _ in range(args.warmup):
-            frame(ren2)
+        # the same schedule as the timed loop above (frames in flight or frame by frame)
+        frames(args.warmup, ren2)
         barrier()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a0.record(stream)
-        for _ in range(args.steps):
-            frame(ren2)
+        frames(args.steps, ren2)
         a1.record(stream)
         barrier()
         nccl_ms = max_over_ranks(a0.elapsed_time(a1)) / args.steps
@@ -656,6 +702,8 @@ def main():
             "data": "synthetic",
             "config": {"workload": workload, "triangles": args.triangles, "sampler": "sobol-owen", "kernel": args.kernel,
                        "views": VIEWS, "size": [WIDTH, HEIGHT], "spp_per_frame": SPP, "accumulated_spp_at_end": accumulated_spp,
+                       "frames_in_flight": ("2: tr_pt_render_begin(k + 1) is issued before tr_pt_render_end(k); the timed region begins and ends exactly K frames (pipeline fill and drain included)"
+                                            if fif else "1: frame by frame"),
                        "rays_definition": "traversal queries actually traced (closest + shadow); NEE shadow rays whose BSDF weight is "
                                           "exactly 0 are proven moot and not traced",
                        "culled_shadow_rays_per_frame": culled_all,

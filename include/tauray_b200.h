@@ -368,6 +368,21 @@ int tr_pt_reset_accumulation(tr_pt_ctx* ctx, int reset_sample_counter);
  * (NULL = the context's own stream). */
 int tr_pt_render(tr_pt_ctx* ctx, void* cuda_stream);
 
+/* == frames in flight on the device (the reference keeps MAX_FRAMES_IN_FLIGHT = 2 command buffers going,
+ * src/context.hh; rt_renderer::render is called for frame k + 1 while frame k executes). tr_pt_render == begin + end.
+ * tr_pt_render_begin enqueues, on a stream of the context's own, everything of the next frame that only touches the
+ * frame's own state: camera rays, traversal and shading of every bounce (ordered behind what `cuda_stream` holds at the
+ * time of the call, e.g. tr_pt_set_cameras_async). tr_pt_render_end enqueues on `cuda_stream`, behind that work, the
+ * accumulation into the colour target and the stores of the stitch -- the only part that touches shared state -- for the
+ * OLDEST begun frame. Call order `begin(0); { begin(k + 1); end(k); }` keeps two frames' traversal launches queued: the
+ * SMs one frame's persistent grids release while they drain go to the other frame. At most two
+ * frames may be begun. Results (tr_pt_read_*, tr_pt_get_stats, tr_pt_get_full_image_info) refer to the frame ended
+ * last. Frames that need more than one wavefront batch, aux G-buffer layers, samples_per_pass > 1, the megakernel or
+ * the instrumentation are rendered whole by tr_pt_render_end (one frame begun at a time). Scene changes
+ * (tr_pt_set_scene, tr_pt_update_instances) need every begun frame ended. */
+int tr_pt_render_begin(tr_pt_ctx* ctx, void* cuda_stream);
+int tr_pt_render_end(tr_pt_ctx* ctx, void* cuda_stream);
+
 /* == feature_stage (src/feature_stage.cc:21-110, shader/rt_feature.rgen): one AOV pass. */
 int tr_pt_render_feature(tr_pt_ctx* ctx, int feature, const float default_value[4],
                          void* cuda_stream);

@@ -102,6 +102,29 @@ struct tr_pt_ctx
     tr_pt_stats stats{};
     bool rendered = false;
     int update_mode = TR_UPDATE_REBUILD;     // tr_pt_set_update_mode
+    // frames in flight (tr_pt_render_begin / tr_pt_render_end): up to two begun frames, each with its own wavefront state,
+    // streams, counters and camera table; `deferred` = the frame is not eligible and is rendered whole by tr_pt_render_end
+    struct Flight
+    {
+        tr_wavefront wf{};
+        std::vector<void*> allocs;
+        tr_overlap overlap{};
+        cudaStream_t stream = nullptr;
+        cudaEvent_t traced = nullptr, finished = nullptr, ev_begin = nullptr, ev_end = nullptr;
+        Counters* counters = nullptr;
+        tr_camera_pair* cameras = nullptr;
+        uint32_t camera_views = 0;
+        RenderParams* P = nullptr;
+        uint32_t batch = 1;
+        uint32_t read_half = 0;
+        uint64_t launches = 0;
+        bool used = false, deferred = false;
+    };
+    Flight flights[2];
+    int flight_head = 0, flight_count = 0;
+    cudaEvent_t flight_call = nullptr;
+    Counters* stats_counters = nullptr;      // whose counters / events tr_pt_get_stats reads (the last finished frame's)
+    cudaEvent_t stats_begin = nullptr, stats_end = nullptr;
     float4* peers[8] = {};
     int peer_count = 0;
     int peer_self = -1;
@@ -232,6 +255,19 @@ cudaError_t wait_last_stream(tr_pt_ctx* c, cudaStream_t next)
     return cudaSuccess;
 }
 
+// Blocking setters also wait for the frames in flight (tr_pt_render_begin): those run on their own streams.
+cudaError_t quiesce(tr_pt_ctx* c, cudaStream_t next)
+{
+    for(auto& f : c->flights)
+        if(f.stream && f.used)
+        {
+            cudaError_t e = cudaStreamSynchronize(f.stream);
+            if(e == cudaSuccess && f.overlap.aux) e = cudaStreamSynchronize(f.overlap.aux);
+            if(e != cudaSuccess) return e;
+        }
+    return wait_last_stream(c, next);
+}
+
 const size_t k_layer_texel_bytes[TR_GBUFFER_LAYER_COUNT] = {16, 8, 8, 8, 4, 4, 16, 16, 4};
 
 void free_gbuffer(tr_pt_ctx* c)
@@ -245,6 +281,31 @@ void free_gbuffer(tr_pt_ctx* c)
 }
 
 // (re)allocates the colour target and the wavefront buffers for the current cameras/distribution
+static int alloc_wavefront(tr_pt_ctx* c, tr_wavefront& w, std::vector<void*>& allocs, uint32_t slots)
+{
+    free_list(allocs);
+    memset(&w, 0, sizeof(w));
+    const size_t n = std::max<uint32_t>(slots, 1);
+    TRY_CUDA(c, dev_alloc(allocs, &w.pos_pdf, n));
+    TRY_CUDA(c, dev_alloc(allocs, &w.dir_seed, n));
+    TRY_CUDA(c, dev_alloc(allocs, &w.atten_reg, n));
+    TRY_CUDA(c, dev_alloc(allocs, &w.lobes, n));
+    TRY_CUDA(c, dev_alloc(allocs, &w.diffuse, n));
+    TRY_CUDA(c, dev_alloc(allocs, &w.reflection, n));
+    TRY_CUDA(c, dev_alloc(allocs, &w.fh_emission, n));
+    TRY_CUDA(c, dev_alloc(allocs, &w.fh_albedo, n));
+    TRY_CUDA(c, dev_alloc(allocs, &w.rs_seed, n));
+    TRY_CUDA(c, dev_alloc(allocs, &w.hits, n));
+    TRY_CUDA(c, dev_alloc(allocs, &w.nee, 4 * n));
+    TRY_CUDA(c, dev_alloc(allocs, &w.sum_color, c->opt.samples_per_pass > 1 ? 3 * n : 1));   // colour, diffuse, reflection sums
+    TRY_CUDA(c, dev_alloc(allocs, &w.queue[0], n));
+    TRY_CUDA(c, dev_alloc(allocs, &w.queue[1], n));
+    TRY_CUDA(c, dev_alloc(allocs, &w.shadow_queue, n));
+    TRY_CUDA(c, dev_alloc(allocs, &w.counts, 4 * 64 + 2));
+    w.capacity = slots;
+    return TR_OK;
+}
+
 int prepare_targets(tr_pt_ctx* c)
 {
     if(!c->has_scene) return fail(c, TR_ERR_NO_SCENE, "tr_pt_set_scene has not been called");
@@ -304,27 +365,8 @@ int prepare_targets(tr_pt_ctx* c)
     if(slots64 * batch >= (1ull << 31)) return fail(c, TR_ERR_UNSUPPORTED, "more than 2^31 launch slots in flight");
     if(c->opt.kernel_mode == TR_KERNEL_WAVEFRONT && c->opt.estimator == TR_ESTIMATOR_PATH_TRACER && (c->wf.capacity < slots || !c->wf.counts))
     {
-        free_list(c->wf_allocs);
-        tr_wavefront& w = c->wf;
-        memset(&w, 0, sizeof(w));
-        const size_t n = std::max<uint32_t>(slots, 1);
-        TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.pos_pdf, n));
-        TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.dir_seed, n));
-        TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.atten_reg, n));
-        TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.lobes, n));
-        TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.diffuse, n));
-        TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.reflection, n));
-        TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.fh_emission, n));
-        TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.fh_albedo, n));
-        TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.rs_seed, n));
-        TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.hits, n));
-        TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.nee, 4 * n));
-        TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.sum_color, c->opt.samples_per_pass > 1 ? 3 * n : 1));   // colour, diffuse, reflection sums
-        TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.queue[0], n));
-        TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.queue[1], n));
-        TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.shadow_queue, n));
-        TRY_CUDA(c, dev_alloc(c->wf_allocs, &w.counts, 4 * 64 + 2));
-        w.capacity = slots;
+        const int rc = alloc_wavefront(c, c->wf, c->wf_allocs, slots);
+        if(rc) return rc;
     }
     return TR_OK;
 }
@@ -472,6 +514,20 @@ void tr_pt_destroy(tr_pt_ctx* c)
     if(!c) return;
     DeviceGuard guard(c->device);
     if(c->stream) cudaStreamSynchronize(c->stream);
+    for(auto& f : c->flights)
+    {
+        if(f.stream) cudaStreamSynchronize(f.stream);
+        if(f.overlap.aux) { cudaStreamSynchronize(f.overlap.aux); cudaStreamDestroy(f.overlap.aux); }
+        if(f.overlap.shaded) cudaEventDestroy(f.overlap.shaded);
+        if(f.overlap.shadowed) cudaEventDestroy(f.overlap.shadowed);
+        for(cudaEvent_t ev : {f.traced, f.finished, f.ev_begin, f.ev_end}) if(ev) cudaEventDestroy(ev);
+        if(f.stream) cudaStreamDestroy(f.stream);
+        if(f.counters) cudaFree(f.counters);
+        if(f.cameras) cudaFree(f.cameras);
+        free_list(f.allocs);
+        delete f.P;
+    }
+    if(c->flight_call) cudaEventDestroy(c->flight_call);
     free_scene(c);
     free_list(c->wf_allocs);
     if(c->cameras) cudaFree(c->cameras);
@@ -688,8 +744,9 @@ int tr_pt_set_scene(tr_pt_ctx* c, const tr_pt_scene_desc* s)
         if((uint64_t)e->width * e->height >= (1ull << 31)) return fail(c, TR_ERR_UNSUPPORTED, "environment map too large");
     }
     if(s->instance_count && (!s->instances || !s->meshes)) return fail(c, TR_ERR_INVALID_ARGUMENT, "null instance tables");
+    if(c->flight_count) return fail(c, TR_ERR_INVALID_ARGUMENT, "frames in flight: call tr_pt_render_end first");
     DeviceGuard guard(c->device);
-    TRY_CUDA(c, wait_last_stream(c, c->stream));
+    TRY_CUDA(c, quiesce(c, c->stream));
     TRY_CUDA(c, cudaStreamSynchronize(c->stream));
     free_scene(c);
     std::vector<void*>& A = c->scene_allocs;
@@ -837,8 +894,9 @@ int tr_pt_update_instances(tr_pt_ctx* c, const tr_instance* instances, uint32_t 
         if(instances[i].light_base_id >= 0)
             tri_light_count = std::max<uint64_t>(tri_light_count, (uint64_t)instances[i].light_base_id + g.binst[i].triangle_count);
     if(tri_light_count != g.tri_light_count) return fail(c, TR_ERR_INVALID_ARGUMENT, "the tri-light layout (light_base_id) may not change; use tr_pt_set_scene");
+    if(c->flight_count) return fail(c, TR_ERR_INVALID_ARGUMENT, "frames in flight: call tr_pt_render_end first");
     DeviceGuard guard(c->device);
-    if(c->last_stream && c->last_stream != c->stream) TRY_CUDA(c, cudaStreamSynchronize(c->last_stream));
+    TRY_CUDA(c, quiesce(c, c->stream));
     TRY_CUDA(c, cudaStreamSynchronize(c->stream));
     // per-frame update: the fast radix-tree rebuild, or a refit of the tree the scene has (tr_pt_set_update_mode)
     const int rc = transform_and_build(c, instances, instance_count, false, c->update_mode == TR_UPDATE_REFIT);
@@ -858,7 +916,7 @@ int tr_pt_set_cameras(tr_pt_ctx* c, const tr_camera_pair* pairs, uint32_t view_c
 {
     if(!c || !pairs || view_count == 0) return fail(c, TR_ERR_INVALID_ARGUMENT, "null argument");
     DeviceGuard guard(c->device);
-    TRY_CUDA(c, wait_last_stream(c, c->stream));
+    TRY_CUDA(c, quiesce(c, c->stream));
     TRY_CUDA(c, cudaStreamSynchronize(c->stream));
     if(view_count != c->views || !c->cameras)
     {
@@ -910,6 +968,7 @@ int tr_pt_reset_accumulation(tr_pt_ctx* c, int reset_sample_counter)
 int tr_pt_render(tr_pt_ctx* c, void* cuda_stream)
 {
     if(!c) return TR_ERR_INVALID_ARGUMENT;
+    if(c->flight_count) return fail(c, TR_ERR_INVALID_ARGUMENT, "frames in flight: call tr_pt_render_end first");
     DeviceGuard guard(c->device);
     int rc = prepare_targets(c);
     if(rc) return rc;
@@ -980,7 +1039,139 @@ int tr_pt_render(tr_pt_ctx* c, void* cuda_stream)
     TRY_CUDA(c, cudaEventRecord(c->ev_end, st));
     c->last_stream = st;
     c->stats.kernel_launches = launches;
+    c->stats_counters = c->counters; c->stats_begin = c->ev_begin; c->stats_end = c->ev_end;
     c->rendered = true;
+    return TR_OK;
+}
+
+// ---- frames in flight --------------------------------------------------------------------------------------------
+// tr_pt_render_begin enqueues everything of a frame that only touches the frame's own wavefront state -- camera rays, the
+// traversal and shade passes of every bounce -- on a stream of its own; tr_pt_render_end enqueues, on the caller's stream
+// and after that work, the one kernel that touches shared state: the accumulation into the colour target and the peer
+// stores of the stitch. With begin(k + 1) issued before end(k) the traversal launches of two frames are in the queue
+// at any time, and the SMs one frame's persistent grids release while they drain go to the other's.
+static bool flight_eligible(const tr_pt_ctx* c)
+{
+    const uint32_t pass_count = (uint32_t)(c->opt.samples_per_pixel / c->opt.samples_per_pass);
+    return c->opt.kernel_mode == TR_KERNEL_WAVEFRONT && c->opt.estimator == TR_ESTIMATOR_PATH_TRACER && c->opt.samples_per_pass == 1 &&
+           pass_count <= c->pass_batch && c->gbuffer_mask == 0 && c->instrumentation == 0;
+}
+
+int tr_pt_render_begin(tr_pt_ctx* c, void* cuda_stream)
+{
+    if(!c) return TR_ERR_INVALID_ARGUMENT;
+    if(c->flight_count >= 2) return fail(c, TR_ERR_INVALID_ARGUMENT, "two frames are in flight already: call tr_pt_render_end");
+    DeviceGuard guard(c->device);
+    int rc = prepare_targets(c);
+    if(rc) return rc;
+    if(c->restore_pending_layers & c->gbuffer_mask)
+        return fail(c, TR_ERR_INVALID_ARGUMENT, "restored checkpoint: write the aux G-buffer layers back (tr_pt_write_gbuffer_layer) before rendering");
+    tr_pt_ctx::Flight& F = c->flights[(c->flight_head + c->flight_count) % 2];
+    const bool whole = !flight_eligible(c);
+    if(c->flight_count && (whole || c->flights[c->flight_head].deferred))
+        return fail(c, TR_ERR_UNSUPPORTED, "this configuration renders frame by frame: end the begun frame before the next begins");
+    F.deferred = whole;
+    if(F.deferred) { c->flight_count++; return TR_OK; }        // rendered whole by tr_pt_render_end
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+    if(!F.stream)
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);              // lo = the LOWEST priority: finish + barrier kernels of the caller go first
+        TRY_CUDA(c, cudaStreamCreateWithPriority(&F.stream, cudaStreamNonBlocking, lo));
+        TRY_CUDA(c, cudaStreamCreateWithPriority(&F.overlap.aux, cudaStreamNonBlocking, lo));
+        TRY_CUDA(c, cudaEventCreateWithFlags(&F.overlap.shaded, cudaEventDisableTiming));
+        TRY_CUDA(c, cudaEventCreateWithFlags(&F.overlap.shadowed, cudaEventDisableTiming));
+        TRY_CUDA(c, cudaEventCreateWithFlags(&F.traced, cudaEventDisableTiming));
+        TRY_CUDA(c, cudaEventCreateWithFlags(&F.finished, cudaEventDisableTiming));
+        TRY_CUDA(c, cudaEventCreate(&F.ev_begin));
+        TRY_CUDA(c, cudaEventCreate(&F.ev_end));
+        TRY_CUDA(c, cudaMalloc((void**)&F.counters, sizeof(Counters)));
+        F.P = new RenderParams();
+    }
+    if(!c->flight_call) TRY_CUDA(c, cudaEventCreateWithFlags(&c->flight_call, cudaEventDisableTiming));
+    FrameParams fp;
+    fill_frame(c, fp);
+    const uint32_t pass_count = (uint32_t)(c->opt.samples_per_pixel / c->opt.samples_per_pass);
+    const uint64_t slots = (uint64_t)fp.ray_count_x * fp.ray_count_y * fp.views * pass_count;
+    if(F.wf.capacity < slots || !F.wf.counts)
+    {
+        if(F.used) { TRY_CUDA(c, cudaStreamSynchronize(F.stream)); TRY_CUDA(c, cudaStreamSynchronize(F.overlap.aux)); }
+        rc = alloc_wavefront(c, F.wf, F.allocs, (uint32_t)slots);
+        if(rc) return rc;
+    }
+    if(F.camera_views != c->views || !F.cameras)
+    {
+        if(F.used) TRY_CUDA(c, cudaStreamSynchronize(F.stream));
+        if(F.cameras) cudaFree(F.cameras);
+        F.cameras = nullptr;
+        TRY_CUDA(c, cudaMalloc((void**)&F.cameras, sizeof(tr_camera_pair) * c->views));
+        F.camera_views = c->views;
+    }
+    RenderParams& P = *F.P;
+    fill_params(c, P);
+    rc = select_full_image_half(c, P);
+    if(rc) return rc;
+    F.read_half = c->full_cur_half;
+    P.frame.sample_counter = c->frame_counter * (uint32_t)c->opt.samples_per_pixel;
+    P.frame.rng_seed = c->opt.rng_seed != 0 ? host_pcg((uint32_t)c->opt.rng_seed) : 0;
+    P.frame.samples_accumulated = (uint32_t)c->accumulated_samples;
+    P.frame.previous_samples = 0;
+    P.last_pass = 1;
+    P.counters = F.counters;
+    P.cameras = F.cameras;
+    c->frame_counter++;
+    c->accumulated_samples += c->opt.samples_per_pixel;
+    F.batch = pass_count;
+    F.launches = 0;
+    // On the caller's stream, behind whatever it has enqueued (a camera upload): the frame's own copy of the camera table
+    // -- the next frame's upload must not change the table under this frame. By then the frame that used this slot two
+    // frames ago has been finished on the same stream (tr_pt_render_end), so its kernels no longer read the copy.
+    TRY_CUDA(c, wait_last_stream(c, st));
+    TRY_CUDA(c, cudaMemcpyAsync(F.cameras, c->cameras, sizeof(tr_camera_pair) * c->views, cudaMemcpyDeviceToDevice, st));
+    TRY_CUDA(c, cudaEventRecord(c->flight_call, st));
+    TRY_CUDA(c, cudaStreamWaitEvent(F.stream, c->flight_call, 0));
+    if(F.used) TRY_CUDA(c, cudaStreamWaitEvent(F.stream, F.finished, 0));     // the slot's wavefront state is free again
+    TRY_CUDA(c, cudaMemsetAsync(F.counters, 0, sizeof(Counters), F.stream));
+    TRY_CUDA(c, cudaEventRecord(F.ev_begin, F.stream));
+    cudaError_t e = tr_render_pass_wavefront(F.stream, P, F.wf, c->sm_count, &F.launches, nullptr, F.batch, &F.overlap, TR_PHASE_TRACE);
+    if(e != cudaSuccess) return fail_cuda(c, e, "render pass launch");
+    TRY_CUDA(c, cudaEventRecord(F.traced, F.stream));
+    F.used = true;
+    c->flight_count++;
+    return TR_OK;
+}
+
+int tr_pt_render_end(tr_pt_ctx* c, void* cuda_stream)
+{
+    if(!c) return TR_ERR_INVALID_ARGUMENT;
+    if(c->flight_count == 0) return fail(c, TR_ERR_INVALID_ARGUMENT, "tr_pt_render_end without tr_pt_render_begin");
+    DeviceGuard guard(c->device);
+    tr_pt_ctx::Flight& F = c->flights[c->flight_head];
+    if(F.deferred)
+    {
+        c->flight_count = 0;
+        c->flight_head = (c->flight_head + 1) % 2;
+        return tr_pt_render(c, cuda_stream);
+    }
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+    RenderParams& P = *F.P;
+    // asynchronous read-backs of the target this frame writes finish first, on the device
+    for(auto& pc : c->pending_copies)
+        if(pc.src && pc.src == P.color) { TRY_CUDA(c, cudaStreamWaitEvent(st, pc.done, 0)); pc.src = nullptr; }
+    TRY_CUDA(c, cudaStreamWaitEvent(st, F.traced, 0));
+    cudaError_t e = tr_render_pass_wavefront(st, P, F.wf, c->sm_count, &F.launches, nullptr, F.batch, nullptr, TR_PHASE_FINISH);
+    if(e != cudaSuccess) return fail_cuda(c, e, "render pass launch");
+    TRY_CUDA(c, cudaEventRecord(F.finished, st));
+    TRY_CUDA(c, cudaEventRecord(F.ev_end, st));
+    TRY_CUDA(c, cudaEventRecord(c->ev_end, st));               // tr_pt_read_color_async orders its copy behind this
+    c->color = P.color;
+    c->full_cur_half = F.read_half;                            // what the read-backs of this frame address
+    c->last_stream = st;
+    c->stats.kernel_launches = F.launches;
+    c->stats_counters = F.counters; c->stats_begin = F.ev_begin; c->stats_end = F.ev_end;
+    c->rendered = true;
+    c->flight_head = (c->flight_head + 1) % 2;
+    c->flight_count--;
     return TR_OK;
 }
 
@@ -1236,12 +1427,13 @@ int tr_pt_get_stats(tr_pt_ctx* c, tr_pt_stats* stats)
     DeviceGuard guard(c->device);
     if(c->rendered)
     {
-        TRY_CUDA(c, cudaEventSynchronize(c->ev_end));
+        cudaEvent_t sb = c->stats_begin ? c->stats_begin : c->ev_begin, se = c->stats_end ? c->stats_end : c->ev_end;
+        TRY_CUDA(c, cudaEventSynchronize(se));
         float ms = 0.0f;
-        cudaEventElapsedTime(&ms, c->ev_begin, c->ev_end);
+        cudaEventElapsedTime(&ms, sb, se);
         c->stats.render_ms = ms;
         Counters h;
-        TRY_CUDA(c, cudaMemcpy(&h, c->counters, sizeof(h), cudaMemcpyDeviceToHost));
+        TRY_CUDA(c, cudaMemcpy(&h, c->stats_counters ? c->stats_counters : c->counters, sizeof(h), cudaMemcpyDeviceToHost));
         c->stats.closest_rays = h.closest_rays;
         c->stats.shadow_rays = h.shadow_rays;
         c->stats.paths = h.paths;

@@ -1651,7 +1651,7 @@ static int env_int(const char* name, int dflt)
 }
 
 cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const RenderParams& P_in, const tr_wavefront& wf, int sm_count, uint64_t* launches,
-                                     tr_launch_timer* timer, uint32_t batch, const tr_overlap* overlap)
+                                     tr_launch_timer* timer, uint32_t batch, const tr_overlap* overlap, int phase)
 {
     // per-launch timing needs one stream; TR_TUNE_OVERLAP=0 switches the second stream off for A/B runs
     static const int k_overlap = env_int("TR_TUNE_OVERLAP", 1);
@@ -1739,6 +1739,14 @@ cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const RenderParams& P_
     // layers written only while prev_samples == 0 (pass 0 = the first `base` slots of a batch)
     const bool first_sample_layers = (P.gbuffer_mask & ~((1u << TR_GBUFFER_COLOR) | (1u << TR_GBUFFER_DIFFUSE) | (1u << TR_GBUFFER_REFLECTION))) != 0 &&
                                      P.frame.samples_accumulated + P.frame.previous_samples == 0;
+    if(phase != TR_PHASE_ALL && spp != 1) return cudaErrorInvalidValue;
+    if(phase == TR_PHASE_FINISH)
+    {
+        // the second half of a frame in flight: only the accumulation (and the peer stores), on the caller's stream
+        k_wf_finish<<<grid_finish, WF_BLOCK, 0, stream>>>(P, wf, 0, base, batch);
+        ++*launches;
+        return cudaGetLastError();
+    }
     for(uint32_t i = 0; i < spp; ++i)
     {
         cudaError_t e = cudaMemsetAsync(wf.counts, 0, sizeof(uint32_t) * (4 * D + 2), stream);
@@ -1831,6 +1839,7 @@ cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const RenderParams& P_
             cudaError_t e2 = cudaStreamWaitEvent(stream, overlap->shadowed, 0);
             if(e2 != cudaSuccess) return e2;
         }
+        if(phase == TR_PHASE_TRACE) break;
         MARK(TR_KCLASS_OTHER);
         SLOT("finish");
         k_wf_finish<<<grid_finish, WF_BLOCK, 0, stream>>>(P, wf, i, base, batch);

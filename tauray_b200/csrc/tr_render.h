@@ -68,9 +68,13 @@ struct tr_overlap
 cudaError_t tr_render_init_constants();
 const uint4* tr_render_sobol_chunks();
 // One pass (= samples_per_pass samples of every slot) of path_tracer.rgen.
+// `phase`: TR_PHASE_ALL, or -- for frames in flight (tr_pt_render_begin / tr_pt_render_end) -- TR_PHASE_TRACE (everything up to
+// the last shade pass: only the wavefront state is written) and TR_PHASE_FINISH (k_wf_finish: the accumulation into the colour
+// target and the peer stores) as two calls on different streams. Single-sample passes only.
+enum { TR_PHASE_TRACE = 1, TR_PHASE_FINISH = 2, TR_PHASE_ALL = 3 };
 cudaError_t tr_render_pass_wavefront(cudaStream_t stream, const trd::RenderParams& P, const tr_wavefront& wf,
                                      int sm_count, uint64_t* launches, tr_launch_timer* timer, uint32_t batch,
-                                     const tr_overlap* overlap = nullptr);
+                                     const tr_overlap* overlap = nullptr, int phase = TR_PHASE_ALL);
 cudaError_t tr_render_pass_megakernel(cudaStream_t stream, const trd::RenderParams& P, int sm_count, uint64_t* launches,
                                       tr_launch_timer* timer);
 cudaError_t tr_render_pass_direct(cudaStream_t stream, const trd::RenderParams& P, int sm_count, uint64_t* launches,

@@ -28,7 +28,7 @@ EXPORTS = [
     "tr_pt_last_error", "tr_pt_abi_version", "tr_pt_alloc_full_image", "tr_pt_ipc_get_handle",
     "tr_pt_ipc_open_handle", "tr_pt_ipc_close_handle", "tr_pt_set_color_buffer", "tr_pt_read_full_image", "tr_pt_enable_peer_access",
     "tr_pt_get_full_image_info", "tr_pt_set_stitch_double_buffer", "tr_pt_set_render_in_full_image", "tr_pt_read_full_image_range",
-    "tr_pt_read_full_layer", "tr_pt_read_color_async", "tr_pt_read_full_image_range_async", "tr_pt_set_update_mode", "tr_pt_set_cameras_async",
+    "tr_pt_read_full_layer", "tr_pt_read_color_async", "tr_pt_read_full_image_range_async", "tr_pt_set_update_mode", "tr_pt_set_cameras_async", "tr_pt_render_begin", "tr_pt_render_end",
 ]
 
 
@@ -59,6 +59,8 @@ def lib():
     l.tr_pt_set_distribution.argtypes = [vp, C.POINTER(abi.Distribution)]
     l.tr_pt_reset_accumulation.argtypes = [vp, C.c_int]
     l.tr_pt_render.argtypes = [vp, vp]
+    l.tr_pt_render_begin.argtypes = [vp, vp]
+    l.tr_pt_render_end.argtypes = [vp, vp]
     l.tr_pt_render_feature.argtypes = [vp, C.c_int, C.POINTER(C.c_float), vp]
     l.tr_pt_sync.argtypes = [vp]
     l.tr_pt_get_color_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
@@ -181,6 +183,14 @@ class PathTracer:
     def render(self, stream=None):
         """stage::run: all passes of one frame, asynchronous."""
         self._check(self._l.tr_pt_render(self._ctx, stream), "tr_pt_render")
+
+    def render_begin(self, stream=None):
+        """Frames in flight: everything of the next frame but the accumulation, on a stream of the context's own."""
+        self._check(self._l.tr_pt_render_begin(self._ctx, stream), "tr_pt_render_begin")
+
+    def render_end(self, stream=None):
+        """The accumulation (and stitch stores) of the oldest begun frame, on `stream`."""
+        self._check(self._l.tr_pt_render_end(self._ctx, stream), "tr_pt_render_end")
 
     def render_feature(self, feature, default=(0.0, 0.0, 0.0, 0.0), stream=None):
         dv = (C.c_float * 4)(*default)

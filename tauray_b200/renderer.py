@@ -240,6 +240,34 @@ class RtRenderer:
                 self._set_blend(1.0)
         self.accumulated_frames += 1
 
+    def render_begin(self, stream=None):
+        """Frames in flight on the device (tr_pt_render_begin): camera rays, traversal and shading of the NEXT frame on a
+        stream of the tracer's own, behind what `stream` holds now. Call order begin(0); { begin(k + 1); end(k) }."""
+        if stream is None and self.cuda and self.world > 1:
+            import torch
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        self.tracer.render_begin(stream)
+
+    def render_end(self, stream=None):
+        """The rest of the oldest begun frame on `stream`: accumulation + peer stores (tr_pt_render_end), then the frame's
+        barrier / stitch exactly like render(). The next frame's stores into the stitched images come behind this barrier
+        on the same stream, so the double-buffer argument of render() holds unchanged."""
+        if stream is None and self.cuda and self.world > 1:
+            import torch
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        in_place = self.world > 1 and self.rank == self.primary
+        self.tracer.render_end(stream)
+        if self.world > 1 and self.stitch != "none":
+            if self.cuda and stream is not None:
+                import torch
+                with torch.cuda.stream(torch.cuda.ExternalStream(stream, device=torch.device("cuda", self.device))):
+                    self._stitch(stream, in_place)
+            else:
+                self._stitch(stream, in_place)
+            if self._blend != 1.0:
+                self._set_blend(1.0)
+        self.accumulated_frames += 1
+
     def _stitch(self, stream, in_place):
         import torch
         import torch.distributed as td

@@ -112,6 +112,29 @@ def run_checks(rank, world, local):
     print("rank %d asynchronous read-back with two frames in flight: %s" % (rank, "identical" if same else "DIFFERENT"), flush=True)
     ok = ok and same
     td.barrier()
+    # ---- frames in flight on the device too: begin(k + 1) before end(k) (tr_pt_render_begin / tr_pt_render_end), camera
+    # tables in stream order, read-backs asynchronous, odd ranks' copies late
+    hosts = [torch.zeros(wants[0].shape, dtype=torch.float32).pin_memory() for _ in cam_seq]
+    pinned = [torch.from_numpy(np.frombuffer(ck.tobytes(), dtype=np.uint8).copy()).pin_memory() for ck in cam_seq]
+
+    def begin(k):
+        ren.tracer.set_cameras_async(pinned[k].numpy().view(abi.CAMERA_PAIR), stream.cuda_stream)
+        ren.reset_accumulation()
+        ren.render_begin(stream.cuda_stream)
+
+    begin(0)
+    for k in range(len(cam_seq)):
+        if k + 1 < len(cam_seq):
+            begin(k + 1)
+        ren.render_end(stream.cuda_stream)
+        if rank % 2 == 1:
+            torch.cuda._sleep(100_000_000)
+        ren.read_back_async(hosts[k].data_ptr(), 0, hosts[k].numel() * 4, stream.cuda_stream)
+    torch.cuda.synchronize(local)
+    same = all(hosts[k].numpy().tobytes() == wants[k].tobytes() for k in range(len(cam_seq)))
+    print("rank %d frames in flight on the device (begin / end): %s" % (rank, "identical" if same else "DIFFERENT"), flush=True)
+    ok = ok and same
+    td.barrier()
     ren.close()
     # ---- aux G-buffer layers across devices (src/rt_renderer.cc:370-397): every rank's stitched layers == one device's
     layers = [abi.GBUFFER_DIFFUSE, abi.GBUFFER_REFLECTION, abi.GBUFFER_ALBEDO, abi.GBUFFER_MATERIAL, abi.GBUFFER_NORMAL,

@@ -32,4 +32,4 @@ def test_two_ranks_nccl_and_peer_stitch():
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "_nccl_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-3000:])
-    assert r.stdout.count("identical") == (3 + 1 + 1 + 2 + 4) * world and "DIFFERENT" not in r.stdout, r.stdout[-3000:]
+    assert r.stdout.count("identical") == (3 + 1 + 1 + 1 + 2 + 4) * world and "DIFFERENT" not in r.stdout, r.stdout[-3000:]

@@ -30,6 +30,17 @@ with PathTracer(opt) as pt:
         ms = 1e3 * (time.perf_counter() - t0) / frames
         st = pt.stats()
         if timing == 0:
-            print("world %d: %.3f ms/frame (ideal %.3f of the full frame's)" % (world, ms, 1.0 / world), end="  ")
+            # the same with two frames in flight (tr_pt_render_begin / tr_pt_render_end)
+            pt.reset_accumulation(); pt.render_begin()
+            for _ in range(3):
+                pt.reset_accumulation(); pt.render_begin(); pt.render_end()
+            pt.sync()
+            t0 = time.perf_counter()
+            for _ in range(frames):
+                pt.reset_accumulation(); pt.render_begin(); pt.render_end()
+            pt.sync()
+            ms2 = 1e3 * (time.perf_counter() - t0) / frames
+            pt.render_end(); pt.sync()
+            print("world %d: %.3f ms/frame (ideal %.3f of the full frame's), two frames in flight %.3f" % (world, ms, 1.0 / world, ms2), end="  ")
         else:
             print("closest %.3f shadow %.3f shade %.3f other %.3f" % (st["closest_ms"], st["shadow_ms"], st["shade_ms"], st["other_ms"]))
