@@ -181,6 +181,10 @@ public:
 
     // stage::run (src/stage.cc:35-76): `stream` carries the ordering the reference expresses as dependencies.
     void run(void* cuda_stream = nullptr) { check(tr_pt_render(ctx, cuda_stream), ctx, "tr_pt_render"); }
+    // two frames in flight (MAX_FRAMES_IN_FLIGHT = 2): run == run_begin + run_end; call run_begin for frame k + 1 before
+    // run_end for frame k and the traversal work of both frames is queued on the device
+    void run_begin(void* cuda_stream = nullptr) { check(tr_pt_render_begin(ctx, cuda_stream), ctx, "tr_pt_render_begin"); }
+    void run_end(void* cuda_stream = nullptr) { check(tr_pt_render_end(ctx, cuda_stream), ctx, "tr_pt_render_end"); }
     void sync() { check(tr_pt_sync(ctx), ctx, "tr_pt_sync"); }
     void reset_accumulated_samples() { check(tr_pt_reset_accumulation(ctx, 0), ctx, "tr_pt_reset_accumulation"); }
     void reset_sample_counter() { check(tr_pt_reset_accumulation(ctx, 1), ctx, "tr_pt_reset_accumulation"); }
