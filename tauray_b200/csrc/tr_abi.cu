@@ -119,6 +119,8 @@ struct tr_pt_ctx
         uint32_t read_half = 0;
         uint64_t launches = 0;
         bool used = false, deferred = false;
+        uint32_t deferred_frame_counter = 0;
+        int deferred_accumulated = 0;
     };
     Flight flights[2];
     int flight_head = 0, flight_count = 0;
@@ -965,10 +967,17 @@ int tr_pt_reset_accumulation(tr_pt_ctx* c, int reset_sample_counter)
     return TR_OK;
 }
 
+static int render_whole(tr_pt_ctx* c, void* cuda_stream);
+
 int tr_pt_render(tr_pt_ctx* c, void* cuda_stream)
 {
     if(!c) return TR_ERR_INVALID_ARGUMENT;
     if(c->flight_count) return fail(c, TR_ERR_INVALID_ARGUMENT, "frames in flight: call tr_pt_render_end first");
+    return render_whole(c, cuda_stream);
+}
+
+static int render_whole(tr_pt_ctx* c, void* cuda_stream)
+{
     DeviceGuard guard(c->device);
     int rc = prepare_targets(c);
     if(rc) return rc;
@@ -1067,11 +1076,20 @@ int tr_pt_render_begin(tr_pt_ctx* c, void* cuda_stream)
     if(c->restore_pending_layers & c->gbuffer_mask)
         return fail(c, TR_ERR_INVALID_ARGUMENT, "restored checkpoint: write the aux G-buffer layers back (tr_pt_write_gbuffer_layer) before rendering");
     tr_pt_ctx::Flight& F = c->flights[(c->flight_head + c->flight_count) % 2];
-    const bool whole = !flight_eligible(c);
-    if(c->flight_count && (whole || c->flights[c->flight_head].deferred))
-        return fail(c, TR_ERR_UNSUPPORTED, "this configuration renders frame by frame: end the begun frame before the next begins");
-    F.deferred = whole;
-    if(F.deferred) { c->flight_count++; return TR_OK; }        // rendered whole by tr_pt_render_end
+    // a frame the split does not fit is only noted here and rendered whole, frame by frame, by tr_pt_render_end; while such
+    // a frame is pending the following ones are deferred too (the order of the frames is the order of the calls)
+    F.deferred = !flight_eligible(c) || (c->flight_count && c->flights[c->flight_head].deferred);
+    if(F.deferred)
+    {
+        // the frame's place in the accumulation is taken NOW (a tr_pt_reset_accumulation for the next frame may follow before
+        // this one is ended), like the split path does
+        F.deferred_frame_counter = c->frame_counter;
+        F.deferred_accumulated = c->accumulated_samples;
+        c->frame_counter++;
+        c->accumulated_samples += c->opt.samples_per_pixel;
+        c->flight_count++;
+        return TR_OK;
+    }
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
     if(!F.stream)
     {
@@ -1149,9 +1167,16 @@ int tr_pt_render_end(tr_pt_ctx* c, void* cuda_stream)
     tr_pt_ctx::Flight& F = c->flights[c->flight_head];
     if(F.deferred)
     {
-        c->flight_count = 0;
         c->flight_head = (c->flight_head + 1) % 2;
-        return tr_pt_render(c, cuda_stream);
+        c->flight_count--;
+        const uint32_t now_counter = c->frame_counter;
+        const int now_accumulated = c->accumulated_samples;
+        c->frame_counter = F.deferred_frame_counter;
+        c->accumulated_samples = F.deferred_accumulated;
+        const int rc = render_whole(c, cuda_stream);
+        c->frame_counter = now_counter;
+        c->accumulated_samples = now_accumulated;
+        return rc;
     }
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
     RenderParams& P = *F.P;

@@ -136,11 +136,13 @@ def test_refit_updates_equal_a_fresh_scene(mode):
 
 
 def test_an_identity_refit_reproduces_the_built_tree():
-    """Refitting to the unchanged instance records must give back the boxes the build wrote: the same image AND the same
-    number of node visits and triangle tests (a looser box would still render the right image). The visit counts of the
-    persistent kernel depend a little on which rays share a warp (postponed triangle groups), hence the 0.1 % allowance."""
+    """Refitting to the unchanged instance records must give back the boxes the build wrote: the same image AND exactly the
+    same number of node visits and triangle tests (a looser box would still render the right image). Counted with the
+    megakernel organisation -- one ray per thread, a fixed traversal order -- because the visit counts of the persistent
+    wavefront kernel depend a little on which rays happen to share a warp (postponed triangle groups)."""
     from tauray_b200 import synthetic
     opt = abi.default_options(max_ray_depth=3, samples_per_pixel=1, local_sampler=abi.SAMPLER_SOBOL_OWEN)
+    opt.kernel_mode = abi.KERNEL_MEGAKERNEL
     size = (160, 90)
     scene = synthetic.atrium(20000)
     cams = synthetic.atrium_cameras(size[0] / size[1])
@@ -156,7 +158,5 @@ def test_an_identity_refit_reproduces_the_built_tree():
         got = _render(pt, cams, dist)
         st1 = pt.stats()
     assert bits_equal(got, want)
-    for k in ("closest_rays", "shadow_rays"):
-        assert st0[k] == st1[k] and st0[k] > 0, k
-    for k in ("closest_node_visits", "closest_triangle_tests", "shadow_node_visits", "shadow_triangle_tests"):
-        assert st0[k] > 0 and abs(st0[k] - st1[k]) <= 1e-3 * st0[k], (k, st0[k], st1[k])
+    for k in ("closest_rays", "shadow_rays", "closest_node_visits", "closest_triangle_tests", "shadow_node_visits", "shadow_triangle_tests"):
+        assert st0[k] == st1[k] and st0[k] > 0, (k, st0[k], st1[k])

@@ -183,9 +183,19 @@ def test_begin_end_falls_back_for_frames_it_cannot_split():
         want = pt.read_color().copy()
         pt.reset_accumulation()
         pt.render_begin()
+        pt.render_begin()                                        # such frames queue up and are rendered one by one
         with pytest.raises(TaurayB200Error):
-            pt.render_begin()
-            pt.render_end()                                      # two deferred frames cannot be pending
+            pt.render_begin()                                    # ... but never more than two
         pt.render_end()
         pt.sync()
         assert bits_equal(pt.read_color(), want)
+        # the second frame took its place in the accumulation when it was begun: samples 2..3 on top of the first
+        pt.render_end()
+        pt.sync()
+        with PathTracer(opt) as ref:
+            ref.set_scene(scene); ref.set_cameras(_cams(0)); ref.set_distribution(full_dist(SIZE))
+            ref.set_gbuffer_layers([abi.GBUFFER_ALBEDO])
+            ref.render(); ref.render(); ref.sync()
+            assert bits_equal(pt.read_color(), ref.read_color())
+        with pytest.raises(TaurayB200Error):
+            pt.render_end()
