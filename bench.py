@@ -449,12 +449,15 @@ def main():
     # N = 1: two device targets (tr_pt_set_color_buffer) + tr_pt_read_color_async; N > 1: every rank copies its 1/N byte
     # range of the double-buffered stitched image (RtRenderer.read_back_async). Every step's camera upload and image
     # read-back are inside the timed region; the host images are checked afterwards.
-    pipelined = world == 1 and reset_each_step
+    # (an accumulating run keeps ONE target: its staging copy still runs beside the next frame's traversal work when the frames
+    # overlap on the device, and the next accumulation kernel waits for it on the device)
+    pipelined = world == 1 and (reset_each_step or fif)
+    two_targets = pipelined and reset_each_step
     in_flight = pipelined or shared is not None
     e2e_count = [0]
     copied = [None, None]
     if pipelined:
-        targets = [torch.empty((VIEWS, HEIGHT, WIDTH, 4), dtype=torch.float32, device="cuda") for _ in range(2)]
+        targets = [torch.empty((VIEWS, HEIGHT, WIDTH, 4), dtype=torch.float32, device="cuda") for _ in range(2)] if two_targets else None
         hosts = [torch.empty((VIEWS, HEIGHT, WIDTH, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
         copy_stream = torch.cuda.Stream(device=local_rank)
 
@@ -478,7 +481,7 @@ def main():
             frame_end()                                     # ... then this frame's accumulation / stitch
         else:
             ren.tracer.set_cameras_async(cam_np, sptr)      # H2D (pinned), in stream order
-            if pipelined:
+            if two_targets:
                 ren.tracer.set_color_buffer(targets[b].data_ptr(), targets[b].numel() * 4)
             frame()
         if pipelined:
@@ -492,7 +495,7 @@ def main():
 
     def e2e_issue(k):
         ren.tracer.set_cameras_async(cam_np, sptr)          # H2D (pinned), in stream order
-        if pipelined:
+        if two_targets:
             ren.tracer.set_color_buffer(targets[k & 1].data_ptr(), targets[k & 1].numel() * 4)
         frame_begin()
 
@@ -516,10 +519,13 @@ def main():
     h2d = cam_host.numel() * world
     d2h = img_bytes
     e2e_image_ok = None
-    if pipelined:
+    if two_targets:
         # both host images hold a finished frame of the checked camera, rendered from a clean accumulation
         e2e_image_ok = all(sha256_of(h.numpy()) == image_sha for h in hosts)
         ren.tracer.set_color_buffer(None, 0)
+    elif pipelined:
+        # accumulating run: the host image of the last step must be the colour target as it stands now
+        e2e_image_ok = sha256_of(hosts[(args.steps - 1) & 1].numpy()) == sha256_of(ren.tracer.read_color())
     if shared is not None:
         # one more frame from a clean accumulation so that the shared host image must equal the checked one
         ren.reset_accumulation()
@@ -725,7 +731,8 @@ def main():
             "stitch_compare": stitch_compare,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_s / args.steps * 1e3,
-                    "readback": ("two frames in flight: two device targets, staging copies on a copy stream into two pinned host images (tr_pt_read_color_async)"
+                    "readback": (("two frames in flight: two device targets, staging copies on a copy stream into two pinned host images (tr_pt_read_color_async)"
+                                  if two_targets else "two frames in flight: one accumulating device target, staging copies on a copy stream into two pinned host images (tr_pt_read_color_async)")
                                  if pipelined else "one pinned host image") if world == 1 else
                                 ("two frames in flight: every rank copies its 1/N byte range of the double-buffered stitched image into one of two shared pinned host images on a copy stream%s" % ("" if pinned else " (NOT pinned: cudaHostRegister failed)")
                                  if ren.stitch == "peer" else "rank 0 copies the stitched image"),
