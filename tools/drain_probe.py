@@ -1,7 +1,13 @@
 #!/usr/bin/env python3
-"""Development aid: TR_DEBUG_DRAIN=1 python tools/drain_probe.py <world> -- prints, per traversal launch of one frame of
-one rank's share, when the queue ran empty and when the last warp left (tr_render.cu, TR_DEBUG_DRAIN)."""
+"""Development aid: python tools/drain_probe.py <world> -- prints, for one frame of one rank's share of the bench frame, the
+start and end of every kernel (%globaltimer), and per traversal launch when the queue ran empty, when the last warp left
+and a histogram of the warps' exit times (tr_render.cu, TR_DEBUG_DRAIN). TR_TUNE_SPLIT_STAGE=1 adds tail splitting."""
 import os, sys
+# the probes live in the SPLIT instantiation of the traversal kernel; its tail stage stays off unless asked for, so that
+# what is timed is the shipped schedule
+os.environ.setdefault("TR_DEBUG_DRAIN", "1")
+os.environ.setdefault("TR_TUNE_SPLIT", "3")
+os.environ.setdefault("TR_TUNE_SPLIT_STAGE", "0")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tauray_b200 import abi, distribution, synthetic
 from tauray_b200.library import PathTracer
