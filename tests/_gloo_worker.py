@@ -27,6 +27,16 @@ class OracleTracer:
     def render(self, stream=None):
         self.o.render()
 
+    # frames in flight (tr_pt_render_begin / tr_pt_render_end): the stand-in only keeps the order of the frames
+    def render_begin(self, stream=None):
+        self.begun = getattr(self, "begun", 0) + 1
+        assert self.begun <= 2
+
+    def render_end(self, stream=None):
+        assert getattr(self, "begun", 0) > 0
+        self.begun -= 1
+        self.o.render()
+
     def close(self):
         self.o.close()
 
@@ -84,7 +94,15 @@ def main():
     ren.set_scene(testscenes.cornell(), cams)
     if workloads:
         ren.set_device_workloads(workloads)
-    ren.render()
+    if len(sys.argv) > 3 and sys.argv[3] == "begin_end":
+        # three frames through RtRenderer.render_begin / render_end: begin(k + 1) before end(k), the stitch after every end
+        ren.render_begin()
+        ren.render_begin()
+        ren.render_end()
+        ren.reset_accumulation()
+        ren.render_end()
+    else:
+        ren.render()
     img = ren.image()
     np.save(os.path.join(out_dir, "rank%d.npy" % rank), img)
     ren.close()

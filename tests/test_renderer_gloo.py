@@ -31,11 +31,14 @@ def single_device_image(size):
     return o.read_color()
 
 
-@pytest.mark.parametrize("world,workloads", [(2, ""), (3, "0.5,0.3,0.2"), (2, "scanline"), (3, "scanline_primary0")])
-def test_multi_rank_stitch_equals_single_device(tmp_path, oracle_lib, world, workloads):
+@pytest.mark.parametrize("world,workloads,schedule", [(2, "", ""), (3, "0.5,0.3,0.2", ""), (2, "scanline", ""), (3, "scanline_primary0", ""),
+                                                      (2, "", "begin_end")])
+def test_multi_rank_stitch_equals_single_device(tmp_path, oracle_lib, world, workloads, schedule):
+    """`begin_end`: the frames go through RtRenderer.render_begin / render_end (two frames in flight: the stitch of a frame
+    follows its end, the next frame is begun before); the last frame starts from a clean accumulation like the others."""
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(free_port()),
-           os.path.join(ROOT, "tests", "_gloo_worker.py"), str(tmp_path), workloads]
+           os.path.join(ROOT, "tests", "_gloo_worker.py"), str(tmp_path), workloads, schedule]
     env = dict(os.environ, OMP_NUM_THREADS="1", CUDA_VISIBLE_DEVICES="")
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-3000:]
