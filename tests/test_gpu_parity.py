@@ -228,7 +228,10 @@ def test_errors_are_reported_not_swallowed():
                                  {"TR_TUNE_BUILDER": "lbvh", "TR_TUNE_BOTTOM": "0"}, {"TR_TUNE_BUILDER": "sah", "TR_TUNE_SAH_AXES": "0"},
                                  {"TR_TUNE_BUILDER": "sah", "TR_TUNE_SAH_AXES": "2", "TR_TUNE_BOTTOM": "16"},
                                  {"TR_TUNE_COOP": "3"}, {"TR_TUNE_COOP": "3", "TR_TUNE_COOP_GROUPS": "4", "TR_TUNE_COOP_WAIT": "1"},
-                                 {"TR_TUNE_NEAREST": "1"}, {"TR_TUNE_TMA": "3"}, {"TR_TUNE_TMA": "0", "TR_TUNE_SHADE_SPEC": "0"}])
+                                 {"TR_TUNE_NEAREST": "1"}, {"TR_TUNE_TMA": "3"}, {"TR_TUNE_TMA": "0", "TR_TUNE_SHADE_SPEC": "0"},
+                                 {"TR_TUNE_SPLIT": "3"}, {"TR_TUNE_SPLIT": "3", "TR_TUNE_SPLIT_STEPS": "4"},
+                                 {"TR_TUNE_FUSE": "3", "TR_TUNE_SPLIT": "3", "TR_TUNE_SPLIT_STEPS": "8"}, {"TR_TUNE_FUSE": "1"},
+                                 {"TR_TUNE_SHADE_PREFETCH": "2"}, {"TR_TUNE_KEEP_CLOSED": "8"}, {"TR_TUNE_OVERLAP": "0"}])
 def test_image_does_not_depend_on_the_tree_or_the_schedule(env):
     """The predicate, not the acceleration structure, defines the image: every hierarchy builder (radix tree, binned SAH
     with any axis rule, PLOC), other leaf sizes, bottom-node cuts and traversal schedules, and the measured-and-rejected
